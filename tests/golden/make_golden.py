@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Extract the reference's own fixtures into small, committed golden files.
+
+Run in the build container only (it reads ``/root/reference``, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+For every fixture ``tests/<name>/results.tgz`` of the reference it writes ``tests/golden/<name>.npz`` with
+
+* the model record rebuilt from the cached MEAD logs (site ranges, protons, Gmodel, Gintr, raw W), and
+* the golden outputs the reference's logs/curve files hold for the microstate path: ``Gmicro`` lists,
+  analytic and MC titration curves, pH-7 probability tables, double-move pair lists, and (where
+  shipped) the 8-decimal ``job.gint`` / ``job.inter`` tables.
+
+Nothing here is executed by the product; the files are test data.
+"""
+
+import io
+import os
+import re
+import sys
+import tarfile
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from pcetk_b200 import formats  # noqa: E402
+
+REFERENCE = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# name -> (log file inside results/, analytic-curves dir, MC-curves dirs)
+# NB twosites: directory names are swapped relative to their content (twosites.py:45-53 attaches
+# the MC sampler before writing "curves_analytic"); see SURVEY.md section 0.
+FIXTURES = {
+    "twosites": dict(log="twosites.out", analytic="curves_mc", mc=["curves_analytic"]),
+    "lysozyme": dict(log="lysozyme.out", analytic="curves_analytic", mc=["curves_mc"]),
+    "defensin": dict(log="defensin.out", analytic="curves_analytic", mc=["curves_custom", "curves_gmct"]),
+    "lysozyme_full_test": dict(log="lysozyme.out", analytic="curves_analytic", mc=["curves_custom", "curves_gmct"]),
+    "rubredoxin": dict(log="rubredoxin.out", analytic="curves_analytic", mc=["curves_custom", "curves_gmct"]),
+    "ifp20": dict(log="ifp20.out", analytic=None, mc=["curves"]),
+}
+
+
+def find(root, name):
+    for base, _dirs, files in os.walk(root):
+        if name in files:
+            return os.path.join(base, name)
+    return None
+
+
+def parse_gmicro(log_text):
+    """All 'Gmicro = x' titles (twosites.py:24-29 style) in order of appearance."""
+    return [float(x) for x in re.findall(r"Gmicro\s*=\s*(-?\d+\.\d+)", log_text)]
+
+
+def parse_state_gmicro_table(log_text):
+    """The 'State  Gmicro' two-column table (first N microstate energies; defensin.py, lysozyme_full_test)."""
+    values = []
+    lines = log_text.splitlines()
+    for i, line in enumerate(lines):
+        if re.match(r"^\s*State\s+Gmicro\s*$", line):
+            for row in lines[i + 2:]:
+                m = re.match(r"^\s*(\d+)\s+(-?\d+\.\d+)\s*$", row)
+                if not m:
+                    break
+                values.append(float(m.group(2)))
+            break
+    return values
+
+
+def parse_pairs(log_text):
+    """First 'Found N pair(s) of strongly interacting sites' block (MCModelDefault.pyx:176-194)."""
+    lines = log_text.splitlines()
+    for i, line in enumerate(lines):
+        m = re.match(r"^Found (\d+) pairs? of strongly interacting sites", line)
+        if m:
+            pairs = []
+            for row in lines[i + 1:i + 1 + int(m.group(1))]:
+                pm = re.match(r"^\s*(\S+)\s+(\S+)\s+(-?\d+)\s+--\s+(\S+)\s+(\S+)\s+(-?\d+)\s+:\s+(-?\d+\.\d+)", row)
+                pairs.append(((pm.group(1), pm.group(2), int(pm.group(3))), (pm.group(4), pm.group(5), int(pm.group(6))), float(pm.group(7))))
+            return pairs
+    return []
+
+
+def parse_probability_tables(log_text, record):
+    """Every 'Probabilities of instances' table (CEModel.SummaryProbabilities, CEModel.py:220-274) -> list of p[ninst] (4 dp)."""
+    tables = []
+    lines = log_text.splitlines()
+    i = 0
+    site_index = {s: k for k, s in enumerate(record.site_labels)}
+    while i < len(lines):
+        if "Probabilities of instances" in lines[i]:
+            p = np.full(record.ninstances, np.nan)
+            j = i + 2
+            while j < len(lines) and not lines[j].startswith("---"):
+                t = lines[j].split()
+                key = (t[0], t[1], int(t[2]))
+                k = site_index[key]
+                first = int(record.site_first[k])
+                values = t[3:]
+                for q in range(len(values) // 2):
+                    p[first + q] = float(values[2 * q + 1])
+                j += 1
+            tables.append(p)
+            i = j
+        i += 1
+    return tables
+
+
+def main():
+    parameters_dir = os.path.join(REFERENCE, "parameters", "sites")
+    est = [os.path.join(REFERENCE, "tests", "ifp20", n) for n in ("BLF.est", "ACB.est", "ACC.est")]
+    parameters = formats.load_site_parameters(parameters_dir, est)
+    for name, spec in FIXTURES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            with tarfile.open(os.path.join(REFERENCE, "tests", name, "results.tgz")) as tar:
+                tar.extractall(tmp)
+            results = os.path.join(tmp, "results")
+            with open(os.path.join(results, spec["log"])) as handle:
+                log_text = handle.read()
+            record = formats.model_from_mead_directory(name, log_text, os.path.join(results, "mead"), parameters)
+            payload = record.to_npz_dict()
+
+            # Gintr as printed in the log (4 dp) is a cross-check of the rebuild
+            rows = formats.parse_instance_table(log_text)
+            payload["golden_gintr_4dp"] = np.array([r[-1] for r in rows])
+
+            gm = parse_gmicro(log_text)
+            if not gm:
+                gm = parse_state_gmicro_table(log_text)
+            payload["golden_gmicro"] = np.array(gm, dtype=np.float64)
+
+            pairs = parse_pairs(log_text)
+            site_index = {s: k for k, s in enumerate(record.site_labels)}
+            payload["golden_pairs"] = np.array([[site_index[a], site_index[b]] for a, b, _w in pairs], dtype=np.int32).reshape(-1, 2)
+            payload["golden_pairs_wmax"] = np.array([w for _a, _b, w in pairs], dtype=np.float64)
+
+            tables = parse_probability_tables(log_text, record)
+            if tables:
+                payload["golden_prob_tables_ph7"] = np.stack(tables)
+
+            if spec["analytic"]:
+                ph, p = formats.read_curves_directory(os.path.join(results, spec["analytic"]), record)
+                payload["golden_curve_ph"] = ph
+                payload["golden_curve_analytic"] = p
+            for k, d in enumerate(spec["mc"]):
+                ph, p = formats.read_curves_directory(os.path.join(results, d), record)
+                payload["golden_curve_ph"] = ph
+                payload["golden_curve_mc_%s" % d] = p
+
+            gint = find(results, "job.gint")
+            inter = find(results, "job.inter")
+            if gint and inter:
+                grows = formats.read_gintr(gint)
+                payload["golden_job_gint"] = np.array([r[4] for r in grows])
+                payload["golden_job_protons"] = np.array([r[5] for r in grows], dtype=np.int32)
+                n = record.ninstances
+                wsym = np.zeros((n, n))
+                wraw = np.zeros((n, n))
+                index = {(r[0], r[1]): i for i, r in enumerate(grows)}
+                for r in formats.read_w(inter):
+                    wsym[index[(r[0], r[1])], index[(r[4], r[5])]] = r[8]
+                    wraw[index[(r[0], r[1])], index[(r[4], r[5])]] = r[9]
+                payload["golden_job_wsym"] = wsym
+                payload["golden_job_wraw"] = wraw
+                # keep a verbatim head of each table as a reader/writer format fixture
+                with open(gint) as handle:
+                    payload["golden_job_gint_head"] = np.array("".join(handle.readlines()[:8]))
+                with open(inter) as handle:
+                    payload["golden_job_inter_head"] = np.array("".join(handle.readlines()[:8]))
+
+            if name == "twosites":
+                # verbatim MEAD logs of one instance: parser fixture
+                for fn in ("site_HSP.out", "model_HSP.out"):
+                    with open(os.path.join(results, "mead", "PRTA", "HIS5", fn)) as handle:
+                        payload["golden_mead_%s" % fn.replace(".", "_")] = np.array(handle.read())
+
+            path = os.path.join(OUT, name + ".npz")
+            np.savez_compressed(path, **payload)
+            print("%-20s nsites=%3d ninst=%3d nstates=%.4g gmicro=%d pairs=%d -> %s (%d KB)" % (
+                name, record.nsites, record.ninstances, float(record.nstates), len(gm), len(pairs), os.path.basename(path), os.path.getsize(path) // 1024))
+
+    # lysozyme_traj: per-scan MC energies at pH 7 (stat_mc.dat) and move counters; same model as 'lysozyme'
+    with tempfile.TemporaryDirectory() as tmp:
+        with tarfile.open(os.path.join(REFERENCE, "tests", "lysozyme_traj", "results.tgz")) as tar:
+            tar.extractall(tmp)
+        stat = find(tmp, "stat_mc.dat")
+        energies = np.loadtxt(stat)
+        log = find(tmp, "lyso_mc_traj.out")
+        with open(log) as handle:
+            text = handle.read()
+        counters = []
+        for row in text.splitlines():
+            m = re.match(r"^\s*(\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s+(\d+)\s*$", row)
+            if m:
+                counters.append([int(x) for x in m.groups()])
+        np.savez_compressed(os.path.join(OUT, "lysozyme_traj.npz"), stat_mc=energies, counters=np.array(counters, dtype=np.int64))
+        print("lysozyme_traj        energies=%d counters=%d" % (len(energies), len(counters)))
+
+
+if __name__ == "__main__":
+    main()
