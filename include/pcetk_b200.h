@@ -1,0 +1,169 @@
+/* pcetk_b200.h -- C ABI of the B200 microstate engine.
+ *
+ * Drop-in boundary for the hot path of efliks/pcetk: everything the reference's Cython layer
+ * (extensions/cython/ContinuumElectrostatics.{StateVector,EnergyModel,MCModelDefault}.pyx) binds from
+ *   extensions/cinclude/StateVector.h:53-84, EnergyModel.h:64-101, MCModelDefault.h:58-71
+ * has an entry point here, flattened to opaque handles, plain pointers and sizes (no torch types), so
+ * that ctypes / Cython / cgo / JNI can bind it.  Each declaration names the reference interface it
+ * replaces.  See INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns a pce_status (0 = ok); pce_last_error() gives the text for the calling thread
+ *     (the reference threads a `Status *` out-parameter instead, Status.h in pCore);
+ *   - instance indices are GLOBAL instance indices unless a parameter is called `local`;
+ *   - a model handle is safe for one call at a time; results are returned in caller-owned buffers and
+ *     are also stored in the model's probability array, as the reference does (EnergyModel.h:50);
+ *   - pointers named d_* are DEVICE pointers on the model's device, all others are HOST pointers;
+ *   - kernels are launched on the stream set with pce_set_stream (default: the legacy default stream);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with PCE_ERR_CUDA.
+ */
+#ifndef PCETK_B200_H
+#define PCETK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pce_model pce_model; /* replaces EnergyModel + its private StateVector (EnergyModel.h:39-60) */
+typedef struct pce_mc    pce_mc;    /* replaces MCModelDefault (MCModelDefault.h:41-54) */
+
+typedef enum {
+    PCE_OK            = 0,
+    PCE_ERR_ALLOC     = 1, /* Status_MemoryAllocationFailure */
+    PCE_ERR_INDEX     = 2, /* Status_IndexOutOfRange */
+    PCE_ERR_VALUE     = 3, /* Status_ValueError */
+    PCE_ERR_SHAPE     = 4, /* Status_ArrayNonConformableSizes */
+    PCE_ERR_STATE     = 5, /* call order: sites not set, interactions not symmetrised, ... */
+    PCE_ERR_CUDA      = 6, /* CUDA runtime error or no device */
+    PCE_ERR_LIMIT     = 7  /* too many states / instances for the requested kernel */
+} pce_status;
+
+/* ---- library / device -------------------------------------------------------------------------- */
+const char *pce_last_error (void);
+const char *pce_version (void);
+int pce_device_count (int *count);
+int pce_device_name (int device, char *buffer, int length);
+int pce_set_stream (pce_model *model, void *cuda_stream);       /* cudaStream_t; NULL = default stream */
+int pce_synchronize (pce_model *model);
+/* launch counter: kernels launched by this library since the last reset (bench.py's gpu_launches) */
+long long pce_launch_count (int reset);
+
+/* ---- model: allocation (EnergyModel_Allocate / _Deallocate, EnergyModel.h:64-65) ---------------- */
+int  pce_model_create (int nsites, int ninstances, double temperature, int device, pce_model **out);
+void pce_model_destroy (pce_model *model);
+int  pce_model_nsites (const pce_model *model);
+int  pce_model_ninstances (const pce_model *model);
+double pce_model_temperature (const pce_model *model);
+
+/* StateVector_SetSite (StateVector.h:68) for the model's site table; ranges must be contiguous and
+ * ascending across sites (EnergyModel.c:217-221 relies on it). */
+int pce_model_set_site (pce_model *model, int site, int first, int last);
+int pce_model_set_sites (pce_model *model, const int32_t *first, const int32_t *last);
+int pce_model_get_site (const pce_model *model, int site, int *first, int *last);
+/* number of microstates as a double (exact below 2^53); EnergyModel.pyx:86-110 computes the capped int */
+int pce_model_nstates (const pce_model *model, double *nstates);
+
+/* EnergyModel_Set* / _Get* (EnergyModel.h:87-99) */
+int pce_model_set_gmodel (pce_model *model, int instance, double value);
+int pce_model_set_gintr (pce_model *model, int instance, double value);
+int pce_model_set_protons (pce_model *model, int instance, int value);
+int pce_model_set_probability (pce_model *model, int instance, double value);
+int pce_model_set_interaction (pce_model *model, int instance_a, int instance_b, double value);
+int pce_model_get_gmodel (const pce_model *model, int instance, double *value);
+int pce_model_get_gintr (const pce_model *model, int instance, double *value);
+int pce_model_get_protons (const pce_model *model, int instance, int *value);
+int pce_model_get_probability (const pce_model *model, int instance, double *value);
+int pce_model_get_interaction (const pce_model *model, int instance_a, int instance_b, double *value);
+int pce_model_get_interaction_symmetric (const pce_model *model, int instance_a, int instance_b, double *value); /* EnergyModel_GetInterSymmetric */
+int pce_model_get_deviation (const pce_model *model, int instance_a, int instance_b, double *value);             /* EnergyModel_GetDeviation */
+/* bulk forms of the setters / getters (any pointer may be NULL to skip it); interactions is
+ * ninstances x ninstances row-major, raw (EnergyModel.h:46) */
+int pce_model_load (pce_model *model, const double *gintr, const double *gmodel, const int32_t *protons, const double *interactions);
+int pce_model_get_probabilities (const pce_model *model, double *probabilities);
+int pce_model_set_probabilities (pce_model *model, const double *probabilities);
+int pce_model_get_symmetric_matrix (const pce_model *model, double *w /* ninstances^2 */);
+
+/* EnergyModel_CheckInteractionsSymmetric / _SymmetrizeInteractions / _ResetInteractions /
+ * _ScaleInteractions (EnergyModel.h:68-71) */
+int pce_model_check_symmetric (const pce_model *model, double tolerance, double *max_deviation, int *is_symmetric);
+int pce_model_symmetrize (pce_model *model);
+int pce_model_reset_interactions (pce_model *model);
+int pce_model_scale_interactions (pce_model *model, double scale);
+/* EnergyModel_StateVectorFromProbabilities (EnergyModel.h:72), without the reference's off-by-one */
+int pce_model_state_from_probabilities (const pce_model *model, int32_t *state_global);
+
+/* copy the model to its device (done implicitly by compute calls when the host copy changed) */
+int pce_model_upload (pce_model *model);
+
+/* ---- kernel 1: microstate energies --------------------------------------------------------------
+ * EnergyModel_CalculateMicrostateEnergy[Unfolded] (EnergyModel.h:75-76), batched: `states` holds
+ * nstates rows of nsites GLOBAL instance indices; out[s * nph + q] = G(state s, pH q).
+ * Bit-identical to the reference's arithmetic (same summation order, no FMA contraction). */
+int pce_energy (pce_model *model, const int32_t *states, long long nstates, const double *ph, int nph, int unfolded, double *out);
+int pce_energy_device (pce_model *model, const int32_t *d_states, long long nstates, const double *d_ph, int nph, int unfolded, double *d_out);
+
+/* ---- kernel 2: exhaustive enumeration ------------------------------------------------------------
+ * EnergyModel_CalculateProbabilitiesAnalytically[Unfolded], _CalculateZfolded/_Zunfolded
+ * (EnergyModel.h:79-86) for a whole pH grid in one call.  States are binned by proton count, so one
+ * enumeration serves every pH value (kernel 2).
+ *
+ * pce_analytic_bins_size: number of doubles in a bins buffer for this model.
+ * pce_analytic_bins     : enumerate shard `shard` of `nshards` (equal slices of the outer state index)
+ *                         into d_bins (device, zeroed by the call).  Bins of different shards ADD, which
+ *                         is the only multi-GPU exchange the path needs (one all-reduce(sum)).
+ * pce_analytic_finish   : (host) turn summed bins into probabilities for each pH: out_p[q*ninst + k];
+ *                         out_lnz[q] = ln sum_s exp(-(G_s(pH_q) - gzero)/RT) (may be NULL); also stores
+ *                         the last pH's probabilities in the model.
+ * pce_analytic          : the three steps on one device with host buffers.
+ * max_states: refuse above this many states (reference: 2^26, EnergyModel.pyx:11,156); <= 0 = engine limit. */
+long long pce_analytic_bins_size (const pce_model *model);
+int pce_analytic_bins (pce_model *model, const double *ph, int nph, int unfolded, int shard, int nshards, double max_states, double *d_bins);
+int pce_analytic_finish (pce_model *model, const double *bins /* host */, const double *ph, int nph, int unfolded, double gzero,
+                         double *out_p, double *out_lnz);
+int pce_analytic (pce_model *model, const double *ph, int nph, int unfolded, double gzero, double max_states, double *out_p, double *out_lnz);
+/* exact minimum microstate energy at one pH (the shift the reference applies, EnergyModel.c:262-275):
+ * with it, Z as returned by EnergyModel_CalculateZfolded is exp(lnz + Gmin/RT). */
+int pce_analytic_gmin (pce_model *model, double ph, int unfolded, double max_states, double *gmin);
+
+/* ---- kernel 3: Metropolis Monte Carlo -----------------------------------------------------------
+ * MCModelDefault_Allocate / _Deallocate / _LinkToEnergyModel / _FindPairs (MCModelDefault.h:58-68).
+ * seed <= 0 seeds from the clock like the reference (MCModelDefault.c:32-34).  nchains independent
+ * chains are run per pH value (the reference runs one). */
+int  pce_mc_create (pce_model *model, double limit, int nequil, int nprod, long long seed, int nchains, pce_mc **out);
+void pce_mc_destroy (pce_mc *mc);
+int  pce_mc_npairs (const pce_mc *mc);
+int  pce_mc_get_pair (const pce_mc *mc, int index, int *site_a, int *site_b, double *wmax);   /* StateVector_GetPair */
+int  pce_mc_set_scans (pce_mc *mc, int nequil, int nprod);
+int  pce_mc_set_chains (pce_mc *mc, int nchains);
+int  pce_mc_set_kernel (pce_mc *mc, int kernel);   /* 0 = auto, 1 = chain-per-thread, 2 = chain-per-warp */
+int  pce_mc_get_info (const pce_mc *mc, int *kernel, int *nchains, int *nequil, int *nprod, long long *seed);
+
+/* MCModelDefault_Equilibration + _Production (MCModelDefault.h:70-71) for nph pH values x nchains
+ * chains in one launch.  Chains [chain_offset, chain_offset + nchains) of a global ensemble are run
+ * (ranks of a multi-GPU job pass disjoint offsets; streams depend only on (seed, pH index offset +
+ * q, chain)).  Outputs (any may be NULL):
+ *   counts  [nph * ninst]  production scans during which each instance was active, summed over chains
+ *   counters[nph * 4]      moves, moves accepted, double moves, double moves accepted (production)
+ *   esum    [nph]          sum over chains and production scans of the microstate energy
+ * pce_mc_run also stores counts/(nchains*nprod) of the LAST pH value in the model's probabilities. */
+int pce_mc_run (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
+                long long *counts, long long *counters, double *esum);
+int pce_mc_run_device (pce_mc *mc, const double *ph /* host */, int nph, int ph_index_offset, long long chain_offset,
+                       long long *d_counts, long long *d_counters, double *d_esum);
+/* per-chain outputs for parity tests against the chain specification (oracle_mc_philox_chain):
+ * chain_counts[nph*nchains*ninst], chain_state[nph*nchains*nsites], chain_energy[nph*nchains] */
+int pce_mc_run_chains (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
+                       long long *chain_counts, int32_t *chain_state, double *chain_energy, double *chain_esum, long long *chain_counters);
+/* MCModelDefault.pyx:79-159 trajectory mode: energies[nprod] of chain 0 after every production scan */
+int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, long long *counts, long long *counters);
+
+/* ---- test hooks ----------------------------------------------------------------------------------- */
+/* Philox4x32-10 blocks computed ON THE DEVICE: out[4*i..] for counters ctr[4*i..], one key */
+int pce_test_philox (int device, const uint32_t *ctr, int nblocks, const uint32_t key[2], uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCETK_B200_H */

@@ -1,0 +1,103 @@
+"""Substate: energies of all protonation forms of a few selected sites around the most probable state
+(``ContinuumElectrostatics/Substate.py``).  The reference makes one C call per substate from a Python loop
+(:91-119); here every substate goes into one kernel-1 batch.
+"""
+
+import numpy as np
+
+from .errors import ContinuumElectrostaticsError
+from .log import logFile, LogFileActive
+from .StateVector import StateVector
+
+
+def StateVector_FromProbabilities(meadModel):
+    """State vector of the most probable instance per site (Substate.py:232-246; ties -> highest index, as ``max`` of pairs)."""
+    if not meadModel.isProbability:
+        raise ContinuumElectrostaticsError("First calculate probabilities.")
+    vector = StateVector(meadModel)
+    for siteIndex, site in enumerate(meadModel.sites):
+        pairs = [(instance.probability, instanceIndex) for instanceIndex, instance in enumerate(site.instances)]
+        _probability, instanceIndex = max(pairs)
+        vector[siteIndex] = instanceIndex
+    return vector
+
+
+class Substate(object):
+    """Substate of a protonation state."""
+
+    def __init__(self, meadModel, selectedSites, pH=7.0, log=logFile):
+        """|selectedSites| is a sequence of (segmentName, residueName, residueSerial)."""
+        pairs, indicesOfSites = [], []
+        for selectedSegment, selectedResidueName, selectedResidueSerial in selectedSites:
+            for siteIndex, site in enumerate(meadModel.sites):
+                if site.segName == selectedSegment and site.resSerial == selectedResidueSerial:
+                    indicesOfSites.append(siteIndex)
+                    break
+            else:
+                raise ContinuumElectrostaticsError("Site %s %s %d not found." % (selectedSegment, selectedResidueName, selectedResidueSerial))
+            pairs.append([selectedSegment, selectedResidueSerial])
+        self.indicesOfSites = indicesOfSites
+        self.isCalculated = False
+        self.substates = None
+        self.owner = meadModel
+        self.pH = pH
+        self.vector = self._DetermineLowestEnergyVector()
+        self.vector.DefineSubstate(pairs)
+        if LogFileActive(log):
+            nsites = len(indicesOfSites)
+            log.Text("\nSubstate is initialized with %d site%s.\n" % (nsites, "s" if nsites > 1 else ""))
+
+    def _DetermineLowestEnergyVector(self):
+        owner = self.owner
+        backup = owner.energyModel.GetProbabilities() if owner.isProbability else None
+        owner.CalculateProbabilities(pH=self.pH, log=None)
+        vector = StateVector_FromProbabilities(owner)
+        if backup is not None:
+            owner.energyModel.SetProbabilities(backup)
+        else:
+            owner.isProbability = False       # (the reference misspells this attribute, Substate.py:63)
+        return vector
+
+    def CalculateSubstateEnergies(self, log=logFile):
+        """Enumerate the substate with IncrementSubstate and evaluate all of it in one batch (Substate.py:91-119)."""
+        if not self.isCalculated:
+            vector = self.vector
+            vector.ResetSubstate()
+            states, locals_ = [], []
+            increment = True
+            while increment:
+                states.append(vector.GlobalIndices())
+                locals_.append([vector[siteIndex] for siteIndex in self.indicesOfSites])
+                increment = vector.IncrementSubstate()
+            energies = self.owner.energyModel.CalculateMicrostateEnergies(np.stack(states), pH=float(self.pH))
+            substates = [[float(energy), indices] for energy, indices in zip(energies, locals_)]
+            substates.sort()
+            self.substates = substates
+            self.zeroEnergy = substates[0][0]
+            self.isCalculated = True
+            if LogFileActive(log):
+                log.Text("\nCalculating substate energies at pH=%.1f complete.\n" % self.pH)
+
+    def Summary(self, relativeEnergy=True, roundCharge=True, title="", log=logFile):
+        """Table of substate energies (Substate.py:122-168; the Charge column needs atomic charges, which the
+        precomputed-energy input does not carry, so it is omitted)."""
+        if self.isCalculated and LogFileActive(log):
+            owner = self.owner
+            header = ["State", "Gmicro", "Protons"] + ["%s %s %d" % (owner.sites[i].segName, owner.sites[i].resName, owner.sites[i].resSerial)
+                                                       for i in self.indicesOfSites]
+            rows = [header]
+            for stateIndex, (energy, indicesOfInstances) in enumerate(self.substates):
+                if relativeEnergy:
+                    energy = energy - self.zeroEnergy
+                nprotons, labels = 0, []
+                for siteIndex, instanceIndex in zip(self.indicesOfSites, indicesOfInstances):
+                    instance = owner.sites[siteIndex].instances[instanceIndex]
+                    nprotons += instance.protons
+                    labels.append(instance.label)
+                rows.append(["%6d" % (stateIndex + 1), "%9.2f" % energy, "%d" % nprotons] + labels)
+            log.Table(rows, title=title or None)
+
+
+class MEADSubstate(Substate):
+    """A class to maintain backward compatibility (Substate.py:224-226)."""
+    pass

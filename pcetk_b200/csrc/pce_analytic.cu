@@ -1,0 +1,727 @@
+// pce_analytic.cu -- kernel 2: exhaustive enumeration of the partition function.
+//
+// Replaces EnergyModel_CalculateZ / _CalculateProbabilitiesFromZ / _CalculateProbabilitiesAnalytically
+// (extensions/csource/EnergyModel.c:252-281, 318-337, 342-371).  The reference recomputes every
+// microstate energy from scratch (O(nsites^2/2) gathers per state, its own TODO at :264-267), stores
+// nstates Boltzmann factors, and repeats all of it for every pH value.  This kernel does neither:
+//
+//   (1) G_s(pH) = A_s + n_s * R T ln10 * pH, so states are BINNED BY PROTON COUNT n_s and one
+//       enumeration at a reference pH* serves the whole pH grid:
+//           Z(pH)    = sum_n  Zbin[n]    * 10^(-n (pH - pH*)),
+//           p_a(pH)  = sum_n  Sbin[a][n] * 10^(-n (pH - pH*)) / Z(pH);
+//   (2) sites are split into roles -- M (one configuration per thread, fixed for the kernel), I (a few
+//       configurations looped in registers), O (looped by the CTA, "tiles"), F (fixed per CTA, "chunk") --
+//       and the energy of a state is a sum of terms that each depend on one role group plus static
+//       cross terms.  The Boltzmann factor is therefore a PRODUCT of table entries:
+//           b = cOut * eLo[m_lo] * eHi[m_hi] * xMM[m] * eI[i] * xMI[m][i]
+//       with a handful of exp() per tile instead of one per state;
+//   (3) per-instance sums need no work in the inner loop for sites whose instance is fixed per thread (M)
+//       or per CTA (F): they fall out of the per-thread bins at the end.  The sites that were looped (I, O)
+//       are covered by a second enumeration with the roles rotated.
+//
+// Every partial result is a plain sum with a common reference energy, so shards of the chunk range -- on
+// one GPU or many -- combine by addition (one all-reduce).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "pce_common.cuh"
+
+using pce::fail;
+
+namespace {
+
+constexpr int kBlock     = 256;   // threads per CTA = max configurations of the M group
+constexpr int kMaxM      = 8;
+constexpr int kMaxI      = 4;
+constexpr int kIStates   = 16;    // max configurations of the I group (per-thread register table)
+constexpr int kMaxOuter  = 96;    // max sites in O + F
+constexpr int kMaxMI     = 320;   // max instances in M + I sites
+constexpr long long kMaxChunks = 16384;
+
+struct EnumParams {
+    int nsites, ninst, ldw, unfolded;
+    const double  *gt;          // tilted intrinsic energies G'[a] = G[a] - protons[a]*mu(pH*)
+    const double  *w;
+    const int32_t *protons, *first;
+    int   nM, nLo, nI, nO, nF;  // group sizes; M = Lo (first nLo) + Hi
+    int   P_lo, P_hi, P_M, P_I;
+    long long P_O;              // tiles per chunk
+    long long chunk_begin, nchunks;
+    int   Nb;                   // number of proton-count bins
+    double beta, gref;
+    int16_t siteM[kMaxM], radM[kMaxM];
+    int16_t siteI[kMaxI], radI[kMaxI];
+    int16_t siteOut[kMaxOuter], radOut[kMaxOuter];   // O sites first (fastest digit first), then F sites
+    double *T;                  // [nchunks][Nb][kBlock] per-thread bins
+};
+
+__device__ __forceinline__ double block_min (double v, double *scratch) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin (v, __shfl_xor_sync (0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads ();
+    double r = scratch[0];
+    for (int k = 1; k < kBlock / 32; k++) r = fmin (r, scratch[k]);
+    __syncthreads ();
+    return r;
+}
+
+// One CTA per chunk (configuration of the F sites).  See the file header for the algorithm.
+__global__ void __launch_bounds__ (kBlock) k_enum (const EnumParams p) {
+    extern __shared__ __align__ (16) unsigned char smem[];
+    double *bins = (double *) smem;                          // [Nb][kBlock]
+    __shared__ double  s_gF[kMaxMI], s_gOut[kMaxMI];         // outer-site fields on the M/I instances
+    __shared__ double  s_eLo[kBlock], s_eHi[kBlock], s_eI[kIStates];
+    __shared__ int32_t s_instMI[kMaxMI];                     // compact list of the M and I instances
+    __shared__ int32_t s_offM[kMaxM + 1], s_offI[kMaxI + 1]; // start of each site in the compact list
+    __shared__ int32_t s_aOut[kMaxOuter];                    // active instance of every outer site
+    __shared__ int32_t s_nI[kIStates];                       // protons of each I configuration
+    __shared__ double  s_scratch[kBlock / 32];
+    __shared__ double  s_cOut, s_cExp, s_AF;
+    __shared__ int     s_nOut, s_nF;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nOuter = p.nO + p.nF, ldw = p.ldw;
+    const bool folded = !p.unfolded;
+    const long long chunk = p.chunk_begin + blockIdx.x;
+
+    // ---- static setup -------------------------------------------------------------------------
+    if (tid == 0) {
+        int o = 0;
+        for (int i = 0; i < p.nM; i++) { s_offM[i] = o; for (int k = 0; k < p.radM[i]; k++) s_instMI[o++] = p.first[p.siteM[i]] + k; }
+        s_offM[p.nM] = o;
+        for (int i = 0; i < p.nI; i++) { s_offI[i] = o; for (int k = 0; k < p.radI[i]; k++) s_instMI[o++] = p.first[p.siteI[i]] + k; }
+        s_offI[p.nI] = o;
+        // F digits of this chunk (F sites are the high digits of the outer odometer)
+        long long c = chunk;
+        for (int j = p.nO; j < nOuter; j++) { s_aOut[j] = p.first[p.siteOut[j]] + (int) (c % p.radOut[j]); c /= p.radOut[j]; }
+        for (int j = 0; j < p.nO; j++) s_aOut[j] = p.first[p.siteOut[j]];
+    }
+    for (int e = tid; e < p.Nb * kBlock; e += kBlock) bins[e] = 0.0;
+    __syncthreads ();
+    const int nMI = s_offI[p.nI];
+
+    // I configurations: protons and I-I interaction energy (same for all threads)
+    if (tid < p.P_I) {
+        int x = tid, np = 0;
+        for (int i = 0; i < p.nI; i++) { np += p.protons[s_instMI[s_offI[i] + x % p.radI[i]]]; x /= p.radI[i]; }
+        s_nI[tid] = np;
+    }
+
+    // this thread's M configuration
+    const bool mine = tid < p.P_M;
+    int    aM[kMaxM];
+    int    m_lo = 0, m_hi = 0, nMp = 0;
+    double eMM = 0.0;
+    {
+        int x = mine ? tid : 0, stride_lo = 1, stride_hi = 1;
+#pragma unroll
+        for (int i = 0; i < kMaxM; i++) {
+            aM[i] = 0;
+            if (i < p.nM) {
+                const int d = x % p.radM[i];
+                x /= p.radM[i];
+                aM[i] = p.first[p.siteM[i]] + d;
+                nMp += p.protons[aM[i]];
+                if (i < p.nLo) { m_lo += d * stride_lo; stride_lo *= p.radM[i]; } else { m_hi += d * stride_hi; stride_hi *= p.radM[i]; }
+            }
+        }
+        if (folded) {
+#pragma unroll
+            for (int i = 0; i < kMaxM; i++)
+#pragma unroll
+                for (int j = 0; j < kMaxM; j++)
+                    if (j < i && i < p.nM) eMM += p.w[(size_t) aM[i] * ldw + aM[j]];
+        }
+    }
+    // static cross terms E_MI(m,i) + E_II(i)
+    double xMI[kIStates];
+#pragma unroll
+    for (int i = 0; i < kIStates; i++) {
+        double e = 0.0;
+        if (i < p.P_I && folded) {
+            int aI[kMaxI];
+            int x = i;
+#pragma unroll
+            for (int k = 0; k < kMaxI; k++) { aI[k] = 0; if (k < p.nI) { aI[k] = p.first[p.siteI[k]] + x % p.radI[k]; x /= p.radI[k]; } }
+#pragma unroll
+            for (int k = 0; k < kMaxI; k++) {
+                if (k < p.nI) {
+                    const double *row = p.w + (size_t) aI[k] * ldw;
+#pragma unroll
+                    for (int l = 0; l < kMaxI; l++) if (l < k) e += row[aI[l]];
+#pragma unroll
+                    for (int l = 0; l < kMaxM; l++) if (l < p.nM) e += row[aM[l]];
+                }
+            }
+        }
+        xMI[i] = e;
+    }
+    // normalise the static factors by their minima over all (m) and (m,i): every factor <= 1
+    {
+        double vmin = mine ? eMM : DBL_MAX;
+        const double minMM = block_min (vmin, s_scratch);
+        vmin = DBL_MAX;
+#pragma unroll
+        for (int i = 0; i < kIStates; i++) if (mine && i < p.P_I) vmin = fmin (vmin, xMI[i]);
+        const double minMI = block_min (vmin, s_scratch);
+        eMM = mine ? exp (-p.beta * (eMM - minMM)) : 0.0;
+#pragma unroll
+        for (int i = 0; i < kIStates; i++) xMI[i] = (mine && i < p.P_I) ? exp (-p.beta * (xMI[i] - minMI)) : 0.0;
+        if (tid == 0) s_AF = minMM + minMI;   // carried into cOut below (s_AF is completed next)
+    }
+    __syncthreads ();
+
+    // ---- per chunk: fields of the F sites on the M/I instances, F-F energy, F protons ------------
+    for (int j = tid; j < nMI; j += kBlock) {
+        const int a = s_instMI[j];
+        double acc = p.gt[a];
+        if (folded) for (int f = p.nO; f < nOuter; f++) acc += p.w[(size_t) a * ldw + s_aOut[f]];
+        s_gF[j] = acc;
+    }
+    if (warp == kBlock / 32 - 1) {
+        double e = 0.0;
+        int    np = 0;
+        for (int f = p.nO + lane; f < nOuter; f += 32) {
+            const int a = s_aOut[f];
+            e += p.gt[a];
+            np += p.protons[a];
+            if (folded) for (int f2 = p.nO; f2 < f; f2++) e += p.w[(size_t) a * ldw + s_aOut[f2]];
+        }
+        e = pce::warp_sum (e);
+        for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
+        if (lane == 0) { s_AF += e; s_nF = np; }
+    }
+    __syncthreads ();
+
+    // ---- tiles ---------------------------------------------------------------------------------------
+    for (long long tile = 0; tile < p.P_O; tile++) {
+        // (a) fields of the O sites on the M/I instances; (b) O energy incl. O-F cross terms, O protons
+        for (int j = tid; j < nMI; j += kBlock) {
+            const int a = s_instMI[j];
+            double acc = s_gF[j];
+            if (folded) for (int o = 0; o < p.nO; o++) acc += p.w[(size_t) a * ldw + s_aOut[o]];
+            s_gOut[j] = acc;
+        }
+        if (warp == kBlock / 32 - 1) {
+            double e = 0.0;
+            int    np = 0;
+            for (int o = lane; o < p.nO; o += 32) {
+                const int a = s_aOut[o];
+                e += p.gt[a];
+                np += p.protons[a];
+                if (folded) {
+                    const double *row = p.w + (size_t) a * ldw;
+                    for (int o2 = 0; o2 < o; o2++) e += row[s_aOut[o2]];
+                    for (int f = p.nO; f < nOuter; f++) e += row[s_aOut[f]];
+                }
+            }
+            e = pce::warp_sum (e);
+            for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
+            if (lane == 0) { s_cOut = s_AF + e; s_nOut = s_nF + np; }
+        }
+        __syncthreads ();
+
+        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the
+        // per-site minima, so every table thread can normalise its own entry.
+        double min_lo = 0.0, min_hi = 0.0, min_i = 0.0;
+        {
+            // only the threads that need them evaluate the minima
+            const bool need = tid < p.P_lo || (tid >= 64 && tid < 64 + p.P_hi) || (tid >= 128 && tid < 128 + p.P_I) || tid == kBlock - 1;
+            if (need) {
+                for (int i = 0; i < p.nM; i++) {
+                    double v = DBL_MAX;
+                    for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, s_gOut[j]);
+                    if (i < p.nLo) min_lo += v; else min_hi += v;
+                }
+                for (int i = 0; i < p.nI; i++) {
+                    double v = DBL_MAX;
+                    for (int j = s_offI[i]; j < s_offI[i + 1]; j++) v = fmin (v, s_gOut[j]);
+                    min_i += v;
+                }
+            }
+        }
+        // Lo entries by threads [0, P_lo), Hi by [64, 64+P_hi) or a strided loop when the tables are large
+        for (int x = tid; x < p.P_lo; x += kBlock) {
+            int y = x;
+            double s = 0.0;
+            for (int i = 0; i < p.nLo; i++) { s += s_gOut[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
+            s_eLo[x] = exp (-p.beta * (s - min_lo));
+        }
+        if (tid >= 64 && tid < 64 + p.P_hi) {          // P_hi <= 64 by construction of the Lo/Hi split
+            int y = tid - 64;
+            double s = 0.0;
+            for (int i = p.nLo; i < p.nM; i++) { s += s_gOut[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
+            s_eHi[tid - 64] = exp (-p.beta * (s - min_hi));
+        }
+        if (tid >= 128 && tid < 128 + p.P_I) {
+            int y = tid - 128;
+            double s = 0.0;
+            for (int i = 0; i < p.nI; i++) { s += s_gOut[s_offI[i] + y % p.radI[i]]; y /= p.radI[i]; }
+            s_eI[tid - 128] = exp (-p.beta * (s - min_i));
+        }
+        if (tid == kBlock - 1) s_cExp = exp (-p.beta * ((s_cOut + min_lo + min_hi + min_i) - p.gref));
+        __syncthreads ();
+
+        // (f) accumulate this thread's P_I states of the tile into its proton-count bins
+        if (mine) {
+            const double c_tile = s_cExp * s_eLo[m_lo] * s_eHi[m_hi] * eMM;
+            double *mybins = bins + (size_t) (s_nOut + nMp) * kBlock + tid;
+#pragma unroll
+            for (int i = 0; i < kIStates; i++) {
+                if (i < p.P_I) {
+                    const double b = c_tile * (s_eI[i] * xMI[i]);
+                    mybins[(size_t) s_nI[i] * kBlock] += b;
+                }
+            }
+        }
+        __syncthreads ();
+        // (g) next O configuration
+        if (tid == 0) {
+            for (int o = 0; o < p.nO; o++) {
+                const int f = p.first[p.siteOut[o]];
+                if (s_aOut[o] - f + 1 < p.radOut[o]) { s_aOut[o]++; break; }
+                s_aOut[o] = f;
+            }
+        }
+        __syncthreads ();
+    }
+
+    // ---- flush ---------------------------------------------------------------------------------------
+    double *out = p.T + (size_t) blockIdx.x * p.Nb * kBlock;
+    for (int e = tid; e < p.Nb * kBlock; e += kBlock) out[e] = bins[e];
+}
+
+// Mtab[n][tid] = sum over chunks of T[chunk][n][tid]; one thread per (n, tid), chunks in order (deterministic)
+__global__ void k_reduce_chunks (const double *__restrict__ T, long long nchunks, int Nb, double *__restrict__ Mtab) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Nb * kBlock) return;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const size_t stride = (size_t) Nb * kBlock;
+    long long c = 0;
+    for (; c + 3 < nchunks; c += 4) {
+        a0 += T[(size_t) c * stride + e];
+        a1 += T[(size_t) (c + 1) * stride + e];
+        a2 += T[(size_t) (c + 2) * stride + e];
+        a3 += T[(size_t) (c + 3) * stride + e];
+    }
+    for (; c < nchunks; c++) a0 += T[(size_t) c * stride + e];
+    Mtab[e] = (a0 + a1) + (a2 + a3);
+}
+
+// Ftab[chunk][n] = sum over threads of T[chunk][n][tid]; one warp per (chunk, n)
+__global__ void k_reduce_threads (const double *__restrict__ T, long long nchunks, int Nb, double *__restrict__ Ftab) {
+    const long long wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= nchunks * Nb) return;
+    const double *row = T + (size_t) wid * kBlock;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kBlock / 32; k++) acc += row[lane + 32 * k];
+    acc = pce::warp_sum (acc);
+    if (lane == 0) Ftab[wid] = acc;
+}
+
+// Marginals.  rows: 0 = Z, 1 + a = instance a.  One block per row to fill; threads over bins.
+//   M site instance a: sum over tid with digit(tid) = a of Mtab[n][tid]
+//   F site instance a: sum over chunks with digit(chunk) = a of Ftab[chunk][n]
+struct MarginalParams {
+    int Nb, P_M, nM, nF, nO, write_z;
+    long long chunk_begin, nchunks;
+    int16_t siteM[kMaxM], radM[kMaxM], coverM[kMaxM];
+    int16_t siteF[kMaxOuter], radF[kMaxOuter], coverF[kMaxOuter];
+    const int32_t *first;
+    const double  *Mtab, *Ftab;
+    double        *bins;    // [(1+ninst)][Nb], accumulated (+=)
+};
+
+__global__ void k_marginals (const MarginalParams p) {
+    // blockIdx.x enumerates: 0 -> Z; then (M site i, digit d) for covered M sites; then (F site j, digit d)
+    int b = blockIdx.x;
+    const int n = threadIdx.x;
+    if (n >= p.Nb) return;
+    if (b == 0) {
+        if (!p.write_z) return;
+        double acc = 0.0;
+        for (int t = 0; t < p.P_M; t++) acc += p.Mtab[(size_t) n * kBlock + t];
+        p.bins[n] += acc;
+        return;
+    }
+    b -= 1;
+    long long stride = 1;
+    for (int i = 0; i < p.nM; i++) {
+        if (b < p.radM[i]) {
+            if (!p.coverM[i]) return;
+            double acc = 0.0;
+            for (int t = 0; t < p.P_M; t++)
+                if ((t / stride) % p.radM[i] == b) acc += p.Mtab[(size_t) n * kBlock + t];
+            p.bins[(size_t) (1 + p.first[p.siteM[i]] + b) * p.Nb + n] += acc;
+            return;
+        }
+        b -= p.radM[i];
+        stride *= p.radM[i];
+    }
+    stride = 1;
+    for (int j = 0; j < p.nF; j++) {
+        if (b < p.radF[j]) {
+            if (!p.coverF[j]) return;
+            double acc = 0.0;
+            for (long long c = 0; c < p.nchunks; c++)
+                if (((p.chunk_begin + c) / stride) % p.radF[j] == b) acc += p.Ftab[(size_t) c * p.Nb + n];
+            p.bins[(size_t) (1 + p.first[p.siteF[j]] + b) * p.Nb + n] += acc;
+            return;
+        }
+        b -= p.radF[j];
+        stride *= p.radF[j];
+    }
+}
+
+__global__ void k_tilt (int ninst, const double *__restrict__ g, const int32_t *__restrict__ protons, double mu_star, double *__restrict__ gt) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < ninst) gt[a] = g[a] - (double) protons[a] * mu_star;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side planning
+// ---------------------------------------------------------------------------------------------------
+struct RunPlan {
+    std::vector<int> M, I, O, F;       // site ids
+    int nLo = 0;
+    std::vector<uint8_t> coverM, coverF;   // whether this run provides the marginals of the site
+};
+
+struct Plan {
+    std::vector<RunPlan> runs;
+    int    Nb = 0;
+    double ph_star = 7.0, gref = 0.0;
+    double nstates = 1.0;
+};
+
+int radix (const pce_model *m, int s) { return m->last[s] - m->first[s] + 1; }
+
+// reference energy: a local minimum of the energy at pH* found by coordinate descent from the per-site
+// minima of the tilted intrinsic energies.  Only its rough value matters (it centres the exponent range).
+double reference_energy (const pce_model *m, int unfolded, double ph_star) {
+    const double mu = pce::mu_of (m->temperature, ph_star);
+    const size_t n = (size_t) m->ninst;
+    const std::vector<double> &g = unfolded ? m->gmodel : m->gintr;
+    std::vector<int> a (m->nsites);
+    auto tilted = [&] (int k) { return g[k] - m->protons[k] * mu; };
+    for (int i = 0; i < m->nsites; i++) {
+        int best = m->first[i];
+        for (int k = m->first[i]; k <= m->last[i]; k++) if (tilted (k) < tilted (best)) best = k;
+        a[i] = best;
+    }
+    if (!unfolded) {
+        for (int sweep = 0; sweep < 20; sweep++) {
+            bool changed = false;
+            for (int i = 0; i < m->nsites; i++) {
+                int best = a[i];
+                double ebest = 0.0;
+                bool have = false;
+                for (int k = m->first[i]; k <= m->last[i]; k++) {
+                    double e = tilted (k);
+                    for (int j = 0; j < m->nsites; j++) if (j != i) e += m->wsym[(size_t) k * n + a[j]];
+                    if (!have || e < ebest) { have = true; ebest = e; best = k; }
+                }
+                if (best != a[i]) { a[i] = best; changed = true; }
+            }
+            if (!changed) break;
+        }
+    }
+    double e = 0.0;
+    for (int i = 0; i < m->nsites; i++) {
+        e += tilted (a[i]);
+        if (!unfolded) for (int j = 0; j < i; j++) e += m->wsym[(size_t) a[i] * n + a[j]];
+    }
+    return e;
+}
+
+int max_protons_total (const pce_model *m) {
+    int total = 0;
+    for (int i = 0; i < m->nsites; i++) {
+        int best = 0;
+        for (int k = m->first[i]; k <= m->last[i]; k++) best = std::max (best, (int) m->protons[k]);
+        total += best;
+    }
+    return total;
+}
+
+int make_plan (const pce_model *m, const double *ph, int nph, int unfolded, Plan *plan) {
+    if (m->nsites > kMaxOuter) return fail (PCE_ERR_LIMIT, "too many sites for analytic enumeration");
+    for (int k = 0; k < m->ninst; k++) if (m->protons[k] < 0) return fail (PCE_ERR_VALUE, "negative proton count");
+    double lo = ph[0], hi = ph[0];
+    for (int q = 1; q < nph; q++) { lo = std::min (lo, ph[q]); hi = std::max (hi, ph[q]); }
+    plan->ph_star = 0.5 * (lo + hi);
+    const int ptotal = max_protons_total (m);
+    plan->Nb = ptotal + 1;
+    if (0.5 * (hi - lo) * PCE_LN10 * ptotal > 600.0)
+        return fail (PCE_ERR_LIMIT, "pH range too wide for one enumeration pass; split the pH grid");
+    plan->gref = reference_energy (m, unfolded, plan->ph_star);
+    plan->nstates = 1.0;
+    for (int i = 0; i < m->nsites; i++) plan->nstates *= radix (m, i);
+
+    std::vector<uint8_t> covered (m->nsites, 0);
+    int ncovered = 0;
+    plan->runs.clear ();
+    while (ncovered < m->nsites || plan->runs.empty ()) {
+        RunPlan run;
+        std::vector<uint8_t> used (m->nsites, 0);
+        // M: uncovered sites first, then any, while the product of radices fits in a CTA
+        long long pm = 1;
+        for (int pass = 0; pass < 2; pass++)
+            for (int s = 0; s < m->nsites && (int) run.M.size () < kMaxM; s++) {
+                if (used[s] || (pass == 0 && covered[s])) continue;
+                if (pm * radix (m, s) <= kBlock) { run.M.push_back (s); used[s] = 1; pm *= radix (m, s); }
+            }
+        // Lo / Hi split: balance the two table sizes
+        {
+            long long plo = 1;
+            run.nLo = 0;
+            for (size_t i = 0; i < run.M.size (); i++) {
+                if (plo * plo >= pm) break;
+                plo *= radix (m, run.M[i]); run.nLo = (int) i + 1;
+            }
+        }
+        // I: covered sites preferred (their marginals are not needed from this run)
+        long long pi = 1;
+        for (int pass = 0; pass < 2; pass++)
+            for (int s = 0; s < m->nsites && (int) run.I.size () < kMaxI; s++) {
+                if (used[s] || (pass == 0 && !covered[s])) continue;
+                // keep at least the uncovered sites that fit in F out of I when possible
+                if (pi * radix (m, s) <= kIStates) { run.I.push_back (s); used[s] = 1; pi *= radix (m, s); }
+            }
+        // outer sites: covered ones become the low (O) digits, uncovered ones the high (F) digits
+        std::vector<int> outer;
+        for (int s = 0; s < m->nsites; s++) if (!used[s] && covered[s]) outer.push_back (s);
+        for (int s = 0; s < m->nsites; s++) if (!used[s] && !covered[s]) outer.push_back (s);
+        // F = as many high digits as keep the chunk count within kMaxChunks
+        long long pf = 1;
+        int nF = 0;
+        for (int j = (int) outer.size () - 1; j >= 0; j--) {
+            if (pf * radix (m, outer[j]) > kMaxChunks) break;
+            pf *= radix (m, outer[j]); nF++;
+        }
+        const int nO = (int) outer.size () - nF;
+        run.O.assign (outer.begin (), outer.begin () + nO);
+        run.F.assign (outer.begin () + nO, outer.end ());
+        run.coverM.assign (run.M.size (), 0);
+        run.coverF.assign (run.F.size (), 0);
+        int newly = 0;
+        for (size_t i = 0; i < run.M.size (); i++) if (!covered[run.M[i]]) { run.coverM[i] = 1; covered[run.M[i]] = 1; newly++; }
+        for (size_t j = 0; j < run.F.size (); j++) if (!covered[run.F[j]]) { run.coverF[j] = 1; covered[run.F[j]] = 1; newly++; }
+        ncovered += newly;
+        plan->runs.push_back (run);
+        if (newly == 0 && ncovered < m->nsites) return fail (PCE_ERR_LIMIT, "cannot cover all sites (too many states)");
+        if (plan->runs.size () > 16) return fail (PCE_ERR_LIMIT, "too many enumeration passes");
+    }
+    return PCE_OK;
+}
+
+// scratch buffers kept per model would complicate the model struct; they are allocated per call (the
+// enumeration is milliseconds to seconds, the allocations are microseconds)
+int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshards, double *d_bins) {
+    const size_t nbins_total = (size_t) (1 + m->ninst) * plan.Nb;
+    PCE_CUDA (cudaMemsetAsync (d_bins, 0, nbins_total * sizeof (double), m->stream));
+    pce::DeviceBuffer<double> d_gt, d_T, d_Mtab, d_Ftab;
+    PCE_CUDA (d_gt.resize (m->ninst));
+    const double mu_star = pce::mu_of (m->temperature, plan.ph_star);
+    k_tilt<<<(m->ninst + 127) / 128, 128, 0, m->stream>>> (m->ninst, unfolded ? m->d_gmodel.ptr : m->d_gintr.ptr, m->d_protons.ptr, mu_star, d_gt.ptr);
+    pce::count_launch ();
+    int status = PCE_OK;
+    for (size_t r = 0; r < plan.runs.size () && status == PCE_OK; r++) {
+        const RunPlan &run = plan.runs[r];
+        EnumParams p;
+        std::memset (&p, 0, sizeof (p));
+        p.nsites = m->nsites; p.ninst = m->ninst; p.ldw = m->ldw; p.unfolded = unfolded;
+        p.gt = d_gt.ptr; p.w = m->d_w.ptr; p.protons = m->d_protons.ptr; p.first = m->d_first.ptr;
+        p.nM = (int) run.M.size (); p.nLo = run.nLo; p.nI = (int) run.I.size (); p.nO = (int) run.O.size (); p.nF = (int) run.F.size ();
+        p.P_lo = p.P_hi = p.P_I = 1;
+        int nMI = 0;
+        for (int i = 0; i < p.nM; i++) {
+            p.siteM[i] = (int16_t) run.M[i]; p.radM[i] = (int16_t) radix (m, run.M[i]); nMI += p.radM[i];
+            if (i < p.nLo) p.P_lo *= p.radM[i]; else p.P_hi *= p.radM[i];
+        }
+        p.P_M = p.P_lo * p.P_hi;
+        if (p.P_hi > 64 || p.P_M > kBlock) return fail (PCE_ERR_LIMIT, "internal: thread-level site split out of range");
+        for (int i = 0; i < p.nI; i++) { p.siteI[i] = (int16_t) run.I[i]; p.radI[i] = (int16_t) radix (m, run.I[i]); p.P_I *= p.radI[i]; nMI += p.radI[i]; }
+        if (nMI > kMaxMI) return fail (PCE_ERR_LIMIT, "too many instances in the thread-level sites");
+        p.P_O = 1;
+        long long pf = 1;
+        for (int j = 0; j < p.nO; j++) { p.siteOut[j] = (int16_t) run.O[j]; p.radOut[j] = (int16_t) radix (m, run.O[j]); p.P_O *= p.radOut[j]; }
+        for (int j = 0; j < p.nF; j++) { p.siteOut[p.nO + j] = (int16_t) run.F[j]; p.radOut[p.nO + j] = (int16_t) radix (m, run.F[j]); pf *= p.radOut[p.nO + j]; }
+        p.Nb = plan.Nb; p.beta = 1.0 / (PCE_R * m->temperature); p.gref = plan.gref;
+        // this shard's slice of the chunk range
+        const long long c0 = pf * shard / nshards, c1 = pf * (shard + 1) / nshards;
+        p.chunk_begin = c0; p.nchunks = c1 - c0;
+        if (p.nchunks <= 0) continue;
+        const size_t smem = (size_t) plan.Nb * kBlock * sizeof (double);
+        size_t limit = 0;
+        {
+            int value = 0;
+            PCE_CUDA (cudaDeviceGetAttribute (&value, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+            limit = (size_t) value;
+        }
+        if (smem + 12 * 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
+        PCE_CUDA (d_T.resize ((size_t) p.nchunks * plan.Nb * kBlock));
+        PCE_CUDA (d_Mtab.resize ((size_t) plan.Nb * kBlock));
+        PCE_CUDA (d_Ftab.resize ((size_t) p.nchunks * plan.Nb));
+        p.T = d_T.ptr;
+        PCE_CUDA (cudaFuncSetAttribute (k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        k_enum<<<(unsigned) p.nchunks, kBlock, smem, m->stream>>> (p);
+        PCE_CUDA (cudaGetLastError ());
+        k_reduce_chunks<<<(plan.Nb * kBlock + 127) / 128, 128, 0, m->stream>>> (d_T.ptr, p.nchunks, plan.Nb, d_Mtab.ptr);
+        PCE_CUDA (cudaGetLastError ());
+        {
+            const long long warps = p.nchunks * plan.Nb;
+            const long long blocks = (warps * 32 + 255) / 256;
+            k_reduce_threads<<<(unsigned) blocks, 256, 0, m->stream>>> (d_T.ptr, p.nchunks, plan.Nb, d_Ftab.ptr);
+            PCE_CUDA (cudaGetLastError ());
+        }
+        MarginalParams mp;
+        std::memset (&mp, 0, sizeof (mp));
+        mp.Nb = plan.Nb; mp.P_M = p.P_M; mp.nM = p.nM; mp.nF = p.nF; mp.nO = p.nO; mp.write_z = r == 0 ? 1 : 0;
+        mp.chunk_begin = c0; mp.nchunks = p.nchunks;
+        int rows = 1;
+        for (int i = 0; i < p.nM; i++) { mp.siteM[i] = p.siteM[i]; mp.radM[i] = p.radM[i]; mp.coverM[i] = run.coverM[i]; rows += p.radM[i]; }
+        for (int j = 0; j < p.nF; j++) { mp.siteF[j] = p.siteOut[p.nO + j]; mp.radF[j] = p.radOut[p.nO + j]; mp.coverF[j] = run.coverF[j]; rows += mp.radF[j]; }
+        mp.first = m->d_first.ptr; mp.Mtab = d_Mtab.ptr; mp.Ftab = d_Ftab.ptr; mp.bins = d_bins;
+        const int threads = (plan.Nb + 31) & ~31;
+        k_marginals<<<rows, threads, 0, m->stream>>> (mp);
+        PCE_CUDA (cudaGetLastError ());
+        pce::count_launch (4);
+    }
+    cudaError_t err = cudaStreamSynchronize (m->stream);   // scratch buffers are released below
+    d_gt.release (); d_T.release (); d_Mtab.release (); d_Ftab.release ();
+    if (err != cudaSuccess) return fail (PCE_ERR_CUDA, std::string ("analytic enumeration: ") + cudaGetErrorString (err));
+    return status;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" long long pce_analytic_bins_size (const pce_model *m) {
+    if (m == nullptr) return -1;
+    return (long long) (1 + m->ninst) * (max_protons_total (m) + 1);
+}
+
+static int check_analytic_preconditions (pce_model *m, int unfolded, double max_states, double *nstates) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    int status = m->sites_ok ();
+    if (status != PCE_OK) return status;
+    if (!unfolded && !m->symmetrized) return fail (PCE_ERR_STATE, "First calculate electrostatic energies.");
+    double n = 1.0;
+    for (int i = 0; i < m->nsites; i++) n *= (double) radix (m, i);
+    const double engine_limit = 17592186044416.0;   // 2^44
+    if (max_states <= 0.0 || max_states > engine_limit) max_states = engine_limit;
+    if (n > max_states) {
+        char text[128];
+        snprintf (text, sizeof (text), "Maximum number of states for analytic treatment (%.0f) exceeded.", max_states);
+        return fail (PCE_ERR_LIMIT, text);
+    }
+    if (nstates) *nstates = n;
+    return PCE_OK;
+}
+
+extern "C" int pce_analytic_bins (pce_model *m, const double *ph, int nph, int unfolded, int shard, int nshards, double max_states, double *d_bins) {
+    int status = check_analytic_preconditions (m, unfolded, max_states, nullptr);
+    if (status != PCE_OK) return status;
+    if (nph < 1 || shard < 0 || nshards < 1 || shard >= nshards) return fail (PCE_ERR_VALUE, "invalid pH list or shard");
+    status = m->upload ();
+    if (status != PCE_OK) return status;
+    Plan plan;
+    status = make_plan (m, ph, nph, unfolded, &plan);
+    if (status != PCE_OK) return status;
+    return run_plan (m, plan, unfolded, shard, nshards, d_bins);
+}
+
+extern "C" int pce_analytic_finish (pce_model *m, const double *bins, const double *ph, int nph, int unfolded, double gzero,
+                                    double *out_p, double *out_lnz) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    Plan plan;
+    int status = make_plan (m, ph, nph, unfolded, &plan);
+    if (status != PCE_OK) return status;
+    const int Nb = plan.Nb;
+    const long double beta = 1.0L / ((long double) PCE_R * m->temperature);
+    const long double mu_star = pce::mu_of (m->temperature, plan.ph_star);
+    std::vector<long double> weight (Nb);
+    for (int q = 0; q < nph; q++) {
+        // weight of bin n relative to pH*: exp(-beta * n * (mu* - mu)), shifted by the largest log-term of Z
+        const long double mu = pce::mu_of (m->temperature, ph[q]);
+        long double shift = -1.0e300L;
+        for (int n = 0; n < Nb; n++) {
+            if (bins[n] > 0.0) {
+                const long double t = logl ((long double) bins[n]) - beta * n * (mu_star - mu);
+                if (t > shift) shift = t;
+            }
+        }
+        long double z = 0.0L;
+        for (int n = 0; n < Nb; n++) {
+            weight[n] = expl (-beta * n * (mu_star - mu) - shift);
+            z += (long double) bins[n] * weight[n];
+        }
+        if (!(z > 0.0L)) return fail (PCE_ERR_STATE, "partition function underflowed; split the pH grid");
+        for (int a = 0; a < m->ninst; a++) {
+            const double *row = bins + (size_t) (1 + a) * Nb;
+            long double s = 0.0L;
+            for (int n = 0; n < Nb; n++) s += (long double) row[n] * weight[n];
+            const double value = (double) (s / z);
+            if (out_p) out_p[(size_t) q * m->ninst + a] = value;
+            if (q == nph - 1) m->prob[a] = value;
+        }
+        if (out_lnz) out_lnz[q] = (double) (logl (z) + shift - beta * ((long double) plan.gref - gzero));
+    }
+    return PCE_OK;
+}
+
+extern "C" int pce_analytic (pce_model *m, const double *ph, int nph, int unfolded, double gzero, double max_states, double *out_p, double *out_lnz) {
+    int status = check_analytic_preconditions (m, unfolded, max_states, nullptr);
+    if (status != PCE_OK) return status;
+    PCE_CUDA (cudaSetDevice (m->device));
+    const long long n = pce_analytic_bins_size (m);
+    pce::DeviceBuffer<double> d_bins;
+    PCE_CUDA (d_bins.resize ((size_t) n));
+    status = pce_analytic_bins (m, ph, nph, unfolded, 0, 1, max_states, d_bins.ptr);
+    std::vector<double> bins ((size_t) n);
+    if (status == PCE_OK) {
+        cudaError_t err = cudaMemcpy (bins.data (), d_bins.ptr, (size_t) n * sizeof (double), cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) status = fail (PCE_ERR_CUDA, std::string ("analytic readback: ") + cudaGetErrorString (err));
+    }
+    d_bins.release ();
+    if (status != PCE_OK) return status;
+    return pce_analytic_finish (m, bins.data (), ph, nph, unfolded, gzero, out_p, out_lnz);
+}
+
+extern "C" int pce_analytic_gmin (pce_model *m, double ph, int unfolded, double max_states, double *gmin) {
+    // Exact minimum over all states, evaluated with kernel 1 on batches of enumerated states.
+    // (Needed only to reproduce the reference's Gmin-relative Z, EnergyModel.c:262-275.)
+    double nstates = 0.0;
+    int status = check_analytic_preconditions (m, unfolded, max_states, &nstates);
+    if (status != PCE_OK) return status;
+    if (nstates > 268435456.0) return fail (PCE_ERR_LIMIT, "pce_analytic_gmin supports at most 2^28 states");
+    const long long total = (long long) nstates, batch = 1 << 20;
+    std::vector<int32_t> states;
+    std::vector<double>  out;
+    double best = DBL_MAX;
+    std::vector<int> digit (m->nsites, 0);
+    for (long long s0 = 0; s0 < total; s0 += batch) {
+        const long long nb = std::min (batch, total - s0);
+        states.resize ((size_t) nb * m->nsites);
+        out.resize ((size_t) nb);
+        for (long long s = 0; s < nb; s++) {
+            for (int i = 0; i < m->nsites; i++) states[(size_t) s * m->nsites + i] = m->first[i] + digit[i];
+            for (int i = 0; i < m->nsites; i++) {     // StateVector_Increment, StateVector.c:370-384
+                if (digit[i] + 1 < radix (m, i)) { digit[i]++; break; }
+                digit[i] = 0;
+            }
+        }
+        status = pce_energy (m, states.data (), nb, &ph, 1, unfolded, out.data ());
+        if (status != PCE_OK) return status;
+        for (long long s = 0; s < nb; s++) best = std::min (best, out[(size_t) s]);
+    }
+    *gmin = best;
+    return PCE_OK;
+}

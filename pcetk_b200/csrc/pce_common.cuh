@@ -1,0 +1,111 @@
+// pce_common.cuh -- shared host/device definitions of the B200 microstate engine.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pcetk_b200.h"
+
+// Reference constants, EnergyModel.h:31-32 / MCModelDefault.h:39
+#define PCE_R 0.001987165392
+#define PCE_LN10 2.302585092994
+#define PCE_TOO_SMALL (-500.0)
+
+namespace pce {
+
+void set_error (const std::string &message);
+int  fail (int status, const std::string &message);
+void count_launch (int n = 1);
+
+#define PCE_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t err__ = (call);                                                                      \
+        if (err__ != cudaSuccess) {                                                                      \
+            return pce::fail (PCE_ERR_CUDA, std::string (#call) + ": " + cudaGetErrorString (err__));    \
+        }                                                                                                \
+    } while (0)
+
+// mu(pH) = -R*T*ln10*pH with the reference's evaluation order (EnergyModel.c:223): ((-R*T)*ln10)*pH
+inline double mu_of (double temperature, double ph) { return -PCE_R * temperature * PCE_LN10 * ph; }
+
+template <typename T>
+struct DeviceBuffer {
+    T     *ptr   = nullptr;
+    size_t count = 0;
+    cudaError_t resize (size_t n) {
+        if (n <= count && ptr != nullptr) return cudaSuccess;
+        release ();
+        cudaError_t err = cudaMalloc ((void **) &ptr, (n > 0 ? n : 1) * sizeof (T));
+        if (err == cudaSuccess) count = n; else ptr = nullptr;
+        return err;
+    }
+    void release () {
+        if (ptr != nullptr) cudaFree (ptr);
+        ptr = nullptr; count = 0;
+    }
+};
+
+}  // namespace pce
+
+// The model: host copy (authoritative for setters/getters) + device mirror.
+struct pce_model {
+    int    nsites = 0, ninst = 0, device = 0;
+    double temperature = 300.0;
+    std::vector<int32_t> first, last;          // [nsites]
+    std::vector<uint8_t> site_set;             // [nsites]
+    std::vector<int32_t> protons;              // [ninst]
+    std::vector<double>  gmodel, gintr, prob;  // [ninst]
+    std::vector<double>  wraw;                 // [ninst*ninst] EnergyModel.h:46 "interactions"
+    std::vector<double>  wsym;                 // [ninst*ninst] full square of EnergyModel.h:48 "symmetricmatrix"
+    bool   symmetrized = false;
+    bool   dirty       = true;                 // host copy newer than device copy
+    cudaStream_t stream = nullptr;
+
+    // device mirror
+    int ldw = 0;                               // row stride of d_w in doubles (multiple of 4)
+    pce::DeviceBuffer<int32_t> d_first, d_nsite_inst, d_site_of_inst, d_protons;
+    pce::DeviceBuffer<double>  d_gintr, d_gmodel, d_w;
+
+    int  sites_ok () const;                    // PCE_OK when every site is set, contiguous and ascending
+    int  upload ();
+};
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace pce {
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+// Philox4x32-10 (Salmon et al., SC'11); bit-identical to oracle_philox4x32_10.
+__host__ __device__ __forceinline__ Philox4 philox4x32_10 (uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi0 = __umulhi (0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi (0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        const uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
+        const uint32_t hi0 = (uint32_t) (p0 >> 32), lo0 = (uint32_t) p0, hi1 = (uint32_t) (p1 >> 32), lo1 = (uint32_t) p1;
+#endif
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox4 out = { c0, c1, c2, c3 };
+    return out;
+}
+
+__device__ __forceinline__ double warp_sum (double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync (0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace pce
+#endif

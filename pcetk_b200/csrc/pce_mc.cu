@@ -1,0 +1,832 @@
+// pce_mc.cu -- kernel 3: Metropolis Monte Carlo over the (pH x chain) grid.
+//
+// Replaces extensions/csource/MCModelDefault.c (Move :90-122, DoubleMove :127-172, MCScan :178-209,
+// UpdateProbabilities :215-226, FindPairs :231-288, Production/Equilibration :298-327).
+//
+// Algorithm (specified operation for operation by oracle_mc_philox_chain in oracle/pce_oracle.c):
+//   * every chain keeps cached fields h[k] = sum_j W[k][a_j]; a proposal costs O(1) (dW = h[new]-h[old]),
+//     an accepted move costs one coalesced axpy over two rows of W -- instead of the reference's 2*nsites
+//     strided gathers per trial (MCModelDefault.c:109-111);
+//   * random numbers are Philox4x32-10 blocks addressed by (seed, pH index, chain, trial), two trials
+//     per block, so any chain can be replayed in isolation and nothing has to be checkpointed;
+//   * occupancies are residence times (scan of last change per site) instead of nsites increments per scan.
+//
+// Two kernels:
+//   k_mc_thread  one chain per THREAD, model + per-chain state in shared memory.  For fixture-sized
+//                models (ninst <= 256).  Accepted moves are applied warp-cooperatively so that the
+//                axpy never runs with 1/32 lanes.
+//   k_mc_warp    one chain per WARP, fields in shared memory, W rows streamed from L2 with 128-bit
+//                loads.  For models whose W does not fit on chip (the 1000-site synthetic: 72 MB).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "pce_common.cuh"
+
+using pce::fail;
+
+struct pce_mc {
+    pce_model *model = nullptr;
+    double     limit = 2.0;
+    int        nequil = 500, nprod = 20000, nchains = 1, kernel = 0;
+    uint64_t   seed = 1;
+    std::vector<int32_t> pair_a, pair_b;
+    std::vector<double>  pair_wmax;
+    pce::DeviceBuffer<int32_t> d_pair_a, d_pair_b;
+    pce::DeviceBuffer<double>  d_ph, d_esum;
+    pce::DeviceBuffer<unsigned long long> d_counts;
+    pce::DeviceBuffer<long long> d_counters;
+    bool pairs_dirty = true;
+};
+
+namespace {
+
+struct McParams {
+    int nsites, ninst, npairs, ldw;
+    const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
+    const double  *gintr, *w, *ph;
+    int       nph, ph_index_offset, nchains, nequil, nprod;
+    long long chain_offset;
+    uint32_t  k0, k1;
+    double    temperature;
+    unsigned long long *counts;     // [nph*ninst]
+    long long          *counters;   // [nph*4]
+    double             *esum;       // [nph]
+    // optional per-chain outputs (parity tests)
+    long long *chain_counts;        // [nph*nchains*ninst]
+    int32_t   *chain_state;         // [nph*nchains*nsites]
+    double    *chain_energy, *chain_esum;   // [nph*nchains]
+    long long *chain_counters;      // [nph*nchains*4]
+    double    *trajectory;          // [nprod] energies of chain 0 of pH 0
+    int        w_in_smem;
+};
+
+// shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
+struct ThreadLayout {
+    size_t off_w, off_h, off_gintr, off_counts, off_since, off_first, off_nsi, off_prot, off_pa, off_pb, off_state, total;
+    int    hstride, ldws;
+    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int block, int w_in_smem) {
+        hstride = ninst | 1;                       // odd: lanes of a warp fall on distinct bank pairs
+        ldws    = ninst | 1;
+        size_t o = 0;
+        off_w = o;      o += w_in_smem ? (size_t) ninst * ldws * 8 : 0;
+        off_h = o;      o += (size_t) block * hstride * 8;
+        off_gintr = o;  o += (size_t) ninst * 8;
+        off_counts = o; o += (size_t) ninst * 8;
+        off_since = o;  o += (size_t) nsites * block * 4;
+        off_first = o;  o += (size_t) nsites * 4;
+        off_nsi = o;    o += (size_t) nsites * 4;
+        off_prot = o;   o += (size_t) ninst * 4;
+        off_pa = o;     o += (size_t) (npairs > 0 ? npairs : 1) * 4;
+        off_pb = o;     o += (size_t) (npairs > 0 ? npairs : 1) * 4;
+        off_state = o;  o += (size_t) nsites * block;
+        total = (o + 15) & ~(size_t) 15;
+    }
+};
+
+__device__ __forceinline__ double ph_to_mu (double temperature, double ph) {
+    // -R*T*ln10*pH, left to right (EnergyModel.c:223 / MCModelDefault.c:114)
+    return __dmul_rn (__dmul_rn (__dmul_rn (-PCE_R, temperature), PCE_LN10), ph);
+}
+
+// MCModelDefault_Metropolis (MCModelDefault.c:71-85).  The fp32 exp only screens: whenever it cannot
+// decide with a 1e-3 relative margin the fp64 exp is evaluated, so the decision equals u < exp(-x).
+__device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
+    if (x < 0.0) return true;
+    if (-x < PCE_TOO_SMALL) return false;
+    const float uf = __uint2float_rn (w1) * 2.3283064365386963e-10f;
+    const float ef = __expf (-(float) x);
+    if (uf < ef * 0.999f) return true;
+    if (uf > ef * 1.001f) return false;
+    return ((double) w1 * (1.0 / 4294967296.0)) < exp (-x);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_mc_thread
+// ---------------------------------------------------------------------------------------------------
+template <bool PER_CHAIN>
+__global__ void __launch_bounds__ (256) k_mc_thread (const McParams p) {
+    extern __shared__ __align__ (16) unsigned char smem[];
+    const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
+    const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, p.w_in_smem);
+    double             *s_w      = (double *) (smem + L.off_w);
+    double             *s_h      = (double *) (smem + L.off_h);
+    double             *s_gintr  = (double *) (smem + L.off_gintr);
+    unsigned long long *s_counts = (unsigned long long *) (smem + L.off_counts);
+    uint32_t           *s_since  = (uint32_t *) (smem + L.off_since);
+    int32_t            *s_first  = (int32_t *) (smem + L.off_first);
+    int32_t            *s_nsi    = (int32_t *) (smem + L.off_nsi);
+    int32_t            *s_prot   = (int32_t *) (smem + L.off_prot);
+    int32_t            *s_pa     = (int32_t *) (smem + L.off_pa);
+    int32_t            *s_pb     = (int32_t *) (smem + L.off_pb);
+    uint8_t            *s_state  = smem + L.off_state;
+
+    const int nsites = p.nsites, ninst = p.ninst;
+    const int blocks_per_ph = (p.nchains + B - 1) / B;
+    const int q     = blockIdx.x / blocks_per_ph;                 // pH point of this block
+    const int local = (blockIdx.x % blocks_per_ph) * B + tid;     // chain within this launch
+    const bool active = local < p.nchains;
+    const uint32_t chain = (uint32_t) (p.chain_offset + local);
+    const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
+
+    // stage the model
+    const double *wrow_base;
+    int           wld;
+    if (p.w_in_smem) {
+        for (int e = tid; e < ninst * ninst; e += B) s_w[(e / ninst) * L.ldws + (e % ninst)] = p.w[(size_t) (e / ninst) * p.ldw + (e % ninst)];
+        wrow_base = s_w; wld = L.ldws;
+    } else {
+        wrow_base = p.w; wld = p.ldw;
+    }
+    for (int k = tid; k < ninst; k += B) { s_gintr[k] = p.gintr[k]; s_prot[k] = p.protons[k]; s_counts[k] = 0ull; }
+    for (int i = tid; i < nsites; i += B) { s_first[i] = p.first[i]; s_nsi[i] = p.nsi[i]; }
+    for (int i = tid; i < p.npairs; i += B) { s_pa[i] = p.pair_a[i]; s_pb[i] = p.pair_b[i]; }
+
+    // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i)
+    {
+        pce::Philox4 r = { 0, 0, 0, 0 };
+        for (int i = 0; i < nsites; i++) {
+            if ((i & 3) == 0) r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
+            const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+            const int f = p.first[i], n = p.nsi[i];
+            s_state[i * B + tid] = (uint8_t) (f + (int) __umulhi (word, (uint32_t) n));
+            s_since[i * B + tid] = 0u;
+        }
+    }
+    __syncthreads ();
+
+    // fields, cooperatively: for each chain c of this warp, lanes over k, j sequential (spec order)
+    for (int c = 0; c < 32; c++) {
+        double *hc = s_h + (size_t) (warp_base + c) * L.hstride;
+        for (int k = lane; k < ninst; k += 32) {
+            const double *row = wrow_base + (size_t) k * wld;
+            double acc = 0.0;
+            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, row[s_state[j * B + warp_base + c]]);
+            hc[k] = acc;
+        }
+    }
+    __syncwarp ();
+
+    const double mu   = ph_to_mu (p.temperature, p.ph[q]);
+    const double beta = 1.0 / (PCE_R * p.temperature);
+    double *myh = s_h + (size_t) tid * L.hstride;
+
+    // initial energy in the reference's order (EnergyModel.c:204-224)
+    double g;
+    {
+        double gi = 0.0, ws = 0.0;
+        int    np = 0;
+        for (int i = 0; i < nsites; i++) {
+            const int ai = s_state[i * B + tid];
+            gi = __dadd_rn (gi, s_gintr[ai]);
+            np += s_prot[ai];
+            const double *row = wrow_base + (size_t) ai * wld;
+            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[s_state[j * B + tid]]);
+        }
+        g = __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws);
+    }
+
+    const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
+    const long long nscans = (long long) p.nequil + p.nprod;
+    unsigned long long t = 0;
+    uint32_t c_moves = 0, c_macc = 0, c_flips = 0, c_facc = 0;
+    double   esum = 0.0;
+    pce::Philox4 r = { 0, 0, 0, 0 };
+
+    for (long long scan = 0; scan < nscans; scan++) {
+        const bool     production = scan >= p.nequil;
+        const uint32_t tp = production ? (uint32_t) (scan - p.nequil) : 0u;
+        for (uint32_t mv = 0; mv < nmoves; mv++, t++) {
+            uint32_t w0, w1;
+            if ((t & 1ull) == 0ull) {
+                const unsigned long long b = t >> 1;
+                r = pce::philox4x32_10 ((uint32_t) b, (uint32_t) (b >> 32), chain, phidx, p.k0, p.k1);
+                w0 = r.x; w1 = r.y;
+            } else {
+                w0 = r.z; w1 = r.w;
+            }
+            // proposal
+            const uint32_t idx = __umulhi (w0, nmoves);
+            const uint32_t lo  = w0 * nmoves;
+            const bool     dbl = idx >= (uint32_t) nsites;
+            int sa, sb = 0;
+            if (dbl) { sa = s_pa[idx - nsites]; sb = s_pb[idx - nsites]; } else { sa = (int) idx; }
+            const int na = s_nsi[sa], oa = s_state[sa * B + tid];
+            bool valid = active && na >= 2;
+            const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
+            const uint32_t lo2 = lo * (uint32_t) (na - 1);
+            int ia = s_first[sa] + (int) ka;
+            if (ia >= oa) ia++;
+            if (!valid) ia = oa;
+            double dgintr = __dsub_rn (s_gintr[ia], s_gintr[oa]);
+            int    dprot  = s_prot[ia] - s_prot[oa];
+            double dw     = __dsub_rn (myh[ia], myh[oa]);
+            int ib = 0, ob = 0;
+            if (dbl) {
+                const int nb = s_nsi[sb];
+                ob = s_state[sb * B + tid];
+                if (nb < 2) valid = false;
+                const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
+                ib = s_first[sb] + (int) kb;
+                if (ib >= ob) ib++;
+                if (!valid) { ib = ob; ia = oa; }
+                dgintr = __dadd_rn (dgintr, __dsub_rn (s_gintr[ib], s_gintr[ob]));
+                dprot += s_prot[ib] - s_prot[ob];
+                const double *ra = wrow_base + (size_t) ia * wld, *ro = wrow_base + (size_t) oa * wld;
+                const double cross = __dadd_rn (__dsub_rn (__dsub_rn (ra[ib], ra[ob]), ro[ib]), ro[ob]);
+                dw = __dadd_rn (__dadd_rn (dw, __dsub_rn (myh[ib], myh[ob])), cross);
+            }
+            const double dg = __dadd_rn (__dsub_rn (dgintr, __dmul_rn ((double) dprot, mu)), dw);
+            const bool accept = valid && metropolis (__dmul_rn (dg, beta), w1);
+            if (production && active) { if (dbl) c_flips++; else c_moves++; }
+
+            // apply accepted moves: one accepting chain at a time, all 32 lanes on its field vector
+            unsigned pending = __ballot_sync (0xffffffffu, accept);
+            while (pending) {
+                const int src = __ffs (pending) - 1;
+                pending &= pending - 1;
+                const int  xia = __shfl_sync (0xffffffffu, ia, src), xoa = __shfl_sync (0xffffffffu, oa, src);
+                const int  xib = __shfl_sync (0xffffffffu, ib, src), xob = __shfl_sync (0xffffffffu, ob, src);
+                const bool xdb = __shfl_sync (0xffffffffu, (int) dbl, src) != 0;
+                double       *hc  = s_h + (size_t) (warp_base + src) * L.hstride;
+                const double *rna = wrow_base + (size_t) xia * wld, *roa = wrow_base + (size_t) xoa * wld;
+                const double *rnb = wrow_base + (size_t) xib * wld, *rob = wrow_base + (size_t) xob * wld;
+                for (int k = lane; k < ninst; k += 32) {
+                    double v = __dadd_rn (hc[k], __dsub_rn (rna[k], roa[k]));
+                    if (xdb) v = __dadd_rn (v, __dsub_rn (rnb[k], rob[k]));
+                    hc[k] = v;
+                }
+            }
+            __syncwarp ();
+            if (accept) {
+                g = __dadd_rn (g, dg);
+                const uint32_t since_a = s_since[sa * B + tid];
+                if (PER_CHAIN) p.chain_counts[((size_t) q * p.nchains + local) * ninst + oa] += (long long) (tp - since_a);
+                else if (tp != since_a) atomicAdd (&s_counts[oa], (unsigned long long) (tp - since_a));
+                s_since[sa * B + tid] = tp;
+                s_state[sa * B + tid] = (uint8_t) ia;
+                if (dbl) {
+                    const uint32_t since_b = s_since[sb * B + tid];
+                    if (PER_CHAIN) p.chain_counts[((size_t) q * p.nchains + local) * ninst + ob] += (long long) (tp - since_b);
+                    else if (tp != since_b) atomicAdd (&s_counts[ob], (unsigned long long) (tp - since_b));
+                    s_since[sb * B + tid] = tp;
+                    s_state[sb * B + tid] = (uint8_t) ib;
+                    if (production) c_facc++;
+                } else if (production) c_macc++;
+            }
+        }
+        if (production) {
+            esum += g;
+            if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0) p.trajectory[scan - p.nequil] = g;
+        }
+    }
+
+    // flush residence times of the final state
+    if (active) {
+        for (int i = 0; i < nsites; i++) {
+            const int      a = s_state[i * B + tid];
+            const uint32_t d = (uint32_t) p.nprod - s_since[i * B + tid];
+            if (PER_CHAIN) p.chain_counts[((size_t) q * p.nchains + local) * ninst + a] += (long long) d;
+            else if (d) atomicAdd (&s_counts[a], (unsigned long long) d);
+        }
+        if (PER_CHAIN) {
+            const size_t c = (size_t) q * p.nchains + local;
+            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = s_state[i * B + tid];
+            p.chain_energy[c] = g;
+            p.chain_esum[c]   = esum;
+            p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
+            p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
+        }
+    }
+    if (!PER_CHAIN) {
+        __syncthreads ();
+        if (p.counts != nullptr)
+            for (int k = tid; k < ninst; k += B)
+                if (s_counts[k]) atomicAdd (&p.counts[(size_t) q * ninst + k], s_counts[k]);
+        // counters and energy sums: warp reduce, one atomic per warp
+        double es = active ? esum : 0.0;
+        unsigned long long cm = c_moves, ca = c_macc, cf = c_flips, cfa = c_facc;
+        for (int o = 16; o > 0; o >>= 1) {
+            es  += __shfl_xor_sync (0xffffffffu, es, o);
+            cm  += __shfl_xor_sync (0xffffffffu, cm, o);
+            ca  += __shfl_xor_sync (0xffffffffu, ca, o);
+            cf  += __shfl_xor_sync (0xffffffffu, cf, o);
+            cfa += __shfl_xor_sync (0xffffffffu, cfa, o);
+        }
+        if (lane == 0) {
+            if (p.esum != nullptr) atomicAdd (&p.esum[q], es);
+            if (p.counters != nullptr) {
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], cm);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], ca);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 2], cf);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 3], cfa);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_mc_warp: one chain per warp.  Every lane evaluates the (warp-uniform) proposal; accepted moves are
+// applied by all lanes with 128-bit loads of the W rows from L2.
+// Shared memory per warp: h[ldh] doubles | since[nsites] u32 | state[nsites] u16
+// ---------------------------------------------------------------------------------------------------
+struct WarpLayout {
+    size_t off_h, off_since, off_state, per_warp;
+    int    ldh;
+    __host__ __device__ WarpLayout (int nsites, int ninst) {
+        ldh = (ninst + 3) & ~3;
+        size_t o = 0;
+        off_h = o;     o += (size_t) ldh * 8;
+        off_since = o; o += (size_t) nsites * 4;
+        off_state = o; o += (size_t) nsites * 2;
+        per_warp = (o + 15) & ~(size_t) 15;
+    }
+};
+
+template <bool PER_CHAIN>
+__global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
+    extern __shared__ __align__ (16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const WarpLayout L (p.nsites, p.ninst);
+    unsigned char *base   = smem + (size_t) wib * L.per_warp;
+    double        *h      = (double *) (base + L.off_h);
+    uint32_t      *since  = (uint32_t *) (base + L.off_since);
+    uint16_t      *state  = (uint16_t *) (base + L.off_state);
+
+    const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
+    const int blocks_per_ph = (p.nchains + warps - 1) / warps;
+    const int q     = blockIdx.x / blocks_per_ph;
+    const int local = (blockIdx.x % blocks_per_ph) * warps + wib;
+    if (local >= p.nchains) return;                                // whole warp leaves together
+    const uint32_t chain = (uint32_t) (p.chain_offset + local);
+    const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
+
+    for (int i = lane; i < nsites; i += 32) {
+        pce::Philox4 r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
+        const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
+        state[i] = (uint16_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
+        since[i] = 0u;
+    }
+    __syncwarp ();
+    // fields: lanes over k, j sequential (spec order); W[k][a_j] gathers, once per chain
+    for (int k = lane; k < L.ldh; k += 32) {
+        double acc = 0.0;
+        if (k < ninst) {
+            const double *row = p.w + (size_t) k * ldw;
+            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, __ldg (row + state[j]));
+        }
+        h[k] = acc;
+    }
+    __syncwarp ();
+
+    const double mu   = ph_to_mu (p.temperature, p.ph[q]);
+    const double beta = 1.0 / (PCE_R * p.temperature);
+
+    // initial energy.  The reference order (EnergyModel.c:204-224) is a serial sum over i then j < i; here
+    // lanes take rows i = lane, lane+32, ... and the partial sums are combined, so the value may differ
+    // from the serial sum in the last bits.  It only seeds the tracked energy (informational output).
+    double g;
+    {
+        double gi = 0.0, ws = 0.0;
+        int    np = 0;
+        for (int i = lane; i < nsites; i += 32) {
+            const int ai = state[i];
+            gi += __ldg (p.gintr + ai);
+            np += __ldg (p.protons + ai);
+            const double *row = p.w + (size_t) ai * ldw;
+            for (int j = 0; j < i; j++) ws += __ldg (row + state[j]);
+        }
+        gi = pce::warp_sum (gi); ws = pce::warp_sum (ws);
+        for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
+        g = __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws);
+    }
+
+    const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
+    const long long nscans = (long long) p.nequil + p.nprod;
+    unsigned long long t = 0;
+    uint32_t c_moves = 0, c_macc = 0, c_flips = 0, c_facc = 0;
+    double   esum = 0.0;
+    pce::Philox4 r = { 0, 0, 0, 0 };
+    unsigned long long *counts = PER_CHAIN ? (unsigned long long *) (p.chain_counts + ((size_t) q * p.nchains + local) * ninst)
+                                           : p.counts + (size_t) q * ninst;
+
+    for (long long scan = 0; scan < nscans; scan++) {
+        const bool     production = scan >= p.nequil;
+        const uint32_t tp = production ? (uint32_t) (scan - p.nequil) : 0u;
+        for (uint32_t mv = 0; mv < nmoves; mv++, t++) {
+            uint32_t w0, w1;
+            if ((t & 1ull) == 0ull) {
+                const unsigned long long b = t >> 1;
+                r = pce::philox4x32_10 ((uint32_t) b, (uint32_t) (b >> 32), chain, phidx, p.k0, p.k1);
+                w0 = r.x; w1 = r.y;
+            } else {
+                w0 = r.z; w1 = r.w;
+            }
+            const uint32_t idx = __umulhi (w0, nmoves);
+            const uint32_t lo  = w0 * nmoves;
+            const bool     dbl = idx >= (uint32_t) nsites;
+            int sa, sb = 0;
+            if (dbl) { sa = __ldg (p.pair_a + (idx - nsites)); sb = __ldg (p.pair_b + (idx - nsites)); } else { sa = (int) idx; }
+            const int na = __ldg (p.nsi + sa), oa = state[sa];
+            bool valid = na >= 2;
+            const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
+            const uint32_t lo2 = lo * (uint32_t) (na - 1);
+            int ia = __ldg (p.first + sa) + (int) ka;
+            if (ia >= oa) ia++;
+            if (!valid) ia = oa;
+            double dgintr = __dsub_rn (__ldg (p.gintr + ia), __ldg (p.gintr + oa));
+            int    dprot  = __ldg (p.protons + ia) - __ldg (p.protons + oa);
+            double dw     = __dsub_rn (h[ia], h[oa]);
+            int ib = 0, ob = 0;
+            if (dbl) {
+                const int nb = __ldg (p.nsi + sb);
+                ob = state[sb];
+                if (nb < 2) valid = false;
+                const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
+                ib = __ldg (p.first + sb) + (int) kb;
+                if (ib >= ob) ib++;
+                if (!valid) { ib = ob; ia = oa; }
+                dgintr = __dadd_rn (dgintr, __dsub_rn (__ldg (p.gintr + ib), __ldg (p.gintr + ob)));
+                dprot += __ldg (p.protons + ib) - __ldg (p.protons + ob);
+                const double *ra = p.w + (size_t) ia * ldw, *ro = p.w + (size_t) oa * ldw;
+                const double cross = __dadd_rn (__dsub_rn (__dsub_rn (__ldg (ra + ib), __ldg (ra + ob)), __ldg (ro + ib)), __ldg (ro + ob));
+                dw = __dadd_rn (__dadd_rn (dw, __dsub_rn (h[ib], h[ob])), cross);
+            }
+            const double dg = __dadd_rn (__dsub_rn (dgintr, __dmul_rn ((double) dprot, mu)), dw);
+            const bool accept = valid && metropolis (__dmul_rn (dg, beta), w1);
+            if (production) { if (dbl) c_flips++; else c_moves++; }
+            if (!accept) continue;                                  // warp-uniform
+
+            // h += W[ia] - W[oa] (+ W[ib] - W[ob]); rows are 32-byte aligned (ldw multiple of 4)
+            {
+                const double2 *rna = (const double2 *) (p.w + (size_t) ia * ldw), *roa = (const double2 *) (p.w + (size_t) oa * ldw);
+                const double2 *rnb = (const double2 *) (p.w + (size_t) ib * ldw), *rob = (const double2 *) (p.w + (size_t) ob * ldw);
+                double2       *h2  = (double2 *) h;
+                const int      n2  = L.ldh >> 1;
+                if (!dbl) {
+#pragma unroll 4
+                    for (int k = lane; k < n2; k += 32) {
+                        const double2 a = __ldg (rna + k), b = __ldg (roa + k);
+                        double2 v = h2[k];
+                        v.x = __dadd_rn (v.x, __dsub_rn (a.x, b.x));
+                        v.y = __dadd_rn (v.y, __dsub_rn (a.y, b.y));
+                        h2[k] = v;
+                    }
+                } else {
+#pragma unroll 2
+                    for (int k = lane; k < n2; k += 32) {
+                        const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
+                        double2 v = h2[k];
+                        v.x = __dadd_rn (__dadd_rn (v.x, __dsub_rn (a.x, b.x)), __dsub_rn (c.x, d.x));
+                        v.y = __dadd_rn (__dadd_rn (v.y, __dsub_rn (a.y, b.y)), __dsub_rn (c.y, d.y));
+                        h2[k] = v;
+                    }
+                }
+            }
+            g = __dadd_rn (g, dg);
+            if (lane == 0) {
+                const uint32_t since_a = since[sa];
+                if (tp != since_a) atomicAdd (&counts[oa], (unsigned long long) (tp - since_a));
+                since[sa] = tp;
+                state[sa] = (uint16_t) ia;
+                if (dbl) {
+                    const uint32_t since_b = since[sb];
+                    if (tp != since_b) atomicAdd (&counts[ob], (unsigned long long) (tp - since_b));
+                    since[sb] = tp;
+                    state[sb] = (uint16_t) ib;
+                }
+            }
+            if (production) { if (dbl) c_facc++; else c_macc++; }
+            __syncwarp ();
+        }
+        if (production) {
+            esum += g;
+            if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan - p.nequil] = g;
+        }
+    }
+    __syncwarp ();
+    for (int i = lane; i < nsites; i += 32) {
+        const uint32_t d = (uint32_t) p.nprod - since[i];
+        if (d) atomicAdd (&counts[state[i]], (unsigned long long) d);
+    }
+    if (PER_CHAIN) {
+        const size_t c = (size_t) q * p.nchains + local;
+        for (int i = lane; i < nsites; i += 32) p.chain_state[c * nsites + i] = state[i];
+        if (lane == 0) {
+            p.chain_energy[c] = g;
+            p.chain_esum[c]   = esum;
+            p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
+            p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
+        }
+    } else if (lane == 0) {
+        if (p.esum != nullptr) atomicAdd (&p.esum[q], esum);
+        if (p.counters != nullptr) {
+            atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
+            atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
+            atomicAdd ((unsigned long long *) &p.counters[q * 4 + 2], (unsigned long long) c_flips);
+            atomicAdd ((unsigned long long *) &p.counters[q * 4 + 3], (unsigned long long) c_facc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch planning
+// ---------------------------------------------------------------------------------------------------
+struct Plan { int kernel, block, w_in_smem; size_t smem; };
+
+int smem_limit (int device, size_t *limit) {
+    int value = 0;
+    PCE_CUDA (cudaDeviceGetAttribute (&value, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *limit = (size_t) value;
+    return PCE_OK;
+}
+
+// chain-per-thread plan: prefer W in shared memory and the block size with the most resident warps per SM
+bool plan_thread (const pce_mc *mc, size_t limit, Plan *plan) {
+    const pce_model *m = mc->model;
+    if (m->ninst > 256) return false;
+    const size_t per_sm = 228 * 1024;
+    int best_warps = 0;
+    for (int w_in = 1; w_in >= 0; w_in--) {
+        for (int block : { 256, 128, 64, 32 }) {
+            ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in);
+            if (L.total > limit) continue;
+            int ctas = (int) std::min<size_t> (per_sm / (L.total + 1024), (size_t) (2048 / block));
+            ctas = std::min (ctas, 32);
+            const int warps = ctas * block / 32;
+            if (warps > best_warps) { best_warps = warps; plan->kernel = 1; plan->block = block; plan->w_in_smem = w_in; plan->smem = L.total; }
+        }
+        if (best_warps >= 8) break;     // W on chip with at least 8 warps/SM: take it
+    }
+    return best_warps >= 2;
+}
+
+bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
+    const pce_model *m = mc->model;
+    if (m->ninst > 65535) return false;
+    WarpLayout L (m->nsites, m->ninst);
+    if (L.per_warp > limit) return false;
+    int warps = (int) std::min<size_t> (limit / L.per_warp, 16);   // up to 16 warps per block
+    // several blocks per SM when the per-warp footprint is small
+    plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = (size_t) warps * L.per_warp;
+    return true;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+static int find_pairs (pce_mc *mc) {
+    // MCModelDefault_FindPairs + _FindMaxInteraction, MCModelDefault.c:231-288: sites i > j are a pair
+    // when max |W| over their instances reaches the limit; order (i ascending, j < i ascending).
+    const pce_model *m = mc->model;
+    const size_t n = (size_t) m->ninst;
+    mc->pair_a.clear (); mc->pair_b.clear (); mc->pair_wmax.clear ();
+    for (int i = 0; i < m->nsites; i++)
+        for (int j = 0; j < i; j++) {
+            double wmax = 0.0;
+            for (int a = m->first[i]; a <= m->last[i]; a++)
+                for (int b = m->first[j]; b <= m->last[j]; b++) {
+                    const double v = std::fabs (m->wsym[(size_t) a * n + b]);
+                    if (v > wmax) wmax = v;
+                }
+            if (wmax >= mc->limit) { mc->pair_a.push_back (i); mc->pair_b.push_back (j); mc->pair_wmax.push_back (wmax); }
+        }
+    mc->pairs_dirty = true;
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int nprod, long long seed, int nchains, pce_mc **out) {
+    if (out == nullptr) return fail (PCE_ERR_VALUE, "null output handle");
+    *out = nullptr;
+    if (model == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    if (!model->symmetrized) return fail (PCE_ERR_STATE, "First calculate electrostatic energies.");
+    int status = model->sites_ok ();
+    if (status != PCE_OK) return status;
+    if (nequil < 0 || nprod < 1 || nchains < 1) return fail (PCE_ERR_VALUE, "invalid scan or chain counts");
+    pce_mc *mc = new (std::nothrow) pce_mc ();
+    if (mc == nullptr) return fail (PCE_ERR_ALLOC, "Cannot allocate Monte Carlo model.");
+    mc->model = model; mc->limit = limit; mc->nequil = nequil; mc->nprod = nprod; mc->nchains = nchains;
+    if (seed <= 0) {   // MCModelDefault.c:32-34: time() when no seed is given
+        seed = (long long) std::chrono::duration_cast<std::chrono::nanoseconds> (std::chrono::system_clock::now ().time_since_epoch ()).count ();
+    }
+    mc->seed = (uint64_t) seed;
+    find_pairs (mc);
+    *out = mc;
+    return PCE_OK;
+}
+
+extern "C" void pce_mc_destroy (pce_mc *mc) {
+    if (mc == nullptr) return;
+    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_ph.release (); mc->d_esum.release ();
+    mc->d_counts.release (); mc->d_counters.release ();
+    delete mc;
+}
+
+extern "C" int pce_mc_npairs (const pce_mc *mc) { return mc ? (int) mc->pair_a.size () : -1; }
+
+extern "C" int pce_mc_get_pair (const pce_mc *mc, int index, int *site_a, int *site_b, double *wmax) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    if (index < 0 || index >= (int) mc->pair_a.size ()) return fail (PCE_ERR_INDEX, "Index (" + std::to_string (index) + ") out of range.");
+    *site_a = mc->pair_a[index]; *site_b = mc->pair_b[index]; *wmax = mc->pair_wmax[index];
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_set_scans (pce_mc *mc, int nequil, int nprod) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    if (nequil < 0 || nprod < 1) return fail (PCE_ERR_VALUE, "invalid scan counts");
+    mc->nequil = nequil; mc->nprod = nprod;
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_set_chains (pce_mc *mc, int nchains) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    if (nchains < 1) return fail (PCE_ERR_VALUE, "invalid chain count");
+    mc->nchains = nchains;
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_set_kernel (pce_mc *mc, int kernel) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    if (kernel < 0 || kernel > 2) return fail (PCE_ERR_VALUE, "kernel must be 0 (auto), 1 (thread) or 2 (warp)");
+    mc->kernel = kernel;
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_get_info (const pce_mc *mc, int *kernel, int *nchains, int *nequil, int *nprod, long long *seed) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    if (kernel) *kernel = mc->kernel;
+    if (nchains) *nchains = mc->nchains;
+    if (nequil) *nequil = mc->nequil;
+    if (nprod) *nprod = mc->nprod;
+    if (seed) *seed = (long long) mc->seed;
+    return PCE_OK;
+}
+
+static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset, bool per_chain, McParams &p) {
+    pce_model *m = mc->model;
+    if (nph <= 0) return PCE_OK;
+    if ((long long) mc->nequil + mc->nprod > 4294967295LL) return fail (PCE_ERR_LIMIT, "too many scans");
+    int status = m->upload ();
+    if (status != PCE_OK) return status;
+    // the W matrix may have changed since the pairs were found (ScaleInteractions etc.): keep the reference's
+    // behaviour (pairs are fixed at Initialize, MCModelDefault.pyx:37-54) and only upload them once
+    const int npairs = (int) mc->pair_a.size ();
+    if (mc->pairs_dirty) {
+        PCE_CUDA (mc->d_pair_a.resize (npairs > 0 ? npairs : 1));
+        PCE_CUDA (mc->d_pair_b.resize (npairs > 0 ? npairs : 1));
+        if (npairs > 0) {
+            PCE_CUDA (cudaMemcpyAsync (mc->d_pair_a.ptr, mc->pair_a.data (), npairs * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+            PCE_CUDA (cudaMemcpyAsync (mc->d_pair_b.ptr, mc->pair_b.data (), npairs * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+            PCE_CUDA (cudaStreamSynchronize (m->stream));
+        }
+        mc->pairs_dirty = false;
+    }
+    PCE_CUDA (mc->d_ph.resize (nph));
+    PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
+
+    size_t limit = 0;
+    status = smem_limit (m->device, &limit);
+    if (status != PCE_OK) return status;
+    Plan plan = { 0, 0, 0, 0 };
+    bool ok = false;
+    if (mc->kernel == 1) ok = plan_thread (mc, limit, &plan);
+    else if (mc->kernel == 2) ok = plan_warp (mc, limit, &plan);
+    else ok = plan_thread (mc, limit, &plan) || plan_warp (mc, limit, &plan);
+    if (!ok) return fail (PCE_ERR_LIMIT, "model too large for the selected Monte Carlo kernel");
+
+    p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
+    p.first = m->d_first.ptr; p.nsi = m->d_nsite_inst.ptr; p.protons = m->d_protons.ptr;
+    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr;
+    p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.ph = mc->d_ph.ptr;
+    p.nph = nph; p.ph_index_offset = ph_index_offset; p.nchains = mc->nchains; p.nequil = mc->nequil; p.nprod = mc->nprod;
+    p.chain_offset = chain_offset;
+    p.k0 = (uint32_t) mc->seed; p.k1 = (uint32_t) (mc->seed >> 32);
+    p.temperature = m->temperature;
+    p.w_in_smem = plan.w_in_smem;
+
+    const int chains_per_block = plan.kernel == 1 ? plan.block : plan.block / 32;
+    const long long blocks = (long long) nph * ((mc->nchains + chains_per_block - 1) / chains_per_block);
+    if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
+    if (plan.kernel == 1) {
+        auto kernel = per_chain ? k_mc_thread<true> : k_mc_thread<false>;
+        PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
+        kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
+    } else {
+        auto kernel = per_chain ? k_mc_warp<true> : k_mc_warp<false>;
+        PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
+        kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
+    }
+    pce::count_launch ();
+    PCE_CUDA (cudaGetLastError ());
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_run_device (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
+                                  long long *d_counts, long long *d_counters, double *d_esum) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    pce_model *m = mc->model;
+    PCE_CUDA (cudaSetDevice (m->device));
+    if (d_counts) PCE_CUDA (cudaMemsetAsync (d_counts, 0, (size_t) nph * m->ninst * sizeof (long long), m->stream));
+    if (d_counters) PCE_CUDA (cudaMemsetAsync (d_counters, 0, (size_t) nph * 4 * sizeof (long long), m->stream));
+    if (d_esum) PCE_CUDA (cudaMemsetAsync (d_esum, 0, (size_t) nph * sizeof (double), m->stream));
+    McParams p;
+    std::memset (&p, 0, sizeof (p));
+    p.counts = (unsigned long long *) d_counts; p.counters = d_counters; p.esum = d_esum;
+    return launch_mc (mc, ph, nph, ph_index_offset, chain_offset, false, p);
+}
+
+extern "C" int pce_mc_run (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
+                           long long *counts, long long *counters, double *esum) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    pce_model *m = mc->model;
+    if (nph <= 0) return PCE_OK;
+    PCE_CUDA (cudaSetDevice (m->device));
+    PCE_CUDA (mc->d_counts.resize ((size_t) nph * m->ninst));
+    PCE_CUDA (mc->d_counters.resize ((size_t) nph * 4));
+    PCE_CUDA (mc->d_esum.resize (nph));
+    int status = pce_mc_run_device (mc, ph, nph, ph_index_offset, chain_offset, (long long *) mc->d_counts.ptr, mc->d_counters.ptr, mc->d_esum.ptr);
+    if (status != PCE_OK) return status;
+    std::vector<long long> host_counts ((size_t) nph * m->ninst);
+    PCE_CUDA (cudaMemcpyAsync (host_counts.data (), mc->d_counts.ptr, host_counts.size () * sizeof (long long), cudaMemcpyDeviceToHost, m->stream));
+    if (counters) PCE_CUDA (cudaMemcpyAsync (counters, mc->d_counters.ptr, (size_t) nph * 4 * sizeof (long long), cudaMemcpyDeviceToHost, m->stream));
+    if (esum) PCE_CUDA (cudaMemcpyAsync (esum, mc->d_esum.ptr, (size_t) nph * sizeof (double), cudaMemcpyDeviceToHost, m->stream));
+    PCE_CUDA (cudaStreamSynchronize (m->stream));
+    if (counts) std::memcpy (counts, host_counts.data (), host_counts.size () * sizeof (long long));
+    // probabilities of the last pH point into the model (MCModelDefault.c:310-311: counts / nprod)
+    const double scale = 1.0 / ((double) mc->nchains * (double) mc->nprod);
+    for (int k = 0; k < m->ninst; k++) m->prob[k] = (double) host_counts[(size_t) (nph - 1) * m->ninst + k] * scale;
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_run_chains (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
+                                  long long *chain_counts, int32_t *chain_state, double *chain_energy, double *chain_esum, long long *chain_counters) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    pce_model *m = mc->model;
+    if (nph <= 0) return PCE_OK;
+    PCE_CUDA (cudaSetDevice (m->device));
+    const size_t nc = (size_t) nph * mc->nchains;
+    pce::DeviceBuffer<long long> d_counts, d_counters;
+    pce::DeviceBuffer<int32_t>   d_state;
+    pce::DeviceBuffer<double>    d_energy, d_esum;
+    PCE_CUDA (d_counts.resize (nc * m->ninst)); PCE_CUDA (d_counters.resize (nc * 4));
+    PCE_CUDA (d_state.resize (nc * m->nsites)); PCE_CUDA (d_energy.resize (nc)); PCE_CUDA (d_esum.resize (nc));
+    PCE_CUDA (cudaMemsetAsync (d_counts.ptr, 0, nc * m->ninst * sizeof (long long), m->stream));
+    McParams p;
+    std::memset (&p, 0, sizeof (p));
+    p.chain_counts = d_counts.ptr; p.chain_state = d_state.ptr; p.chain_energy = d_energy.ptr; p.chain_esum = d_esum.ptr;
+    p.chain_counters = d_counters.ptr;
+    int status = launch_mc (mc, ph, nph, ph_index_offset, chain_offset, true, p);
+    if (status == PCE_OK) {
+        cudaError_t err = cudaStreamSynchronize (m->stream);
+        if (err == cudaSuccess && chain_counts) err = cudaMemcpy (chain_counts, d_counts.ptr, nc * m->ninst * sizeof (long long), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && chain_state) err = cudaMemcpy (chain_state, d_state.ptr, nc * m->nsites * sizeof (int32_t), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && chain_energy) err = cudaMemcpy (chain_energy, d_energy.ptr, nc * sizeof (double), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && chain_esum) err = cudaMemcpy (chain_esum, d_esum.ptr, nc * sizeof (double), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && chain_counters) err = cudaMemcpy (chain_counters, d_counters.ptr, nc * 4 * sizeof (long long), cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) status = fail (PCE_ERR_CUDA, std::string ("mc per-chain readback: ") + cudaGetErrorString (err));
+    }
+    d_counts.release (); d_counters.release (); d_state.release (); d_energy.release (); d_esum.release ();
+    return status;
+}
+
+extern "C" int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, long long *counts, long long *counters) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    pce_model *m = mc->model;
+    PCE_CUDA (cudaSetDevice (m->device));
+    const int saved_chains = mc->nchains;
+    mc->nchains = 1;                                   // the reference's trajectory is one chain (MCModelDefault.pyx:79-159)
+    pce::DeviceBuffer<long long> d_counts, d_counters;
+    pce::DeviceBuffer<int32_t>   d_state;
+    pce::DeviceBuffer<double>    d_energy, d_esum, d_traj;
+    int status = PCE_OK;
+    do {
+        cudaError_t err = d_counts.resize (m->ninst);
+        if (err == cudaSuccess) err = d_counters.resize (4);
+        if (err == cudaSuccess) err = d_state.resize (m->nsites);
+        if (err == cudaSuccess) err = d_energy.resize (1);
+        if (err == cudaSuccess) err = d_esum.resize (1);
+        if (err == cudaSuccess) err = d_traj.resize (mc->nprod);
+        if (err == cudaSuccess) err = cudaMemsetAsync (d_counts.ptr, 0, m->ninst * sizeof (long long), m->stream);
+        if (err != cudaSuccess) { status = fail (PCE_ERR_CUDA, std::string ("trajectory buffers: ") + cudaGetErrorString (err)); break; }
+        McParams p;
+        std::memset (&p, 0, sizeof (p));
+        p.chain_counts = d_counts.ptr; p.chain_state = d_state.ptr; p.chain_energy = d_energy.ptr; p.chain_esum = d_esum.ptr;
+        p.chain_counters = d_counters.ptr; p.trajectory = d_traj.ptr;
+        status = launch_mc (mc, &ph, 1, 0, 0, true, p);
+        if (status != PCE_OK) break;
+        err = cudaStreamSynchronize (m->stream);
+        if (err == cudaSuccess && energies) err = cudaMemcpy (energies, d_traj.ptr, mc->nprod * sizeof (double), cudaMemcpyDeviceToHost);
+        std::vector<long long> host_counts (m->ninst);
+        if (err == cudaSuccess) err = cudaMemcpy (host_counts.data (), d_counts.ptr, m->ninst * sizeof (long long), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && counters) err = cudaMemcpy (counters, d_counters.ptr, 4 * sizeof (long long), cudaMemcpyDeviceToHost);
+        if (err != cudaSuccess) { status = fail (PCE_ERR_CUDA, std::string ("trajectory readback: ") + cudaGetErrorString (err)); break; }
+        if (counts) std::memcpy (counts, host_counts.data (), m->ninst * sizeof (long long));
+        for (int k = 0; k < m->ninst; k++) m->prob[k] = (double) host_counts[k] / (double) mc->nprod;
+    } while (0);
+    mc->nchains = saved_chains;
+    d_counts.release (); d_counters.release (); d_state.release (); d_energy.release (); d_esum.release (); d_traj.release ();
+    return status;
+}

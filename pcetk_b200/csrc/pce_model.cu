@@ -1,0 +1,417 @@
+// pce_model.cu -- model container, setters/getters, symmetrisation, upload, and kernel 1
+// (batched microstate energies).  Replaces the data side of extensions/csource/EnergyModel.c.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+
+#include "pce_common.cuh"
+
+namespace pce {
+
+static thread_local std::string g_last_error;
+static std::atomic<long long>   g_launches (0);
+
+void set_error (const std::string &message) { g_last_error = message; }
+int  fail (int status, const std::string &message) { g_last_error = message; return status; }
+void count_launch (int n) { g_launches.fetch_add (n); }
+
+}  // namespace pce
+
+using pce::fail;
+
+extern "C" const char *pce_last_error (void) { return pce::g_last_error.c_str (); }
+extern "C" const char *pce_version (void) { return "pcetk_b200 0.1 (sm_100a)"; }
+
+extern "C" long long pce_launch_count (int reset) {
+    long long value = pce::g_launches.load ();
+    if (reset) pce::g_launches.store (0);
+    return value;
+}
+
+extern "C" int pce_device_count (int *count) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount (&n);
+    if (err != cudaSuccess) { *count = 0; return fail (PCE_ERR_CUDA, std::string ("cudaGetDeviceCount: ") + cudaGetErrorString (err)); }
+    *count = n;
+    return PCE_OK;
+}
+
+extern "C" int pce_device_name (int device, char *buffer, int length) {
+    cudaDeviceProp prop;
+    PCE_CUDA (cudaGetDeviceProperties (&prop, device));
+    snprintf (buffer, (size_t) length, "%s (sm_%d%d, %d SMs)", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+    return PCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// allocation
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pce_model_create (int nsites, int ninstances, double temperature, int device, pce_model **out) {
+    if (out == nullptr) return fail (PCE_ERR_VALUE, "null output handle");
+    *out = nullptr;
+    if (nsites < 0 || ninstances < 0 || ninstances < nsites) return fail (PCE_ERR_VALUE, "invalid numbers of sites / instances");
+    pce_model *m = nullptr;
+    try {
+        m = new pce_model ();
+        m->nsites = nsites; m->ninst = ninstances; m->temperature = temperature; m->device = device;
+        m->first.assign (nsites, 0); m->last.assign (nsites, -1); m->site_set.assign (nsites, 0);
+        m->protons.assign (ninstances, 0);
+        m->gmodel.assign (ninstances, 0.0); m->gintr.assign (ninstances, 0.0); m->prob.assign (ninstances, 0.0);
+        m->wraw.assign ((size_t) ninstances * ninstances, 0.0);
+        m->wsym.assign ((size_t) ninstances * ninstances, 0.0);
+    } catch (const std::bad_alloc &) {
+        delete m;
+        return fail (PCE_ERR_ALLOC, "Cannot allocate energy model.");
+    }
+    *out = m;
+    return PCE_OK;
+}
+
+extern "C" void pce_model_destroy (pce_model *m) {
+    if (m == nullptr) return;   // (the reference dereferences before its NULL check, EnergyModel.c:64-73)
+    int current = 0;
+    if (cudaGetDevice (&current) == cudaSuccess) {
+        cudaSetDevice (m->device);
+        m->d_first.release (); m->d_nsite_inst.release (); m->d_site_of_inst.release (); m->d_protons.release ();
+        m->d_gintr.release (); m->d_gmodel.release (); m->d_w.release ();
+        cudaSetDevice (current);
+    }
+    delete m;
+}
+
+extern "C" int pce_model_nsites (const pce_model *m) { return m ? m->nsites : -1; }
+extern "C" int pce_model_ninstances (const pce_model *m) { return m ? m->ninst : -1; }
+extern "C" double pce_model_temperature (const pce_model *m) { return m ? m->temperature : 0.0; }
+
+extern "C" int pce_set_stream (pce_model *m, void *cuda_stream) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    m->stream = (cudaStream_t) cuda_stream;
+    return PCE_OK;
+}
+
+extern "C" int pce_synchronize (pce_model *m) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    PCE_CUDA (cudaSetDevice (m->device));
+    PCE_CUDA (cudaStreamSynchronize (m->stream));
+    return PCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sites
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pce_model_set_site (pce_model *m, int site, int first, int last) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    if (site < 0 || site >= m->nsites) return fail (PCE_ERR_INDEX, "Index (" + std::to_string (site) + ") out of range.");
+    if (first < 0 || last < first || last >= m->ninst) return fail (PCE_ERR_VALUE, "invalid instance range");
+    m->first[site] = first; m->last[site] = last; m->site_set[site] = 1;
+    m->dirty = true;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_set_sites (pce_model *m, const int32_t *first, const int32_t *last) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    for (int i = 0; i < m->nsites; i++) {
+        int status = pce_model_set_site (m, i, first[i], last[i]);
+        if (status != PCE_OK) return status;
+    }
+    return m->sites_ok ();
+}
+
+extern "C" int pce_model_get_site (const pce_model *m, int site, int *first, int *last) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    if (site < 0 || site >= m->nsites) return fail (PCE_ERR_INDEX, "Index (" + std::to_string (site) + ") out of range.");
+    *first = m->first[site]; *last = m->last[site];
+    return PCE_OK;
+}
+
+int pce_model::sites_ok () const {
+    int expect = 0;
+    for (int i = 0; i < nsites; i++) {
+        if (!site_set[i]) return fail (PCE_ERR_STATE, "site " + std::to_string (i) + " has not been set");
+        if (first[i] != expect) return fail (PCE_ERR_VALUE, "site instance ranges must be contiguous and ascending");
+        expect = last[i] + 1;
+    }
+    if (expect != ninst) return fail (PCE_ERR_VALUE, "site ranges do not cover all instances");
+    return PCE_OK;
+}
+
+extern "C" int pce_model_nstates (const pce_model *m, double *nstates) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    int status = m->sites_ok ();
+    if (status != PCE_OK) return status;
+    double n = 1.0;
+    for (int i = 0; i < m->nsites; i++) n *= (double) (m->last[i] - m->first[i] + 1);
+    *nstates = n;
+    return PCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// element access (EnergyModel.c:145-199)
+// ---------------------------------------------------------------------------------------------------
+#define CHECK_INSTANCE(m, k)                                                                            \
+    if ((m) == nullptr) return fail (PCE_ERR_VALUE, "null model");                                     \
+    if ((k) < 0 || (k) >= (m)->ninst) return fail (PCE_ERR_INDEX, "Index (" + std::to_string (k) + ") out of range.");
+
+extern "C" int pce_model_set_gmodel (pce_model *m, int k, double v) { CHECK_INSTANCE (m, k); m->gmodel[k] = v; m->dirty = true; return PCE_OK; }
+extern "C" int pce_model_set_gintr (pce_model *m, int k, double v) { CHECK_INSTANCE (m, k); m->gintr[k] = v; m->dirty = true; return PCE_OK; }
+extern "C" int pce_model_set_protons (pce_model *m, int k, int v) { CHECK_INSTANCE (m, k); m->protons[k] = v; m->dirty = true; return PCE_OK; }
+extern "C" int pce_model_set_probability (pce_model *m, int k, double v) { CHECK_INSTANCE (m, k); m->prob[k] = v; return PCE_OK; }
+extern "C" int pce_model_set_interaction (pce_model *m, int a, int b, double v) {
+    CHECK_INSTANCE (m, a); CHECK_INSTANCE (m, b);
+    m->wraw[(size_t) a * m->ninst + b] = v;    // raw matrix only; the symmetric copy changes on Symmetrize (EnergyModel.c:197-199)
+    return PCE_OK;
+}
+extern "C" int pce_model_get_gmodel (const pce_model *m, int k, double *v) { CHECK_INSTANCE (m, k); *v = m->gmodel[k]; return PCE_OK; }
+extern "C" int pce_model_get_gintr (const pce_model *m, int k, double *v) { CHECK_INSTANCE (m, k); *v = m->gintr[k]; return PCE_OK; }
+extern "C" int pce_model_get_protons (const pce_model *m, int k, int *v) { CHECK_INSTANCE (m, k); *v = m->protons[k]; return PCE_OK; }
+extern "C" int pce_model_get_probability (const pce_model *m, int k, double *v) { CHECK_INSTANCE (m, k); *v = m->prob[k]; return PCE_OK; }
+extern "C" int pce_model_get_interaction (const pce_model *m, int a, int b, double *v) {
+    CHECK_INSTANCE (m, a); CHECK_INSTANCE (m, b);
+    *v = m->wraw[(size_t) a * m->ninst + b];
+    return PCE_OK;
+}
+extern "C" int pce_model_get_interaction_symmetric (const pce_model *m, int a, int b, double *v) {
+    CHECK_INSTANCE (m, a); CHECK_INSTANCE (m, b);
+    *v = m->wsym[(size_t) a * m->ninst + b];
+    return PCE_OK;
+}
+extern "C" int pce_model_get_deviation (const pce_model *m, int a, int b, double *v) {
+    CHECK_INSTANCE (m, a); CHECK_INSTANCE (m, b);
+    const double wij = m->wraw[(size_t) a * m->ninst + b], wji = m->wraw[(size_t) b * m->ninst + a];
+    *v = (wij + wji) * .5 - wij;               // EnergyModel.c:169-176
+    return PCE_OK;
+}
+
+extern "C" int pce_model_load (pce_model *m, const double *gintr, const double *gmodel, const int32_t *protons, const double *interactions) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    const size_t n = (size_t) m->ninst;
+    if (gintr) std::memcpy (m->gintr.data (), gintr, n * sizeof (double));
+    if (gmodel) std::memcpy (m->gmodel.data (), gmodel, n * sizeof (double));
+    if (protons) std::memcpy (m->protons.data (), protons, n * sizeof (int32_t));
+    if (interactions) std::memcpy (m->wraw.data (), interactions, n * n * sizeof (double));
+    m->dirty = true;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_get_probabilities (const pce_model *m, double *p) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    std::memcpy (p, m->prob.data (), (size_t) m->ninst * sizeof (double));
+    return PCE_OK;
+}
+extern "C" int pce_model_set_probabilities (pce_model *m, const double *p) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    std::memcpy (m->prob.data (), p, (size_t) m->ninst * sizeof (double));
+    return PCE_OK;
+}
+extern "C" int pce_model_get_symmetric_matrix (const pce_model *m, double *w) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    std::memcpy (w, m->wsym.data (), (size_t) m->ninst * m->ninst * sizeof (double));
+    return PCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// symmetry (EnergyModel.c:78-101)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pce_model_check_symmetric (const pce_model *m, double tolerance, double *max_deviation, int *is_symmetric) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    const size_t n = (size_t) m->ninst;
+    double maxd = 0.0;
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j < i; j++) {
+            const double d = std::fabs (m->wraw[i * n + j] - m->wraw[j * n + i]);
+            if (d > maxd) maxd = d;
+        }
+    if (max_deviation) *max_deviation = maxd;
+    if (is_symmetric) *is_symmetric = maxd <= tolerance ? 1 : 0;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_symmetrize (pce_model *m) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    const size_t n = (size_t) m->ninst;
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j <= i; j++) {
+            const double v = 0.5 * (m->wraw[i * n + j] + m->wraw[j * n + i]);
+            m->wsym[i * n + j] = v;
+            m->wsym[j * n + i] = v;
+        }
+    m->symmetrized = true;
+    m->dirty = true;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_reset_interactions (pce_model *m) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    std::fill (m->wsym.begin (), m->wsym.end (), 0.0);
+    m->symmetrized = true;
+    m->dirty = true;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_scale_interactions (pce_model *m, double scale) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    for (double &v : m->wsym) v *= scale;
+    m->dirty = true;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_state_from_probabilities (const pce_model *m, int32_t *state) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    int status = m->sites_ok ();
+    if (status != PCE_OK) return status;
+    for (int i = 0; i < m->nsites; i++) {      // EnergyModel.c:107-140 with the loop bound fixed (nsites, not nsites+1)
+        int    maxi = m->first[i];
+        double maxp = -1.0;
+        for (int k = m->first[i]; k <= m->last[i]; k++)
+            if (m->prob[k] > maxp) { maxp = m->prob[k]; maxi = k; }
+        state[i] = maxi;
+    }
+    return PCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------------------
+int pce_model::upload () {
+    int status = sites_ok ();
+    if (status != PCE_OK) return status;
+    PCE_CUDA (cudaSetDevice (device));
+    if (!dirty && d_w.ptr != nullptr) return PCE_OK;
+    ldw = (ninst + 3) & ~3;
+    PCE_CUDA (d_first.resize (nsites)); PCE_CUDA (d_nsite_inst.resize (nsites));
+    PCE_CUDA (d_site_of_inst.resize (ninst)); PCE_CUDA (d_protons.resize (ninst));
+    PCE_CUDA (d_gintr.resize (ninst)); PCE_CUDA (d_gmodel.resize (ninst));
+    PCE_CUDA (d_w.resize ((size_t) ninst * ldw));
+    std::vector<int32_t> ns (nsites), site_of (ninst);
+    for (int i = 0; i < nsites; i++) {
+        ns[i] = last[i] - first[i] + 1;
+        for (int k = first[i]; k <= last[i]; k++) site_of[k] = i;
+    }
+    PCE_CUDA (cudaMemcpyAsync (d_first.ptr, first.data (), nsites * sizeof (int32_t), cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaMemcpyAsync (d_nsite_inst.ptr, ns.data (), nsites * sizeof (int32_t), cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaMemcpyAsync (d_site_of_inst.ptr, site_of.data (), ninst * sizeof (int32_t), cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaMemcpyAsync (d_protons.ptr, protons.data (), ninst * sizeof (int32_t), cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaMemcpyAsync (d_gintr.ptr, gintr.data (), ninst * sizeof (double), cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaMemcpyAsync (d_gmodel.ptr, gmodel.data (), ninst * sizeof (double), cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaMemsetAsync (d_w.ptr, 0, (size_t) ninst * ldw * sizeof (double), stream));
+    PCE_CUDA (cudaMemcpy2DAsync (d_w.ptr, (size_t) ldw * sizeof (double), wsym.data (), (size_t) ninst * sizeof (double),
+                                 (size_t) ninst * sizeof (double), (size_t) ninst, cudaMemcpyHostToDevice, stream));
+    PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors above die with this scope
+    dirty = false;
+    return PCE_OK;
+}
+
+extern "C" int pce_model_upload (pce_model *m) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    return m->upload ();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel 1: microstate energies.  One thread per state walks the sites in the reference's order
+// (EnergyModel.c:204-224): Gintr and proton sums over sites, W summed over j < i with the row of a_i --
+// sequential fp64 adds without FMA contraction, so the result is bit-identical to the reference.
+// The pH-independent sums are formed once and every pH of the batch is emitted from them.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (128) k_energy (const int32_t *__restrict__ states, long long nstates, int nsites, int ninst, int ldw,
+                                                  const double *__restrict__ base,      // Gintr (folded) or Gmodel (unfolded)
+                                                  const int32_t *__restrict__ protons, const double *__restrict__ w, int unfolded,
+                                                  const double *__restrict__ ph, double temperature, int nph, double *__restrict__ out) {
+    const long long s = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstates) return;
+    const int32_t *state = states + s * nsites;
+    double g = 0.0, wsum = 0.0;
+    int    np = 0;
+    for (int i = 0; i < nsites; i++) {
+        const int ai = state[i];
+        g = __dadd_rn (g, base[ai]);
+        np += protons[ai];
+        if (!unfolded) {
+            const double *row = w + (size_t) ai * ldw;
+            for (int j = 0; j < i; j++) wsum = __dadd_rn (wsum, row[state[j]]);
+        }
+    }
+    for (int q = 0; q < nph; q++) {
+        // mu = -R*T*ln10*pH evaluated left to right like EnergyModel.c:223
+        const double mu = __dmul_rn (__dmul_rn (__dmul_rn (-PCE_R, temperature), PCE_LN10), ph[q]);
+        double value = __dsub_rn (g, __dmul_rn ((double) np, mu));
+        if (!unfolded) value = __dadd_rn (value, wsum);
+        out[s * nph + q] = value;
+    }
+}
+
+static int validate_states_host (const pce_model *m, const int32_t *states, long long nstates) {
+    for (long long s = 0; s < nstates; s++)
+        for (int i = 0; i < m->nsites; i++) {
+            const int a = states[s * m->nsites + i];
+            if (a < m->first[i] || a > m->last[i]) return fail (PCE_ERR_VALUE, "Invalid value (" + std::to_string (a) + ").");
+        }
+    return PCE_OK;
+}
+
+extern "C" int pce_energy_device (pce_model *m, const int32_t *d_states, long long nstates, const double *d_ph, int nph, int unfolded, double *d_out) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    if (!unfolded && !m->symmetrized) return fail (PCE_ERR_STATE, "First calculate electrostatic energies.");
+    int status = m->upload ();
+    if (status != PCE_OK) return status;
+    if (nstates <= 0 || nph <= 0) return PCE_OK;
+    const int threads = 128;
+    const long long blocks = (nstates + threads - 1) / threads;
+    if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many states in one energy batch");
+    k_energy<<<(unsigned) blocks, threads, 0, m->stream>>> (d_states, nstates, m->nsites, m->ninst, m->ldw,
+                                                            unfolded ? m->d_gmodel.ptr : m->d_gintr.ptr, m->d_protons.ptr, m->d_w.ptr,
+                                                            unfolded, d_ph, m->temperature, nph, d_out);
+    pce::count_launch ();
+    PCE_CUDA (cudaGetLastError ());
+    return PCE_OK;
+}
+
+extern "C" int pce_energy (pce_model *m, const int32_t *states, long long nstates, const double *ph, int nph, int unfolded, double *out) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    int status = m->sites_ok ();
+    if (status != PCE_OK) return status;
+    status = validate_states_host (m, states, nstates);
+    if (status != PCE_OK) return status;
+    if (nstates <= 0 || nph <= 0) return PCE_OK;
+    status = m->upload ();
+    if (status != PCE_OK) return status;
+    pce::DeviceBuffer<int32_t> d_states;
+    pce::DeviceBuffer<double>  d_mu, d_out;
+    PCE_CUDA (d_states.resize ((size_t) nstates * m->nsites));
+    PCE_CUDA (d_mu.resize (nph));
+    PCE_CUDA (d_out.resize ((size_t) nstates * nph));
+    PCE_CUDA (cudaMemcpyAsync (d_states.ptr, states, (size_t) nstates * m->nsites * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+    PCE_CUDA (cudaMemcpyAsync (d_mu.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
+    status = pce_energy_device (m, d_states.ptr, nstates, d_mu.ptr, nph, unfolded, d_out.ptr);
+    if (status == PCE_OK) {
+        cudaError_t err = cudaMemcpyAsync (out, d_out.ptr, (size_t) nstates * nph * sizeof (double), cudaMemcpyDeviceToHost, m->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize (m->stream);
+        if (err != cudaSuccess) status = fail (PCE_ERR_CUDA, std::string ("energy readback: ") + cudaGetErrorString (err));
+    }
+    d_states.release (); d_mu.release (); d_out.release ();
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// test hook: Philox on the device
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_philox (const uint32_t *ctr, int nblocks, uint32_t k0, uint32_t k1, uint32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblocks) return;
+    pce::Philox4 r = pce::philox4x32_10 (ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+extern "C" int pce_test_philox (int device, const uint32_t *ctr, int nblocks, const uint32_t key[2], uint32_t *out) {
+    PCE_CUDA (cudaSetDevice (device));
+    pce::DeviceBuffer<uint32_t> d_ctr, d_out;
+    PCE_CUDA (d_ctr.resize ((size_t) 4 * nblocks));
+    PCE_CUDA (d_out.resize ((size_t) 4 * nblocks));
+    PCE_CUDA (cudaMemcpy (d_ctr.ptr, ctr, (size_t) 4 * nblocks * sizeof (uint32_t), cudaMemcpyHostToDevice));
+    k_philox<<<(nblocks + 127) / 128, 128>>> (d_ctr.ptr, nblocks, key[0], key[1], d_out.ptr);
+    pce::count_launch ();
+    PCE_CUDA (cudaGetLastError ());
+    PCE_CUDA (cudaMemcpy (out, d_out.ptr, (size_t) 4 * nblocks * sizeof (uint32_t), cudaMemcpyDeviceToHost));
+    d_ctr.release (); d_out.release ();
+    return PCE_OK;
+}

@@ -367,7 +367,7 @@ def format_gintr_lines(site_names, inst_rows, precision=4):
     ``precision`` argument and always prints 4 decimals; here the argument is honoured, with the
     reference's 4 as the default."""
     items = (("siteID", 8, 0), ("instID", 8, 0), ("siteLabel", 14, -1), ("instLabel", 10, -1),
-             ("Gintr", 12, precision), ("protons", 8, 0))
+             ("Gintr", max(12, precision + 8), precision), ("protons", 8, 0))
     header, form = _table_format(items)
     lines = [header]
     for site_index, inst_index, inst_label, gintr, protons in inst_rows:
@@ -380,7 +380,8 @@ def format_w_lines(site_names, inst_rows, wsym, wraw, precision=4):
     ``(siteIndex, instIndex, instLabel)`` in global-instance order."""
     items = (("idSiteA", 8, 0), ("idInstA", 8, 0), ("labSiteA", 14, -1), ("labInstA", 10, -1),
              ("idSiteB", 8, 0), ("idInstB", 8, 0), ("labSiteB", 14, -1), ("labInstB", 10, -1),
-             ("Wij_symm", 10, precision), ("Wij", 10, precision), ("Wij_err", 10, precision))
+             ("Wij_symm", max(10, precision + 8), precision), ("Wij", max(10, precision + 8), precision),
+             ("Wij_err", max(10, precision + 8), precision))
     header, form = _table_format(items)
     lines = [header]
     for a, (sa, ia, la) in enumerate(inst_rows):

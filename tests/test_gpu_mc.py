@@ -1,0 +1,140 @@
+"""Kernel 3 (Metropolis MC) through the C ABI.
+
+Two kinds of parity: (1) EXACT -- every chain must reproduce the executable chain specification
+(oracle_mc_philox_chain: Philox stream, proposal mapping, cached fields, Metropolis rule) count for count; (2)
+STATISTICAL -- ensembles must match the exact (enumerated) probabilities and the reference MCModelDefault within
+|dp| <= 0.01 (BASELINE.json north_star) at the scan counts stated in each test."""
+
+import numpy as np
+import pytest
+
+import oracle
+import pcetk_b200 as P
+from conftest import load_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def make(name, **kw):
+    rec, gold = load_fixture(name)
+    model = P.MEADModel(rec, log=None)
+    sampler = P.MCModelDefault(**kw)
+    model.DefineMCModel(sampler, log=None)
+    return rec, gold, model, sampler
+
+
+@pytest.mark.parametrize("name", ["twosites", "defensin", "lysozyme", "ifp20"])
+def test_pairs_match_reference_logs(name):
+    rec, gold, _model, sampler = make(name, nprod=10)
+    pairs = sampler.GetPairs()
+    assert [[a, b] for a, b, _w in pairs] == gold["golden_pairs"].tolist()
+    assert np.abs(np.array([w for _a, _b, w in pairs]) - gold["golden_pairs_wmax"]).max() <= 5.1e-7
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("name,nequil,nprod", [("twosites", 20, 300), ("lysozyme", 30, 200), ("ifp20", 10, 60)])
+def test_chains_equal_specification(port, name, nequil, nprod, kernel):
+    rec, _gold, model, sampler = make(name, nequil=nequil, nprod=nprod, randomSeed=987654321, nchains=40, kernel=kernel)
+    wsym = port.symmetrize(rec.interactions)
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    sampler.chainOffset = 7
+    out = sampler.RunChains([2.0, 7.5], phIndexOffset=3)
+    for q, ph in enumerate([2.0, 7.5]):
+        for chain in (0, 1, 31, 32, 39):
+            spec = port.mc_philox_chain(rec, wsym, pairs, nequil, nprod, sampler.seed, 7 + chain, 3 + q, ph)
+            assert np.array_equal(out["counts"][q, chain], spec["counts"])
+            assert np.array_equal(out["state"][q, chain], spec["state"])
+            assert out["counters"][q, chain].tolist() == spec["counters"].tolist()
+            if kernel == 1:
+                assert out["energy"][q, chain] == spec["energy"]
+                assert out["esum"][q, chain] == spec["esum"]
+            else:   # the warp kernel seeds the tracked energy from a lane-parallel sum
+                assert abs(out["energy"][q, chain] - spec["energy"]) < 1e-9
+    # the aggregate entry point must equal the sum of its chains
+    counts, counters, esum = sampler.RunCounts([2.0, 7.5], phIndexOffset=3)
+    assert np.array_equal(counts, out["counts"].sum(axis=1))
+    assert np.array_equal(counters, out["counters"].sum(axis=1))
+    assert np.abs(esum / out["esum"].sum(axis=1) - 1.0).max() < 1e-12
+
+
+@pytest.mark.parametrize("name,grid", [("twosites", [2.0, 4.0, 6.0, 7.0, 9.0]), ("defensin", [2.0, 7.0, 12.5]), ("lysozyme", [3.0, 6.0, 7.0, 10.0])])
+def test_ensemble_vs_exact_probabilities(port, name, grid):
+    """256 chains x 20000 production scans per pH value (5.1e6 scans): |dp| <= 0.01 and a 5-sigma z-score bound using
+    the reference's measured seed-to-seed sigma (<= 0.0079 per 20000 scans)."""
+    rec, _gold, model, sampler = make(name, nequil=500, nprod=20000, randomSeed=20240611, nchains=256)
+    wsym = port.symmetrize(rec.interactions)
+    p = model.CalculateProbabilitiesBatch(grid)
+    for row, ph in zip(p, grid):
+        exact, _z, _g = port.analytic(rec, wsym, ph)
+        assert np.abs(row - exact).max() <= 0.01
+        assert np.abs(row - exact).max() <= 5.0 * 0.0079 / np.sqrt(256)
+        assert abs(row.sum() - rec.nsites) < 1e-9
+
+
+def test_single_chain_matches_reference_accuracy_class(port):
+    """One chain at the reference's defaults (500 + 20000 scans) is as accurate as the reference's own single chain
+    (its curves differ from the exact ones by up to 0.018)."""
+    rec, _gold, model, sampler = make("lysozyme", randomSeed=5, nchains=1)
+    wsym = port.symmetrize(rec.interactions)
+    model.CalculateProbabilities(pH=7.0, log=None)
+    exact, _z, _g = port.analytic(rec, wsym, 7.0)
+    assert np.abs(model.energyModel.GetProbabilities() - exact).max() <= 0.03
+
+
+def test_ifp20_vs_reference_mc(port):
+    """ifp20 (73 sites, 4- and 5-instance sites, 49 double-move pairs) cannot be enumerated: compare 256 GPU chains with
+    the mean of 16 seeds of the reference-semantics sampler (MT19937 port, bit-identical to the compiled reference)."""
+    rec, _gold, model, sampler = make("ifp20", nequil=500, nprod=4000, randomSeed=99, nchains=256)
+    wsym = port.symmetrize(rec.interactions)
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    p = model.CalculateProbabilitiesBatch([7.0])[0]
+    ref = np.mean([port.mc_mt(rec, wsym, pairs, 500, 8000, 1000 + seed, [7.0])[0][0] for seed in range(16)], axis=0)
+    assert np.abs(p - ref).max() <= 0.01
+    counts, counters, _esum = sampler.RunCounts([7.0])
+    moves, macc, flips, facc = counters[0]
+    assert moves + flips == 256 * 4000 * (73 + 49)
+    assert abs(moves / (moves + flips) - 73.0 / 122.0) < 0.002
+
+
+def test_mean_energy_and_acceptance_vs_lysozyme_traj_fixture(port):
+    """lysozyme_traj: stat_mc.dat holds the reference's per-scan energies at pH 7 (mean -17.3828, min -18.044242) and
+    lyso_mc_traj.out its per-500-scan counters (~6.5 % single-move acceptance)."""
+    rec, _gold, model, sampler = make("lysozyme", nequil=500, nprod=20000, randomSeed=31, nchains=64)
+    gold = np.load("tests/golden/lysozyme_traj.npz")
+    counts, counters, esum = sampler.RunCounts([7.0])
+    mean_energy = esum[0] / (64 * 20000)
+    assert abs(mean_energy - (-17.3769)) < 0.01                     # exact Boltzmann mean
+    assert abs(mean_energy - gold["stat_mc"].mean()) < 0.03
+    moves, macc, flips, facc = counters[0]
+    ref = gold["counters"][gold["counters"][:, 0] > 500]            # production blocks
+    ref_rate = ref[:, 2].sum() / ref[:, 1].sum()
+    assert abs(macc / moves - ref_rate) < 0.005
+    # trajectory mode: one chain, energies on the enumerated energy set, minimum = global minimum
+    import os
+    import tempfile
+    sampler.nchains = 1
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "stat.dat")
+        model.CalculateProbabilities(pH=7.0, trajectoryFilename=path, log=None)
+        energies = np.loadtxt(path)
+    assert energies.shape == (20000,)
+    assert abs(energies.min() - gold["stat_mc"].min()) < 1e-5
+    assert abs(energies.mean() - (-17.3769)) < 0.08
+
+
+def test_titration_curve_lysozyme_ph0_20(port):
+    """BASELINE config 2: lysozyme MC titration curve, pH 0..20 step 0.5 (41 points), 64 chains x 20000 scans per point,
+    against the exact curve from kernel 2 (itself checked against the oracle) and the reference's curve files (0..14)."""
+    rec, gold, model, sampler = make("lysozyme", nequil=500, nprod=20000, randomSeed=77, nchains=64)
+    curves = P.TitrationCurves(model, curveSampling=0.5, curveStart=0.0, curveStop=20.0, log=None)
+    curves.CalculateCurves(log=None)
+    assert curves.nsteps == 41
+    mc = np.array([[p for site in step for p in site] for step in curves.steps])
+    model.DefineMCModel(None)
+    exact = model.CalculateProbabilitiesBatch(curves.pHValues())
+    assert np.abs(mc - exact).max() <= 0.01
+    assert np.abs(mc[:29] - gold["golden_curve_analytic"]).max() <= 0.01
+    assert np.abs(mc[:29] - gold["golden_curve_mc_curves_mc"]).max() <= 0.03     # the reference's single-chain curves
+    curves.CalculateHalfpKs()
+    his = [k for k, s in enumerate(rec.site_labels) if s[1] == "HIS"][0]
+    assert len(curves.halves[his][0]) >= 1
