@@ -178,6 +178,7 @@ def main():
     parser.add_argument("--chains", type=int, default=0, help="chains per pH value per GPU (default depends on the workload)")
     parser.add_argument("--nprod", type=int, default=0, help="production scans per chain (default: reference's 20000; synthM: 20)")
     parser.add_argument("--nequil", type=int, default=-1)
+    parser.add_argument("--waves", type=int, default=2, help="when --chains is not given: chains = waves x (chains resident on the GPU) / 41")
     parser.add_argument("--kernel", type=int, default=0, help="MC kernel: 0 auto, 1 chain-per-thread, 2 chain-per-warp")
     parser.add_argument("--cpu-threads", type=int, default=0)
     parser.add_argument("--cpu-nprod", type=int, default=20000)
@@ -246,6 +247,7 @@ def main():
 
         units_per_step = float(record.nstates)          # microstates enumerated per curve (all 41 pH values served)
         metric, unit = "analytic_microstates_per_s", "states/s"
+        launch_info = {"passes": len(groups)}
         workload = "synthetic 32 sites x 2 instances, 2^32 microstates, analytic probabilities on pH 0..20 step 0.5 (41 pts) per step"
         h2d = record.ninstances * ((record.ninstances + 3) // 4 * 4) * 8 + record.ninstances * 20 + record.nsites * 8
         d2h = int(nbins) * 8 * len(groups)
@@ -259,6 +261,12 @@ def main():
         grid_all = ph_grid()
         sampler = P.MCModelDefault(nequil=nequil, nprod=nprod, randomSeed=20241019, nchains=chains, kernel=args.kernel)
         model.DefineMCModel(sampler, log=None)
+        if not args.chains:
+            # size the ensemble to whole waves of the launch geometry (chain-major linear grid)
+            plan = sampler.LaunchPlan(len(grid_all))
+            chains = max(1, (args.waves * plan["chains_per_wave"]) // len(grid_all))
+            sampler.nchains = chains
+        plan = sampler.LaunchPlan(len(grid_all))
         sampler.chainOffset = rank * chains
         npairs = sampler.npairs
         nmoves = record.nsites + npairs
@@ -287,6 +295,7 @@ def main():
 
         units_per_step = float(len(grid_all)) * chains * (nequil + nprod) * nmoves
         metric, unit = "mc_trial_moves_per_s", "moves/s"
+        launch_info = plan
         workload = "%s (%d sites / %d instances / %d pairs) MC titration curve pH 0..20 step 0.5 (41 pts), nequil %d, nprod %d, %d chains per pH per GPU" % (
             record.name, record.nsites, record.ninstances, npairs, nequil, nprod, chains)
         h2d = record.ninstances * ((record.ninstances + 3) // 4 * 4) * 8 + record.ninstances * 20 + record.nsites * 8 + len(grid_all) * 8
@@ -364,7 +373,8 @@ def main():
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak" if args.workload != "synthA" else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "reference fixture model, synthetic chains" if args.workload in ("lysozyme", "ifp20", "defensin") else "synthetic",
-            "config": {"workload": workload, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "chains sharded over %d GPU(s), one all-reduce of counts" % world},
+            "config": {"workload": workload, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "chains sharded over %d GPU(s), one all-reduce of counts" % world,
+                       "launch": launch_info},
             "clocks": clock_info, "gpu_launches": launches, "roofline": roofline,
         }
         if e2e is not None:

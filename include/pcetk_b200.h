@@ -139,6 +139,9 @@ int  pce_mc_set_scans (pce_mc *mc, int nequil, int nprod);
 int  pce_mc_set_chains (pce_mc *mc, int nchains);
 int  pce_mc_set_kernel (pce_mc *mc, int kernel);   /* 0 = auto, 1 = chain-per-thread, 2 = chain-per-warp */
 int  pce_mc_get_info (const pce_mc *mc, int *kernel, int *nchains, int *nequil, int *nprod, long long *seed);
+/* launch geometry the sampler would use for nph pH values (any output may be NULL): chains_per_wave is the number of
+ * chains resident on the whole device at once -- size nph*nchains as a multiple of it to run in full waves */
+int  pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm, int *chains_per_wave, long long *smem_bytes);
 
 /* MCModelDefault_Equilibration + _Production (MCModelDefault.h:70-71) for nph pH values x nchains
  * chains in one launch.  Chains [chain_offset, chain_offset + nchains) of a global ensemble are run

@@ -339,8 +339,10 @@ static uint32_t mulhi32 (uint32_t a, uint32_t b, uint32_t *lo) {
  *              :97: a uniform type draw followed by an independent uniform site draw); the new
  *              instance is uniform over the *other* instances (k in [0,n-1), skip current) instead of
  *              the reference's rejection loop (MCModelDefault.c:99-101) -- same distribution.
- *   energy   : cached fields h[k] = sum_j W[k][a_j]; dW = h[new]-h[old] (+ pair cross term), equal in
- *              exact arithmetic to the loops of MCModelDefault.c:109-111 and :152-159.
+ *   energy   : everything in units of RT.  wb = beta*W, gtb[k] = beta*(Gintr[k] - protons[k]*mu(pH)); every chain
+ *              caches the fused fields hb[k] = gtb[k] + sum_j wb[k][a_j].  A single move then has
+ *              dG/RT = hb[new] - hb[old]; a double move adds the second site and the pair cross term.  Equal in
+ *              exact arithmetic to MCModelDefault.c:103-117 and :146-164 (same-site W is zero by construction).
  *   accept   : MCModelDefault_Metropolis (MCModelDefault.c:71-85) with u = w1 * 2^-32.
  *   counting : residence times, equal to adding 1 to the active instance of every site after every
  *              production scan (MCModelDefault.c:215-226, :306-309).
@@ -357,8 +359,12 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
     const size_t n = (size_t) ninst;
     int       *state = (int *) malloc (sizeof (int) * (size_t) nsites);
     long long *since = (long long *) calloc ((size_t) nsites, sizeof (long long));
-    double    *h     = (double *) malloc (sizeof (double) * n);
+    double    *hb    = (double *) malloc (sizeof (double) * n);
+    double    *wb    = (double *) malloc (sizeof (double) * n * n);
     uint32_t   word[4];
+    const double mu   = mu_of (temperature, pH);
+    const double beta = 1.0 / (PCE_R * temperature);
+    for (size_t e = 0; e < n * n; e++) wb[e] = beta * w[e];
     /* initial state */
     for (int i = 0; i < nsites; i++) {
         if ((i & 3) == 0 || i == 0) {
@@ -368,13 +374,11 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
         state[i] = first[i] + (int) mulhi32 (word[i & 3], (uint32_t) (last[i] - first[i] + 1), NULL);
     }
     for (size_t k = 0; k < n; k++) {
-        double acc = 0.0;
-        for (int j = 0; j < nsites; j++) acc += w[k * n + (size_t) state[j]];
-        h[k] = acc;
+        double acc = beta * (gintr[k] - (double) protons[k] * mu);
+        for (int j = 0; j < nsites; j++) acc += wb[k * n + (size_t) state[j]];
+        hb[k] = acc;
     }
-    double g = energy_folded (&m, state, pH);
-    const double mu   = mu_of (temperature, pH);
-    const double beta = 1.0 / (PCE_R * temperature);
+    double grt = beta * energy_folded (&m, state, pH);
     const uint32_t nmoves = (uint32_t) (nsites + npairs);
     for (size_t k = 0; k < n; k++) counts[k] = 0;
     counters[0] = counters[1] = counters[2] = counters[3] = 0;
@@ -408,17 +412,11 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
             }
             if (production) counters[sb >= 0 ? 2 : 0]++;
             if (!valid) continue;
-            double dgintr = gintr[ia] - gintr[oa];
-            int    dprot  = protons[ia] - protons[oa];
-            double dw     = h[ia] - h[oa];
+            double x = hb[ia] - hb[oa];
             if (sb >= 0) {
-                dgintr = dgintr + (gintr[ib] - gintr[ob]);
-                dprot  = dprot + (protons[ib] - protons[ob]);
-                double cross = w[(size_t) ia * n + ib] - w[(size_t) ia * n + ob] - w[(size_t) oa * n + ib] + w[(size_t) oa * n + ob];
-                dw = (dw + (h[ib] - h[ob])) + cross;
+                double cross = wb[(size_t) ia * n + ib] - wb[(size_t) ia * n + ob] - wb[(size_t) oa * n + ib] + wb[(size_t) oa * n + ob];
+                x = (x + (hb[ib] - hb[ob])) + cross;
             }
-            const double dg = (dgintr - (double) dprot * mu) + dw;
-            const double x  = dg * beta;
             int accept;
             if (x < 0.0) accept = 1;
             else if (-x < PCE_TOO_SMALL) accept = 0;
@@ -428,18 +426,18 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
             counts[oa] += tp - since[sa]; since[sa] = tp; state[sa] = ia;
             if (sb >= 0) { counts[ob] += tp - since[sb]; since[sb] = tp; state[sb] = ib; }
             for (size_t k = 0; k < n; k++) {
-                double v = h[k] + (w[(size_t) ia * n + k] - w[(size_t) oa * n + k]);
-                if (sb >= 0) v = v + (w[(size_t) ib * n + k] - w[(size_t) ob * n + k]);
-                h[k] = v;
+                double v = hb[k] + (wb[(size_t) ia * n + k] - wb[(size_t) oa * n + k]);
+                if (sb >= 0) v = v + (wb[(size_t) ib * n + k] - wb[(size_t) ob * n + k]);
+                hb[k] = v;
             }
-            g = g + dg;
+            grt = grt + x;
         }
-        if (production) es += g;
+        if (production) es += grt;
     }
     for (int i = 0; i < nsites; i++) counts[state[i]] += (long long) nprod - since[i];
-    if (esum) *esum = es;
+    if (esum) *esum = es / beta;
     if (final_state) for (int i = 0; i < nsites; i++) final_state[i] = state[i];
-    if (final_energy) *final_energy = g;
-    free (state); free (since); free (h);
+    if (final_energy) *final_energy = grt / beta;
+    free (state); free (since); free (hb); free (wb);
     return 0;
 }

@@ -83,6 +83,14 @@ class MCModelDefault(object):
             pairs.append((a.value, b.value, w.value))
         return pairs
 
+    def LaunchPlan(self, nph=1):
+        """Launch geometry for ``nph`` pH values: dict(kernel, block, ctas_per_sm, chains_per_wave, smem_bytes)."""
+        self._requireOwner()
+        self._configure()
+        k, b, c, w, s = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0), C.c_longlong(0)
+        _native.check(self._lib.pce_mc_plan(self._handle, int(nph), C.byref(k), C.byref(b), C.byref(c), C.byref(w), C.byref(s)))
+        return dict(kernel=k.value, block=b.value, ctas_per_sm=c.value, chains_per_wave=w.value, smem_bytes=s.value)
+
     # ---- sampling -----------------------------------------------------------------------------------------
     def _requireOwner(self):
         if self.owner is None or not self._handle:

@@ -83,6 +83,7 @@ SIGNATURES = {
     "pce_mc_set_chains": (_int, [_void, _int]),
     "pce_mc_set_kernel": (_int, [_void, _int]),
     "pce_mc_get_info": (_int, [_void, _pint, _pint, _pint, _pint, _pll]),
+    "pce_mc_plan": (_int, [_void, _int, _pint, _pint, _pint, _pint, _pll]),
     "pce_mc_run": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void]),
     "pce_mc_run_device": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void]),
     "pce_mc_run_chains": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void, _void, _void]),

@@ -40,6 +40,8 @@ constexpr int kMaxOuter  = 96;    // max sites in O + F
 constexpr int kMaxMI     = 320;   // max instances in M + I sites
 constexpr long long kMaxChunks = 16384;
 
+constexpr int kTB = 4;            // tiles (outer configurations) processed per synchronisation round
+
 struct EnumParams {
     int nsites, ninst, ldw, unfolded;
     const double  *gt;          // tilted intrinsic energies G'[a] = G[a] - protons[a]*mu(pH*)
@@ -55,6 +57,11 @@ struct EnumParams {
     int16_t siteI[kMaxI], radI[kMaxI];
     int16_t siteOut[kMaxOuter], radOut[kMaxOuter];   // O sites first (fastest digit first), then F sites
     double *T;                  // [nchunks][Nb][kBlock] per-thread bins
+    // per-thread statics, computed once by k_enum_static: xs[(1 + kIStates) * kBlock] = xMM then xMI[i], coalesced;
+    // ms[3 * kBlock] = m_lo, m_hi, protons of the M configuration; shift = minMM + minMI
+    double  *xs;
+    int32_t *ms;
+    double  *shift;
 };
 
 __device__ __forceinline__ double block_min (double v, double *scratch) {
@@ -67,56 +74,17 @@ __device__ __forceinline__ double block_min (double v, double *scratch) {
     return r;
 }
 
-// One CTA per chunk (configuration of the F sites).  See the file header for the algorithm.
-__global__ void __launch_bounds__ (kBlock) k_enum (const EnumParams p) {
-    extern __shared__ __align__ (16) unsigned char smem[];
-    double *bins = (double *) smem;                          // [Nb][kBlock]
-    __shared__ double  s_gF[kMaxMI], s_gOut[kMaxMI];         // outer-site fields on the M/I instances
-    __shared__ double  s_eLo[kBlock], s_eHi[kBlock], s_eI[kIStates];
-    __shared__ int32_t s_instMI[kMaxMI];                     // compact list of the M and I instances
-    __shared__ int32_t s_offM[kMaxM + 1], s_offI[kMaxI + 1]; // start of each site in the compact list
-    __shared__ int32_t s_aOut[kMaxOuter];                    // active instance of every outer site
-    __shared__ int32_t s_nI[kIStates];                       // protons of each I configuration
-    __shared__ double  s_scratch[kBlock / 32];
-    __shared__ double  s_cOut, s_cExp, s_AF;
-    __shared__ int     s_nOut, s_nF;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nOuter = p.nO + p.nF, ldw = p.ldw;
-    const bool folded = !p.unfolded;
-    const long long chunk = p.chunk_begin + blockIdx.x;
-
-    // ---- static setup -------------------------------------------------------------------------
-    if (tid == 0) {
-        int o = 0;
-        for (int i = 0; i < p.nM; i++) { s_offM[i] = o; for (int k = 0; k < p.radM[i]; k++) s_instMI[o++] = p.first[p.siteM[i]] + k; }
-        s_offM[p.nM] = o;
-        for (int i = 0; i < p.nI; i++) { s_offI[i] = o; for (int k = 0; k < p.radI[i]; k++) s_instMI[o++] = p.first[p.siteI[i]] + k; }
-        s_offI[p.nI] = o;
-        // F digits of this chunk (F sites are the high digits of the outer odometer)
-        long long c = chunk;
-        for (int j = p.nO; j < nOuter; j++) { s_aOut[j] = p.first[p.siteOut[j]] + (int) (c % p.radOut[j]); c /= p.radOut[j]; }
-        for (int j = 0; j < p.nO; j++) s_aOut[j] = p.first[p.siteOut[j]];
-    }
-    for (int e = tid; e < p.Nb * kBlock; e += kBlock) bins[e] = 0.0;
-    __syncthreads ();
-    const int nMI = s_offI[p.nI];
-
-    // I configurations: protons and I-I interaction energy (same for all threads)
-    if (tid < p.P_I) {
-        int x = tid, np = 0;
-        for (int i = 0; i < p.nI; i++) { np += p.protons[s_instMI[s_offI[i] + x % p.radI[i]]]; x /= p.radI[i]; }
-        s_nI[tid] = np;
-    }
-
-    // this thread's M configuration
-    const bool mine = tid < p.P_M;
+// Static per-thread factors: they depend on the thread's M configuration only, so they are computed once per
+// enumeration (one CTA) instead of once per chunk.
+__global__ void __launch_bounds__ (kBlock) k_enum_static (const EnumParams p) {
+    __shared__ double s_scratch[kBlock / 32];
+    const int tid = threadIdx.x, ldw = p.ldw;
+    const bool folded = !p.unfolded, mine = tid < p.P_M;
     int    aM[kMaxM];
     int    m_lo = 0, m_hi = 0, nMp = 0;
     double eMM = 0.0;
     {
         int x = mine ? tid : 0, stride_lo = 1, stride_hi = 1;
-#pragma unroll
         for (int i = 0; i < kMaxM; i++) {
             aM[i] = 0;
             if (i < p.nM) {
@@ -127,187 +95,229 @@ __global__ void __launch_bounds__ (kBlock) k_enum (const EnumParams p) {
                 if (i < p.nLo) { m_lo += d * stride_lo; stride_lo *= p.radM[i]; } else { m_hi += d * stride_hi; stride_hi *= p.radM[i]; }
             }
         }
-        if (folded) {
-#pragma unroll
-            for (int i = 0; i < kMaxM; i++)
-#pragma unroll
-                for (int j = 0; j < kMaxM; j++)
-                    if (j < i && i < p.nM) eMM += p.w[(size_t) aM[i] * ldw + aM[j]];
-        }
+        if (folded)
+            for (int i = 0; i < p.nM; i++)
+                for (int j = 0; j < i; j++) eMM += p.w[(size_t) aM[i] * ldw + aM[j]];
     }
     // static cross terms E_MI(m,i) + E_II(i)
     double xMI[kIStates];
-#pragma unroll
     for (int i = 0; i < kIStates; i++) {
         double e = 0.0;
         if (i < p.P_I && folded) {
             int aI[kMaxI];
             int x = i;
-#pragma unroll
             for (int k = 0; k < kMaxI; k++) { aI[k] = 0; if (k < p.nI) { aI[k] = p.first[p.siteI[k]] + x % p.radI[k]; x /= p.radI[k]; } }
-#pragma unroll
-            for (int k = 0; k < kMaxI; k++) {
-                if (k < p.nI) {
-                    const double *row = p.w + (size_t) aI[k] * ldw;
-#pragma unroll
-                    for (int l = 0; l < kMaxI; l++) if (l < k) e += row[aI[l]];
-#pragma unroll
-                    for (int l = 0; l < kMaxM; l++) if (l < p.nM) e += row[aM[l]];
-                }
+            for (int k = 0; k < p.nI; k++) {
+                const double *row = p.w + (size_t) aI[k] * ldw;
+                for (int l = 0; l < k; l++) e += row[aI[l]];
+                for (int l = 0; l < p.nM; l++) e += row[aM[l]];
             }
         }
         xMI[i] = e;
     }
-    // normalise the static factors by their minima over all (m) and (m,i): every factor <= 1
-    {
-        double vmin = mine ? eMM : DBL_MAX;
-        const double minMM = block_min (vmin, s_scratch);
-        vmin = DBL_MAX;
-#pragma unroll
-        for (int i = 0; i < kIStates; i++) if (mine && i < p.P_I) vmin = fmin (vmin, xMI[i]);
-        const double minMI = block_min (vmin, s_scratch);
-        eMM = mine ? exp (-p.beta * (eMM - minMM)) : 0.0;
-#pragma unroll
-        for (int i = 0; i < kIStates; i++) xMI[i] = (mine && i < p.P_I) ? exp (-p.beta * (xMI[i] - minMI)) : 0.0;
-        if (tid == 0) s_AF = minMM + minMI;   // carried into cOut below (s_AF is completed next)
-    }
-    __syncthreads ();
+    // normalise by the minima over all (m) and (m,i): every factor <= 1; the minima go into the tile constant
+    double vmin = mine ? eMM : DBL_MAX;
+    const double minMM = block_min (vmin, s_scratch);
+    vmin = DBL_MAX;
+    for (int i = 0; i < kIStates; i++) if (mine && i < p.P_I) vmin = fmin (vmin, xMI[i]);
+    const double minMI = block_min (vmin, s_scratch);
+    p.xs[tid] = mine ? exp (-p.beta * (eMM - minMM)) : 0.0;
+    for (int i = 0; i < kIStates; i++) p.xs[(1 + i) * kBlock + tid] = (mine && i < p.P_I) ? exp (-p.beta * (xMI[i] - minMI)) : 0.0;
+    p.ms[tid] = m_lo; p.ms[kBlock + tid] = m_hi; p.ms[2 * kBlock + tid] = nMp;
+    if (tid == 0) *p.shift = minMM + minMI;
+}
 
-    // ---- per chunk: fields of the F sites on the M/I instances, F-F energy, F protons ------------
+// One CTA per chunk (configuration of the F sites).  See the file header for the algorithm.  Tiles (O
+// configurations) are processed kTB per round: fields and tables for kTB tiles are built between two barriers,
+// then every thread accumulates its kTB x P_I states.
+__global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
+    extern __shared__ __align__ (16) unsigned char smem[];
+    double *bins = (double *) smem;                          // [Nb][kBlock]
+    __shared__ double  s_gF[kMaxMI];                         // F-site fields on the M/I instances (per chunk)
+    __shared__ double  s_gOut[kTB][kMaxMI];                  // + O-site fields (per tile)
+    __shared__ double  s_eLo[kTB][kBlock], s_eHi[kTB][64], s_eI[kTB][kIStates];
+    __shared__ int32_t s_instMI[kMaxMI];                     // compact list of the M and I instances
+    __shared__ int32_t s_offM[kMaxM + 1], s_offI[kMaxI + 1]; // start of each site in the compact list
+    __shared__ int32_t s_aF[kMaxOuter];                      // active instance of every F site
+    __shared__ int32_t s_nI[kIStates];                       // protons of each I configuration
+    __shared__ double  s_cOut[kTB], s_cExp[kTB], s_AF;
+    __shared__ int     s_nOut[kTB], s_nF;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ldw = p.ldw;
+    const bool folded = !p.unfolded;
+    const long long chunk = p.chunk_begin + blockIdx.x;
+
+    // ---- setup -----------------------------------------------------------------------------------------
+    if (tid == 0) {
+        int o = 0;
+        for (int i = 0; i < p.nM; i++) { s_offM[i] = o; for (int k = 0; k < p.radM[i]; k++) s_instMI[o++] = p.first[p.siteM[i]] + k; }
+        s_offM[p.nM] = o;
+        for (int i = 0; i < p.nI; i++) { s_offI[i] = o; for (int k = 0; k < p.radI[i]; k++) s_instMI[o++] = p.first[p.siteI[i]] + k; }
+        s_offI[p.nI] = o;
+        long long c = chunk;                                 // F digits of this chunk
+        for (int j = 0; j < p.nF; j++) { s_aF[j] = p.first[p.siteOut[p.nO + j]] + (int) (c % p.radOut[p.nO + j]); c /= p.radOut[p.nO + j]; }
+    }
+    for (int e = tid; e < p.Nb * kBlock; e += kBlock) bins[e] = 0.0;
+    __syncthreads ();
+    const int nMI = s_offI[p.nI];
+    if (tid < p.P_I) {
+        int x = tid, np = 0;
+        for (int i = 0; i < p.nI; i++) { np += p.protons[s_instMI[s_offI[i] + x % p.radI[i]]]; x /= p.radI[i]; }
+        s_nI[tid] = np;
+    }
+    // this thread's statics
+    const bool mine = tid < p.P_M;
+    const double eMM = p.xs[tid];
+    double xMI[kIStates];
+#pragma unroll
+    for (int i = 0; i < kIStates; i++) xMI[i] = p.xs[(1 + i) * kBlock + tid];
+    const int m_lo = p.ms[tid], m_hi = p.ms[kBlock + tid], nMp = p.ms[2 * kBlock + tid];
+    const double static_shift = *p.shift;
+
+    // per chunk: fields of the F sites on the M/I instances, F-F energy, F protons
     for (int j = tid; j < nMI; j += kBlock) {
         const int a = s_instMI[j];
         double acc = p.gt[a];
-        if (folded) for (int f = p.nO; f < nOuter; f++) acc += p.w[(size_t) a * ldw + s_aOut[f]];
+        if (folded) for (int f = 0; f < p.nF; f++) acc += p.w[(size_t) a * ldw + s_aF[f]];
         s_gF[j] = acc;
     }
     if (warp == kBlock / 32 - 1) {
         double e = 0.0;
         int    np = 0;
-        for (int f = p.nO + lane; f < nOuter; f += 32) {
-            const int a = s_aOut[f];
+        for (int f = lane; f < p.nF; f += 32) {
+            const int a = s_aF[f];
             e += p.gt[a];
             np += p.protons[a];
-            if (folded) for (int f2 = p.nO; f2 < f; f2++) e += p.w[(size_t) a * ldw + s_aOut[f2]];
+            if (folded) for (int f2 = 0; f2 < f; f2++) e += p.w[(size_t) a * ldw + s_aF[f2]];
         }
         e = pce::warp_sum (e);
         for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
-        if (lane == 0) { s_AF += e; s_nF = np; }
+        if (lane == 0) { s_AF = static_shift + e; s_nF = np; }
     }
     __syncthreads ();
 
-    // ---- tiles ---------------------------------------------------------------------------------------
-    for (long long tile = 0; tile < p.P_O; tile++) {
-        // (a) fields of the O sites on the M/I instances; (b) O energy incl. O-F cross terms, O protons
-        for (int j = tid; j < nMI; j += kBlock) {
+    // ---- rounds of kTB tiles ---------------------------------------------------------------------------
+    for (long long tile0 = 0; tile0 < p.P_O; tile0 += kTB) {
+        // (a) O-site fields on the M/I instances: thread (tb, j) decodes the O digits of tile tb on the fly
+        for (int e = tid; e < kTB * nMI; e += kBlock) {
+            const int tb = e / nMI, j = e - tb * nMI;
             const int a = s_instMI[j];
             double acc = s_gF[j];
-            if (folded) for (int o = 0; o < p.nO; o++) acc += p.w[(size_t) a * ldw + s_aOut[o]];
-            s_gOut[j] = acc;
+            if (folded) {
+                unsigned x = (unsigned) (tile0 + tb);
+                const double *row = p.w + (size_t) a * ldw;
+                for (int o = 0; o < p.nO; o++) {
+                    const unsigned r = (unsigned) p.radOut[o], d = x % r;
+                    x /= r;
+                    acc += row[p.first[p.siteOut[o]] + (int) d];
+                }
+            }
+            s_gOut[tb][j] = acc;
         }
-        if (warp == kBlock / 32 - 1) {
+        // (b) O energy incl. O-O and O-F terms, O protons: warp (7 - tb) takes tile tb, lanes over O sites
+        if (warp >= kBlock / 32 - kTB) {
+            const int tb = kBlock / 32 - 1 - warp;
             double e = 0.0;
             int    np = 0;
-            for (int o = lane; o < p.nO; o += 32) {
-                const int a = s_aOut[o];
-                e += p.gt[a];
-                np += p.protons[a];
-                if (folded) {
-                    const double *row = p.w + (size_t) a * ldw;
-                    for (int o2 = 0; o2 < o; o2++) e += row[s_aOut[o2]];
-                    for (int f = p.nO; f < nOuter; f++) e += row[s_aOut[f]];
+            if (tile0 + tb < p.P_O) {
+                for (int o = lane; o < p.nO; o += 32) {
+                    // digits of the sites below o are needed for the O-O terms: decode from the start
+                    unsigned x = (unsigned) (tile0 + tb);
+                    int a = 0;
+                    double eo = 0.0;
+                    const double *row = nullptr;
+                    // first pass: find this lane's own instance
+                    unsigned y = x;
+                    for (int o2 = 0; o2 <= o; o2++) { const unsigned r = (unsigned) p.radOut[o2]; a = p.first[p.siteOut[o2]] + (int) (y % r); y /= r; }
+                    row = p.w + (size_t) a * ldw;
+                    eo = p.gt[a];
+                    np += p.protons[a];
+                    if (folded) {
+                        for (int o2 = 0; o2 < o; o2++) { const unsigned r = (unsigned) p.radOut[o2]; eo += row[p.first[p.siteOut[o2]] + (int) (x % r)]; x /= r; }
+                        for (int f = 0; f < p.nF; f++) eo += row[s_aF[f]];
+                    }
+                    e += eo;
                 }
             }
             e = pce::warp_sum (e);
             for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
-            if (lane == 0) { s_cOut = s_AF + e; s_nOut = s_nF + np; }
+            if (lane == 0) { s_cOut[tb] = s_AF + e; s_nOut[tb] = s_nF + np; }
         }
         __syncthreads ();
 
-        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the
-        // per-site minima, so every table thread can normalise its own entry.
-        double min_lo = 0.0, min_hi = 0.0, min_i = 0.0;
+        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the per-site
+        // minima, so every table thread normalises its own entry.  Work items: kTB x (P_lo + P_hi + P_I + 1).
         {
-            // only the threads that need them evaluate the minima
-            const bool need = tid < p.P_lo || (tid >= 64 && tid < 64 + p.P_hi) || (tid >= 128 && tid < 128 + p.P_I) || tid == kBlock - 1;
-            if (need) {
-                for (int i = 0; i < p.nM; i++) {
-                    double v = DBL_MAX;
-                    for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, s_gOut[j]);
-                    if (i < p.nLo) min_lo += v; else min_hi += v;
-                }
-                for (int i = 0; i < p.nI; i++) {
-                    double v = DBL_MAX;
-                    for (int j = s_offI[i]; j < s_offI[i + 1]; j++) v = fmin (v, s_gOut[j]);
-                    min_i += v;
+            const int per_tile = p.P_lo + p.P_hi + p.P_I + 1;
+            for (int e = tid; e < kTB * per_tile; e += kBlock) {
+                const int tb = e / per_tile, x = e - tb * per_tile;
+                const double *g = s_gOut[tb];
+                double min_lo = 0.0, min_hi = 0.0, min_i = 0.0;
+                const bool is_lo = x < p.P_lo, is_hi = !is_lo && x < p.P_lo + p.P_hi, is_i = !is_lo && !is_hi && x < per_tile - 1;
+                const bool is_c = x == per_tile - 1;
+                if (is_lo || is_c) for (int i = 0; i < p.nLo; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_lo += v; }
+                if (is_hi || is_c) for (int i = p.nLo; i < p.nM; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_hi += v; }
+                if (is_i || is_c) for (int i = 0; i < p.nI; i++) { double v = DBL_MAX; for (int j = s_offI[i]; j < s_offI[i + 1]; j++) v = fmin (v, g[j]); min_i += v; }
+                if (is_lo) {
+                    int y = x;
+                    double s = 0.0;
+                    for (int i = 0; i < p.nLo; i++) { s += g[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
+                    s_eLo[tb][x] = exp (-p.beta * (s - min_lo));
+                } else if (is_hi) {
+                    int y = x - p.P_lo;
+                    double s = 0.0;
+                    for (int i = p.nLo; i < p.nM; i++) { s += g[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
+                    s_eHi[tb][x - p.P_lo] = exp (-p.beta * (s - min_hi));
+                } else if (is_i) {
+                    int y = x - p.P_lo - p.P_hi;
+                    double s = 0.0;
+                    for (int i = 0; i < p.nI; i++) { s += g[s_offI[i] + y % p.radI[i]]; y /= p.radI[i]; }
+                    s_eI[tb][x - p.P_lo - p.P_hi] = exp (-p.beta * (s - min_i));
+                } else {
+                    s_cExp[tb] = (tile0 + tb < p.P_O) ? exp (-p.beta * ((s_cOut[tb] + min_lo + min_hi + min_i) - p.gref)) : 0.0;
                 }
             }
         }
-        // Lo entries by threads [0, P_lo), Hi by [64, 64+P_hi) or a strided loop when the tables are large
-        for (int x = tid; x < p.P_lo; x += kBlock) {
-            int y = x;
-            double s = 0.0;
-            for (int i = 0; i < p.nLo; i++) { s += s_gOut[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
-            s_eLo[x] = exp (-p.beta * (s - min_lo));
-        }
-        if (tid >= 64 && tid < 64 + p.P_hi) {          // P_hi <= 64 by construction of the Lo/Hi split
-            int y = tid - 64;
-            double s = 0.0;
-            for (int i = p.nLo; i < p.nM; i++) { s += s_gOut[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
-            s_eHi[tid - 64] = exp (-p.beta * (s - min_hi));
-        }
-        if (tid >= 128 && tid < 128 + p.P_I) {
-            int y = tid - 128;
-            double s = 0.0;
-            for (int i = 0; i < p.nI; i++) { s += s_gOut[s_offI[i] + y % p.radI[i]]; y /= p.radI[i]; }
-            s_eI[tid - 128] = exp (-p.beta * (s - min_i));
-        }
-        if (tid == kBlock - 1) s_cExp = exp (-p.beta * ((s_cOut + min_lo + min_hi + min_i) - p.gref));
         __syncthreads ();
 
-        // (f) accumulate this thread's P_I states of the tile into its proton-count bins
+        // (f) accumulate this thread's kTB x P_I states into its proton-count bins
         if (mine) {
-            const double c_tile = s_cExp * s_eLo[m_lo] * s_eHi[m_hi] * eMM;
-            double *mybins = bins + (size_t) (s_nOut + nMp) * kBlock + tid;
 #pragma unroll
-            for (int i = 0; i < kIStates; i++) {
-                if (i < p.P_I) {
-                    const double b = c_tile * (s_eI[i] * xMI[i]);
-                    mybins[(size_t) s_nI[i] * kBlock] += b;
+            for (int tb = 0; tb < kTB; tb++) {
+                const double c_tile = s_cExp[tb] * s_eLo[tb][m_lo] * s_eHi[tb][m_hi] * eMM;
+                double *mybins = bins + (s_nOut[tb] + nMp) * kBlock + tid;
+#pragma unroll
+                for (int i = 0; i < kIStates; i++) {
+                    if (i < p.P_I) mybins[s_nI[i] * kBlock] += c_tile * (s_eI[tb][i] * xMI[i]);
                 }
-            }
-        }
-        __syncthreads ();
-        // (g) next O configuration
-        if (tid == 0) {
-            for (int o = 0; o < p.nO; o++) {
-                const int f = p.first[p.siteOut[o]];
-                if (s_aOut[o] - f + 1 < p.radOut[o]) { s_aOut[o]++; break; }
-                s_aOut[o] = f;
             }
         }
         __syncthreads ();
     }
 
-    // ---- flush ---------------------------------------------------------------------------------------
+    // ---- flush -------------------------------------------------------------------------------------------
     double *out = p.T + (size_t) blockIdx.x * p.Nb * kBlock;
     for (int e = tid; e < p.Nb * kBlock; e += kBlock) out[e] = bins[e];
 }
 
-// Mtab[n][tid] = sum over chunks of T[chunk][n][tid]; one thread per (n, tid), chunks in order (deterministic)
-__global__ void k_reduce_chunks (const double *__restrict__ T, long long nchunks, int Nb, double *__restrict__ Mtab) {
+// out[e] = sum over c < count of in[c * stride + e] for the slice of c owned by blockIdx.y (deterministic order);
+// used twice: chunks -> segments -> one table
+__global__ void k_reduce_rows (const double *__restrict__ in, long long count, int width, int per_segment, double *__restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= Nb * kBlock) return;
+    if (e >= width) return;
+    const long long c0 = (long long) blockIdx.y * per_segment;
+    const long long c1 = c0 + per_segment < count ? c0 + per_segment : count;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    const size_t stride = (size_t) Nb * kBlock;
-    long long c = 0;
-    for (; c + 3 < nchunks; c += 4) {
-        a0 += T[(size_t) c * stride + e];
-        a1 += T[(size_t) (c + 1) * stride + e];
-        a2 += T[(size_t) (c + 2) * stride + e];
-        a3 += T[(size_t) (c + 3) * stride + e];
+    long long c = c0;
+    for (; c + 3 < c1; c += 4) {
+        a0 += in[(size_t) c * width + e];
+        a1 += in[(size_t) (c + 1) * width + e];
+        a2 += in[(size_t) (c + 2) * width + e];
+        a3 += in[(size_t) (c + 3) * width + e];
     }
-    for (; c < nchunks; c++) a0 += T[(size_t) c * stride + e];
-    Mtab[e] = (a0 + a1) + (a2 + a3);
+    for (; c < c1; c++) a0 += in[(size_t) c * width + e];
+    out[(size_t) blockIdx.y * width + e] = (a0 + a1) + (a2 + a3);
 }
 
 // Ftab[chunk][n] = sum over threads of T[chunk][n][tid]; one warp per (chunk, n)
@@ -367,8 +377,9 @@ __global__ void k_marginals (const MarginalParams p) {
         if (b < p.radF[j]) {
             if (!p.coverF[j]) return;
             double acc = 0.0;
-            for (long long c = 0; c < p.nchunks; c++)
-                if (((p.chunk_begin + c) / stride) % p.radF[j] == b) acc += p.Ftab[(size_t) c * p.Nb + n];
+            const unsigned st = (unsigned) stride, rad = (unsigned) p.radF[j], base = (unsigned) p.chunk_begin;
+            for (unsigned c = 0; c < (unsigned) p.nchunks; c++)
+                if (((base + c) / st) % rad == (unsigned) b) acc += p.Ftab[(size_t) c * p.Nb + n];
             p.bins[(size_t) (1 + p.first[p.siteF[j]] + b) * p.Nb + n] += acc;
             return;
         }
@@ -524,7 +535,9 @@ int make_plan (const pce_model *m, const double *ph, int nph, int unfolded, Plan
 int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshards, double *d_bins) {
     const size_t nbins_total = (size_t) (1 + m->ninst) * plan.Nb;
     PCE_CUDA (cudaMemsetAsync (d_bins, 0, nbins_total * sizeof (double), m->stream));
-    pce::DeviceBuffer<double> d_gt, d_T, d_Mtab, d_Ftab;
+    // scratch lives in the model (grow-only): repeated curves do not pay cudaMalloc/cudaFree of ~1 GB
+    pce::DeviceBuffer<double> &d_gt = m->s_gt, &d_T = m->s_T, &d_Mtab = m->s_Mtab, &d_Ftab = m->s_Ftab, &d_seg = m->s_seg, &d_xs = m->s_xs;
+    pce::DeviceBuffer<int32_t> &d_ms = m->s_ms;
     PCE_CUDA (d_gt.resize (m->ninst));
     const double mu_star = pce::mu_of (m->temperature, plan.ph_star);
     k_tilt<<<(m->ninst + 127) / 128, 128, 0, m->stream>>> (m->ninst, unfolded ? m->d_gmodel.ptr : m->d_gintr.ptr, m->d_protons.ptr, mu_star, d_gt.ptr);
@@ -563,15 +576,25 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
             PCE_CUDA (cudaDeviceGetAttribute (&value, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
             limit = (size_t) value;
         }
-        if (smem + 12 * 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
-        PCE_CUDA (d_T.resize ((size_t) p.nchunks * plan.Nb * kBlock));
-        PCE_CUDA (d_Mtab.resize ((size_t) plan.Nb * kBlock));
+        if (smem + 24 * 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
+        const int width = plan.Nb * kBlock;
+        const int per_segment = 64;
+        const int nseg = (int) ((p.nchunks + per_segment - 1) / per_segment);
+        PCE_CUDA (d_T.resize ((size_t) p.nchunks * width));
+        PCE_CUDA (d_seg.resize ((size_t) nseg * width));
+        PCE_CUDA (d_Mtab.resize ((size_t) width));
         PCE_CUDA (d_Ftab.resize ((size_t) p.nchunks * plan.Nb));
-        p.T = d_T.ptr;
+        PCE_CUDA (d_xs.resize ((size_t) (1 + kIStates) * kBlock + 1));
+        PCE_CUDA (d_ms.resize ((size_t) 3 * kBlock));
+        p.T = d_T.ptr; p.xs = d_xs.ptr; p.ms = d_ms.ptr; p.shift = d_xs.ptr + (size_t) (1 + kIStates) * kBlock;
+        k_enum_static<<<1, kBlock, 0, m->stream>>> (p);
+        PCE_CUDA (cudaGetLastError ());
         PCE_CUDA (cudaFuncSetAttribute (k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         k_enum<<<(unsigned) p.nchunks, kBlock, smem, m->stream>>> (p);
         PCE_CUDA (cudaGetLastError ());
-        k_reduce_chunks<<<(plan.Nb * kBlock + 127) / 128, 128, 0, m->stream>>> (d_T.ptr, p.nchunks, plan.Nb, d_Mtab.ptr);
+        k_reduce_rows<<<dim3 ((width + 127) / 128, nseg), 128, 0, m->stream>>> (d_T.ptr, p.nchunks, width, per_segment, d_seg.ptr);
+        PCE_CUDA (cudaGetLastError ());
+        k_reduce_rows<<<dim3 ((width + 127) / 128, 1), 128, 0, m->stream>>> (d_seg.ptr, nseg, width, nseg, d_Mtab.ptr);
         PCE_CUDA (cudaGetLastError ());
         {
             const long long warps = p.nchunks * plan.Nb;
@@ -590,10 +613,9 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         const int threads = (plan.Nb + 31) & ~31;
         k_marginals<<<rows, threads, 0, m->stream>>> (mp);
         PCE_CUDA (cudaGetLastError ());
-        pce::count_launch (4);
+        pce::count_launch (6);
     }
-    cudaError_t err = cudaStreamSynchronize (m->stream);   // scratch buffers are released below
-    d_gt.release (); d_T.release (); d_Mtab.release (); d_Ftab.release ();
+    cudaError_t err = cudaStreamSynchronize (m->stream);
     if (err != cudaSuccess) return fail (PCE_ERR_CUDA, std::string ("analytic enumeration: ") + cudaGetErrorString (err));
     return status;
 }

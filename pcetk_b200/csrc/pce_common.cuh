@@ -67,7 +67,11 @@ struct pce_model {
     // device mirror
     int ldw = 0;                               // row stride of d_w in doubles (multiple of 4)
     pce::DeviceBuffer<int32_t> d_first, d_nsite_inst, d_site_of_inst, d_protons;
-    pce::DeviceBuffer<double>  d_gintr, d_gmodel, d_w;
+    pce::DeviceBuffer<double>  d_gintr, d_gmodel, d_w, d_wb;   // d_wb = W / (R T), for the Monte Carlo kernels
+
+    // scratch of the enumeration kernel (grow-only)
+    pce::DeviceBuffer<double>  s_gt, s_T, s_Mtab, s_Ftab, s_seg, s_xs;
+    pce::DeviceBuffer<int32_t> s_ms;
 
     int  sites_ok () const;                    // PCE_OK when every site is set, contiguous and ascending
     int  upload ();

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "pce_common.cuh"
@@ -45,7 +46,7 @@ namespace {
 struct McParams {
     int nsites, ninst, npairs, ldw;
     const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
-    const double  *gintr, *w, *ph;
+    const double  *gintr, *w, *wb, *ph;      // wb = beta * W (units of RT)
     int       nph, ph_index_offset, nchains, nequil, nprod;
     long long chain_offset;
     uint32_t  k0, k1;
@@ -64,22 +65,21 @@ struct McParams {
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
 struct ThreadLayout {
-    size_t off_w, off_h, off_gintr, off_counts, off_since, off_first, off_nsi, off_prot, off_pa, off_pb, off_state, total;
-    int    hstride, ldws;
-    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int block, int w_in_smem) {
+    size_t off_w, off_h, off_counts, off_since, off_site, off_pair, off_state, total;
+    int    hstride, ldws, kslots;
+    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int block, int w_in_smem, int nchains, int nph) {
         hstride = ninst | 1;                       // odd: lanes of a warp fall on distinct bank pairs
         ldws    = ninst | 1;
+        // a block covers `block` consecutive (pH, chain) pairs of the chain-major grid: at most kslots pH values
+        kslots = (block - 1) / (nchains > 0 ? nchains : 1) + 2;
+        if (kslots > nph) kslots = nph;
         size_t o = 0;
         off_w = o;      o += w_in_smem ? (size_t) ninst * ldws * 8 : 0;
         off_h = o;      o += (size_t) block * hstride * 8;
-        off_gintr = o;  o += (size_t) ninst * 8;
-        off_counts = o; o += (size_t) ninst * 8;
+        off_counts = o; o += (size_t) kslots * ninst * 8;
         off_since = o;  o += (size_t) nsites * block * 4;
-        off_first = o;  o += (size_t) nsites * 4;
-        off_nsi = o;    o += (size_t) nsites * 4;
-        off_prot = o;   o += (size_t) ninst * 4;
-        off_pa = o;     o += (size_t) (npairs > 0 ? npairs : 1) * 4;
-        off_pb = o;     o += (size_t) (npairs > 0 ? npairs : 1) * 4;
+        off_site = o;   o += (size_t) nsites * 4;
+        off_pair = o;   o += (size_t) (npairs > 0 ? npairs : 1) * 4;
         off_state = o;  o += (size_t) nsites * block;
         total = (o + 15) & ~(size_t) 15;
     }
@@ -90,8 +90,8 @@ __device__ __forceinline__ double ph_to_mu (double temperature, double ph) {
     return __dmul_rn (__dmul_rn (__dmul_rn (-PCE_R, temperature), PCE_LN10), ph);
 }
 
-// MCModelDefault_Metropolis (MCModelDefault.c:71-85).  The fp32 exp only screens: whenever it cannot
-// decide with a 1e-3 relative margin the fp64 exp is evaluated, so the decision equals u < exp(-x).
+// MCModelDefault_Metropolis (MCModelDefault.c:71-85) on x = dG/RT.  The fp32 exp only screens: whenever it
+// cannot decide with a 1e-3 relative margin the fp64 exp is evaluated, so the decision equals u < exp(-x).
 __device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
     if (x < 0.0) return true;
     if (-x < PCE_TOO_SMALL) return false;
@@ -103,45 +103,49 @@ __device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_mc_thread
+// k_mc_thread.  The (pH, chain) grid is linearised chain-major (g = q*nchains + chain) and cut into blocks
+// of blockDim.x threads, so the grid can be sized to whole waves whatever nchains is; every thread carries
+// its own pH.  Energies are in units of RT and the intrinsic term is fused into the cached fields, so a
+// proposal is two shared-memory loads and one subtraction.  Trials are processed two per Philox block, with
+// the next block generated ahead of the dependent proposal -> accept -> update chain.
 // ---------------------------------------------------------------------------------------------------
-template <bool PER_CHAIN>
-__global__ void __launch_bounds__ (256) k_mc_thread (const McParams p) {
+template <bool PER_CHAIN, bool W_SMEM>
+__global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
-    const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, p.w_in_smem);
+    const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, W_SMEM ? 1 : 0, p.nchains, p.nph);
     double             *s_w      = (double *) (smem + L.off_w);
     double             *s_h      = (double *) (smem + L.off_h);
-    double             *s_gintr  = (double *) (smem + L.off_gintr);
     unsigned long long *s_counts = (unsigned long long *) (smem + L.off_counts);
     uint32_t           *s_since  = (uint32_t *) (smem + L.off_since);
-    int32_t            *s_first  = (int32_t *) (smem + L.off_first);
-    int32_t            *s_nsi    = (int32_t *) (smem + L.off_nsi);
-    int32_t            *s_prot   = (int32_t *) (smem + L.off_prot);
-    int32_t            *s_pa     = (int32_t *) (smem + L.off_pa);
-    int32_t            *s_pb     = (int32_t *) (smem + L.off_pb);
+    uint32_t           *s_site   = (uint32_t *) (smem + L.off_site);      // first | ninst << 16
+    uint32_t           *s_pair   = (uint32_t *) (smem + L.off_pair);      // site a | site b << 16
     uint8_t            *s_state  = smem + L.off_state;
 
     const int nsites = p.nsites, ninst = p.ninst;
-    const int blocks_per_ph = (p.nchains + B - 1) / B;
-    const int q     = blockIdx.x / blocks_per_ph;                 // pH point of this block
-    const int local = (blockIdx.x % blocks_per_ph) * B + tid;     // chain within this launch
-    const bool active = local < p.nchains;
+    const long long total = (long long) p.nph * p.nchains;
+    const long long g0    = (long long) blockIdx.x * B;             // first (pH, chain) pair of this block
+    const long long gidx  = g0 + tid;
+    const bool active = gidx < total;
+    const long long gclamped = active ? gidx : total - 1;
+    const int q      = (int) (gclamped / p.nchains);                 // pH point of this thread
+    const int local  = (int) (gclamped % p.nchains);                 // chain within this launch
+    const int q_base = (int) (g0 / p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
+    unsigned long long *my_counts = s_counts + (size_t) (q - q_base) * ninst;
+    uint8_t  *my_state = s_state + tid;
+    uint32_t *my_since = s_since + tid;
+    long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
 
-    // stage the model
-    const double *wrow_base;
-    int           wld;
-    if (p.w_in_smem) {
-        for (int e = tid; e < ninst * ninst; e += B) s_w[(e / ninst) * L.ldws + (e % ninst)] = p.w[(size_t) (e / ninst) * p.ldw + (e % ninst)];
-        wrow_base = s_w; wld = L.ldws;
-    } else {
-        wrow_base = p.w; wld = p.ldw;
-    }
-    for (int k = tid; k < ninst; k += B) { s_gintr[k] = p.gintr[k]; s_prot[k] = p.protons[k]; s_counts[k] = 0ull; }
-    for (int i = tid; i < nsites; i += B) { s_first[i] = p.first[i]; s_nsi[i] = p.nsi[i]; }
-    for (int i = tid; i < p.npairs; i += B) { s_pa[i] = p.pair_a[i]; s_pb[i] = p.pair_b[i]; }
+    // stage the model: beta-scaled W, packed site and pair tables
+    if (W_SMEM)
+        for (int e = tid; e < ninst * ninst; e += B) s_w[(e / ninst) * L.ldws + (e % ninst)] = p.wb[(size_t) (e / ninst) * p.ldw + (e % ninst)];
+    const double *wbase = W_SMEM ? s_w : p.wb;
+    const int     wld   = W_SMEM ? L.ldws : p.ldw;
+    for (int k = tid; k < L.kslots * ninst; k += B) s_counts[k] = 0ull;
+    for (int i = tid; i < nsites; i += B) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
+    for (int i = tid; i < p.npairs; i += B) s_pair[i] = (uint32_t) p.pair_a[i] | ((uint32_t) p.pair_b[i] << 16);
 
     // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i)
     {
@@ -149,152 +153,175 @@ __global__ void __launch_bounds__ (256) k_mc_thread (const McParams p) {
         for (int i = 0; i < nsites; i++) {
             if ((i & 3) == 0) r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
             const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-            const int f = p.first[i], n = p.nsi[i];
-            s_state[i * B + tid] = (uint8_t) (f + (int) __umulhi (word, (uint32_t) n));
-            s_since[i * B + tid] = 0u;
+            my_state[i * B] = (uint8_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
+            my_since[i * B] = 0u;
         }
     }
     __syncthreads ();
 
-    // fields, cooperatively: for each chain c of this warp, lanes over k, j sequential (spec order)
+    const double mu   = ph_to_mu (p.temperature, p.ph[q]);
+    const double beta = 1.0 / (PCE_R * p.temperature);
+
+    // fused fields, cooperatively: for each chain c of this warp, lanes over k; hb[k] = gtb[k] + sum_j wb[k][a_j]
+    // with j sequential (spec order).  mu differs per chain (per-thread pH): broadcast it.
     for (int c = 0; c < 32; c++) {
+        const double mu_c = __shfl_sync (0xffffffffu, mu, c);
         double *hc = s_h + (size_t) (warp_base + c) * L.hstride;
+        const uint8_t *sc = s_state + warp_base + c;
         for (int k = lane; k < ninst; k += 32) {
-            const double *row = wrow_base + (size_t) k * wld;
-            double acc = 0.0;
-            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, row[s_state[j * B + warp_base + c]]);
+            const double *row = wbase + (size_t) k * wld;
+            double acc = __dmul_rn (beta, __dsub_rn (p.gintr[k], __dmul_rn ((double) p.protons[k], mu_c)));
+            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, row[sc[j * B]]);
             hc[k] = acc;
         }
     }
     __syncwarp ();
-
-    const double mu   = ph_to_mu (p.temperature, p.ph[q]);
-    const double beta = 1.0 / (PCE_R * p.temperature);
     double *myh = s_h + (size_t) tid * L.hstride;
 
-    // initial energy in the reference's order (EnergyModel.c:204-224)
-    double g;
+    // initial energy in the reference's order (EnergyModel.c:204-224), then to units of RT
+    double grt;
     {
         double gi = 0.0, ws = 0.0;
         int    np = 0;
         for (int i = 0; i < nsites; i++) {
-            const int ai = s_state[i * B + tid];
-            gi = __dadd_rn (gi, s_gintr[ai]);
-            np += s_prot[ai];
-            const double *row = wrow_base + (size_t) ai * wld;
-            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[s_state[j * B + tid]]);
+            const int ai = my_state[i * B];
+            gi = __dadd_rn (gi, p.gintr[ai]);
+            np += p.protons[ai];
+            const double *row = p.w + (size_t) ai * p.ldw;
+            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[my_state[j * B]]);
         }
-        g = __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws);
+        grt = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
     }
 
     const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
-    const long long nscans = (long long) p.nequil + p.nprod;
-    unsigned long long t = 0;
-    uint32_t c_moves = 0, c_macc = 0, c_flips = 0, c_facc = 0;
+    const unsigned long long ntrials = (unsigned long long) ((long long) p.nequil + p.nprod) * nmoves;
+    uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
     double   esum = 0.0;
-    pce::Philox4 r = { 0, 0, 0, 0 };
+    long long scan = 0;
+    uint32_t  mv = 0, tp = 0;
+    bool      production = p.nequil == 0;
 
-    for (long long scan = 0; scan < nscans; scan++) {
-        const bool     production = scan >= p.nequil;
-        const uint32_t tp = production ? (uint32_t) (scan - p.nequil) : 0u;
-        for (uint32_t mv = 0; mv < nmoves; mv++, t++) {
-            uint32_t w0, w1;
-            if ((t & 1ull) == 0ull) {
-                const unsigned long long b = t >> 1;
-                r = pce::philox4x32_10 ((uint32_t) b, (uint32_t) (b >> 32), chain, phidx, p.k0, p.k1);
-                w0 = r.x; w1 = r.y;
-            } else {
-                w0 = r.z; w1 = r.w;
-            }
-            // proposal
-            const uint32_t idx = __umulhi (w0, nmoves);
-            const uint32_t lo  = w0 * nmoves;
-            const bool     dbl = idx >= (uint32_t) nsites;
-            int sa, sb = 0;
-            if (dbl) { sa = s_pa[idx - nsites]; sb = s_pb[idx - nsites]; } else { sa = (int) idx; }
-            const int na = s_nsi[sa], oa = s_state[sa * B + tid];
-            bool valid = active && na >= 2;
-            const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
+    // one trial: proposal from (w0), Metropolis with (w1), cooperative application of accepted moves
+    auto trial = [&] (const uint32_t w0, const uint32_t w1) {
+        const uint32_t idx = __umulhi (w0, nmoves);
+        const uint32_t lo  = w0 * nmoves;
+        const bool     dbl = idx >= (uint32_t) nsites;
+        const uint32_t pr  = dbl ? s_pair[idx - nsites] : idx;
+        const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
+        const uint32_t ia_info = s_site[sa];
+        const int na = (int) (ia_info >> 16), oa = my_state[sa * B];
+        bool valid = active && na >= 2;
+        const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
+        int ia = (int) (ia_info & 0xffffu) + (int) ka;
+        if (ia >= oa) ia++;
+        if (!valid) ia = oa;
+        double x = __dsub_rn (myh[ia], myh[oa]);
+        int ib = 0, ob = 0;
+        if (dbl) {
             const uint32_t lo2 = lo * (uint32_t) (na - 1);
-            int ia = s_first[sa] + (int) ka;
-            if (ia >= oa) ia++;
-            if (!valid) ia = oa;
-            double dgintr = __dsub_rn (s_gintr[ia], s_gintr[oa]);
-            int    dprot  = s_prot[ia] - s_prot[oa];
-            double dw     = __dsub_rn (myh[ia], myh[oa]);
-            int ib = 0, ob = 0;
-            if (dbl) {
-                const int nb = s_nsi[sb];
-                ob = s_state[sb * B + tid];
-                if (nb < 2) valid = false;
-                const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
-                ib = s_first[sb] + (int) kb;
-                if (ib >= ob) ib++;
-                if (!valid) { ib = ob; ia = oa; }
-                dgintr = __dadd_rn (dgintr, __dsub_rn (s_gintr[ib], s_gintr[ob]));
-                dprot += s_prot[ib] - s_prot[ob];
-                const double *ra = wrow_base + (size_t) ia * wld, *ro = wrow_base + (size_t) oa * wld;
-                const double cross = __dadd_rn (__dsub_rn (__dsub_rn (ra[ib], ra[ob]), ro[ib]), ro[ob]);
-                dw = __dadd_rn (__dadd_rn (dw, __dsub_rn (myh[ib], myh[ob])), cross);
-            }
-            const double dg = __dadd_rn (__dsub_rn (dgintr, __dmul_rn ((double) dprot, mu)), dw);
-            const bool accept = valid && metropolis (__dmul_rn (dg, beta), w1);
-            if (production && active) { if (dbl) c_flips++; else c_moves++; }
+            const uint32_t ib_info = s_site[sb];
+            const int nb = (int) (ib_info >> 16);
+            ob = my_state[sb * B];
+            if (nb < 2) valid = false;
+            const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
+            ib = (int) (ib_info & 0xffffu) + (int) kb;
+            if (ib >= ob) ib++;
+            if (!valid) { ib = ob; ia = oa; }
+            const double *ra = wbase + ia * wld, *ro = wbase + oa * wld;
+            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (ra[ib], ra[ob]), ro[ib]), ro[ob]);
+            x = __dadd_rn (__dadd_rn (x, __dsub_rn (myh[ib], myh[ob])), cross);
+            if (production) c_flips++;
+        }
+        const bool accept = valid && metropolis (x, w1);
 
-            // apply accepted moves: one accepting chain at a time, all 32 lanes on its field vector
-            unsigned pending = __ballot_sync (0xffffffffu, accept);
-            while (pending) {
+        // apply accepted moves: one accepting chain at a time, all 32 lanes on its field vector
+        unsigned pending = __ballot_sync (0xffffffffu, accept);
+        if (pending) {
+            const unsigned dblmask = __ballot_sync (0xffffffffu, accept && dbl);
+            const uint32_t packed = (uint32_t) ia | ((uint32_t) oa << 8) | ((uint32_t) ib << 16) | ((uint32_t) ob << 24);
+            do {
                 const int src = __ffs (pending) - 1;
                 pending &= pending - 1;
-                const int  xia = __shfl_sync (0xffffffffu, ia, src), xoa = __shfl_sync (0xffffffffu, oa, src);
-                const int  xib = __shfl_sync (0xffffffffu, ib, src), xob = __shfl_sync (0xffffffffu, ob, src);
-                const bool xdb = __shfl_sync (0xffffffffu, (int) dbl, src) != 0;
-                double       *hc  = s_h + (size_t) (warp_base + src) * L.hstride;
-                const double *rna = wrow_base + (size_t) xia * wld, *roa = wrow_base + (size_t) xoa * wld;
-                const double *rnb = wrow_base + (size_t) xib * wld, *rob = wrow_base + (size_t) xob * wld;
-                for (int k = lane; k < ninst; k += 32) {
-                    double v = __dadd_rn (hc[k], __dsub_rn (rna[k], roa[k]));
-                    if (xdb) v = __dadd_rn (v, __dsub_rn (rnb[k], rob[k]));
-                    hc[k] = v;
+                const uint32_t y = __shfl_sync (0xffffffffu, packed, src);
+                double       *hc  = s_h + (warp_base + src) * L.hstride;
+                const double *rna = wbase + (int) (y & 255u) * wld, *roa = wbase + (int) ((y >> 8) & 255u) * wld;
+                if ((dblmask >> src) & 1u) {
+                    const double *rnb = wbase + (int) ((y >> 16) & 255u) * wld, *rob = wbase + (int) (y >> 24) * wld;
+                    for (int k = lane; k < ninst; k += 64) {
+                        const int  k2 = k + 32;
+                        const bool two = k2 < ninst;
+                        const double h0 = hc[k], a0 = rna[k], b0 = roa[k], c0 = rnb[k], d0 = rob[k];
+                        double h1 = 0.0, a1 = 0.0, b1 = 0.0, c1 = 0.0, d1 = 0.0;
+                        if (two) { h1 = hc[k2]; a1 = rna[k2]; b1 = roa[k2]; c1 = rnb[k2]; d1 = rob[k2]; }
+                        hc[k] = __dadd_rn (__dadd_rn (h0, __dsub_rn (a0, b0)), __dsub_rn (c0, d0));
+                        if (two) hc[k2] = __dadd_rn (__dadd_rn (h1, __dsub_rn (a1, b1)), __dsub_rn (c1, d1));
+                    }
+                } else {
+                    for (int k = lane; k < ninst; k += 64) {
+                        const int  k2 = k + 32;
+                        const bool two = k2 < ninst;
+                        const double h0 = hc[k], a0 = rna[k], b0 = roa[k];
+                        double h1 = 0.0, a1 = 0.0, b1 = 0.0;
+                        if (two) { h1 = hc[k2]; a1 = rna[k2]; b1 = roa[k2]; }
+                        hc[k] = __dadd_rn (h0, __dsub_rn (a0, b0));
+                        if (two) hc[k2] = __dadd_rn (h1, __dsub_rn (a1, b1));
+                    }
                 }
-            }
+            } while (pending);
             __syncwarp ();
             if (accept) {
-                g = __dadd_rn (g, dg);
-                const uint32_t since_a = s_since[sa * B + tid];
-                if (PER_CHAIN) p.chain_counts[((size_t) q * p.nchains + local) * ninst + oa] += (long long) (tp - since_a);
-                else if (tp != since_a) atomicAdd (&s_counts[oa], (unsigned long long) (tp - since_a));
-                s_since[sa * B + tid] = tp;
-                s_state[sa * B + tid] = (uint8_t) ia;
+                grt = __dadd_rn (grt, x);
+                const uint32_t since_a = my_since[sa * B];
+                if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
+                else if (tp != since_a) atomicAdd (&my_counts[oa], (unsigned long long) (tp - since_a));
+                my_since[sa * B] = tp;
+                my_state[sa * B] = (uint8_t) ia;
                 if (dbl) {
-                    const uint32_t since_b = s_since[sb * B + tid];
-                    if (PER_CHAIN) p.chain_counts[((size_t) q * p.nchains + local) * ninst + ob] += (long long) (tp - since_b);
-                    else if (tp != since_b) atomicAdd (&s_counts[ob], (unsigned long long) (tp - since_b));
-                    s_since[sb * B + tid] = tp;
-                    s_state[sb * B + tid] = (uint8_t) ib;
+                    const uint32_t since_b = my_since[sb * B];
+                    if (PER_CHAIN) my_chain_counts[ob] += (long long) (tp - since_b);
+                    else if (tp != since_b) atomicAdd (&my_counts[ob], (unsigned long long) (tp - since_b));
+                    my_since[sb * B] = tp;
+                    my_state[sb * B] = (uint8_t) ib;
                     if (production) c_facc++;
                 } else if (production) c_macc++;
             }
         }
-        if (production) {
-            esum += g;
-            if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0) p.trajectory[scan - p.nequil] = g;
+        // scan bookkeeping (MCModelDefault.c:298-312): after the last trial of a production scan the energy is recorded
+        if (++mv == nmoves) {
+            mv = 0;
+            if (production) {
+                esum += grt;
+                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && active) p.trajectory[scan - p.nequil] = grt / beta;
+            }
+            scan++;
+            production = scan >= p.nequil;
+            tp = production ? (uint32_t) (scan - p.nequil) : 0u;
         }
+    };
+
+    pce::Philox4 rnext = pce::philox4x32_10 (0u, 0u, chain, phidx, p.k0, p.k1);
+    for (unsigned long long b = 0; 2ull * b < ntrials; b++) {
+        const pce::Philox4 r = rnext;
+        const unsigned long long bn = b + 1;
+        rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);   // ahead of its use
+        trial (r.x, r.y);
+        if (2ull * b + 1ull < ntrials) trial (r.z, r.w);
     }
 
     // flush residence times of the final state
+    const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (active) {
         for (int i = 0; i < nsites; i++) {
-            const int      a = s_state[i * B + tid];
-            const uint32_t d = (uint32_t) p.nprod - s_since[i * B + tid];
-            if (PER_CHAIN) p.chain_counts[((size_t) q * p.nchains + local) * ninst + a] += (long long) d;
-            else if (d) atomicAdd (&s_counts[a], (unsigned long long) d);
+            const int      a = my_state[i * B];
+            const uint32_t d = (uint32_t) p.nprod - my_since[i * B];
+            if (PER_CHAIN) my_chain_counts[a] += (long long) d;
+            else if (d) atomicAdd (&my_counts[a], (unsigned long long) d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
-            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = s_state[i * B + tid];
-            p.chain_energy[c] = g;
-            p.chain_esum[c]   = esum;
+            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = my_state[i * B];
+            p.chain_energy[c] = grt / beta;
+            p.chain_esum[c]   = esum / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
             p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
         }
@@ -302,25 +329,18 @@ __global__ void __launch_bounds__ (256) k_mc_thread (const McParams p) {
     if (!PER_CHAIN) {
         __syncthreads ();
         if (p.counts != nullptr)
-            for (int k = tid; k < ninst; k += B)
-                if (s_counts[k]) atomicAdd (&p.counts[(size_t) q * ninst + k], s_counts[k]);
-        // counters and energy sums: warp reduce, one atomic per warp
-        double es = active ? esum : 0.0;
-        unsigned long long cm = c_moves, ca = c_macc, cf = c_flips, cfa = c_facc;
-        for (int o = 16; o > 0; o >>= 1) {
-            es  += __shfl_xor_sync (0xffffffffu, es, o);
-            cm  += __shfl_xor_sync (0xffffffffu, cm, o);
-            ca  += __shfl_xor_sync (0xffffffffu, ca, o);
-            cf  += __shfl_xor_sync (0xffffffffu, cf, o);
-            cfa += __shfl_xor_sync (0xffffffffu, cfa, o);
-        }
-        if (lane == 0) {
-            if (p.esum != nullptr) atomicAdd (&p.esum[q], es);
+            for (int k = tid; k < L.kslots * ninst; k += B) {
+                const int qq = q_base + k / ninst;
+                if (qq < p.nph && s_counts[k]) atomicAdd (&p.counts[(size_t) qq * ninst + (k % ninst)], s_counts[k]);
+            }
+        // counters and energy sums: one atomic per thread (pH values may differ within a warp)
+        if (active) {
+            if (p.esum != nullptr) atomicAdd (&p.esum[q], esum / beta);
             if (p.counters != nullptr) {
-                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], cm);
-                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], ca);
-                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 2], cf);
-                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 3], cfa);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 2], (unsigned long long) c_flips);
+                atomicAdd ((unsigned long long *) &p.counters[q * 4 + 3], (unsigned long long) c_facc);
             }
         }
     }
@@ -328,8 +348,8 @@ __global__ void __launch_bounds__ (256) k_mc_thread (const McParams p) {
 
 // ---------------------------------------------------------------------------------------------------
 // k_mc_warp: one chain per warp.  Every lane evaluates the (warp-uniform) proposal; accepted moves are
-// applied by all lanes with 128-bit loads of the W rows from L2.
-// Shared memory per warp: h[ldh] doubles | since[nsites] u32 | state[nsites] u16
+// applied by all lanes with 128-bit loads of the beta-scaled W rows from L2.
+// Shared memory per warp: hb[ldh] doubles | since[nsites] u32 | state[nsites] u16
 // ---------------------------------------------------------------------------------------------------
 struct WarpLayout {
     size_t off_h, off_since, off_state, per_warp;
@@ -345,7 +365,7 @@ struct WarpLayout {
 };
 
 template <bool PER_CHAIN>
-__global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
+__global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const WarpLayout L (p.nsites, p.ninst);
@@ -355,10 +375,10 @@ __global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
     uint16_t      *state  = (uint16_t *) (base + L.off_state);
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
-    const int blocks_per_ph = (p.nchains + warps - 1) / warps;
-    const int q     = blockIdx.x / blocks_per_ph;
-    const int local = (blockIdx.x % blocks_per_ph) * warps + wib;
-    if (local >= p.nchains) return;                                // whole warp leaves together
+    const long long gidx = (long long) blockIdx.x * warps + wib;       // chain-major linear (pH, chain) index
+    if (gidx >= (long long) p.nph * p.nchains) return;              // whole warp leaves together
+    const int q     = (int) (gidx / p.nchains);
+    const int local = (int) (gidx % p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
 
@@ -369,24 +389,24 @@ __global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
         since[i] = 0u;
     }
     __syncwarp ();
-    // fields: lanes over k, j sequential (spec order); W[k][a_j] gathers, once per chain
+    const double mu   = ph_to_mu (p.temperature, p.ph[q]);
+    const double beta = 1.0 / (PCE_R * p.temperature);
+    // fused fields: lanes over k, j sequential (spec order); wb[k][a_j] gathers, once per chain
     for (int k = lane; k < L.ldh; k += 32) {
         double acc = 0.0;
         if (k < ninst) {
-            const double *row = p.w + (size_t) k * ldw;
+            const double *row = p.wb + (size_t) k * ldw;
+            acc = __dmul_rn (beta, __dsub_rn (__ldg (p.gintr + k), __dmul_rn ((double) __ldg (p.protons + k), mu)));
             for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, __ldg (row + state[j]));
         }
         h[k] = acc;
     }
     __syncwarp ();
 
-    const double mu   = ph_to_mu (p.temperature, p.ph[q]);
-    const double beta = 1.0 / (PCE_R * p.temperature);
-
     // initial energy.  The reference order (EnergyModel.c:204-224) is a serial sum over i then j < i; here
     // lanes take rows i = lane, lane+32, ... and the partial sums are combined, so the value may differ
     // from the serial sum in the last bits.  It only seeds the tracked energy (informational output).
-    double g;
+    double grt;
     {
         double gi = 0.0, ws = 0.0;
         int    np = 0;
@@ -399,92 +419,74 @@ __global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
         }
         gi = pce::warp_sum (gi); ws = pce::warp_sum (ws);
         for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
-        g = __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws);
+        grt = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
     }
 
     const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
-    const long long nscans = (long long) p.nequil + p.nprod;
-    unsigned long long t = 0;
-    uint32_t c_moves = 0, c_macc = 0, c_flips = 0, c_facc = 0;
+    const unsigned long long ntrials = (unsigned long long) ((long long) p.nequil + p.nprod) * nmoves;
+    uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
     double   esum = 0.0;
-    pce::Philox4 r = { 0, 0, 0, 0 };
+    long long scan = 0;
+    uint32_t  mv = 0, tp = 0;
+    bool      production = p.nequil == 0;
     unsigned long long *counts = PER_CHAIN ? (unsigned long long *) (p.chain_counts + ((size_t) q * p.nchains + local) * ninst)
                                            : p.counts + (size_t) q * ninst;
 
-    for (long long scan = 0; scan < nscans; scan++) {
-        const bool     production = scan >= p.nequil;
-        const uint32_t tp = production ? (uint32_t) (scan - p.nequil) : 0u;
-        for (uint32_t mv = 0; mv < nmoves; mv++, t++) {
-            uint32_t w0, w1;
-            if ((t & 1ull) == 0ull) {
-                const unsigned long long b = t >> 1;
-                r = pce::philox4x32_10 ((uint32_t) b, (uint32_t) (b >> 32), chain, phidx, p.k0, p.k1);
-                w0 = r.x; w1 = r.y;
-            } else {
-                w0 = r.z; w1 = r.w;
-            }
-            const uint32_t idx = __umulhi (w0, nmoves);
-            const uint32_t lo  = w0 * nmoves;
-            const bool     dbl = idx >= (uint32_t) nsites;
-            int sa, sb = 0;
-            if (dbl) { sa = __ldg (p.pair_a + (idx - nsites)); sb = __ldg (p.pair_b + (idx - nsites)); } else { sa = (int) idx; }
-            const int na = __ldg (p.nsi + sa), oa = state[sa];
-            bool valid = na >= 2;
-            const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
+    auto trial = [&] (const uint32_t w0, const uint32_t w1) {
+        const uint32_t idx = __umulhi (w0, nmoves);
+        const uint32_t lo  = w0 * nmoves;
+        const bool     dbl = idx >= (uint32_t) nsites;
+        int sa, sb = 0;
+        if (dbl) { sa = __ldg (p.pair_a + (idx - nsites)); sb = __ldg (p.pair_b + (idx - nsites)); } else { sa = (int) idx; }
+        const int na = __ldg (p.nsi + sa), oa = state[sa];
+        bool valid = na >= 2;
+        const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
+        int ia = __ldg (p.first + sa) + (int) ka;
+        if (ia >= oa) ia++;
+        if (!valid) ia = oa;
+        double x = __dsub_rn (h[ia], h[oa]);
+        int ib = 0, ob = 0;
+        if (dbl) {
             const uint32_t lo2 = lo * (uint32_t) (na - 1);
-            int ia = __ldg (p.first + sa) + (int) ka;
-            if (ia >= oa) ia++;
-            if (!valid) ia = oa;
-            double dgintr = __dsub_rn (__ldg (p.gintr + ia), __ldg (p.gintr + oa));
-            int    dprot  = __ldg (p.protons + ia) - __ldg (p.protons + oa);
-            double dw     = __dsub_rn (h[ia], h[oa]);
-            int ib = 0, ob = 0;
-            if (dbl) {
-                const int nb = __ldg (p.nsi + sb);
-                ob = state[sb];
-                if (nb < 2) valid = false;
-                const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
-                ib = __ldg (p.first + sb) + (int) kb;
-                if (ib >= ob) ib++;
-                if (!valid) { ib = ob; ia = oa; }
-                dgintr = __dadd_rn (dgintr, __dsub_rn (__ldg (p.gintr + ib), __ldg (p.gintr + ob)));
-                dprot += __ldg (p.protons + ib) - __ldg (p.protons + ob);
-                const double *ra = p.w + (size_t) ia * ldw, *ro = p.w + (size_t) oa * ldw;
-                const double cross = __dadd_rn (__dsub_rn (__dsub_rn (__ldg (ra + ib), __ldg (ra + ob)), __ldg (ro + ib)), __ldg (ro + ob));
-                dw = __dadd_rn (__dadd_rn (dw, __dsub_rn (h[ib], h[ob])), cross);
-            }
-            const double dg = __dadd_rn (__dsub_rn (dgintr, __dmul_rn ((double) dprot, mu)), dw);
-            const bool accept = valid && metropolis (__dmul_rn (dg, beta), w1);
-            if (production) { if (dbl) c_flips++; else c_moves++; }
-            if (!accept) continue;                                  // warp-uniform
-
-            // h += W[ia] - W[oa] (+ W[ib] - W[ob]); rows are 32-byte aligned (ldw multiple of 4)
-            {
-                const double2 *rna = (const double2 *) (p.w + (size_t) ia * ldw), *roa = (const double2 *) (p.w + (size_t) oa * ldw);
-                const double2 *rnb = (const double2 *) (p.w + (size_t) ib * ldw), *rob = (const double2 *) (p.w + (size_t) ob * ldw);
-                double2       *h2  = (double2 *) h;
-                const int      n2  = L.ldh >> 1;
-                if (!dbl) {
+            const int nb = __ldg (p.nsi + sb);
+            ob = state[sb];
+            if (nb < 2) valid = false;
+            const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
+            ib = __ldg (p.first + sb) + (int) kb;
+            if (ib >= ob) ib++;
+            if (!valid) { ib = ob; ia = oa; }
+            const double *ra = p.wb + (size_t) ia * ldw, *ro = p.wb + (size_t) oa * ldw;
+            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (__ldg (ra + ib), __ldg (ra + ob)), __ldg (ro + ib)), __ldg (ro + ob));
+            x = __dadd_rn (__dadd_rn (x, __dsub_rn (h[ib], h[ob])), cross);
+            if (production) c_flips++;
+        }
+        const bool accept = valid && metropolis (x, w1);      // warp-uniform
+        if (accept) {
+            // hb += wb[ia] - wb[oa] (+ wb[ib] - wb[ob]); rows are 32-byte aligned (ldw multiple of 4)
+            const double2 *rna = (const double2 *) (p.wb + (size_t) ia * ldw), *roa = (const double2 *) (p.wb + (size_t) oa * ldw);
+            const double2 *rnb = (const double2 *) (p.wb + (size_t) ib * ldw), *rob = (const double2 *) (p.wb + (size_t) ob * ldw);
+            double2       *h2  = (double2 *) h;
+            const int      n2  = L.ldh >> 1;
+            if (!dbl) {
 #pragma unroll 4
-                    for (int k = lane; k < n2; k += 32) {
-                        const double2 a = __ldg (rna + k), b = __ldg (roa + k);
-                        double2 v = h2[k];
-                        v.x = __dadd_rn (v.x, __dsub_rn (a.x, b.x));
-                        v.y = __dadd_rn (v.y, __dsub_rn (a.y, b.y));
-                        h2[k] = v;
-                    }
-                } else {
+                for (int k = lane; k < n2; k += 32) {
+                    const double2 a = __ldg (rna + k), b = __ldg (roa + k);
+                    double2 v = h2[k];
+                    v.x = __dadd_rn (v.x, __dsub_rn (a.x, b.x));
+                    v.y = __dadd_rn (v.y, __dsub_rn (a.y, b.y));
+                    h2[k] = v;
+                }
+            } else {
 #pragma unroll 2
-                    for (int k = lane; k < n2; k += 32) {
-                        const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
-                        double2 v = h2[k];
-                        v.x = __dadd_rn (__dadd_rn (v.x, __dsub_rn (a.x, b.x)), __dsub_rn (c.x, d.x));
-                        v.y = __dadd_rn (__dadd_rn (v.y, __dsub_rn (a.y, b.y)), __dsub_rn (c.y, d.y));
-                        h2[k] = v;
-                    }
+                for (int k = lane; k < n2; k += 32) {
+                    const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
+                    double2 v = h2[k];
+                    v.x = __dadd_rn (__dadd_rn (v.x, __dsub_rn (a.x, b.x)), __dsub_rn (c.x, d.x));
+                    v.y = __dadd_rn (__dadd_rn (v.y, __dsub_rn (a.y, b.y)), __dsub_rn (c.y, d.y));
+                    h2[k] = v;
                 }
             }
-            g = __dadd_rn (g, dg);
+            grt = __dadd_rn (grt, x);
             if (lane == 0) {
                 const uint32_t since_a = since[sa];
                 if (tp != since_a) atomicAdd (&counts[oa], (unsigned long long) (tp - since_a));
@@ -500,27 +502,44 @@ __global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
             if (production) { if (dbl) c_facc++; else c_macc++; }
             __syncwarp ();
         }
-        if (production) {
-            esum += g;
-            if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan - p.nequil] = g;
+        if (++mv == nmoves) {
+            mv = 0;
+            if (production) {
+                esum += grt;
+                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan - p.nequil] = grt / beta;
+            }
+            scan++;
+            production = scan >= p.nequil;
+            tp = production ? (uint32_t) (scan - p.nequil) : 0u;
         }
+    };
+
+    pce::Philox4 rnext = pce::philox4x32_10 (0u, 0u, chain, phidx, p.k0, p.k1);
+    for (unsigned long long b = 0; 2ull * b < ntrials; b++) {
+        const pce::Philox4 r = rnext;
+        const unsigned long long bn = b + 1;
+        rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);
+        trial (r.x, r.y);
+        if (2ull * b + 1ull < ntrials) trial (r.z, r.w);
     }
+
     __syncwarp ();
     for (int i = lane; i < nsites; i += 32) {
         const uint32_t d = (uint32_t) p.nprod - since[i];
         if (d) atomicAdd (&counts[state[i]], (unsigned long long) d);
     }
+    const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (PER_CHAIN) {
         const size_t c = (size_t) q * p.nchains + local;
         for (int i = lane; i < nsites; i += 32) p.chain_state[c * nsites + i] = state[i];
         if (lane == 0) {
-            p.chain_energy[c] = g;
-            p.chain_esum[c]   = esum;
+            p.chain_energy[c] = grt / beta;
+            p.chain_esum[c]   = esum / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
             p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
         }
     } else if (lane == 0) {
-        if (p.esum != nullptr) atomicAdd (&p.esum[q], esum);
+        if (p.esum != nullptr) atomicAdd (&p.esum[q], esum / beta);
         if (p.counters != nullptr) {
             atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
             atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
@@ -533,7 +552,7 @@ __global__ void __launch_bounds__ (512) k_mc_warp (const McParams p) {
 // ---------------------------------------------------------------------------------------------------
 // launch planning
 // ---------------------------------------------------------------------------------------------------
-struct Plan { int kernel, block, w_in_smem; size_t smem; };
+struct Plan { int kernel, block, w_in_smem; size_t smem; int ctas_per_sm; };
 
 int smem_limit (int device, size_t *limit) {
     int value = 0;
@@ -542,22 +561,28 @@ int smem_limit (int device, size_t *limit) {
     return PCE_OK;
 }
 
-// chain-per-thread plan: prefer W in shared memory and the block size with the most resident warps per SM
-bool plan_thread (const pce_mc *mc, size_t limit, Plan *plan) {
+// chain-per-thread plan: W in shared memory when it fits, and the block size (multiple of 32, <= 512) that puts the
+// most warps on an SM; ties go to the smaller block (finer-grained waves).
+bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     const pce_model *m = mc->model;
     if (m->ninst > 256) return false;
     const size_t per_sm = 228 * 1024;
     int best_warps = 0;
+    const char *forced = std::getenv ("PCE_MC_BLOCK");      // tuning aid: force the block size
+    const int forced_block = forced ? std::atoi (forced) : 0;
     for (int w_in = 1; w_in >= 0; w_in--) {
-        for (int block : { 256, 128, 64, 32 }) {
-            ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in);
+        for (int block = 32; block <= 512; block += 32) {
+            if (forced_block && block != forced_block) continue;
+            ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in, mc->nchains, nph);
             if (L.total > limit) continue;
             int ctas = (int) std::min<size_t> (per_sm / (L.total + 1024), (size_t) (2048 / block));
             ctas = std::min (ctas, 32);
             const int warps = ctas * block / 32;
-            if (warps > best_warps) { best_warps = warps; plan->kernel = 1; plan->block = block; plan->w_in_smem = w_in; plan->smem = L.total; }
+            if (warps > best_warps) {
+                best_warps = warps; plan->kernel = 1; plan->block = block; plan->w_in_smem = w_in; plan->smem = L.total; plan->ctas_per_sm = ctas;
+            }
         }
-        if (best_warps >= 8) break;     // W on chip with at least 8 warps/SM: take it
+        if (best_warps >= 4) break;     // W on chip with at least 4 warps/SM: take it
     }
     return best_warps >= 2;
 }
@@ -570,6 +595,7 @@ bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
     int warps = (int) std::min<size_t> (limit / L.per_warp, 16);   // up to 16 warps per block
     // several blocks per SM when the per-warp footprint is small
     plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = (size_t) warps * L.per_warp;
+    plan->ctas_per_sm = (int) std::max<size_t> (1, std::min<size_t> ((228 * 1024) / (plan->smem + 1024), (size_t) (2048 / plan->block)));
     return true;
 }
 
@@ -665,6 +691,34 @@ extern "C" int pce_mc_get_info (const pce_mc *mc, int *kernel, int *nchains, int
     return PCE_OK;
 }
 
+static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
+    size_t limit = 0;
+    int status = smem_limit (mc->model->device, &limit);
+    if (status != PCE_OK) return status;
+    bool ok = false;
+    if (mc->kernel == 1) ok = plan_thread (mc, limit, nph, plan);
+    else if (mc->kernel == 2) ok = plan_warp (mc, limit, plan);
+    else ok = plan_thread (mc, limit, nph, plan) || plan_warp (mc, limit, plan);
+    if (!ok) return fail (PCE_ERR_LIMIT, "model too large for the selected Monte Carlo kernel");
+    return PCE_OK;
+}
+
+extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm, int *chains_per_wave, long long *smem_bytes) {
+    if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    PCE_CUDA (cudaSetDevice (mc->model->device));
+    Plan plan = { 0, 0, 0, 0, 1 };
+    int status = make_mc_plan (mc, nph, &plan);
+    if (status != PCE_OK) return status;
+    int sms = 0;
+    PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, mc->model->device));
+    if (kernel) *kernel = plan.kernel;
+    if (block) *block = plan.block;
+    if (ctas_per_sm) *ctas_per_sm = plan.ctas_per_sm;
+    if (chains_per_wave) *chains_per_wave = sms * plan.ctas_per_sm * (plan.kernel == 1 ? plan.block : plan.block / 32);
+    if (smem_bytes) *smem_bytes = (long long) plan.smem;
+    return PCE_OK;
+}
+
 static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset, bool per_chain, McParams &p) {
     pce_model *m = mc->model;
     if (nph <= 0) return PCE_OK;
@@ -687,31 +741,27 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     PCE_CUDA (mc->d_ph.resize (nph));
     PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
 
-    size_t limit = 0;
-    status = smem_limit (m->device, &limit);
+    Plan plan = { 0, 0, 0, 0, 1 };
+    status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
-    Plan plan = { 0, 0, 0, 0 };
-    bool ok = false;
-    if (mc->kernel == 1) ok = plan_thread (mc, limit, &plan);
-    else if (mc->kernel == 2) ok = plan_warp (mc, limit, &plan);
-    else ok = plan_thread (mc, limit, &plan) || plan_warp (mc, limit, &plan);
-    if (!ok) return fail (PCE_ERR_LIMIT, "model too large for the selected Monte Carlo kernel");
 
     p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
     p.first = m->d_first.ptr; p.nsi = m->d_nsite_inst.ptr; p.protons = m->d_protons.ptr;
     p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr;
-    p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.ph = mc->d_ph.ptr;
+    p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.wb = m->d_wb.ptr; p.ph = mc->d_ph.ptr;
     p.nph = nph; p.ph_index_offset = ph_index_offset; p.nchains = mc->nchains; p.nequil = mc->nequil; p.nprod = mc->nprod;
     p.chain_offset = chain_offset;
     p.k0 = (uint32_t) mc->seed; p.k1 = (uint32_t) (mc->seed >> 32);
     p.temperature = m->temperature;
     p.w_in_smem = plan.w_in_smem;
 
-    const int chains_per_block = plan.kernel == 1 ? plan.block : plan.block / 32;
-    const long long blocks = (long long) nph * ((mc->nchains + chains_per_block - 1) / chains_per_block);
+    long long blocks;
+    if (plan.kernel == 1) blocks = ((long long) nph * mc->nchains + plan.block - 1) / plan.block;     // chain-major linear grid
+    else blocks = ((long long) nph * mc->nchains + plan.block / 32 - 1) / (plan.block / 32);
     if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
     if (plan.kernel == 1) {
-        auto kernel = per_chain ? k_mc_thread<true> : k_mc_thread<false>;
+        auto kernel = per_chain ? (plan.w_in_smem ? k_mc_thread<true, true> : k_mc_thread<true, false>)
+                                : (plan.w_in_smem ? k_mc_thread<false, true> : k_mc_thread<false, false>);
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     } else {

@@ -74,7 +74,8 @@ extern "C" void pce_model_destroy (pce_model *m) {
     if (cudaGetDevice (&current) == cudaSuccess) {
         cudaSetDevice (m->device);
         m->d_first.release (); m->d_nsite_inst.release (); m->d_site_of_inst.release (); m->d_protons.release ();
-        m->d_gintr.release (); m->d_gmodel.release (); m->d_w.release ();
+        m->d_gintr.release (); m->d_gmodel.release (); m->d_w.release (); m->d_wb.release ();
+        m->s_gt.release (); m->s_T.release (); m->s_Mtab.release (); m->s_Ftab.release (); m->s_seg.release (); m->s_xs.release (); m->s_ms.release ();
         cudaSetDevice (current);
     }
     delete m;
@@ -297,6 +298,15 @@ int pce_model::upload () {
     PCE_CUDA (cudaMemsetAsync (d_w.ptr, 0, (size_t) ninst * ldw * sizeof (double), stream));
     PCE_CUDA (cudaMemcpy2DAsync (d_w.ptr, (size_t) ldw * sizeof (double), wsym.data (), (size_t) ninst * sizeof (double),
                                  (size_t) ninst * sizeof (double), (size_t) ninst, cudaMemcpyHostToDevice, stream));
+    {   // W in units of RT for the Monte Carlo kernels: one rounding per element, identical to the chain specification
+        const double beta = 1.0 / (PCE_R * temperature);
+        std::vector<double> wb ((size_t) ninst * ldw, 0.0);
+        for (int a = 0; a < ninst; a++)
+            for (int b = 0; b < ninst; b++) wb[(size_t) a * ldw + b] = beta * wsym[(size_t) a * ninst + b];
+        PCE_CUDA (d_wb.resize ((size_t) ninst * ldw));
+        PCE_CUDA (cudaMemcpyAsync (d_wb.ptr, wb.data (), wb.size () * sizeof (double), cudaMemcpyHostToDevice, stream));
+        PCE_CUDA (cudaStreamSynchronize (stream));
+    }
     PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors above die with this scope
     dirty = false;
     return PCE_OK;
