@@ -40,7 +40,7 @@ constexpr int kMaxOuter  = 96;    // max sites in O + F
 constexpr int kMaxMI     = 320;   // max instances in M + I sites
 constexpr long long kMaxChunks = 16384;
 
-constexpr int kTB = 4;            // tiles (outer configurations) processed per synchronisation round
+constexpr int kTB = 8;            // tiles (outer configurations) processed per synchronisation round
 
 struct EnumParams {
     int nsites, ninst, ldw, unfolded;
@@ -56,6 +56,12 @@ struct EnumParams {
     int16_t siteM[kMaxM], radM[kMaxM];
     int16_t siteI[kMaxI], radI[kMaxI];
     int16_t siteOut[kMaxOuter], radOut[kMaxOuter];   // O sites first (fastest digit first), then F sites
+    int16_t firstOut[kMaxOuter];                     // first instance of each outer site
+    unsigned strideO[kMaxOuter];                     // digit stride of each O site within the tile index
+    int16_t permI[kIStates], binI[kIStates];         // I configurations sorted by proton count; protons of each
+    unsigned flushI;                                 // bit i set: sorted configuration i is the last of its proton count
+    int      nMI, pow2O;                             // instances in M+I sites; every O radix a power of two
+    uint8_t  shiftO[kMaxOuter];                      // digit shift of each O site when pow2O
     double *T;                  // [nchunks][Nb][kBlock] per-thread bins
     // per-thread statics, computed once by k_enum_static: xs[(1 + kIStates) * kBlock] = xMM then xMI[i], coalesced;
     // ms[3 * kBlock] = m_lo, m_hi, protons of the M configuration; shift = minMM + minMI
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__ (kBlock) k_enum_static (const EnumParams p) {
         double e = 0.0;
         if (i < p.P_I && folded) {
             int aI[kMaxI];
-            int x = i;
+            int x = p.permI[i];                                  // sorted position -> I configuration
             for (int k = 0; k < kMaxI; k++) { aI[k] = 0; if (k < p.nI) { aI[k] = p.first[p.siteI[k]] + x % p.radI[k]; x /= p.radI[k]; } }
             for (int k = 0; k < p.nI; k++) {
                 const double *row = p.w + (size_t) aI[k] * ldw;
@@ -127,44 +133,81 @@ __global__ void __launch_bounds__ (kBlock) k_enum_static (const EnumParams p) {
     if (tid == 0) *p.shift = minMM + minMI;
 }
 
+// Dynamic shared-memory carve-up of k_enum (same arithmetic on host and device).
+struct EnumLayout {
+    size_t off_bins, off_gF, off_gOut, off_eLo, off_eHi, off_eI, off_cOut, off_cExp, off_inst, off_aF, off_nOut, off_idx, total;
+    int    nMI, nIdx;
+    __host__ __device__ EnumLayout (int Nb, int nMI_, int P_lo, int P_hi, int P_I, int nF, int nM) {
+        nMI = nMI_; nIdx = P_lo + P_hi + P_I;
+        size_t o = 0;
+        off_bins = o; o += (size_t) Nb * kBlock * 8;
+        off_gF = o;   o += (size_t) nMI * 8;
+        off_gOut = o; o += (size_t) kTB * nMI * 8;
+        off_eLo = o;  o += (size_t) kTB * P_lo * 8;
+        off_eHi = o;  o += (size_t) kTB * P_hi * 8;
+        off_eI = o;   o += (size_t) kTB * P_I * 8;
+        off_cOut = o; o += (size_t) kTB * 8;
+        off_cExp = o; o += (size_t) kTB * 8;
+        off_inst = o; o += (size_t) nMI * 4;
+        off_aF = o;   o += (size_t) (nF > 0 ? nF : 1) * 4;
+        off_nOut = o; o += (size_t) kTB * 4;
+        off_idx = o;  o += (size_t) nIdx * kMaxM * 2;      // per table entry: compact-list index of each of its sites
+        total = (o + 15) & ~(size_t) 15;
+    }
+};
+
 // One CTA per chunk (configuration of the F sites).  See the file header for the algorithm.  Tiles (O
 // configurations) are processed kTB per round: fields and tables for kTB tiles are built between two barriers,
 // then every thread accumulates its kTB x P_I states.
 __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
-    double *bins = (double *) smem;                          // [Nb][kBlock]
-    __shared__ double  s_gF[kMaxMI];                         // F-site fields on the M/I instances (per chunk)
-    __shared__ double  s_gOut[kTB][kMaxMI];                  // + O-site fields (per tile)
-    __shared__ double  s_eLo[kTB][kBlock], s_eHi[kTB][64], s_eI[kTB][kIStates];
-    __shared__ int32_t s_instMI[kMaxMI];                     // compact list of the M and I instances
-    __shared__ int32_t s_offM[kMaxM + 1], s_offI[kMaxI + 1]; // start of each site in the compact list
-    __shared__ int32_t s_aF[kMaxOuter];                      // active instance of every F site
-    __shared__ int32_t s_nI[kIStates];                       // protons of each I configuration
-    __shared__ double  s_cOut[kTB], s_cExp[kTB], s_AF;
-    __shared__ int     s_nOut[kTB], s_nF;
+    const EnumLayout L (p.Nb, p.nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM);
+    double   *bins   = (double *) (smem + L.off_bins);       // [Nb][kBlock]
+    double   *s_gF   = (double *) (smem + L.off_gF);         // F-site fields on the M/I instances (per chunk)
+    double   *s_gOut = (double *) (smem + L.off_gOut);       // [kTB][nMI] + O-site fields (per tile)
+    double   *s_eLo  = (double *) (smem + L.off_eLo);        // [kTB][P_lo]
+    double   *s_eHi  = (double *) (smem + L.off_eHi);        // [kTB][P_hi]
+    double   *s_eI   = (double *) (smem + L.off_eI);         // [kTB][P_I]
+    double   *s_cOut = (double *) (smem + L.off_cOut);
+    double   *s_cExp = (double *) (smem + L.off_cExp);
+    int32_t  *s_inst = (int32_t *) (smem + L.off_inst);      // compact list of the M and I instances
+    int32_t  *s_aF   = (int32_t *) (smem + L.off_aF);        // active instance of every F site
+    int32_t  *s_nOut = (int32_t *) (smem + L.off_nOut);
+    uint16_t *s_idx  = (uint16_t *) (smem + L.off_idx);      // [nIdx][kMaxM]
+    __shared__ int32_t s_offM[kMaxM + 1], s_offI[kMaxI + 1];
+    __shared__ double  s_AF;
+    __shared__ int     s_nF;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ldw = p.ldw;
+    const int ldw = p.ldw, nMI = p.nMI;
     const bool folded = !p.unfolded;
     const long long chunk = p.chunk_begin + blockIdx.x;
 
     // ---- setup -----------------------------------------------------------------------------------------
     if (tid == 0) {
         int o = 0;
-        for (int i = 0; i < p.nM; i++) { s_offM[i] = o; for (int k = 0; k < p.radM[i]; k++) s_instMI[o++] = p.first[p.siteM[i]] + k; }
+        for (int i = 0; i < p.nM; i++) { s_offM[i] = o; for (int k = 0; k < p.radM[i]; k++) s_inst[o++] = p.first[p.siteM[i]] + k; }
         s_offM[p.nM] = o;
-        for (int i = 0; i < p.nI; i++) { s_offI[i] = o; for (int k = 0; k < p.radI[i]; k++) s_instMI[o++] = p.first[p.siteI[i]] + k; }
+        for (int i = 0; i < p.nI; i++) { s_offI[i] = o; for (int k = 0; k < p.radI[i]; k++) s_inst[o++] = p.first[p.siteI[i]] + k; }
         s_offI[p.nI] = o;
         long long c = chunk;                                 // F digits of this chunk
-        for (int j = 0; j < p.nF; j++) { s_aF[j] = p.first[p.siteOut[p.nO + j]] + (int) (c % p.radOut[p.nO + j]); c /= p.radOut[p.nO + j]; }
+        for (int j = 0; j < p.nF; j++) { s_aF[j] = p.firstOut[p.nO + j] + (int) (c % p.radOut[p.nO + j]); c /= p.radOut[p.nO + j]; }
     }
     for (int e = tid; e < p.Nb * kBlock; e += kBlock) bins[e] = 0.0;
     __syncthreads ();
-    const int nMI = s_offI[p.nI];
-    if (tid < p.P_I) {
-        int x = tid, np = 0;
-        for (int i = 0; i < p.nI; i++) { np += p.protons[s_instMI[s_offI[i] + x % p.radI[i]]]; x /= p.radI[i]; }
-        s_nI[tid] = np;
+    // index tables: which compact-list entries make up table entry x (no divisions in the tile loop)
+    for (int x = tid; x < L.nIdx; x += kBlock) {
+        uint16_t *row = s_idx + x * kMaxM;
+        if (x < p.P_lo) {
+            int y = x;
+            for (int i = 0; i < p.nLo; i++) { row[i] = (uint16_t) (s_offM[i] + y % p.radM[i]); y /= p.radM[i]; }
+        } else if (x < p.P_lo + p.P_hi) {
+            int y = x - p.P_lo;
+            for (int i = p.nLo; i < p.nM; i++) { row[i - p.nLo] = (uint16_t) (s_offM[i] + y % p.radM[i]); y /= p.radM[i]; }
+        } else {
+            int y = p.permI[x - p.P_lo - p.P_hi];                // sorted position -> I configuration
+            for (int i = 0; i < p.nI; i++) { row[i] = (uint16_t) (s_offI[i] + y % p.radI[i]); y /= p.radI[i]; }
+        }
     }
     // this thread's statics
     const bool mine = tid < p.P_M;
@@ -177,7 +220,7 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
 
     // per chunk: fields of the F sites on the M/I instances, F-F energy, F protons
     for (int j = tid; j < nMI; j += kBlock) {
-        const int a = s_instMI[j];
+        const int a = s_inst[j];
         double acc = p.gt[a];
         if (folded) for (int f = 0; f < p.nF; f++) acc += p.w[(size_t) a * ldw + s_aF[f]];
         s_gF[j] = acc;
@@ -197,44 +240,38 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
     }
     __syncthreads ();
 
+    // O digit of a tile: shift/mask when every O radix is a power of two, else divide
+    auto digit = [&] (unsigned x, int o) -> int {
+        return p.pow2O ? (int) ((x >> p.shiftO[o]) & (unsigned) (p.radOut[o] - 1)) : (int) ((x / p.strideO[o]) % (unsigned) p.radOut[o]);
+    };
+
     // ---- rounds of kTB tiles ---------------------------------------------------------------------------
     for (long long tile0 = 0; tile0 < p.P_O; tile0 += kTB) {
-        // (a) O-site fields on the M/I instances: thread (tb, j) decodes the O digits of tile tb on the fly
+        // (a) O-site fields on the M/I instances: one work item per (tile, instance)
         for (int e = tid; e < kTB * nMI; e += kBlock) {
             const int tb = e / nMI, j = e - tb * nMI;
-            const int a = s_instMI[j];
             double acc = s_gF[j];
             if (folded) {
-                unsigned x = (unsigned) (tile0 + tb);
-                const double *row = p.w + (size_t) a * ldw;
-                for (int o = 0; o < p.nO; o++) {
-                    const unsigned r = (unsigned) p.radOut[o], d = x % r;
-                    x /= r;
-                    acc += row[p.first[p.siteOut[o]] + (int) d];
-                }
+                const unsigned x = (unsigned) (tile0 + tb);
+                const double *row = p.w + (size_t) s_inst[j] * ldw;
+                for (int o = 0; o < p.nO; o++) acc += row[p.firstOut[o] + digit (x, o)];
             }
-            s_gOut[tb][j] = acc;
+            s_gOut[tb * nMI + j] = acc;
         }
-        // (b) O energy incl. O-O and O-F terms, O protons: warp (7 - tb) takes tile tb, lanes over O sites
+        // (b) O energy incl. O-O and O-F terms, O protons: the last kTB warps take one tile each, lanes over O sites
         if (warp >= kBlock / 32 - kTB) {
             const int tb = kBlock / 32 - 1 - warp;
             double e = 0.0;
             int    np = 0;
             if (tile0 + tb < p.P_O) {
+                const unsigned x = (unsigned) (tile0 + tb);
                 for (int o = lane; o < p.nO; o += 32) {
-                    // digits of the sites below o are needed for the O-O terms: decode from the start
-                    unsigned x = (unsigned) (tile0 + tb);
-                    int a = 0;
-                    double eo = 0.0;
-                    const double *row = nullptr;
-                    // first pass: find this lane's own instance
-                    unsigned y = x;
-                    for (int o2 = 0; o2 <= o; o2++) { const unsigned r = (unsigned) p.radOut[o2]; a = p.first[p.siteOut[o2]] + (int) (y % r); y /= r; }
-                    row = p.w + (size_t) a * ldw;
-                    eo = p.gt[a];
+                    const int a = p.firstOut[o] + digit (x, o);
+                    const double *row = p.w + (size_t) a * ldw;
+                    double eo = p.gt[a];
                     np += p.protons[a];
                     if (folded) {
-                        for (int o2 = 0; o2 < o; o2++) { const unsigned r = (unsigned) p.radOut[o2]; eo += row[p.first[p.siteOut[o2]] + (int) (x % r)]; x /= r; }
+                        for (int o2 = 0; o2 < o; o2++) eo += row[p.firstOut[o2] + digit (x, o2)];
                         for (int f = 0; f < p.nF; f++) eo += row[s_aF[f]];
                     }
                     e += eo;
@@ -246,34 +283,37 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
         }
         __syncthreads ();
 
-        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the per-site
-        // minima, so every table thread normalises its own entry.  Work items: kTB x (P_lo + P_hi + P_I + 1).
+        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the per-site minima,
+        // so every work item normalises its own entry.  Items are grouped by table (Lo | Hi | I | tile constant) so
+        // that a warp mostly runs one code path.
         {
-            const int per_tile = p.P_lo + p.P_hi + p.P_I + 1;
-            for (int e = tid; e < kTB * per_tile; e += kBlock) {
-                const int tb = e / per_tile, x = e - tb * per_tile;
-                const double *g = s_gOut[tb];
+            const int n_lo = kTB * p.P_lo, n_hi = kTB * p.P_hi, n_i = kTB * p.P_I;
+            for (int e = tid; e < n_lo + n_hi + n_i + kTB; e += kBlock) {
+                int kind, tb, x;
+                if (e < n_lo) { kind = 0; tb = e / p.P_lo; x = e - tb * p.P_lo; }
+                else if (e < n_lo + n_hi) { kind = 1; tb = (e - n_lo) / p.P_hi; x = (e - n_lo) - tb * p.P_hi; }
+                else if (e < n_lo + n_hi + n_i) { kind = 2; tb = (e - n_lo - n_hi) / p.P_I; x = (e - n_lo - n_hi) - tb * p.P_I; }
+                else { kind = 3; tb = e - n_lo - n_hi - n_i; x = 0; }
+                const double *g = s_gOut + tb * nMI;
                 double min_lo = 0.0, min_hi = 0.0, min_i = 0.0;
-                const bool is_lo = x < p.P_lo, is_hi = !is_lo && x < p.P_lo + p.P_hi, is_i = !is_lo && !is_hi && x < per_tile - 1;
-                const bool is_c = x == per_tile - 1;
-                if (is_lo || is_c) for (int i = 0; i < p.nLo; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_lo += v; }
-                if (is_hi || is_c) for (int i = p.nLo; i < p.nM; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_hi += v; }
-                if (is_i || is_c) for (int i = 0; i < p.nI; i++) { double v = DBL_MAX; for (int j = s_offI[i]; j < s_offI[i + 1]; j++) v = fmin (v, g[j]); min_i += v; }
-                if (is_lo) {
-                    int y = x;
+                if (kind == 0 || kind == 3) for (int i = 0; i < p.nLo; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_lo += v; }
+                if (kind == 1 || kind == 3) for (int i = p.nLo; i < p.nM; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_hi += v; }
+                if (kind == 2 || kind == 3) for (int i = 0; i < p.nI; i++) { double v = DBL_MAX; for (int j = s_offI[i]; j < s_offI[i + 1]; j++) v = fmin (v, g[j]); min_i += v; }
+                if (kind == 0) {
+                    const uint16_t *row = s_idx + x * kMaxM;
                     double s = 0.0;
-                    for (int i = 0; i < p.nLo; i++) { s += g[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
-                    s_eLo[tb][x] = exp (-p.beta * (s - min_lo));
-                } else if (is_hi) {
-                    int y = x - p.P_lo;
+                    for (int i = 0; i < p.nLo; i++) s += g[row[i]];
+                    s_eLo[tb * p.P_lo + x] = exp (-p.beta * (s - min_lo));
+                } else if (kind == 1) {
+                    const uint16_t *row = s_idx + (p.P_lo + x) * kMaxM;
                     double s = 0.0;
-                    for (int i = p.nLo; i < p.nM; i++) { s += g[s_offM[i] + y % p.radM[i]]; y /= p.radM[i]; }
-                    s_eHi[tb][x - p.P_lo] = exp (-p.beta * (s - min_hi));
-                } else if (is_i) {
-                    int y = x - p.P_lo - p.P_hi;
+                    for (int i = 0; i < p.nM - p.nLo; i++) s += g[row[i]];
+                    s_eHi[tb * p.P_hi + x] = exp (-p.beta * (s - min_hi));
+                } else if (kind == 2) {
+                    const uint16_t *row = s_idx + (p.P_lo + p.P_hi + x) * kMaxM;
                     double s = 0.0;
-                    for (int i = 0; i < p.nI; i++) { s += g[s_offI[i] + y % p.radI[i]]; y /= p.radI[i]; }
-                    s_eI[tb][x - p.P_lo - p.P_hi] = exp (-p.beta * (s - min_i));
+                    for (int i = 0; i < p.nI; i++) s += g[row[i]];
+                    s_eI[tb * p.P_I + x] = exp (-p.beta * (s - min_i));
                 } else {
                     s_cExp[tb] = (tile0 + tb < p.P_O) ? exp (-p.beta * ((s_cOut[tb] + min_lo + min_hi + min_i) - p.gref)) : 0.0;
                 }
@@ -281,15 +321,21 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
         }
         __syncthreads ();
 
-        // (f) accumulate this thread's kTB x P_I states into its proton-count bins
+        // (f) accumulate this thread's kTB x P_I states into its proton-count bins.  I configurations are sorted by
+        // proton count, so states of one bin are summed in registers and written with one read-modify-write.
         if (mine) {
-#pragma unroll
+#pragma unroll 2
             for (int tb = 0; tb < kTB; tb++) {
-                const double c_tile = s_cExp[tb] * s_eLo[tb][m_lo] * s_eHi[tb][m_hi] * eMM;
+                const double c_tile = s_cExp[tb] * s_eLo[tb * p.P_lo + m_lo] * s_eHi[tb * p.P_hi + m_hi] * eMM;
                 double *mybins = bins + (s_nOut[tb] + nMp) * kBlock + tid;
+                const double *eI = s_eI + tb * p.P_I;
+                double acc = 0.0;
 #pragma unroll
                 for (int i = 0; i < kIStates; i++) {
-                    if (i < p.P_I) mybins[s_nI[i] * kBlock] += c_tile * (s_eI[tb][i] * xMI[i]);
+                    if (i < p.P_I) {
+                        acc += eI[i] * xMI[i];
+                        if ((p.flushI >> i) & 1u) { mybins[p.binI[i] * kBlock] += c_tile * acc; acc = 0.0; }
+                    }
                 }
             }
         }
@@ -346,45 +392,61 @@ struct MarginalParams {
     double        *bins;    // [(1+ninst)][Nb], accumulated (+=)
 };
 
-__global__ void k_marginals (const MarginalParams p) {
-    // blockIdx.x enumerates: 0 -> Z; then (M site i, digit d) for covered M sites; then (F site j, digit d)
+__global__ void __launch_bounds__ (kBlock) k_marginals (const MarginalParams p) {
+    // blockIdx.x enumerates: 0 -> Z; then (M site i, digit d) for every M site; then (F site j, digit d).
+    // Each block sums, for every bin n, the source entries whose digit matches: entries are spread over the 256
+    // threads (entry e -> thread e % 256) and combined in a fixed order, so the result is deterministic.
+    __shared__ double s_part[kBlock / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int b = blockIdx.x;
-    const int n = threadIdx.x;
-    if (n >= p.Nb) return;
+    int kind = 0, row = 0;              // 0 = Z (all threads of Mtab), 1 = M site, 2 = F site
+    unsigned stride = 1, rad = 1, digit = 0;
     if (b == 0) {
         if (!p.write_z) return;
+    } else {
+        b -= 1;
+        bool found = false;
+        unsigned st = 1;
+        for (int i = 0; i < p.nM && !found; i++) {
+            if (b < p.radM[i]) {
+                if (!p.coverM[i]) return;
+                kind = 1; row = 1 + p.first[p.siteM[i]] + b; stride = st; rad = (unsigned) p.radM[i]; digit = (unsigned) b; found = true;
+            } else { b -= p.radM[i]; st *= (unsigned) p.radM[i]; }
+        }
+        st = 1;
+        for (int j = 0; j < p.nF && !found; j++) {
+            if (b < p.radF[j]) {
+                if (!p.coverF[j]) return;
+                kind = 2; row = 1 + p.first[p.siteF[j]] + b; stride = st; rad = (unsigned) p.radF[j]; digit = (unsigned) b; found = true;
+            } else { b -= p.radF[j]; st *= (unsigned) p.radF[j]; }
+        }
+        if (!found) return;
+    }
+    const long long count = kind == 2 ? p.nchunks : p.P_M;
+    const unsigned  base  = kind == 2 ? (unsigned) p.chunk_begin : 0u;
+    // which of this thread's entries match (up to 64 entries per thread: 16384 chunks / 256 threads)
+    unsigned long long mask = 0ull;
+    for (int k = 0; k < 64; k++) {
+        const long long e = tid + (long long) kBlock * k;
+        if (e < count && (kind == 0 || ((base + (unsigned) e) / stride) % rad == digit)) mask |= 1ull << k;
+    }
+    for (int n = 0; n < p.Nb; n++) {
         double acc = 0.0;
-        for (int t = 0; t < p.P_M; t++) acc += p.Mtab[(size_t) n * kBlock + t];
-        p.bins[n] += acc;
-        return;
-    }
-    b -= 1;
-    long long stride = 1;
-    for (int i = 0; i < p.nM; i++) {
-        if (b < p.radM[i]) {
-            if (!p.coverM[i]) return;
-            double acc = 0.0;
-            for (int t = 0; t < p.P_M; t++)
-                if ((t / stride) % p.radM[i] == b) acc += p.Mtab[(size_t) n * kBlock + t];
-            p.bins[(size_t) (1 + p.first[p.siteM[i]] + b) * p.Nb + n] += acc;
-            return;
+        for (int k = 0; k < 64; k++) {
+            if ((mask >> k) & 1ull) {
+                const long long e = tid + (long long) kBlock * k;
+                acc += kind == 2 ? p.Ftab[(size_t) e * p.Nb + n] : p.Mtab[(size_t) n * kBlock + e];
+            }
         }
-        b -= p.radM[i];
-        stride *= p.radM[i];
-    }
-    stride = 1;
-    for (int j = 0; j < p.nF; j++) {
-        if (b < p.radF[j]) {
-            if (!p.coverF[j]) return;
-            double acc = 0.0;
-            const unsigned st = (unsigned) stride, rad = (unsigned) p.radF[j], base = (unsigned) p.chunk_begin;
-            for (unsigned c = 0; c < (unsigned) p.nchunks; c++)
-                if (((base + c) / st) % rad == (unsigned) b) acc += p.Ftab[(size_t) c * p.Nb + n];
-            p.bins[(size_t) (1 + p.first[p.siteF[j]] + b) * p.Nb + n] += acc;
-            return;
+        acc = pce::warp_sum (acc);
+        if (lane == 0) s_part[warp] = acc;
+        __syncthreads ();
+        if (tid == 0) {
+            double total = 0.0;
+            for (int w = 0; w < kBlock / 32; w++) total += s_part[w];
+            p.bins[(size_t) row * p.Nb + n] += total;
         }
-        b -= p.radF[j];
-        stride *= p.radF[j];
+        __syncthreads ();
     }
 }
 
@@ -564,19 +626,49 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         long long pf = 1;
         for (int j = 0; j < p.nO; j++) { p.siteOut[j] = (int16_t) run.O[j]; p.radOut[j] = (int16_t) radix (m, run.O[j]); p.P_O *= p.radOut[j]; }
         for (int j = 0; j < p.nF; j++) { p.siteOut[p.nO + j] = (int16_t) run.F[j]; p.radOut[p.nO + j] = (int16_t) radix (m, run.F[j]); pf *= p.radOut[p.nO + j]; }
+        {
+            unsigned stride = 1, shift = 0;
+            p.pow2O = 1;
+            for (int j = 0; j < p.nO; j++) {
+                p.strideO[j] = stride; stride *= (unsigned) p.radOut[j];
+                const int r = p.radOut[j];
+                if (r & (r - 1)) p.pow2O = 0;
+                p.shiftO[j] = (uint8_t) shift;
+                int bits = 0;
+                while ((1 << bits) < r) bits++;
+                shift += (unsigned) bits;
+            }
+            p.nMI = nMI;
+            for (int j = 0; j < p.nO + p.nF; j++) p.firstOut[j] = (int16_t) m->first[p.siteOut[j]];
+            // I configurations sorted by proton count (stable)
+            std::vector<std::pair<int, int>> order;
+            for (int c = 0; c < p.P_I; c++) {
+                int x = c, np = 0;
+                for (int i = 0; i < p.nI; i++) { np += m->protons[m->first[p.siteI[i]] + x % p.radI[i]]; x /= p.radI[i]; }
+                order.push_back (std::make_pair (np, c));
+            }
+            std::stable_sort (order.begin (), order.end ());
+            p.flushI = 0;
+            for (int i = 0; i < p.P_I; i++) {
+                p.permI[i] = (int16_t) order[i].second; p.binI[i] = (int16_t) order[i].first;
+                if (i + 1 == p.P_I || order[i + 1].first != order[i].first) p.flushI |= 1u << i;
+            }
+        }
+        if (p.P_O > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many tiles per chunk");
         p.Nb = plan.Nb; p.beta = 1.0 / (PCE_R * m->temperature); p.gref = plan.gref;
         // this shard's slice of the chunk range
         const long long c0 = pf * shard / nshards, c1 = pf * (shard + 1) / nshards;
         p.chunk_begin = c0; p.nchunks = c1 - c0;
         if (p.nchunks <= 0) continue;
-        const size_t smem = (size_t) plan.Nb * kBlock * sizeof (double);
+        const EnumLayout layout (plan.Nb, nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM);
+        const size_t smem = layout.total;
         size_t limit = 0;
         {
             int value = 0;
             PCE_CUDA (cudaDeviceGetAttribute (&value, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
             limit = (size_t) value;
         }
-        if (smem + 24 * 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
+        if (smem + 2 * 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
         const int width = plan.Nb * kBlock;
         const int per_segment = 64;
         const int nseg = (int) ((p.nchunks + per_segment - 1) / per_segment);
@@ -610,8 +702,7 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         for (int i = 0; i < p.nM; i++) { mp.siteM[i] = p.siteM[i]; mp.radM[i] = p.radM[i]; mp.coverM[i] = run.coverM[i]; rows += p.radM[i]; }
         for (int j = 0; j < p.nF; j++) { mp.siteF[j] = p.siteOut[p.nO + j]; mp.radF[j] = p.radOut[p.nO + j]; mp.coverF[j] = run.coverF[j]; rows += mp.radF[j]; }
         mp.first = m->d_first.ptr; mp.Mtab = d_Mtab.ptr; mp.Ftab = d_Ftab.ptr; mp.bins = d_bins;
-        const int threads = (plan.Nb + 31) & ~31;
-        k_marginals<<<rows, threads, 0, m->stream>>> (mp);
+        k_marginals<<<rows, kBlock, 0, m->stream>>> (mp);
         PCE_CUDA (cudaGetLastError ());
         pce::count_launch (6);
     }

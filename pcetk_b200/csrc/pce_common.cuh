@@ -85,20 +85,16 @@ namespace pce {
 
 struct Philox4 { uint32_t x, y, z, w; };
 
-// Philox4x32-10 (Salmon et al., SC'11); bit-identical to oracle_philox4x32_10.
+// Philox4x32-10 (Salmon et al., SC'11); bit-identical to oracle_philox4x32_10.  The two 32x32->64 products per
+// round compile to one IMAD.WIDE.U32 each.
 __host__ __device__ __forceinline__ Philox4 philox4x32_10 (uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-#ifdef __CUDA_ARCH__
-        const uint32_t hi0 = __umulhi (0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi (0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-#else
-        const uint64_t p0 = (uint64_t) 0xD2511F53u * c0, p1 = (uint64_t) 0xCD9E8D57u * c2;
-        const uint32_t hi0 = (uint32_t) (p0 >> 32), lo0 = (uint32_t) p0, hi1 = (uint32_t) (p1 >> 32), lo1 = (uint32_t) p1;
-#endif
-        const uint32_t n0 = hi1 ^ c1 ^ k0;
-        const uint32_t n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        const unsigned long long p0 = (unsigned long long) 0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long) 0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t) (p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t) (p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t) p1; c3 = (uint32_t) p0; c0 = n0; c2 = n2;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     Philox4 out = { c0, c1, c2, c3 };

@@ -90,16 +90,24 @@ __device__ __forceinline__ double ph_to_mu (double temperature, double ph) {
     return __dmul_rn (__dmul_rn (__dmul_rn (-PCE_R, temperature), PCE_LN10), ph);
 }
 
-// MCModelDefault_Metropolis (MCModelDefault.c:71-85) on x = dG/RT.  The fp32 exp only screens: whenever it
-// cannot decide with a 1e-3 relative margin the fp64 exp is evaluated, so the decision equals u < exp(-x).
-__device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
+// MCModelDefault_Metropolis (MCModelDefault.c:71-85) on x = dG/RT: accept if x < 0; reject if x > 500; else accept
+// iff u < exp(-x), u = w1 * 2^-32.  An fp32 exp screens: lanes it cannot decide with a 1e-3 relative margin (and the
+// corner cases) take the fp64 path, so the decision always equals the fp64 rule.
+__device__ __noinline__ bool metropolis_exact (double x, uint32_t w1) {
     if (x < 0.0) return true;
     if (-x < PCE_TOO_SMALL) return false;
+    return ((double) w1 * (1.0 / 4294967296.0)) < exp (-x);
+}
+
+__device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
     const float uf = __uint2float_rn (w1) * 2.3283064365386963e-10f;
     const float ef = __expf (-(float) x);
-    if (uf < ef * 0.999f) return true;
-    if (uf > ef * 1.001f) return false;
-    return ((double) w1 * (1.0 / 4294967296.0)) < exp (-x);
+    bool accept = (x < 0.0) || (uf < ef * 0.999f);
+    const bool unsure = !accept && (uf <= ef * 1.001f) && (x <= 500.0);
+    if (__any_sync (__activemask (), unsure)) {
+        if (unsure) accept = metropolis_exact (x, w1);
+    }
+    return accept;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -202,35 +210,40 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     bool      production = p.nequil == 0;
 
     // one trial: proposal from (w0), Metropolis with (w1), cooperative application of accepted moves
+    const bool has_pairs = p.npairs > 0;
     auto trial = [&] (const uint32_t w0, const uint32_t w1) {
-        const uint32_t idx = __umulhi (w0, nmoves);
-        const uint32_t lo  = w0 * nmoves;
+        const unsigned long long prod = (unsigned long long) w0 * nmoves;
+        const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
         const bool     dbl = idx >= (uint32_t) nsites;
-        const uint32_t pr  = dbl ? s_pair[idx - nsites] : idx;
+        const uint32_t pr  = dbl ? s_pair[idx - nsites] : (idx | (idx << 16));     // single move: site b = site a
         const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
         const uint32_t ia_info = s_site[sa];
         const int na = (int) (ia_info >> 16), oa = my_state[sa * B];
         bool valid = active && na >= 2;
-        const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
-        int ia = (int) (ia_info & 0xffffu) + (int) ka;
+        const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
+        int ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
         if (ia >= oa) ia++;
-        if (!valid) ia = oa;
-        double x = __dsub_rn (myh[ia], myh[oa]);
         int ib = 0, ob = 0;
-        if (dbl) {
-            const uint32_t lo2 = lo * (uint32_t) (na - 1);
+        double x;
+        if (has_pairs) {
+            // evaluated for every lane (a warp almost always holds a double move); for single moves ib == ob and the
+            // extra terms are exactly zero, so the value equals the single-move formula bit for bit
             const uint32_t ib_info = s_site[sb];
             const int nb = (int) (ib_info >> 16);
             ob = my_state[sb * B];
-            if (nb < 2) valid = false;
-            const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
+            const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
             ib = (int) (ib_info & 0xffffu) + (int) kb;
             if (ib >= ob) ib++;
-            if (!valid) { ib = ob; ia = oa; }
+            if (dbl && nb < 2) valid = false;
+            if (!dbl) ib = ob;
+            if (!valid) { ia = oa; ib = ob; }
             const double *ra = wbase + ia * wld, *ro = wbase + oa * wld;
             const double cross = __dadd_rn (__dsub_rn (__dsub_rn (ra[ib], ra[ob]), ro[ib]), ro[ob]);
-            x = __dadd_rn (__dadd_rn (x, __dsub_rn (myh[ib], myh[ob])), cross);
-            if (production) c_flips++;
+            x = __dadd_rn (__dadd_rn (__dsub_rn (myh[ia], myh[oa]), __dsub_rn (myh[ib], myh[ob])), cross);
+            if (production && dbl) c_flips++;
+        } else {
+            if (!valid) ia = oa;
+            x = __dsub_rn (myh[ia], myh[oa]);
         }
         const bool accept = valid && metropolis (x, w1);
 
@@ -247,6 +260,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
                 const double *rna = wbase + (int) (y & 255u) * wld, *roa = wbase + (int) ((y >> 8) & 255u) * wld;
                 if ((dblmask >> src) & 1u) {
                     const double *rnb = wbase + (int) ((y >> 16) & 255u) * wld, *rob = wbase + (int) (y >> 24) * wld;
+#pragma unroll 1
                     for (int k = lane; k < ninst; k += 64) {
                         const int  k2 = k + 32;
                         const bool two = k2 < ninst;
@@ -257,6 +271,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
                         if (two) hc[k2] = __dadd_rn (__dadd_rn (h1, __dsub_rn (a1, b1)), __dsub_rn (c1, d1));
                     }
                 } else {
+#pragma unroll 1
                     for (int k = lane; k < ninst; k += 64) {
                         const int  k2 = k + 32;
                         const bool two = k2 < ninst;
@@ -304,8 +319,11 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
         const pce::Philox4 r = rnext;
         const unsigned long long bn = b + 1;
         rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);   // ahead of its use
-        trial (r.x, r.y);
-        if (2ull * b + 1ull < ntrials) trial (r.z, r.w);
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {          // one copy of the trial body in the instruction cache
+            if (half && 2ull * b + 1ull >= ntrials) break;
+            trial (half ? r.z : r.x, half ? r.w : r.y);
+        }
     }
 
     // flush residence times of the final state
@@ -519,8 +537,11 @@ __global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
         const pce::Philox4 r = rnext;
         const unsigned long long bn = b + 1;
         rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);
-        trial (r.x, r.y);
-        if (2ull * b + 1ull < ntrials) trial (r.z, r.w);
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {          // one copy of the trial body in the instruction cache
+            if (half && 2ull * b + 1ull >= ntrials) break;
+            trial (half ? r.z : r.x, half ? r.w : r.y);
+        }
     }
 
     __syncwarp ();
