@@ -60,7 +60,7 @@ struct EnumParams {
     unsigned strideO[kMaxOuter];                     // digit stride of each O site within the tile index
     int16_t permI[kIStates], binI[kIStates];         // I configurations sorted by proton count; protons of each
     unsigned flushI;                                 // bit i set: sorted configuration i is the last of its proton count
-    int      nMI, pow2O;                             // instances in M+I sites; every O radix a power of two
+    int      nMI, pow2O, nOinst, canon;              // instances in M+I sites; every O radix a power of two; instances in O sites; canonical I group (-1: no)
     uint8_t  shiftO[kMaxOuter];                      // digit shift of each O site when pow2O
     double *T;                  // [nchunks][Nb][kBlock] per-thread bins
     // per-thread statics, computed once by k_enum_static: xs[(1 + kIStates) * kBlock] = xMM then xMI[i], coalesced;
@@ -133,65 +133,92 @@ __global__ void __launch_bounds__ (kBlock) k_enum_static (const EnumParams p) {
     if (tid == 0) *p.shift = minMM + minMI;
 }
 
+constexpr int kMaxO = 32;         // max sites looped by the CTA (O); larger problems put more sites into F
+
 // Dynamic shared-memory carve-up of k_enum (same arithmetic on host and device).
 struct EnumLayout {
-    size_t off_bins, off_gF, off_gOut, off_eLo, off_eHi, off_eI, off_cOut, off_cExp, off_inst, off_aF, off_nOut, off_idx, total;
-    int    nMI, nIdx;
-    __host__ __device__ EnumLayout (int Nb, int nMI_, int P_lo, int P_hi, int P_I, int nF, int nM) {
-        nMI = nMI_; nIdx = P_lo + P_hi + P_I;
+    size_t off_bins, off_gF, off_gOut, off_smin, off_hF, off_eLo, off_eHi, off_eI, off_cOut, off_cExp, off_inst, off_aF, off_nOut,
+           off_idx, off_pair, off_instO, total;
+    int    nMI, nIdx, nSites, nOinst, nPairs;
+    __host__ __device__ EnumLayout (int Nb, int nMI_, int P_lo, int P_hi, int P_I, int nF, int nM, int nI, int nO, int nOinst_) {
+        nMI = nMI_; nIdx = P_lo + P_hi + P_I; nSites = nM + nI; nOinst = nOinst_; nPairs = nO * (nO - 1) / 2;
         size_t o = 0;
         off_bins = o; o += (size_t) Nb * kBlock * 8;
         off_gF = o;   o += (size_t) nMI * 8;
         off_gOut = o; o += (size_t) kTB * nMI * 8;
+        off_smin = o; o += (size_t) kTB * (nSites > 0 ? nSites : 1) * 8;
+        off_hF = o;   o += (size_t) (nOinst > 0 ? nOinst : 1) * 8;
         off_eLo = o;  o += (size_t) kTB * P_lo * 8;
         off_eHi = o;  o += (size_t) kTB * P_hi * 8;
-        off_eI = o;   o += (size_t) kTB * P_I * 8;
+        off_eI = o;   o += (size_t) kTB * 16 * 8;            // padded to 16 entries (128-bit loads)
         off_cOut = o; o += (size_t) kTB * 8;
         off_cExp = o; o += (size_t) kTB * 8;
         off_inst = o; o += (size_t) nMI * 4;
         off_aF = o;   o += (size_t) (nF > 0 ? nF : 1) * 4;
         off_nOut = o; o += (size_t) kTB * 4;
+        off_instO = o; o += (size_t) (nOinst > 0 ? nOinst : 1) * 4;
         off_idx = o;  o += (size_t) nIdx * kMaxM * 2;      // per table entry: compact-list index of each of its sites
+        off_pair = o; o += (size_t) (nPairs > 0 ? nPairs : 1) * 2;
         total = (o + 15) & ~(size_t) 15;
     }
 };
 
+__host__ __device__ constexpr unsigned canon_flush_mask (int n) {
+    // I configurations of n binary one-proton sites sorted by proton count: bins of C(n,k) entries
+    return n == 4 ? 0xC411u : n == 3 ? 0xC9u : n == 2 ? 0xDu : n == 1 ? 0x3u : 0x1u;
+}
+
 // One CTA per chunk (configuration of the F sites).  See the file header for the algorithm.  Tiles (O
 // configurations) are processed kTB per round: fields and tables for kTB tiles are built between two barriers,
-// then every thread accumulates its kTB x P_I states.
-__global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
+// then every thread accumulates its kTB x P_I states.  CANON >= 0: the I group is CANON binary sites whose two
+// instances differ by one proton, so the proton-count structure of the I configurations is known at compile time.
+template <int CANON>
+__global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
+    static_assert (kTB == kBlock / 32, "one warp per tile in phase (b)");
     extern __shared__ __align__ (16) unsigned char smem[];
-    const EnumLayout L (p.Nb, p.nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM);
+    const EnumLayout L (p.Nb, p.nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM, p.nI, p.nO, p.nOinst);
     double   *bins   = (double *) (smem + L.off_bins);       // [Nb][kBlock]
     double   *s_gF   = (double *) (smem + L.off_gF);         // F-site fields on the M/I instances (per chunk)
     double   *s_gOut = (double *) (smem + L.off_gOut);       // [kTB][nMI] + O-site fields (per tile)
+    double   *s_smin = (double *) (smem + L.off_smin);       // [kTB][nM+nI] per-site minimum of gOut
+    double   *s_hF   = (double *) (smem + L.off_hF);         // F-site fields + intrinsic energy on the O instances
     double   *s_eLo  = (double *) (smem + L.off_eLo);        // [kTB][P_lo]
     double   *s_eHi  = (double *) (smem + L.off_eHi);        // [kTB][P_hi]
-    double   *s_eI   = (double *) (smem + L.off_eI);         // [kTB][P_I]
+    double   *s_eI   = (double *) (smem + L.off_eI);         // [kTB][16]
     double   *s_cOut = (double *) (smem + L.off_cOut);
     double   *s_cExp = (double *) (smem + L.off_cExp);
     int32_t  *s_inst = (int32_t *) (smem + L.off_inst);      // compact list of the M and I instances
     int32_t  *s_aF   = (int32_t *) (smem + L.off_aF);        // active instance of every F site
     int32_t  *s_nOut = (int32_t *) (smem + L.off_nOut);
+    int32_t  *s_instO = (int32_t *) (smem + L.off_instO);    // compact list of the O instances (global index | protons << 16)
     uint16_t *s_idx  = (uint16_t *) (smem + L.off_idx);      // [nIdx][kMaxM]
-    __shared__ int32_t s_offM[kMaxM + 1], s_offI[kMaxI + 1];
+    uint16_t *s_pair = (uint16_t *) (smem + L.off_pair);     // O-O pairs: o | o2 << 8
+    __shared__ int32_t s_off[kMaxM + kMaxI + 1];             // start of each M / I site in the compact list
+    __shared__ int32_t s_offO[kMaxO + 1];
     __shared__ double  s_AF;
     __shared__ int     s_nF;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ldw = p.ldw, nMI = p.nMI;
+    const int ldw = p.ldw, nMI = p.nMI, nS = p.nM + p.nI;
     const bool folded = !p.unfolded;
     const long long chunk = p.chunk_begin + blockIdx.x;
 
     // ---- setup -----------------------------------------------------------------------------------------
     if (tid == 0) {
         int o = 0;
-        for (int i = 0; i < p.nM; i++) { s_offM[i] = o; for (int k = 0; k < p.radM[i]; k++) s_inst[o++] = p.first[p.siteM[i]] + k; }
-        s_offM[p.nM] = o;
-        for (int i = 0; i < p.nI; i++) { s_offI[i] = o; for (int k = 0; k < p.radI[i]; k++) s_inst[o++] = p.first[p.siteI[i]] + k; }
-        s_offI[p.nI] = o;
+        for (int i = 0; i < p.nM; i++) { s_off[i] = o; for (int k = 0; k < p.radM[i]; k++) s_inst[o++] = p.first[p.siteM[i]] + k; }
+        for (int i = 0; i < p.nI; i++) { s_off[p.nM + i] = o; for (int k = 0; k < p.radI[i]; k++) s_inst[o++] = p.first[p.siteI[i]] + k; }
+        s_off[nS] = o;
         long long c = chunk;                                 // F digits of this chunk
         for (int j = 0; j < p.nF; j++) { s_aF[j] = p.firstOut[p.nO + j] + (int) (c % p.radOut[p.nO + j]); c /= p.radOut[p.nO + j]; }
+        o = 0;
+        int np = 0;
+        for (int j = 0; j < p.nO; j++) {
+            s_offO[j] = o;
+            for (int k = 0; k < p.radOut[j]; k++) { const int a = p.firstOut[j] + k; s_instO[o++] = a | (p.protons[a] << 16); }
+            for (int j2 = 0; j2 < j; j2++) s_pair[np++] = (uint16_t) (j | (j2 << 8));
+        }
+        s_offO[p.nO] = o;
     }
     for (int e = tid; e < p.Nb * kBlock; e += kBlock) bins[e] = 0.0;
     __syncthreads ();
@@ -200,13 +227,13 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
         uint16_t *row = s_idx + x * kMaxM;
         if (x < p.P_lo) {
             int y = x;
-            for (int i = 0; i < p.nLo; i++) { row[i] = (uint16_t) (s_offM[i] + y % p.radM[i]); y /= p.radM[i]; }
+            for (int i = 0; i < p.nLo; i++) { row[i] = (uint16_t) (s_off[i] + y % p.radM[i]); y /= p.radM[i]; }
         } else if (x < p.P_lo + p.P_hi) {
             int y = x - p.P_lo;
-            for (int i = p.nLo; i < p.nM; i++) { row[i - p.nLo] = (uint16_t) (s_offM[i] + y % p.radM[i]); y /= p.radM[i]; }
+            for (int i = p.nLo; i < p.nM; i++) { row[i - p.nLo] = (uint16_t) (s_off[i] + y % p.radM[i]); y /= p.radM[i]; }
         } else {
             int y = p.permI[x - p.P_lo - p.P_hi];                // sorted position -> I configuration
-            for (int i = 0; i < p.nI; i++) { row[i] = (uint16_t) (s_offI[i] + y % p.radI[i]); y /= p.radI[i]; }
+            for (int i = 0; i < p.nI; i++) { row[i] = (uint16_t) (s_off[p.nM + i] + y % p.radI[i]); y /= p.radI[i]; }
         }
     }
     // this thread's statics
@@ -218,12 +245,12 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
     const int m_lo = p.ms[tid], m_hi = p.ms[kBlock + tid], nMp = p.ms[2 * kBlock + tid];
     const double static_shift = *p.shift;
 
-    // per chunk: fields of the F sites on the M/I instances, F-F energy, F protons
-    for (int j = tid; j < nMI; j += kBlock) {
-        const int a = s_inst[j];
+    // per chunk: fields of the F sites on the M/I instances and on the O instances, F-F energy, F protons
+    for (int j = tid; j < nMI + L.nOinst; j += kBlock) {
+        const int a = j < nMI ? s_inst[j] : (s_instO[j - nMI] & 0xffff);
         double acc = p.gt[a];
         if (folded) for (int f = 0; f < p.nF; f++) acc += p.w[(size_t) a * ldw + s_aF[f]];
-        s_gF[j] = acc;
+        if (j < nMI) s_gF[j] = acc; else s_hF[j - nMI] = acc;
     }
     if (warp == kBlock / 32 - 1) {
         double e = 0.0;
@@ -244,37 +271,43 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
     auto digit = [&] (unsigned x, int o) -> int {
         return p.pow2O ? (int) ((x >> p.shiftO[o]) & (unsigned) (p.radOut[o] - 1)) : (int) ((x / p.strideO[o]) % (unsigned) p.radOut[o]);
     };
+    const int n_lo = kTB * p.P_lo, n_hi = kTB * p.P_hi, n_i = kTB * p.P_I;
+    const int n_terms = p.nO + L.nPairs;
 
     // ---- rounds of kTB tiles ---------------------------------------------------------------------------
     for (long long tile0 = 0; tile0 < p.P_O; tile0 += kTB) {
-        // (a) O-site fields on the M/I instances: one work item per (tile, instance)
-        for (int e = tid; e < kTB * nMI; e += kBlock) {
-            const int tb = e / nMI, j = e - tb * nMI;
-            double acc = s_gF[j];
-            if (folded) {
-                const unsigned x = (unsigned) (tile0 + tb);
-                const double *row = p.w + (size_t) s_inst[j] * ldw;
-                for (int o = 0; o < p.nO; o++) acc += row[p.firstOut[o] + digit (x, o)];
+        // (a) O-site fields on the instances of every M / I site, and the per-site minimum: one item per (tile, site)
+        for (int e = tid; e < kTB * nS; e += kBlock) {
+            const int tb = e / nS, s = e - tb * nS;
+            const unsigned x = (unsigned) (tile0 + tb);
+            double vmin = DBL_MAX;
+            for (int j = s_off[s]; j < s_off[s + 1]; j++) {
+                double acc = s_gF[j];
+                if (folded) {
+                    const double *row = p.w + (size_t) s_inst[j] * ldw;
+                    for (int o = 0; o < p.nO; o++) acc += row[p.firstOut[o] + digit (x, o)];
+                }
+                s_gOut[tb * nMI + j] = acc;
+                vmin = fmin (vmin, acc);
             }
-            s_gOut[tb * nMI + j] = acc;
+            s_smin[tb * nS + s] = vmin;
         }
-        // (b) O energy incl. O-O and O-F terms, O protons: the last kTB warps take one tile each, lanes over O sites
-        if (warp >= kBlock / 32 - kTB) {
-            const int tb = kBlock / 32 - 1 - warp;
+        // (b) O energy (intrinsic + O-F via hF, O-O pairs) and O protons: warp tb takes tile tb, lanes over terms
+        {
+            const int tb = warp;
+            const unsigned x = (unsigned) (tile0 + tb);
             double e = 0.0;
             int    np = 0;
             if (tile0 + tb < p.P_O) {
-                const unsigned x = (unsigned) (tile0 + tb);
-                for (int o = lane; o < p.nO; o += 32) {
-                    const int a = p.firstOut[o] + digit (x, o);
-                    const double *row = p.w + (size_t) a * ldw;
-                    double eo = p.gt[a];
-                    np += p.protons[a];
-                    if (folded) {
-                        for (int o2 = 0; o2 < o; o2++) eo += row[p.firstOut[o2] + digit (x, o2)];
-                        for (int f = 0; f < p.nF; f++) eo += row[s_aF[f]];
+                for (int t = lane; t < n_terms; t += 32) {
+                    if (t < p.nO) {
+                        const int k = s_offO[t] + digit (x, t);
+                        e += s_hF[k];
+                        np += s_instO[k] >> 16;
+                    } else if (folded) {
+                        const int pr = s_pair[t - p.nO], o = pr & 0xff, o2 = pr >> 8;
+                        e += p.w[(size_t) (p.firstOut[o] + digit (x, o)) * ldw + p.firstOut[o2] + digit (x, o2)];
                     }
-                    e += eo;
                 }
             }
             e = pce::warp_sum (e);
@@ -283,40 +316,35 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
         }
         __syncthreads ();
 
-        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the per-site minima,
-        // so every work item normalises its own entry.  Items are grouped by table (Lo | Hi | I | tile constant) so
-        // that a warp mostly runs one code path.
-        {
-            const int n_lo = kTB * p.P_lo, n_hi = kTB * p.P_hi, n_i = kTB * p.P_I;
-            for (int e = tid; e < n_lo + n_hi + n_i + kTB; e += kBlock) {
-                int kind, tb, x;
-                if (e < n_lo) { kind = 0; tb = e / p.P_lo; x = e - tb * p.P_lo; }
-                else if (e < n_lo + n_hi) { kind = 1; tb = (e - n_lo) / p.P_hi; x = (e - n_lo) - tb * p.P_hi; }
-                else if (e < n_lo + n_hi + n_i) { kind = 2; tb = (e - n_lo - n_hi) / p.P_I; x = (e - n_lo - n_hi) - tb * p.P_I; }
-                else { kind = 3; tb = e - n_lo - n_hi - n_i; x = 0; }
-                const double *g = s_gOut + tb * nMI;
-                double min_lo = 0.0, min_hi = 0.0, min_i = 0.0;
-                if (kind == 0 || kind == 3) for (int i = 0; i < p.nLo; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_lo += v; }
-                if (kind == 1 || kind == 3) for (int i = p.nLo; i < p.nM; i++) { double v = DBL_MAX; for (int j = s_offM[i]; j < s_offM[i + 1]; j++) v = fmin (v, g[j]); min_hi += v; }
-                if (kind == 2 || kind == 3) for (int i = 0; i < p.nI; i++) { double v = DBL_MAX; for (int j = s_offI[i]; j < s_offI[i + 1]; j++) v = fmin (v, g[j]); min_i += v; }
-                if (kind == 0) {
-                    const uint16_t *row = s_idx + x * kMaxM;
-                    double s = 0.0;
-                    for (int i = 0; i < p.nLo; i++) s += g[row[i]];
-                    s_eLo[tb * p.P_lo + x] = exp (-p.beta * (s - min_lo));
-                } else if (kind == 1) {
-                    const uint16_t *row = s_idx + (p.P_lo + x) * kMaxM;
-                    double s = 0.0;
-                    for (int i = 0; i < p.nM - p.nLo; i++) s += g[row[i]];
-                    s_eHi[tb * p.P_hi + x] = exp (-p.beta * (s - min_hi));
-                } else if (kind == 2) {
-                    const uint16_t *row = s_idx + (p.P_lo + p.P_hi + x) * kMaxM;
-                    double s = 0.0;
-                    for (int i = 0; i < p.nI; i++) s += g[row[i]];
-                    s_eI[tb * p.P_I + x] = exp (-p.beta * (s - min_i));
-                } else {
-                    s_cExp[tb] = (tile0 + tb < p.P_O) ? exp (-p.beta * ((s_cOut[tb] + min_lo + min_hi + min_i) - p.gref)) : 0.0;
-                }
+        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the per-site minima.
+        // Items are grouped by table (Lo | Hi | I | tile constant) so that a warp mostly runs one code path.
+        for (int e = tid; e < n_lo + n_hi + n_i + kTB; e += kBlock) {
+            if (e < n_lo) {
+                const int tb = e / p.P_lo, x = e - tb * p.P_lo;
+                const double *g = s_gOut + tb * nMI, *mn = s_smin + tb * nS;
+                const uint16_t *row = s_idx + x * kMaxM;
+                double s = 0.0;
+                for (int i = 0; i < p.nLo; i++) s += g[row[i]] - mn[i];
+                s_eLo[e] = exp (-p.beta * s);
+            } else if (e < n_lo + n_hi) {
+                const int f = e - n_lo, tb = f / p.P_hi, x = f - tb * p.P_hi;
+                const double *g = s_gOut + tb * nMI, *mn = s_smin + tb * nS + p.nLo;
+                const uint16_t *row = s_idx + (p.P_lo + x) * kMaxM;
+                double s = 0.0;
+                for (int i = 0; i < p.nM - p.nLo; i++) s += g[row[i]] - mn[i];
+                s_eHi[f] = exp (-p.beta * s);
+            } else if (e < n_lo + n_hi + n_i) {
+                const int f = e - n_lo - n_hi, tb = f / p.P_I, x = f - tb * p.P_I;
+                const double *g = s_gOut + tb * nMI, *mn = s_smin + tb * nS + p.nM;
+                const uint16_t *row = s_idx + (p.P_lo + p.P_hi + x) * kMaxM;
+                double s = 0.0;
+                for (int i = 0; i < p.nI; i++) s += g[row[i]] - mn[i];
+                s_eI[tb * 16 + x] = exp (-p.beta * s);
+            } else {
+                const int tb = e - n_lo - n_hi - n_i;
+                double s = s_cOut[tb];
+                for (int i = 0; i < nS; i++) s += s_smin[tb * nS + i];
+                s_cExp[tb] = (tile0 + tb < p.P_O) ? exp (-p.beta * (s - p.gref)) : 0.0;
             }
         }
         __syncthreads ();
@@ -327,14 +355,25 @@ __global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
 #pragma unroll 2
             for (int tb = 0; tb < kTB; tb++) {
                 const double c_tile = s_cExp[tb] * s_eLo[tb * p.P_lo + m_lo] * s_eHi[tb * p.P_hi + m_hi] * eMM;
-                double *mybins = bins + (s_nOut[tb] + nMp) * kBlock + tid;
-                const double *eI = s_eI + tb * p.P_I;
-                double acc = 0.0;
+                double *mybins = bins + (s_nOut[tb] + nMp + p.binI[0]) * kBlock + tid;
+                const double *eI = s_eI + tb * 16;
+                if (CANON >= 0) {
+                    constexpr unsigned mask = canon_flush_mask (CANON >= 0 ? CANON : 0);
+                    double acc = 0.0;
+                    int    k = 0;
 #pragma unroll
-                for (int i = 0; i < kIStates; i++) {
-                    if (i < p.P_I) {
+                    for (int i = 0; i < (1 << (CANON >= 0 ? CANON : 0)); i++) {
                         acc += eI[i] * xMI[i];
-                        if ((p.flushI >> i) & 1u) { mybins[p.binI[i] * kBlock] += c_tile * acc; acc = 0.0; }
+                        if ((mask >> i) & 1u) { mybins[k * kBlock] += c_tile * acc; acc = 0.0; k++; }
+                    }
+                } else {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < kIStates; i++) {
+                        if (i < p.P_I) {
+                            acc += eI[i] * xMI[i];
+                            if ((p.flushI >> i) & 1u) { mybins[(p.binI[i] - p.binI[0]) * kBlock] += c_tile * acc; acc = 0.0; }
+                        }
                     }
                 }
             }
@@ -557,14 +596,21 @@ int make_plan (const pce_model *m, const double *ph, int nph, int unfolded, Plan
                 plo *= radix (m, run.M[i]); run.nLo = (int) i + 1;
             }
         }
-        // I: covered sites preferred (their marginals are not needed from this run)
+        // I: canonical sites (binary, instances one proton apart) so that the kernel's compile-time bin structure applies;
+        // covered ones preferred (their marginals are not needed from this run).  Fallback: any sites (generic kernel).
         long long pi = 1;
+        auto canonical = [&] (int s) { return radix (m, s) == 2 && std::abs (m->protons[m->first[s]] - m->protons[m->first[s] + 1]) == 1; };
         for (int pass = 0; pass < 2; pass++)
             for (int s = 0; s < m->nsites && (int) run.I.size () < kMaxI; s++) {
-                if (used[s] || (pass == 0 && !covered[s])) continue;
-                // keep at least the uncovered sites that fit in F out of I when possible
-                if (pi * radix (m, s) <= kIStates) { run.I.push_back (s); used[s] = 1; pi *= radix (m, s); }
+                if (used[s] || !canonical (s) || (pass == 0 && !covered[s])) continue;
+                if (pi * 2 <= kIStates) { run.I.push_back (s); used[s] = 1; pi *= 2; }
             }
+        if (run.I.empty ())
+            for (int pass = 0; pass < 2; pass++)
+                for (int s = 0; s < m->nsites && (int) run.I.size () < kMaxI; s++) {
+                    if (used[s] || (pass == 0 && !covered[s])) continue;
+                    if (pi * radix (m, s) <= kIStates) { run.I.push_back (s); used[s] = 1; pi *= radix (m, s); }
+                }
         // outer sites: covered ones become the low (O) digits, uncovered ones the high (F) digits
         std::vector<int> outer;
         for (int s = 0; s < m->nsites; s++) if (!used[s] && covered[s]) outer.push_back (s);
@@ -576,6 +622,7 @@ int make_plan (const pce_model *m, const double *ph, int nph, int unfolded, Plan
             if (pf * radix (m, outer[j]) > kMaxChunks) break;
             pf *= radix (m, outer[j]); nF++;
         }
+        if ((int) outer.size () - nF > kMaxO) return fail (PCE_ERR_LIMIT, "too many sites for analytic enumeration");
         const int nO = (int) outer.size () - nF;
         run.O.assign (outer.begin (), outer.begin () + nO);
         run.F.assign (outer.begin () + nO, outer.end ());
@@ -639,6 +686,14 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
                 shift += (unsigned) bits;
             }
             p.nMI = nMI;
+            p.nOinst = 0;
+            for (int j = 0; j < p.nO; j++) p.nOinst += p.radOut[j];
+            if (p.nO > kMaxO) return fail (PCE_ERR_LIMIT, "too many sites for analytic enumeration");
+            p.canon = p.nI;
+            for (int i = 0; i < p.nI; i++) {
+                const int f = m->first[p.siteI[i]];
+                if (p.radI[i] != 2 || std::abs (m->protons[f] - m->protons[f + 1]) != 1) p.canon = -1;
+            }
             for (int j = 0; j < p.nO + p.nF; j++) p.firstOut[j] = (int16_t) m->first[p.siteOut[j]];
             // I configurations sorted by proton count (stable)
             std::vector<std::pair<int, int>> order;
@@ -660,7 +715,7 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         const long long c0 = pf * shard / nshards, c1 = pf * (shard + 1) / nshards;
         p.chunk_begin = c0; p.nchunks = c1 - c0;
         if (p.nchunks <= 0) continue;
-        const EnumLayout layout (plan.Nb, nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM);
+        const EnumLayout layout (plan.Nb, nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM, p.nI, p.nO, p.nOinst);
         const size_t smem = layout.total;
         size_t limit = 0;
         {
@@ -681,8 +736,19 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         p.T = d_T.ptr; p.xs = d_xs.ptr; p.ms = d_ms.ptr; p.shift = d_xs.ptr + (size_t) (1 + kIStates) * kBlock;
         k_enum_static<<<1, kBlock, 0, m->stream>>> (p);
         PCE_CUDA (cudaGetLastError ());
-        PCE_CUDA (cudaFuncSetAttribute (k_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        k_enum<<<(unsigned) p.nchunks, kBlock, smem, m->stream>>> (p);
+        {
+            void (*kernel) (const EnumParams) = k_enum<-1>;
+            switch (p.canon) {
+                case 0: kernel = k_enum<0>; break;
+                case 1: kernel = k_enum<1>; break;
+                case 2: kernel = k_enum<2>; break;
+                case 3: kernel = k_enum<3>; break;
+                case 4: kernel = k_enum<4>; break;
+                default: break;
+            }
+            PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            kernel<<<(unsigned) p.nchunks, kBlock, smem, m->stream>>> (p);
+        }
         PCE_CUDA (cudaGetLastError ());
         k_reduce_rows<<<dim3 ((width + 127) / 128, nseg), 128, 0, m->stream>>> (d_T.ptr, p.nchunks, width, per_segment, d_seg.ptr);
         PCE_CUDA (cudaGetLastError ());
