@@ -76,7 +76,7 @@ struct ThreadLayout {
         size_t o = 0;
         off_w = o;      o += w_in_smem ? (size_t) ninst * ldws * 8 : 0;
         off_h = o;      o += (size_t) block * hstride * 8;
-        off_counts = o; o += (size_t) kslots * ninst * 8;
+        off_counts = o; o += (size_t) kslots * ninst * 4;     // u32: block * nprod < 2^32 is checked on the host
         off_since = o;  o += (size_t) nsites * block * 4;
         off_site = o;   o += (size_t) nsites * 4;
         off_pair = o;   o += (size_t) (npairs > 0 ? npairs : 1) * 4;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, W_SMEM ? 1 : 0, p.nchains, p.nph);
     double             *s_w      = (double *) (smem + L.off_w);
     double             *s_h      = (double *) (smem + L.off_h);
-    unsigned long long *s_counts = (unsigned long long *) (smem + L.off_counts);
+    uint32_t           *s_counts = (uint32_t *) (smem + L.off_counts);
     uint32_t           *s_since  = (uint32_t *) (smem + L.off_since);
     uint32_t           *s_site   = (uint32_t *) (smem + L.off_site);      // first | ninst << 16
     uint32_t           *s_pair   = (uint32_t *) (smem + L.off_pair);      // site a | site b << 16
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     const int q_base = (int) (g0 / p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
-    unsigned long long *my_counts = s_counts + (size_t) (q - q_base) * ninst;
+    uint32_t *my_counts = s_counts + (size_t) (q - q_base) * ninst;
     uint8_t  *my_state = s_state + tid;
     uint32_t *my_since = s_since + tid;
     long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
         for (int e = tid; e < ninst * ninst; e += B) s_w[(e / ninst) * L.ldws + (e % ninst)] = p.wb[(size_t) (e / ninst) * p.ldw + (e % ninst)];
     const double *wbase = W_SMEM ? s_w : p.wb;
     const int     wld   = W_SMEM ? L.ldws : p.ldw;
-    for (int k = tid; k < L.kslots * ninst; k += B) s_counts[k] = 0ull;
+    for (int k = tid; k < L.kslots * ninst; k += B) s_counts[k] = 0u;
     for (int i = tid; i < nsites; i += B) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
     for (int i = tid; i < p.npairs; i += B) s_pair[i] = (uint32_t) p.pair_a[i] | ((uint32_t) p.pair_b[i] << 16);
 
@@ -288,13 +288,13 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
                 grt = __dadd_rn (grt, x);
                 const uint32_t since_a = my_since[sa * B];
                 if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
-                else if (tp != since_a) atomicAdd (&my_counts[oa], (unsigned long long) (tp - since_a));
+                else if (tp != since_a) atomicAdd (&my_counts[oa], tp - since_a);
                 my_since[sa * B] = tp;
                 my_state[sa * B] = (uint8_t) ia;
                 if (dbl) {
                     const uint32_t since_b = my_since[sb * B];
                     if (PER_CHAIN) my_chain_counts[ob] += (long long) (tp - since_b);
-                    else if (tp != since_b) atomicAdd (&my_counts[ob], (unsigned long long) (tp - since_b));
+                    else if (tp != since_b) atomicAdd (&my_counts[ob], tp - since_b);
                     my_since[sb * B] = tp;
                     my_state[sb * B] = (uint8_t) ib;
                     if (production) c_facc++;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
             const int      a = my_state[i * B];
             const uint32_t d = (uint32_t) p.nprod - my_since[i * B];
             if (PER_CHAIN) my_chain_counts[a] += (long long) d;
-            else if (d) atomicAdd (&my_counts[a], (unsigned long long) d);
+            else if (d) atomicAdd (&my_counts[a], d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
         if (p.counts != nullptr)
             for (int k = tid; k < L.kslots * ninst; k += B) {
                 const int qq = q_base + k / ninst;
-                if (qq < p.nph && s_counts[k]) atomicAdd (&p.counts[(size_t) qq * ninst + (k % ninst)], s_counts[k]);
+                if (qq < p.nph && s_counts[k]) atomicAdd (&p.counts[(size_t) qq * ninst + (k % ninst)], (unsigned long long) s_counts[k]);
             }
         // counters and energy sums: one atomic per thread (pH values may differ within a warp)
         if (active) {
@@ -596,6 +596,7 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
             if (forced_block && block != forced_block) continue;
             ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in, mc->nchains, nph);
             if (L.total > limit) continue;
+            if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
             int ctas = (int) std::min<size_t> (per_sm / (L.total + 1024), (size_t) (2048 / block));
             ctas = std::min (ctas, 32);
             const int warps = ctas * block / 32;

@@ -1,0 +1,143 @@
+"""Edge cases of the hot path through the C ABI: ragged instance counts, single-instance sites, no pairs, tiny and
+degenerate models, chain ensembles that straddle pH values inside one block.  Each case is checked against the oracle."""
+
+import numpy as np
+import pytest
+
+import pcetk_b200 as P
+from pcetk_b200.formats import ModelRecord
+from pcetk_b200.synthetic import synth_a, synth_m
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(p, ref):
+    mask = ref > 1e-250
+    return np.abs(p[mask] / ref[mask] - 1.0).max()
+
+
+def ragged_model(nsites=11, seed=3, tautomers=True):
+    """2/3/5-instance sites from the synth-M generator; optionally make some instances tautomers (equal protons)."""
+    rec = synth_m(nsites, seed=seed)
+    if tautomers:
+        protons = rec.protons.copy()
+        for s in range(rec.nsites):
+            if rec.site_last[s] - rec.site_first[s] + 1 == 3:
+                protons[rec.site_first[s] + 1] = protons[rec.site_first[s]]     # two forms with the same proton count
+        rec = ModelRecord(rec.name + "t", rec.site_first, rec.site_last, protons, rec.gmodel, rec.gintr * 0.2, rec.interactions * 0.2,
+                          rec.temperature, rec.site_labels, rec.inst_labels)
+    return rec
+
+
+def single_instance_model():
+    """A site with one instance in the middle of the model (the reference's MC would spin forever on it)."""
+    base = synth_a(6)
+    first = np.array([0, 2, 4, 5, 7, 9], dtype=np.int32)
+    last = np.array([1, 3, 4, 6, 8, 10], dtype=np.int32)
+    keep = [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11]
+    w = base.interactions[np.ix_(keep, keep)]
+    return ModelRecord("single", first, last, base.protons[keep], base.gmodel[keep], base.gintr[keep], w, 300.0,
+                       [("SYN", "SIT", k + 1) for k in range(6)], ["i%d" % k for k in range(11)])
+
+
+@pytest.mark.parametrize("nsites,tautomers", [(11, True), (11, False), (7, True), (1, False), (2, False)])
+def test_analytic_ragged_models(port, nsites, tautomers):
+    rec = ragged_model(nsites, tautomers=tautomers)
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    grid = [0.0, 4.5, 7.0, 9.5, 14.0]
+    p = model.CalculateProbabilitiesBatch(grid)
+    for row, ph in zip(p, grid):
+        ref, _z, _g = port.analytic(rec, wsym, ph)
+        assert rel_err(row, ref) <= 1e-12
+    pu = model.energyModel.CalculateProbabilitiesAnalyticallyBatch(grid, unfolded=True)
+    ref, _z, _g = port.analytic(rec, wsym, 7.0, unfolded=True)
+    assert rel_err(pu[2], ref) <= 1e-12
+
+
+def test_analytic_single_instance_site(port):
+    rec = single_instance_model()
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    p = model.CalculateProbabilitiesBatch([3.0, 7.0])
+    for row, ph in zip(p, [3.0, 7.0]):
+        ref, _z, _g = port.analytic(rec, wsym, ph)
+        assert rel_err(row, ref) <= 1e-12
+    assert abs(p[0, 4] - 1.0) < 1e-14                      # the lone instance is always occupied
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_mc_single_instance_site_and_ragged(port, kernel):
+    for rec in (single_instance_model(), ragged_model(9)):
+        model = P.MEADModel(rec, log=None)
+        wsym = port.symmetrize(rec.interactions)
+        sampler = P.MCModelDefault(nequil=20, nprod=300, randomSeed=31337, nchains=37, kernel=kernel, doubleFlip=0.5)
+        model.DefineMCModel(sampler, log=None)
+        pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+        out = sampler.RunChains([5.0, 8.0])
+        for q, ph in enumerate([5.0, 8.0]):
+            for chain in (0, 17, 36):
+                spec = port.mc_philox_chain(rec, wsym, pairs, 20, 300, sampler.seed, chain, q, ph)
+                assert np.array_equal(out["counts"][q, chain], spec["counts"])
+                assert out["counters"][q, chain].tolist() == spec["counters"].tolist()
+        counts, _c, _e = sampler.RunCounts([5.0, 8.0])
+        assert np.array_equal(counts, out["counts"].sum(axis=1))
+
+
+def test_mc_no_pairs_and_all_pairs(port):
+    rec = ragged_model(8)
+    wsym = port.symmetrize(rec.interactions)
+    for limit, expect in ((1e9, 0), (0.0, 28)):
+        model = P.MEADModel(rec, log=None)
+        sampler = P.MCModelDefault(nequil=10, nprod=200, randomSeed=5, nchains=33, doubleFlip=limit)
+        model.DefineMCModel(sampler, log=None)
+        assert sampler.npairs == expect
+        pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+        out = sampler.RunChains([6.0])
+        spec = port.mc_philox_chain(rec, wsym, pairs, 10, 200, sampler.seed, 32, 0, 6.0)
+        assert np.array_equal(out["counts"][0, 32], spec["counts"])
+
+
+def test_mc_few_chains_many_ph_in_one_block(port):
+    """3 chains x 41 pH values: every block of the chain-major grid straddles many pH values."""
+    rec = ragged_model(9)
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    sampler = P.MCModelDefault(nequil=10, nprod=150, randomSeed=77, nchains=3)
+    model.DefineMCModel(sampler, log=None)
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    grid = np.arange(0.0, 20.5, 0.5)
+    counts, counters, esum = sampler.RunCounts(grid)
+    for q in (0, 13, 40):
+        expect = sum(port.mc_philox_chain(rec, wsym, pairs, 10, 150, sampler.seed, c, q, float(grid[q]))["counts"] for c in range(3))
+        assert np.array_equal(counts[q], expect)
+    assert (counts.sum(axis=1) == 3 * 150 * rec.nsites).all()
+    assert (counters[:, 0] + counters[:, 2] == 3 * 150 * (rec.nsites + sampler.npairs)).all()
+
+
+def test_energy_large_model_bit_exact(port):
+    rec = synth_m(60)
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    rng = np.random.default_rng(9)
+    states = np.stack([[rng.integers(f, l + 1) for f, l in zip(rec.site_first, rec.site_last)] for _ in range(300)]).astype(np.int32)
+    energies = model.energyModel.CalculateMicrostateEnergies(states, pH=[1.0, 13.0])
+    for s in (0, 150, 299):
+        assert energies[s, 0] == port.energy(rec, wsym, states[s], 1.0)
+        assert energies[s, 1] == port.energy(rec, wsym, states[s], 13.0)
+
+
+def test_warp_kernel_on_the_1000_site_model_matches_specification(port):
+    """BASELINE config 5 shape (1000 sites / 3000 instances, W = 72 MB): two short chains, count for count."""
+    rec = synth_m(1000)
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    sampler = P.MCModelDefault(nequil=1, nprod=3, randomSeed=2024, nchains=2)
+    model.DefineMCModel(sampler, log=None)
+    assert sampler.LaunchPlan(1)["kernel"] == 2
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    out = sampler.RunChains([7.0])
+    for chain in (0, 1):
+        spec = port.mc_philox_chain(rec, wsym, pairs, 1, 3, sampler.seed, chain, 0, 7.0)
+        assert np.array_equal(out["counts"][0, chain], spec["counts"])
+        assert np.array_equal(out["state"][0, chain], spec["state"])
