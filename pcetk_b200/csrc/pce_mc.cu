@@ -35,6 +35,7 @@ struct pce_mc {
     std::vector<int32_t> pair_a, pair_b;
     std::vector<double>  pair_wmax;
     pce::DeviceBuffer<int32_t> d_pair_a, d_pair_b;
+    pce::DeviceBuffer<uint32_t> d_pair_packed;
     pce::DeviceBuffer<double>  d_ph, d_esum;
     pce::DeviceBuffer<unsigned long long> d_counts;
     pce::DeviceBuffer<long long> d_counters;
@@ -46,6 +47,7 @@ namespace {
 struct McParams {
     int nsites, ninst, npairs, ldw;
     const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
+    const uint32_t *pair_packed;            // site a | site b << 16
     const double  *gintr, *w, *wb, *ph;      // wb = beta * W (units of RT)
     int       nph, ph_index_offset, nchains, nequil, nprod;
     long long chain_offset;
@@ -108,6 +110,15 @@ __device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
         if (unsure) accept = metropolis_exact (x, w1);
     }
     return accept;
+}
+
+__device__ __forceinline__ double lds_f64 (uint32_t address) {
+    double v;
+    asm volatile ("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(address) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64 (uint32_t address, double v) {
+    asm volatile ("st.shared.f64 [%0], %1;" : : "r"(address), "d"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -211,6 +222,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
 
     // one trial: proposal from (w0), Metropolis with (w1), cooperative application of accepted moves
     const bool has_pairs = p.npairs > 0;
+    const uint32_t h_addr = (uint32_t) __cvta_generic_to_shared (s_h), w_addr = (uint32_t) __cvta_generic_to_shared (s_w);
     auto trial = [&] (const uint32_t w0, const uint32_t w1) {
         const unsigned long long prod = (unsigned long long) w0 * nmoves;
         const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
@@ -247,39 +259,58 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
         }
         const bool accept = valid && metropolis (x, w1);
 
-        // apply accepted moves: one accepting chain at a time, all 32 lanes on its field vector
+        // apply accepted moves: two accepting chains per round, one per half-warp; each lane updates entries
+        // k = sub, sub+16, sub+32, ... of its chain's field vector (hb += wb[new] - wb[old] for one or two sites)
         unsigned pending = __ballot_sync (0xffffffffu, accept);
         if (pending) {
             const unsigned dblmask = __ballot_sync (0xffffffffu, accept && dbl);
             const uint32_t packed = (uint32_t) ia | ((uint32_t) oa << 8) | ((uint32_t) ib << 16) | ((uint32_t) ob << 24);
+            // small field vectors: two chains per round (16 lanes each); larger ones: one chain per round (32 lanes)
+            const int  lpc  = ninst > 64 ? 32 : 16;
+            const int  half = lpc == 16 ? lane >> 4 : 0, sub = lane & (lpc - 1);
             do {
-                const int src = __ffs (pending) - 1;
+                const int s0 = __ffs (pending) - 1;
                 pending &= pending - 1;
-                const uint32_t y = __shfl_sync (0xffffffffu, packed, src);
-                double       *hc  = s_h + (warp_base + src) * L.hstride;
-                const double *rna = wbase + (int) (y & 255u) * wld, *roa = wbase + (int) ((y >> 8) & 255u) * wld;
-                if ((dblmask >> src) & 1u) {
-                    const double *rnb = wbase + (int) ((y >> 16) & 255u) * wld, *rob = wbase + (int) (y >> 24) * wld;
+                int s1 = -1;
+                if (lpc == 16 && pending) { s1 = __ffs (pending) - 1; pending &= pending - 1; }
+                const int  src  = half ? s1 : s0;
+                const bool work = src >= 0;
+                const uint32_t y = __shfl_sync (0xffffffffu, packed, src & 31);
+                if (work) {
+                    const bool two_sites = (dblmask >> src) & 1u;
+                    const int na_ = (int) (y & 255u), oa_ = (int) ((y >> 8) & 255u), nb_ = (int) ((y >> 16) & 255u), ob_ = (int) (y >> 24);
+                    if (W_SMEM) {
+                        const uint32_t hrow = h_addr + (uint32_t) ((warp_base + src) * L.hstride) * 8u;
+                        const uint32_t ra = w_addr + (uint32_t) (na_ * wld) * 8u, ro = w_addr + (uint32_t) (oa_ * wld) * 8u;
+                        const uint32_t rb = w_addr + (uint32_t) (nb_ * wld) * 8u, rp = w_addr + (uint32_t) (ob_ * wld) * 8u;
 #pragma unroll 1
-                    for (int k = lane; k < ninst; k += 64) {
-                        const int  k2 = k + 32;
-                        const bool two = k2 < ninst;
-                        const double h0 = hc[k], a0 = rna[k], b0 = roa[k], c0 = rnb[k], d0 = rob[k];
-                        double h1 = 0.0, a1 = 0.0, b1 = 0.0, c1 = 0.0, d1 = 0.0;
-                        if (two) { h1 = hc[k2]; a1 = rna[k2]; b1 = roa[k2]; c1 = rnb[k2]; d1 = rob[k2]; }
-                        hc[k] = __dadd_rn (__dadd_rn (h0, __dsub_rn (a0, b0)), __dsub_rn (c0, d0));
-                        if (two) hc[k2] = __dadd_rn (__dadd_rn (h1, __dsub_rn (a1, b1)), __dsub_rn (c1, d1));
-                    }
-                } else {
-#pragma unroll 1
-                    for (int k = lane; k < ninst; k += 64) {
-                        const int  k2 = k + 32;
-                        const bool two = k2 < ninst;
-                        const double h0 = hc[k], a0 = rna[k], b0 = roa[k];
-                        double h1 = 0.0, a1 = 0.0, b1 = 0.0;
-                        if (two) { h1 = hc[k2]; a1 = rna[k2]; b1 = roa[k2]; }
-                        hc[k] = __dadd_rn (h0, __dsub_rn (a0, b0));
-                        if (two) hc[k2] = __dadd_rn (h1, __dsub_rn (a1, b1));
+                        for (int k = sub; k < ninst; k += 3 * lpc) {
+                            const uint32_t o0 = (uint32_t) k * 8u, o1 = o0 + (uint32_t) lpc * 8u, o2 = o1 + (uint32_t) lpc * 8u;
+                            const bool p1 = k + lpc < ninst, p2 = k + 2 * lpc < ninst;
+                            double h0 = lds_f64 (hrow + o0), a0 = lds_f64 (ra + o0), b0 = lds_f64 (ro + o0);
+                            double h1 = 0.0, a1 = 0.0, b1 = 0.0, h2 = 0.0, a2 = 0.0, b2 = 0.0;
+                            if (p1) { h1 = lds_f64 (hrow + o1); a1 = lds_f64 (ra + o1); b1 = lds_f64 (ro + o1); }
+                            if (p2) { h2 = lds_f64 (hrow + o2); a2 = lds_f64 (ra + o2); b2 = lds_f64 (ro + o2); }
+                            h0 = __dadd_rn (h0, __dsub_rn (a0, b0)); h1 = __dadd_rn (h1, __dsub_rn (a1, b1)); h2 = __dadd_rn (h2, __dsub_rn (a2, b2));
+                            if (two_sites) {
+                                h0 = __dadd_rn (h0, __dsub_rn (lds_f64 (rb + o0), lds_f64 (rp + o0)));
+                                if (p1) h1 = __dadd_rn (h1, __dsub_rn (lds_f64 (rb + o1), lds_f64 (rp + o1)));
+                                if (p2) h2 = __dadd_rn (h2, __dsub_rn (lds_f64 (rb + o2), lds_f64 (rp + o2)));
+                            }
+                            sts_f64 (hrow + o0, h0);
+                            if (p1) sts_f64 (hrow + o1, h1);
+                            if (p2) sts_f64 (hrow + o2, h2);
+                        }
+                    } else {
+                        double       *hc  = s_h + (warp_base + src) * L.hstride;
+                        const double *rna = p.wb + (size_t) na_ * wld, *roa = p.wb + (size_t) oa_ * wld;
+                        const double *rnb = p.wb + (size_t) nb_ * wld, *rob = p.wb + (size_t) ob_ * wld;
+#pragma unroll 2
+                        for (int k = sub; k < ninst; k += lpc) {
+                            double v = __dadd_rn (hc[k], __dsub_rn (__ldg (rna + k), __ldg (roa + k)));
+                            if (two_sites) v = __dadd_rn (v, __dsub_rn (__ldg (rnb + k), __ldg (rob + k)));
+                            hc[k] = v;
+                        }
                     }
                 }
             } while (pending);
@@ -370,10 +401,12 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
 // Shared memory per warp: hb[ldh] doubles | since[nsites] u32 | state[nsites] u16
 // ---------------------------------------------------------------------------------------------------
 struct WarpLayout {
-    size_t off_h, off_since, off_state, per_warp;
+    size_t off_site, off_h, off_since, off_state, per_warp, shared_bytes;
     int    ldh;
     __host__ __device__ WarpLayout (int nsites, int ninst) {
         ldh = (ninst + 3) & ~3;
+        shared_bytes = ((size_t) nsites * 4 + 15) & ~(size_t) 15;     // packed site table, one copy per CTA
+        off_site = 0;
         size_t o = 0;
         off_h = o;     o += (size_t) ldh * 8;
         off_since = o; o += (size_t) nsites * 4;
@@ -382,19 +415,22 @@ struct WarpLayout {
     }
 };
 
-template <bool PER_CHAIN>
-__global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
+template <bool PER_CHAIN, int MIN_CTAS>
+__global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const WarpLayout L (p.nsites, p.ninst);
-    unsigned char *base   = smem + (size_t) wib * L.per_warp;
+    uint32_t      *s_site = (uint32_t *) smem;                        // first | ninst << 16 per site (CTA-wide)
+    unsigned char *base   = smem + L.shared_bytes + (size_t) wib * L.per_warp;
     double        *h      = (double *) (base + L.off_h);
     uint32_t      *since  = (uint32_t *) (base + L.off_since);
     uint16_t      *state  = (uint16_t *) (base + L.off_state);
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
+    for (int i = threadIdx.x; i < nsites; i += blockDim.x) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
+    __syncthreads ();
     const long long gidx = (long long) blockIdx.x * warps + wib;       // chain-major linear (pH, chain) index
-    if (gidx >= (long long) p.nph * p.nchains) return;              // whole warp leaves together
+    if (gidx >= (long long) p.nph * p.nchains) return;              // whole warp leaves together (no later block barrier)
     const int q     = (int) (gidx / p.nchains);
     const int local = (int) (gidx % p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
@@ -450,32 +486,40 @@ __global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
     unsigned long long *counts = PER_CHAIN ? (unsigned long long *) (p.chain_counts + ((size_t) q * p.nchains + local) * ninst)
                                            : p.counts + (size_t) q * ninst;
 
-    auto trial = [&] (const uint32_t w0, const uint32_t w1) {
+    // proposal target of a random word: site (single move) or packed pair, fetched one Philox block ahead of its use
+    // because it does not depend on the chain's state (hides the L2 latency of the pair table)
+    auto target = [&] (const uint32_t w0) -> uint32_t {
         const uint32_t idx = __umulhi (w0, nmoves);
-        const uint32_t lo  = w0 * nmoves;
+        return idx >= (uint32_t) nsites ? __ldg (p.pair_packed + (idx - nsites)) : (idx | (idx << 16));
+    };
+
+    auto trial = [&] (const uint32_t w0, const uint32_t w1, const uint32_t pr) {
+        const unsigned long long prod = (unsigned long long) w0 * nmoves;
+        const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
         const bool     dbl = idx >= (uint32_t) nsites;
-        int sa, sb = 0;
-        if (dbl) { sa = __ldg (p.pair_a + (idx - nsites)); sb = __ldg (p.pair_b + (idx - nsites)); } else { sa = (int) idx; }
-        const int na = __ldg (p.nsi + sa), oa = state[sa];
+        const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
+        const uint32_t ia_info = s_site[sa];
+        const int na = (int) (ia_info >> 16), oa = state[sa];
         bool valid = na >= 2;
-        const uint32_t ka  = __umulhi (lo, (uint32_t) (na - 1));
-        int ia = __ldg (p.first + sa) + (int) ka;
+        const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
+        int ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
         if (ia >= oa) ia++;
         if (!valid) ia = oa;
         double x = __dsub_rn (h[ia], h[oa]);
         int ib = 0, ob = 0;
         if (dbl) {
-            const uint32_t lo2 = lo * (uint32_t) (na - 1);
-            const int nb = __ldg (p.nsi + sb);
+            const uint32_t ib_info = s_site[sb];
+            const int nb = (int) (ib_info >> 16);
             ob = state[sb];
             if (nb < 2) valid = false;
-            const uint32_t kb = __umulhi (lo2, (uint32_t) (nb - 1));
-            ib = __ldg (p.first + sb) + (int) kb;
+            const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
+            ib = (int) (ib_info & 0xffffu) + (int) kb;
             if (ib >= ob) ib++;
             if (!valid) { ib = ob; ia = oa; }
             const double *ra = p.wb + (size_t) ia * ldw, *ro = p.wb + (size_t) oa * ldw;
-            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (__ldg (ra + ib), __ldg (ra + ob)), __ldg (ro + ib)), __ldg (ro + ob));
-            x = __dadd_rn (__dadd_rn (x, __dsub_rn (h[ib], h[ob])), cross);
+            const double c0 = __ldg (ra + ib), c1 = __ldg (ra + ob), c2 = __ldg (ro + ib), c3 = __ldg (ro + ob);   // 4 loads in flight
+            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (c0, c1), c2), c3);
+            x = __dadd_rn (__dadd_rn (__dsub_rn (h[ia], h[oa]), __dsub_rn (h[ib], h[ob])), cross);
             if (production) c_flips++;
         }
         const bool accept = valid && metropolis (x, w1);      // warp-uniform
@@ -486,7 +530,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
             double2       *h2  = (double2 *) h;
             const int      n2  = L.ldh >> 1;
             if (!dbl) {
-#pragma unroll 4
+#pragma unroll 8
                 for (int k = lane; k < n2; k += 32) {
                     const double2 a = __ldg (rna + k), b = __ldg (roa + k);
                     double2 v = h2[k];
@@ -495,7 +539,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
                     h2[k] = v;
                 }
             } else {
-#pragma unroll 2
+#pragma unroll 4
                 for (int k = lane; k < n2; k += 32) {
                     const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
                     double2 v = h2[k];
@@ -533,14 +577,17 @@ __global__ void __launch_bounds__ (512, 1) k_mc_warp (const McParams p) {
     };
 
     pce::Philox4 rnext = pce::philox4x32_10 (0u, 0u, chain, phidx, p.k0, p.k1);
+    uint32_t tnext0 = target (rnext.x), tnext1 = target (rnext.z);
     for (unsigned long long b = 0; 2ull * b < ntrials; b++) {
         const pce::Philox4 r = rnext;
+        const uint32_t t0 = tnext0, t1 = tnext1;
         const unsigned long long bn = b + 1;
         rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);
+        tnext0 = target (rnext.x); tnext1 = target (rnext.z);
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {          // one copy of the trial body in the instruction cache
             if (half && 2ull * b + 1ull >= ntrials) break;
-            trial (half ? r.z : r.x, half ? r.w : r.y);
+            trial (half ? r.z : r.x, half ? r.w : r.y, half ? t1 : t0);
         }
     }
 
@@ -611,13 +658,13 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
 
 bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
     const pce_model *m = mc->model;
-    if (m->ninst > 65535) return false;
+    if (m->ninst > 65535 || m->nsites > 65535) return false;
     WarpLayout L (m->nsites, m->ninst);
-    if (L.per_warp > limit) return false;
-    int warps = (int) std::min<size_t> (limit / L.per_warp, 16);   // up to 16 warps per block
-    // several blocks per SM when the per-warp footprint is small
-    plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = (size_t) warps * L.per_warp;
+    if (L.per_warp + L.shared_bytes > limit) return false;
+    int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);   // up to 8 warps per block (255 registers each)
+    plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = L.shared_bytes + (size_t) warps * L.per_warp;
     plan->ctas_per_sm = (int) std::max<size_t> (1, std::min<size_t> ((228 * 1024) / (plan->smem + 1024), (size_t) (2048 / plan->block)));
+    plan->ctas_per_sm = std::min (plan->ctas_per_sm, 2);          // the 2-CTA variant is compiled for 128 registers per thread
     return true;
 }
 
@@ -668,7 +715,7 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
-    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_ph.release (); mc->d_esum.release ();
+    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_ph.release (); mc->d_esum.release ();
     mc->d_counts.release (); mc->d_counters.release ();
     delete mc;
 }
@@ -753,6 +800,11 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     if (mc->pairs_dirty) {
         PCE_CUDA (mc->d_pair_a.resize (npairs > 0 ? npairs : 1));
         PCE_CUDA (mc->d_pair_b.resize (npairs > 0 ? npairs : 1));
+        PCE_CUDA (mc->d_pair_packed.resize (npairs > 0 ? npairs : 1));
+        std::vector<uint32_t> packed ((size_t) (npairs > 0 ? npairs : 1), 0u);
+        for (int k = 0; k < npairs; k++) packed[k] = (uint32_t) mc->pair_a[k] | ((uint32_t) mc->pair_b[k] << 16);
+        PCE_CUDA (cudaMemcpyAsync (mc->d_pair_packed.ptr, packed.data (), packed.size () * sizeof (uint32_t), cudaMemcpyHostToDevice, m->stream));
+        PCE_CUDA (cudaStreamSynchronize (m->stream));
         if (npairs > 0) {
             PCE_CUDA (cudaMemcpyAsync (mc->d_pair_a.ptr, mc->pair_a.data (), npairs * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
             PCE_CUDA (cudaMemcpyAsync (mc->d_pair_b.ptr, mc->pair_b.data (), npairs * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
@@ -769,7 +821,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
 
     p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
     p.first = m->d_first.ptr; p.nsi = m->d_nsite_inst.ptr; p.protons = m->d_protons.ptr;
-    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr;
+    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr; p.pair_packed = mc->d_pair_packed.ptr;
     p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.wb = m->d_wb.ptr; p.ph = mc->d_ph.ptr;
     p.nph = nph; p.ph_index_offset = ph_index_offset; p.nchains = mc->nchains; p.nequil = mc->nequil; p.nprod = mc->nprod;
     p.chain_offset = chain_offset;
@@ -787,7 +839,9 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     } else {
-        auto kernel = per_chain ? k_mc_warp<true> : k_mc_warp<false>;
+        // one resident CTA (large fields): up to 255 registers, deep unrolling of the row updates; otherwise 128
+        auto kernel = plan.ctas_per_sm >= 2 ? (per_chain ? k_mc_warp<true, 2> : k_mc_warp<false, 2>)
+                                            : (per_chain ? k_mc_warp<true, 1> : k_mc_warp<false, 1>);
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     }
