@@ -237,9 +237,10 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
         if (ia >= oa) ia++;
         int ib = 0, ob = 0;
         double x;
-        if (has_pairs) {
-            // evaluated for every lane (a warp almost always holds a double move); for single moves ib == ob and the
-            // extra terms are exactly zero, so the value equals the single-move formula bit for bit
+        if (has_pairs && (W_SMEM || dbl)) {
+            // W on chip: evaluated for every lane (a warp almost always holds a double move; no divergent branch); for
+            // single moves ib == ob and the extra terms are exactly zero, so the value equals the single-move formula
+            // bit for bit.  W in global memory: only lanes with a double move pay for the four cross-term loads.
             const uint32_t ib_info = s_site[sb];
             const int nb = (int) (ib_info >> 16);
             ob = my_state[sb * B];
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
             if (!dbl) ib = ob;
             if (!valid) { ia = oa; ib = ob; }
             const double *ra = wbase + ia * wld, *ro = wbase + oa * wld;
-            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (ra[ib], ra[ob]), ro[ib]), ro[ob]);
+            const double c0 = ra[ib], c1 = ra[ob], c2 = ro[ib], c3 = ro[ob];
+            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (c0, c1), c2), c3);
             x = __dadd_rn (__dadd_rn (__dsub_rn (myh[ia], myh[oa]), __dsub_rn (myh[ib], myh[ob])), cross);
             if (production && dbl) c_flips++;
         } else {
@@ -576,18 +578,23 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         }
     };
 
-    pce::Philox4 rnext = pce::philox4x32_10 (0u, 0u, chain, phidx, p.k0, p.k1);
-    uint32_t tnext0 = target (rnext.x), tnext1 = target (rnext.z);
-    for (unsigned long long b = 0; 2ull * b < ntrials; b++) {
-        const pce::Philox4 r = rnext;
-        const uint32_t t0 = tnext0, t1 = tnext1;
-        const unsigned long long bn = b + 1;
-        rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);
-        tnext0 = target (rnext.x); tnext1 = target (rnext.z);
+    // Random numbers for 64 trials at a time: lane l generates Philox block b0 + l (two trials) and fetches the two
+    // proposal targets; each trial then takes its words from the owning lane by shuffle.  Same stream as one block per
+    // two trials generated in order, at 1/32 of the instruction cost, and the pair-table loads run far ahead of their use.
+    for (unsigned long long b0 = 0; 2ull * b0 < ntrials; b0 += 32) {
+        const unsigned long long bl = b0 + (unsigned long long) lane;
+        const pce::Philox4 r = pce::philox4x32_10 ((uint32_t) bl, (uint32_t) (bl >> 32), chain, phidx, p.k0, p.k1);
+        const uint32_t t0 = target (r.x), t1 = target (r.z);
+        const unsigned long long left = ntrials - 2ull * b0;
+        const int nj = left < 64ull ? (int) left : 64;
 #pragma unroll 1
-        for (int half = 0; half < 2; half++) {          // one copy of the trial body in the instruction cache
-            if (half && 2ull * b + 1ull >= ntrials) break;
-            trial (half ? r.z : r.x, half ? r.w : r.y, half ? t1 : t0);
+        for (int j = 0; j < nj; j++) {
+            const int  src = j >> 1;
+            const bool odd = j & 1;
+            const uint32_t w0 = __shfl_sync (0xffffffffu, odd ? r.z : r.x, src);
+            const uint32_t w1 = __shfl_sync (0xffffffffu, odd ? r.w : r.y, src);
+            const uint32_t pr = __shfl_sync (0xffffffffu, odd ? t1 : t0, src);
+            trial (w0, w1, pr);
         }
     }
 

@@ -111,6 +111,50 @@ def parse_probability_tables(log_text, record):
     return tables
 
 
+def parse_substate_table(log_text):
+    """First 'State Gmicro Charge Protons <sites...>' table (Substate.Summary, Substate.py:122-168)."""
+    lines = log_text.splitlines()
+    for i, line in enumerate(lines):
+        if re.match(r"^\s*State\s+Gmicro\s+Charge\s+Protons", line):
+            sites = re.findall(r"(\S+) (\S+) (\d+)", line[line.index("Protons") + 7:])
+            energies, protons, labels = [], [], []
+            for row in lines[i + 2:]:
+                t = row.split()
+                if len(t) < 4 + len(sites) or not t[0].isdigit():
+                    break
+                energies.append(float(t[1])); protons.append(int(t[3])); labels.append("|".join(t[4:4 + len(sites)]))
+            return [(a, b, int(c)) for a, b, c in sites], energies, protons, labels
+    return None
+
+
+def parse_halfpk_table(log_text, record):
+    """First 'pK1/2 values of instances' table (TitrationCurves.PrintHalfpKs): first pK1/2 per instance, NaN for n/a."""
+    lines = log_text.splitlines()
+    site_index = {s: k for k, s in enumerate(record.site_labels)}
+    for i, line in enumerate(lines):
+        if "pK1/2 values of instances" in line:
+            out = np.full(record.ninstances, np.nan)
+            for row in lines[i + 2:]:
+                t = row.split()
+                if len(t) < 5 or row.startswith("---"):
+                    break
+                key = (t[0], t[1], int(t[2]))
+                k = site_index[key]
+                labels = record.inst_labels[int(record.site_first[k]):int(record.site_last[k]) + 1]
+                rest, g = t[3:], int(record.site_first[k])
+                pos = 0
+                for lab in labels:
+                    assert rest[pos] == lab, (rest, lab)
+                    pos += 1
+                    if pos < len(rest) and rest[pos] != "n/a" and rest[pos] not in labels:
+                        out[g] = float(rest[pos])
+                    while pos < len(rest) and rest[pos] not in labels[labels.index(lab) + 1:labels.index(lab) + 2]:
+                        pos += 1
+                    g += 1
+            return out
+    return None
+
+
 def main():
     parameters_dir = os.path.join(REFERENCE, "parameters", "sites")
     est = [os.path.join(REFERENCE, "tests", "ifp20", n) for n in ("BLF.est", "ACB.est", "ACC.est")]
@@ -151,6 +195,17 @@ def main():
                 ph, p = formats.read_curves_directory(os.path.join(results, d), record)
                 payload["golden_curve_ph"] = ph
                 payload["golden_curve_mc_%s" % d] = p
+
+            sub = parse_substate_table(log_text)
+            if sub is not None:
+                sites, energies, protons, labels = sub
+                payload["golden_substate_sites"] = np.array(["%s|%s|%d" % s for s in sites])
+                payload["golden_substate_energy"] = np.array(energies)
+                payload["golden_substate_protons"] = np.array(protons, dtype=np.int32)
+                payload["golden_substate_labels"] = np.array(labels)
+            halfpk = parse_halfpk_table(log_text, record)
+            if halfpk is not None:
+                payload["golden_halfpk"] = halfpk
 
             gint = find(results, "job.gint")
             inter = find(results, "job.inter")

@@ -90,3 +90,26 @@ def test_substate_matches_reference_table(port):
             vector[site_index] = local
         assert energy == port.energy(rec, wsym, vector.GlobalIndices(), 7.0)
     assert substate.substates[0][0] == min(e for e, _ in substate.substates)
+
+
+@pytest.mark.parametrize("name,use_mc", [("defensin", False), ("ifp20", True)])
+def test_substate_tables_golden(name, use_mc):
+    """The substate tables printed in defensin.out (8 rows) and ifp20.out (80 rows: 4 x 5 x 2 x 2 forms of HIS260, the BLF
+    chromophore and two propionates): relative energies to the 2 decimals of the log, proton counts and instance labels."""
+    rec, gold = load_fixture(name)
+    model = P.MEADModel(rec, log=None)
+    if use_mc:      # ifp20 cannot be enumerated; the reference also locates the base state from MC probabilities
+        model.DefineMCModel(P.MCModelDefault(nequil=500, nprod=5000, randomSeed=3, nchains=256), log=None)
+    sites = [tuple(s.split("|")) for s in gold["golden_substate_sites"].tolist()]
+    substate = P.Substate(model, [(a, b, int(c)) for a, b, c in sites], pH=7.0, log=None)
+    substate.CalculateSubstateEnergies(log=None)
+    energies = np.array([e - substate.zeroEnergy for e, _ in substate.substates])
+    assert len(energies) == len(gold["golden_substate_energy"])
+    assert np.abs(energies - gold["golden_substate_energy"]).max() <= 0.0051
+    for (energy, indices), labels, protons in zip(substate.substates, gold["golden_substate_labels"].tolist(), gold["golden_substate_protons"].tolist()):
+        got, nprot = [], 0
+        for site_index, local in zip(substate.indicesOfSites, indices):
+            instance = model.sites[site_index].instances[local]
+            got.append(instance.label)
+            nprot += instance.protons
+        assert "|".join(got) == labels and nprot == protons
