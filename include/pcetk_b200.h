@@ -161,6 +161,10 @@ int pce_mc_run_chains (pce_mc *mc, const double *ph, int nph, int ph_index_offse
                        long long *chain_counts, int32_t *chain_state, double *chain_energy, double *chain_esum, long long *chain_counters);
 /* MCModelDefault.pyx:79-159 trajectory mode: energies[nprod] of chain 0 after every production scan */
 int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, long long *counts, long long *counters);
+/* the same with the per-block counter table of the logging branch: log_rows[(nequil/f + nprod/f) * 5] holds, per block of
+ * f = log_frequency scans (equilibration blocks first), {scans done in the phase, moves, moves accepted, double moves,
+ * double moves accepted} -- the rows MCModelDefault.pyx:85-151 prints */
+int pce_mc_run_logged (pce_mc *mc, double ph, int log_frequency, double *energies, long long *counts, long long *counters, long long *log_rows);
 
 /* ---- test hooks ----------------------------------------------------------------------------------- */
 /* Philox4x32-10 blocks computed ON THE DEVICE: out[4*i..] for counters ctr[4*i..], one key */

@@ -41,6 +41,7 @@ class MCModelDefault(object):
         self._lib = _native.library()
         self.lastCounters = None
         self.lastEnergySums = None
+        self.lastLogRows = None
 
     def __del__(self):
         handle = getattr(self, "_handle", None)
@@ -126,28 +127,41 @@ class MCModelDefault(object):
     def CalculateOwnerProbabilities(self, pH=7.0, logFrequency=0, trajectoryFilename="", log=logFile):
         """Calculate probabilities of the owner (MCModelDefault.pyx:56-159).
 
-        Quiet path: all chains.  With ``logFrequency`` > 0 the per-phase move counters are reported once
-        (the per-block table of the reference is not reproduced); with ``trajectoryFilename`` one chain is
-        run and its energy after every production scan is written, one ``%f`` per line (:127-135)."""
+        Quiet path: all chains in one launch.  With ``logFrequency`` > 0 and/or ``trajectoryFilename`` one chain is run, like
+        the reference: the table of moves / accepted moves / double moves / accepted double moves per ``logFrequency``
+        scans is printed (and kept in ``lastLogRows``), and the energy after every production scan is written to the
+        file, one ``%f`` per line (:127-135)."""
         self._requireOwner()
         self._configure()
-        if trajectoryFilename != "":
+        if trajectoryFilename != "" or logFrequency > 0:
+            # logging / trajectory branch (MCModelDefault.pyx:79-159): one chain, like the reference
             energies = np.zeros(self.nprod, dtype=np.float64)
             counts = np.zeros(self.owner.ninstances, dtype=np.int64)
             counters = np.zeros(4, dtype=np.int64)
-            _native.check(self._lib.pce_mc_run_trajectory(self._handle, float(pH), _native.ptr(energies), _native.ptr(counts), _native.ptr(counters)))
-            with open(trajectoryFilename, "w") as output:
-                for value in energies:
-                    output.write("%f\n" % value)
+            nrows = (self.nequil // logFrequency + self.nprod // logFrequency) if logFrequency > 0 else 0
+            rows = np.zeros((max(nrows, 1), 5), dtype=np.int64)
+            _native.check(self._lib.pce_mc_run_logged(self._handle, float(pH), int(max(logFrequency, 0)), _native.ptr(energies), _native.ptr(counts),
+                                                      _native.ptr(counters), _native.ptr(rows) if nrows else None))
+            if trajectoryFilename != "":
+                with open(trajectoryFilename, "w") as output:
+                    for value in energies:
+                        output.write("%f\n" % value)
             self.lastCounters = counters[None, :]
+            self.lastLogRows = rows[:nrows]
+            if LogFileActive(log) and nrows:
+                nEquilRows = self.nequil // logFrequency
+                table = [("%8s" % "Scan", "%10s" % "Moves", "%10s" % "M-Acc", "%10s" % "Flips", "%10s" % "F-Acc")]
+                for k, row in enumerate(rows[:nrows]):
+                    if k == nEquilRows:
+                        table.append(("** Equilibration phase done **", "", "", "", ""))
+                    table.append(tuple(("%8d" if c == 0 else "%10d") % x for c, x in enumerate(row)))
+                table.append(("** Production phase done **", "", "", "", ""))
+                log.Table(table)
         else:
             self.CalculateOwnerProbabilitiesBatch([float(pH)])
-        if LogFileActive(log):
-            log.Text("\nCompleted %d equilibration scans.\n" % self.nequil)
-            log.Text("\nCompleted %d production scans.\n" % self.nprod)
-            if logFrequency > 0 and self.lastCounters is not None:
-                moves, movesAcc, flips, flipsAcc = [int(x) for x in self.lastCounters[-1]]
-                log.Table([("Moves", "M-Acc", "Flips", "F-Acc"), (moves, movesAcc, flips, flipsAcc)], title="Production counters")
+            if LogFileActive(log):
+                log.Text("\nCompleted %d equilibration scans.\n" % self.nequil)
+                log.Text("\nCompleted %d production scans.\n" % self.nprod)
 
     def RunChains(self, pHs, phIndexOffset=0):
         """Per-chain outputs (parity tests): dict of counts[npH, nchains, ninst], state, energy, esum, counters."""

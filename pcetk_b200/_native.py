@@ -88,6 +88,7 @@ SIGNATURES = {
     "pce_mc_run_device": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void]),
     "pce_mc_run_chains": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void, _void, _void]),
     "pce_mc_run_trajectory": (_int, [_void, _dbl, _void, _void, _void]),
+    "pce_mc_run_logged": (_int, [_void, _dbl, _int, _void, _void, _void, _void]),
     "pce_test_philox": (_int, [_int, _u32p, _int, _u32p, _u32p]),
 }
 

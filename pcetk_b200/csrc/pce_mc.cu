@@ -62,6 +62,8 @@ struct McParams {
     double    *chain_energy, *chain_esum;   // [nph*nchains]
     long long *chain_counters;      // [nph*nchains*4]
     double    *trajectory;          // [nprod] energies of chain 0 of pH 0
+    long long *log_rows;            // [(nequil/f + nprod/f) * 5] scan, moves, accepted, flips, accepted per block of f scans (chain 0, pH 0)
+    int        log_frequency;
     int        w_in_smem;
 };
 
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
     const unsigned long long ntrials = (unsigned long long) ((long long) p.nequil + p.nprod) * nmoves;
     uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
+    uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
     double   esum = 0.0;
     long long scan = 0;
     uint32_t  mv = 0, tp = 0;
@@ -260,6 +263,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
             x = __dsub_rn (myh[ia], myh[oa]);
         }
         const bool accept = valid && metropolis (x, w1);
+        if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) { lg_f++; lg_fa += accept; } else { lg_m++; lg_ma += accept; } }
 
         // apply accepted moves: two accepting chains per round, one per half-warp; each lane updates entries
         // k = sub, sub+16, sub+32, ... of its chain's field vector (hb += wb[new] - wb[old] for one or two sites)
@@ -340,6 +344,17 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
             if (production) {
                 esum += grt;
                 if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && active) p.trajectory[scan - p.nequil] = grt / beta;
+            }
+            if (PER_CHAIN && p.log_rows != nullptr) {        // the per-block counter table of MCModelDefault.pyx:85-151
+                const long long done = (production ? scan - p.nequil : scan) + 1;
+                if (done % p.log_frequency == 0) {
+                    if (q == 0 && local == 0 && active) {
+                        long long *row = p.log_rows + 5 * ((production ? p.nequil / p.log_frequency : 0) + done / p.log_frequency - 1);
+                        row[0] = done; row[1] = lg_m; row[2] = lg_ma; row[3] = lg_f; row[4] = lg_fa;
+                    }
+                    lg_m = lg_ma = lg_f = lg_fa = 0;
+                }
+                if (!production && scan + 1 == p.nequil) lg_m = lg_ma = lg_f = lg_fa = 0;
             }
             scan++;
             production = scan >= p.nequil;
@@ -487,6 +502,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     bool      production = p.nequil == 0;
     unsigned long long *counts = PER_CHAIN ? (unsigned long long *) (p.chain_counts + ((size_t) q * p.nchains + local) * ninst)
                                            : p.counts + (size_t) q * ninst;
+    uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
 
     // proposal target of a random word: site (single move) or packed pair, fetched one Philox block ahead of its use
     // because it does not depend on the chain's state (hides the L2 latency of the pair table)
@@ -525,6 +541,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             if (production) c_flips++;
         }
         const bool accept = valid && metropolis (x, w1);      // warp-uniform
+        if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) { lg_f++; lg_fa += accept; } else { lg_m++; lg_ma += accept; } }
         if (accept) {
             // hb += wb[ia] - wb[oa] (+ wb[ib] - wb[ob]); rows are 32-byte aligned (ldw multiple of 4)
             const double2 *rna = (const double2 *) (p.wb + (size_t) ia * ldw), *roa = (const double2 *) (p.wb + (size_t) oa * ldw);
@@ -571,6 +588,17 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             if (production) {
                 esum += grt;
                 if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan - p.nequil] = grt / beta;
+            }
+            if (PER_CHAIN && p.log_rows != nullptr) {
+                const long long done = (production ? scan - p.nequil : scan) + 1;
+                if (done % p.log_frequency == 0) {
+                    if (q == 0 && local == 0 && lane == 0) {
+                        long long *row = p.log_rows + 5 * ((production ? p.nequil / p.log_frequency : 0) + done / p.log_frequency - 1);
+                        row[0] = done; row[1] = lg_m; row[2] = lg_ma; row[3] = lg_f; row[4] = lg_fa;
+                    }
+                    lg_m = lg_ma = lg_f = lg_fa = 0;
+                }
+                if (!production && scan + 1 == p.nequil) lg_m = lg_ma = lg_f = lg_fa = 0;
             }
             scan++;
             production = scan >= p.nequil;
@@ -926,17 +954,25 @@ extern "C" int pce_mc_run_chains (pce_mc *mc, const double *ph, int nph, int ph_
 }
 
 extern "C" int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, long long *counts, long long *counters) {
+    return pce_mc_run_logged (mc, ph, 0, energies, counts, counters, nullptr);
+}
+
+extern "C" int pce_mc_run_logged (pce_mc *mc, double ph, int log_frequency, double *energies, long long *counts, long long *counters, long long *log_rows) {
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
+    if (log_rows != nullptr && log_frequency < 1) return fail (PCE_ERR_VALUE, "logFrequency must be positive");
     pce_model *m = mc->model;
     PCE_CUDA (cudaSetDevice (m->device));
     const int saved_chains = mc->nchains;
     mc->nchains = 1;                                   // the reference's trajectory is one chain (MCModelDefault.pyx:79-159)
-    pce::DeviceBuffer<long long> d_counts, d_counters;
+    pce::DeviceBuffer<long long> d_counts, d_counters, d_log;
     pce::DeviceBuffer<int32_t>   d_state;
     pce::DeviceBuffer<double>    d_energy, d_esum, d_traj;
+    const size_t nrows = log_rows ? (size_t) (mc->nequil / log_frequency + mc->nprod / log_frequency) : 0;
     int status = PCE_OK;
     do {
         cudaError_t err = d_counts.resize (m->ninst);
+        if (err == cudaSuccess) err = d_log.resize (nrows * 5 + 1);
+        if (err == cudaSuccess) err = cudaMemsetAsync (d_log.ptr, 0, (nrows * 5 + 1) * sizeof (long long), m->stream);
         if (err == cudaSuccess) err = d_counters.resize (4);
         if (err == cudaSuccess) err = d_state.resize (m->nsites);
         if (err == cudaSuccess) err = d_energy.resize (1);
@@ -948,6 +984,7 @@ extern "C" int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, l
         std::memset (&p, 0, sizeof (p));
         p.chain_counts = d_counts.ptr; p.chain_state = d_state.ptr; p.chain_energy = d_energy.ptr; p.chain_esum = d_esum.ptr;
         p.chain_counters = d_counters.ptr; p.trajectory = d_traj.ptr;
+        if (log_rows) { p.log_rows = d_log.ptr; p.log_frequency = log_frequency; }
         status = launch_mc (mc, &ph, 1, 0, 0, true, p);
         if (status != PCE_OK) break;
         err = cudaStreamSynchronize (m->stream);
@@ -955,11 +992,12 @@ extern "C" int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, l
         std::vector<long long> host_counts (m->ninst);
         if (err == cudaSuccess) err = cudaMemcpy (host_counts.data (), d_counts.ptr, m->ninst * sizeof (long long), cudaMemcpyDeviceToHost);
         if (err == cudaSuccess && counters) err = cudaMemcpy (counters, d_counters.ptr, 4 * sizeof (long long), cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess && log_rows && nrows) err = cudaMemcpy (log_rows, d_log.ptr, nrows * 5 * sizeof (long long), cudaMemcpyDeviceToHost);
         if (err != cudaSuccess) { status = fail (PCE_ERR_CUDA, std::string ("trajectory readback: ") + cudaGetErrorString (err)); break; }
         if (counts) std::memcpy (counts, host_counts.data (), m->ninst * sizeof (long long));
         for (int k = 0; k < m->ninst; k++) m->prob[k] = (double) host_counts[k] / (double) mc->nprod;
     } while (0);
     mc->nchains = saved_chains;
-    d_counts.release (); d_counters.release (); d_state.release (); d_energy.release (); d_esum.release (); d_traj.release ();
+    d_counts.release (); d_counters.release (); d_state.release (); d_energy.release (); d_esum.release (); d_traj.release (); d_log.release ();
     return status;
 }

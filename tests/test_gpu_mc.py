@@ -138,3 +138,26 @@ def test_titration_curve_lysozyme_ph0_20(port):
     curves.CalculateHalfpKs()
     his = [k for k, s in enumerate(rec.site_labels) if s[1] == "HIS"][0]
     assert len(curves.halves[his][0]) >= 1
+
+
+def test_logging_branch_counter_table_vs_lyso_mc_traj():
+    """lyso_mc_traj.out: per-500-scan rows (scan, moves, accepted, flips, accepted) of the reference's logging branch."""
+    import io
+    from pcetk_b200.log import TextLog
+
+    rec, _gold, model, sampler = make("lysozyme", nequil=500, nprod=20000, randomSeed=8, nchains=16)
+    gold = np.load("tests/golden/lysozyme_traj.npz")["counters"]
+    out = io.StringIO()
+    model.CalculateProbabilities(pH=7.0, logFrequency=500, log=TextLog(out))
+    rows = sampler.lastLogRows
+    assert rows.shape == (41, 5) == gold.shape
+    assert rows[:, 0].tolist() == gold[:, 0].tolist()                       # 500 | 500, 1000, ... 20000
+    assert (rows[:, 1] + rows[:, 3] == 500 * 24).all()                      # 24 trial moves per scan
+    assert (gold[:, 1] + gold[:, 3] == 500 * 24).all()
+    prod, ref = rows[1:], gold[1:]
+    assert abs(prod[:, 1].mean() - ref[:, 1].mean()) < 60                   # ~10 500 single moves per block
+    assert abs(prod[:, 2].sum() / prod[:, 1].sum() - ref[:, 2].sum() / ref[:, 1].sum()) < 0.01     # acceptance rate
+    assert prod[:, 4].sum() <= prod[:, 3].sum() * 0.01                      # double moves almost never accepted at pH 7
+    assert sampler.lastCounters[0].tolist() == prod[:, 1:].sum(axis=0).tolist()
+    assert "Equilibration phase done" in out.getvalue() and "Production phase done" in out.getvalue()
+    assert abs(model.energyModel.GetProbabilities().sum() - rec.nsites) < 1e-9
