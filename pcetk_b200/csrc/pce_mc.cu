@@ -71,7 +71,7 @@ struct McParams {
 struct ThreadLayout {
     size_t off_w, off_h, off_counts, off_since, off_site, off_pair, off_state, total;
     int    hstride, ldws, kslots;
-    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int block, int w_in_smem, int nchains, int nph) {
+    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int block, int w_in_smem, int nchains, int nph, int since_bytes) {
         hstride = ninst | 1;                       // odd: lanes of a warp fall on distinct bank pairs
         ldws    = ninst | 1;
         // a block covers `block` consecutive (pH, chain) pairs of the chain-major grid: at most kslots pH values
@@ -81,7 +81,8 @@ struct ThreadLayout {
         off_w = o;      o += w_in_smem ? (size_t) ninst * ldws * 8 : 0;
         off_h = o;      o += (size_t) block * hstride * 8;
         off_counts = o; o += (size_t) kslots * ninst * 4;     // u32: block * nprod < 2^32 is checked on the host
-        off_since = o;  o += (size_t) nsites * block * 4;
+        off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
+        o = (o + 3) & ~(size_t) 3;
         off_site = o;   o += (size_t) nsites * 4;
         off_pair = o;   o += (size_t) (npairs > 0 ? npairs : 1) * 4;
         off_state = o;  o += (size_t) nsites * block;
@@ -130,15 +131,15 @@ __device__ __forceinline__ void sts_f64 (uint32_t address, double v) {
 // proposal is two shared-memory loads and one subtraction.  Trials are processed two per Philox block, with
 // the next block generated ahead of the dependent proposal -> accept -> update chain.
 // ---------------------------------------------------------------------------------------------------
-template <bool PER_CHAIN, bool W_SMEM>
+template <bool PER_CHAIN, bool W_SMEM, typename SinceT>
 __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
-    const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, W_SMEM ? 1 : 0, p.nchains, p.nph);
+    const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, W_SMEM ? 1 : 0, p.nchains, p.nph, (int) sizeof (SinceT));
     double             *s_w      = (double *) (smem + L.off_w);
     double             *s_h      = (double *) (smem + L.off_h);
     uint32_t           *s_counts = (uint32_t *) (smem + L.off_counts);
-    uint32_t           *s_since  = (uint32_t *) (smem + L.off_since);
+    SinceT             *s_since  = (SinceT *) (smem + L.off_since);
     uint32_t           *s_site   = (uint32_t *) (smem + L.off_site);      // first | ninst << 16
     uint32_t           *s_pair   = (uint32_t *) (smem + L.off_pair);      // site a | site b << 16
     uint8_t            *s_state  = smem + L.off_state;
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
     uint32_t *my_counts = s_counts + (size_t) (q - q_base) * ninst;
     uint8_t  *my_state = s_state + tid;
-    uint32_t *my_since = s_since + tid;
+    SinceT   *my_since = s_since + tid;
     long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
 
     // stage the model: beta-scaled W, packed site and pair tables
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
             if ((i & 3) == 0) r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
             const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
             my_state[i * B] = (uint8_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
-            my_since[i * B] = 0u;
+            my_since[i * B] = (SinceT) 0;
         }
     }
     __syncthreads ();
@@ -326,13 +327,13 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
                 const uint32_t since_a = my_since[sa * B];
                 if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
                 else if (tp != since_a) atomicAdd (&my_counts[oa], tp - since_a);
-                my_since[sa * B] = tp;
+                my_since[sa * B] = (SinceT) tp;
                 my_state[sa * B] = (uint8_t) ia;
                 if (dbl) {
                     const uint32_t since_b = my_since[sb * B];
                     if (PER_CHAIN) my_chain_counts[ob] += (long long) (tp - since_b);
                     else if (tp != since_b) atomicAdd (&my_counts[ob], tp - since_b);
-                    my_since[sb * B] = tp;
+                    my_since[sb * B] = (SinceT) tp;
                     my_state[sb * B] = (uint8_t) ib;
                     if (production) c_facc++;
                 } else if (production) c_macc++;
@@ -676,7 +677,7 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     for (int w_in = 1; w_in >= 0; w_in--) {
         for (int block = 32; block <= 512; block += 32) {
             if (forced_block && block != forced_block) continue;
-            ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in, mc->nchains, nph);
+            ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
             if (L.total > limit) continue;
             if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
             int ctas = (int) std::min<size_t> (per_sm / (L.total + 1024), (size_t) (2048 / block));
@@ -869,8 +870,13 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     else blocks = ((long long) nph * mc->nchains + plan.block / 32 - 1) / (plan.block / 32);
     if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
     if (plan.kernel == 1) {
-        auto kernel = per_chain ? (plan.w_in_smem ? k_mc_thread<true, true> : k_mc_thread<true, false>)
-                                : (plan.w_in_smem ? k_mc_thread<false, true> : k_mc_thread<false, false>);
+        void (*kernel) (const McParams);
+        if (mc->nprod < 65536)
+            kernel = per_chain ? (plan.w_in_smem ? k_mc_thread<true, true, uint16_t> : k_mc_thread<true, false, uint16_t>)
+                               : (plan.w_in_smem ? k_mc_thread<false, true, uint16_t> : k_mc_thread<false, false, uint16_t>);
+        else
+            kernel = per_chain ? (plan.w_in_smem ? k_mc_thread<true, true, uint32_t> : k_mc_thread<true, false, uint32_t>)
+                               : (plan.w_in_smem ? k_mc_thread<false, true, uint32_t> : k_mc_thread<false, false, uint32_t>);
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     } else {
