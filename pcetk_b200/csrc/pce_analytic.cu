@@ -51,7 +51,8 @@ struct EnumParams {
     int   P_lo, P_hi, P_M, P_I;
     long long P_O;              // tiles per chunk
     long long chunk_begin, nchunks;
-    int   Nb;                   // number of proton-count bins
+    int   Nb, NbRel;            // proton-count bins: absolute (output) / per thread, relative to the thread's M protons
+    int   wstage;               // W sub-blocks (M/I x O, O x O) staged in shared memory per chunk
     double beta, gref;
     int16_t siteM[kMaxM], radM[kMaxM];
     int16_t siteI[kMaxI], radI[kMaxI];
@@ -62,7 +63,7 @@ struct EnumParams {
     unsigned flushI;                                 // bit i set: sorted configuration i is the last of its proton count
     int      nMI, pow2O, nOinst, canon;              // instances in M+I sites; every O radix a power of two; instances in O sites; canonical I group (-1: no)
     uint8_t  shiftO[kMaxOuter];                      // digit shift of each O site when pow2O
-    double *T;                  // [nchunks][Nb][kBlock] per-thread bins
+    double *T;                  // [nchunks][NbRel][kBlock] per-thread bins
     // per-thread statics, computed once by k_enum_static: xs[(1 + kIStates) * kBlock] = xMM then xMI[i], coalesced;
     // ms[3 * kBlock] = m_lo, m_hi, protons of the M configuration; shift = minMM + minMI
     double  *xs;
@@ -137,20 +138,23 @@ constexpr int kMaxO = 32;         // max sites looped by the CTA (O); larger pro
 
 // Dynamic shared-memory carve-up of k_enum (same arithmetic on host and device).
 struct EnumLayout {
-    size_t off_bins, off_gF, off_gOut, off_smin, off_hF, off_eLo, off_eHi, off_eI, off_cOut, off_cExp, off_inst, off_aF, off_nOut,
+    size_t off_bins, off_gF, off_wMO, off_wOO, off_eInst, off_smin, off_hF, off_eLo, off_eHi, off_eI, off_cOut, off_cExp, off_inst, off_aF, off_nOut,
            off_idx, off_pair, off_instO, total;
     int    nMI, nIdx, nSites, nOinst, nPairs;
-    __host__ __device__ EnumLayout (int Nb, int nMI_, int P_lo, int P_hi, int P_I, int nF, int nM, int nI, int nO, int nOinst_) {
+    __host__ __device__ EnumLayout (int Nb, int nMI_, int P_lo, int P_hi, int P_I, int nF, int nM, int nI, int nO, int nOinst_, int wstage) {
         nMI = nMI_; nIdx = P_lo + P_hi + P_I; nSites = nM + nI; nOinst = nOinst_; nPairs = nO * (nO - 1) / 2;
         size_t o = 0;
         off_bins = o; o += (size_t) Nb * kBlock * 8;
         off_gF = o;   o += (size_t) nMI * 8;
-        off_gOut = o; o += (size_t) kTB * nMI * 8;
+        off_wMO = o;  o += wstage ? (size_t) nMI * nOinst_ * 8 : 0;
+        off_wOO = o;  o += wstage ? (size_t) nOinst_ * nOinst_ * 8 : 0;
+        off_eInst = o; o += (size_t) kTB * nMI * 8;
         off_smin = o; o += (size_t) kTB * (nSites > 0 ? nSites : 1) * 8;
         off_hF = o;   o += (size_t) (nOinst > 0 ? nOinst : 1) * 8;
         off_eLo = o;  o += (size_t) kTB * P_lo * 8;
         off_eHi = o;  o += (size_t) kTB * P_hi * 8;
-        off_eI = o;   o += (size_t) kTB * 16 * 8;            // padded to 16 entries (128-bit loads)
+        o = (o + 15) & ~(size_t) 15;
+        off_eI = o;   o += (size_t) kTB * 16 * 8;            // padded to 16 entries, 16-byte aligned (128-bit loads)
         off_cOut = o; o += (size_t) kTB * 8;
         off_cExp = o; o += (size_t) kTB * 8;
         off_inst = o; o += (size_t) nMI * 4;
@@ -176,10 +180,12 @@ template <int CANON>
 __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
     static_assert (kTB == kBlock / 32, "one warp per tile in phase (b)");
     extern __shared__ __align__ (16) unsigned char smem[];
-    const EnumLayout L (p.Nb, p.nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM, p.nI, p.nO, p.nOinst);
-    double   *bins   = (double *) (smem + L.off_bins);       // [Nb][kBlock]
+    const EnumLayout L (p.NbRel, p.nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM, p.nI, p.nO, p.nOinst, p.wstage);
+    double   *bins   = (double *) (smem + L.off_bins);       // [NbRel][kBlock]
     double   *s_gF   = (double *) (smem + L.off_gF);         // F-site fields on the M/I instances (per chunk)
-    double   *s_gOut = (double *) (smem + L.off_gOut);       // [kTB][nMI] + O-site fields (per tile)
+    double   *s_wMO  = (double *) (smem + L.off_wMO);        // [nMI][nOinst] W between M/I instances and O instances
+    double   *s_wOO  = (double *) (smem + L.off_wOO);        // [nOinst][nOinst]
+    double   *s_eInst = (double *) (smem + L.off_eInst);     // [kTB][nMI] exp(-beta (gOut - site minimum)) per instance
     double   *s_smin = (double *) (smem + L.off_smin);       // [kTB][nM+nI] per-site minimum of gOut
     double   *s_hF   = (double *) (smem + L.off_hF);         // F-site fields + intrinsic energy on the O instances
     double   *s_eLo  = (double *) (smem + L.off_eLo);        // [kTB][P_lo]
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
     uint16_t *s_pair = (uint16_t *) (smem + L.off_pair);     // O-O pairs: o | o2 << 8
     __shared__ int32_t s_off[kMaxM + kMaxI + 1];             // start of each M / I site in the compact list
     __shared__ int32_t s_offO[kMaxO + 1];
+    __shared__ uint32_t s_oFirst[kMaxO], s_oShift[kMaxO], s_oRad[kMaxO], s_oStride[kMaxO];   // O-site tables (lane-indexed in phase b)
     __shared__ double  s_AF;
     __shared__ int     s_nF;
 
@@ -214,13 +221,14 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
         o = 0;
         int np = 0;
         for (int j = 0; j < p.nO; j++) {
+            s_oFirst[j] = (uint32_t) p.firstOut[j]; s_oShift[j] = p.shiftO[j]; s_oRad[j] = (uint32_t) p.radOut[j]; s_oStride[j] = p.strideO[j];
             s_offO[j] = o;
             for (int k = 0; k < p.radOut[j]; k++) { const int a = p.firstOut[j] + k; s_instO[o++] = a | (p.protons[a] << 16); }
             for (int j2 = 0; j2 < j; j2++) s_pair[np++] = (uint16_t) (j | (j2 << 8));
         }
         s_offO[p.nO] = o;
     }
-    for (int e = tid; e < p.Nb * kBlock; e += kBlock) bins[e] = 0.0;
+    for (int e = tid; e < p.NbRel * kBlock; e += kBlock) bins[e] = 0.0;
     __syncthreads ();
     // index tables: which compact-list entries make up table entry x (no divisions in the tile loop)
     for (int x = tid; x < L.nIdx; x += kBlock) {
@@ -242,9 +250,16 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
     double xMI[kIStates];
 #pragma unroll
     for (int i = 0; i < kIStates; i++) xMI[i] = p.xs[(1 + i) * kBlock + tid];
-    const int m_lo = p.ms[tid], m_hi = p.ms[kBlock + tid], nMp = p.ms[2 * kBlock + tid];
+    const int m_lo = p.ms[tid], m_hi = p.ms[kBlock + tid];
     const double static_shift = *p.shift;
 
+    // W sub-blocks used by the tile loop, staged once per CTA (they do not depend on the chunk): with shared memory
+    // full there is no L1 left, so every global W read in the loop would be an L2 round trip
+    const int nOi = L.nOinst;
+    if (p.wstage && folded) {
+        for (int e = tid; e < nMI * nOi; e += kBlock) s_wMO[e] = p.w[(size_t) s_inst[e / nOi] * ldw + (s_instO[e % nOi] & 0xffff)];
+        for (int e = tid; e < nOi * nOi; e += kBlock) s_wOO[e] = p.w[(size_t) (s_instO[e / nOi] & 0xffff) * ldw + (s_instO[e % nOi] & 0xffff)];
+    }
     // per chunk: fields of the F sites on the M/I instances and on the O instances, F-F energy, F protons
     for (int j = tid; j < nMI + L.nOinst; j += kBlock) {
         const int a = j < nMI ? s_inst[j] : (s_instO[j - nMI] & 0xffff);
@@ -268,28 +283,44 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
     __syncthreads ();
 
     // O digit of a tile: shift/mask when every O radix is a power of two, else divide
-    auto digit = [&] (unsigned x, int o) -> int {
+    auto digit = [&] (unsigned x, int o) -> int {      // o uniform across the warp: kernel-parameter tables
         return p.pow2O ? (int) ((x >> p.shiftO[o]) & (unsigned) (p.radOut[o] - 1)) : (int) ((x / p.strideO[o]) % (unsigned) p.radOut[o]);
+    };
+    auto digit_s = [&] (unsigned x, int o) -> int {    // o differs per lane: shared-memory tables (no constant-bank replays)
+        return p.pow2O ? (int) ((x >> s_oShift[o]) & (s_oRad[o] - 1u)) : (int) ((x / s_oStride[o]) % s_oRad[o]);
     };
     const int n_lo = kTB * p.P_lo, n_hi = kTB * p.P_hi, n_i = kTB * p.P_I;
     const int n_terms = p.nO + L.nPairs;
 
     // ---- rounds of kTB tiles ---------------------------------------------------------------------------
     for (long long tile0 = 0; tile0 < p.P_O; tile0 += kTB) {
-        // (a) O-site fields on the instances of every M / I site, and the per-site minimum: one item per (tile, site)
+        // (a) O-site fields on the instances of every M / I site, the per-site minimum, and the normalised Boltzmann
+        // factor of every instance: one item per (tile, site).  Table entries are then products of per-site factors.
         for (int e = tid; e < kTB * nS; e += kBlock) {
             const int tb = e / nS, s = e - tb * nS;
             const unsigned x = (unsigned) (tile0 + tb);
+            const int j0 = s_off[s], nj = s_off[s + 1] - j0;
+            double g[8];                                       // a site has at most 8 instances here (checked on the host)
             double vmin = DBL_MAX;
-            for (int j = s_off[s]; j < s_off[s + 1]; j++) {
-                double acc = s_gF[j];
-                if (folded) {
-                    const double *row = p.w + (size_t) s_inst[j] * ldw;
-                    for (int o = 0; o < p.nO; o++) acc += row[p.firstOut[o] + digit (x, o)];
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (c < nj) {
+                    double acc = s_gF[j0 + c];
+                    if (folded) {
+                        if (p.wstage) {
+                            const double *row = s_wMO + (j0 + c) * nOi;
+                            for (int o = 0; o < p.nO; o++) acc += row[s_offO[o] + digit (x, o)];
+                        } else {
+                            const double *row = p.w + (size_t) s_inst[j0 + c] * ldw;
+                            for (int o = 0; o < p.nO; o++) acc += row[p.firstOut[o] + digit (x, o)];
+                        }
+                    }
+                    g[c] = acc;
+                    vmin = fmin (vmin, acc);
                 }
-                s_gOut[tb * nMI + j] = acc;
-                vmin = fmin (vmin, acc);
             }
+#pragma unroll
+            for (int c = 0; c < 8; c++) if (c < nj) s_eInst[tb * nMI + j0 + c] = exp (-p.beta * (g[c] - vmin));
             s_smin[tb * nS + s] = vmin;
         }
         // (b) O energy (intrinsic + O-F via hF, O-O pairs) and O protons: warp tb takes tile tb, lanes over terms
@@ -301,12 +332,13 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
             if (tile0 + tb < p.P_O) {
                 for (int t = lane; t < n_terms; t += 32) {
                     if (t < p.nO) {
-                        const int k = s_offO[t] + digit (x, t);
+                        const int k = s_offO[t] + digit_s (x, t);
                         e += s_hF[k];
                         np += s_instO[k] >> 16;
                     } else if (folded) {
                         const int pr = s_pair[t - p.nO], o = pr & 0xff, o2 = pr >> 8;
-                        e += p.w[(size_t) (p.firstOut[o] + digit (x, o)) * ldw + p.firstOut[o2] + digit (x, o2)];
+                        if (p.wstage) e += s_wOO[(s_offO[o] + digit_s (x, o)) * nOi + s_offO[o2] + digit_s (x, o2)];
+                        else e += p.w[(size_t) ((int) s_oFirst[o] + digit_s (x, o)) * ldw + (int) s_oFirst[o2] + digit_s (x, o2)];
                     }
                 }
             }
@@ -316,35 +348,35 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
         }
         __syncthreads ();
 
-        // (c) tables.  The minimum of a table of sums of independent per-site terms is the sum of the per-site minima.
-        // Items are grouped by table (Lo | Hi | I | tile constant) so that a warp mostly runs one code path.
+        // (c) tables: every entry is the product of the per-site factors of its configuration (each <= 1; the per-site
+        // minima go into the tile constant).  Items are grouped by table (Lo | Hi | I | tile constant).
         for (int e = tid; e < n_lo + n_hi + n_i + kTB; e += kBlock) {
             if (e < n_lo) {
                 const int tb = e / p.P_lo, x = e - tb * p.P_lo;
-                const double *g = s_gOut + tb * nMI, *mn = s_smin + tb * nS;
+                const double *f = s_eInst + tb * nMI;
                 const uint16_t *row = s_idx + x * kMaxM;
-                double s = 0.0;
-                for (int i = 0; i < p.nLo; i++) s += g[row[i]] - mn[i];
-                s_eLo[e] = exp (-p.beta * s);
+                double v = 1.0;
+                for (int i = 0; i < p.nLo; i++) v *= f[row[i]];
+                s_eLo[e] = v;
             } else if (e < n_lo + n_hi) {
-                const int f = e - n_lo, tb = f / p.P_hi, x = f - tb * p.P_hi;
-                const double *g = s_gOut + tb * nMI, *mn = s_smin + tb * nS + p.nLo;
+                const int g = e - n_lo, tb = g / p.P_hi, x = g - tb * p.P_hi;
+                const double *f = s_eInst + tb * nMI;
                 const uint16_t *row = s_idx + (p.P_lo + x) * kMaxM;
-                double s = 0.0;
-                for (int i = 0; i < p.nM - p.nLo; i++) s += g[row[i]] - mn[i];
-                s_eHi[f] = exp (-p.beta * s);
+                double v = 1.0;
+                for (int i = 0; i < p.nM - p.nLo; i++) v *= f[row[i]];
+                s_eHi[g] = v;
             } else if (e < n_lo + n_hi + n_i) {
-                const int f = e - n_lo - n_hi, tb = f / p.P_I, x = f - tb * p.P_I;
-                const double *g = s_gOut + tb * nMI, *mn = s_smin + tb * nS + p.nM;
+                const int g = e - n_lo - n_hi, tb = g / p.P_I, x = g - tb * p.P_I;
+                const double *f = s_eInst + tb * nMI;
                 const uint16_t *row = s_idx + (p.P_lo + p.P_hi + x) * kMaxM;
-                double s = 0.0;
-                for (int i = 0; i < p.nI; i++) s += g[row[i]] - mn[i];
-                s_eI[tb * 16 + x] = exp (-p.beta * s);
+                double v = 1.0;
+                for (int i = 0; i < p.nI; i++) v *= f[row[i]];
+                s_eI[tb * 16 + x] = v;
             } else {
                 const int tb = e - n_lo - n_hi - n_i;
-                double s = s_cOut[tb];
-                for (int i = 0; i < nS; i++) s += s_smin[tb * nS + i];
-                s_cExp[tb] = (tile0 + tb < p.P_O) ? exp (-p.beta * (s - p.gref)) : 0.0;
+                double sum = s_cOut[tb];
+                for (int i = 0; i < nS; i++) sum += s_smin[tb * nS + i];
+                s_cExp[tb] = (tile0 + tb < p.P_O) ? exp (-p.beta * (sum - p.gref)) : 0.0;
             }
         }
         __syncthreads ();
@@ -355,15 +387,23 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
 #pragma unroll 2
             for (int tb = 0; tb < kTB; tb++) {
                 const double c_tile = s_cExp[tb] * s_eLo[tb * p.P_lo + m_lo] * s_eHi[tb * p.P_hi + m_hi] * eMM;
-                double *mybins = bins + (s_nOut[tb] + nMp + p.binI[0]) * kBlock + tid;
+                double *mybins = bins + (s_nOut[tb] + p.binI[0]) * kBlock + tid;
                 const double *eI = s_eI + tb * 16;
                 if (CANON >= 0) {
                     constexpr unsigned mask = canon_flush_mask (CANON >= 0 ? CANON : 0);
+                    constexpr int kN = 1 << (CANON >= 0 ? CANON : 0);
+                    double ev[kN];
+                    if (kN >= 2) {
+#pragma unroll
+                        for (int i = 0; i < kN / 2; i++) { const double2 t = ((const double2 *) eI)[i]; ev[2 * i] = t.x; ev[2 * i + 1] = t.y; }
+                    } else {
+                        ev[0] = eI[0];
+                    }
                     double acc = 0.0;
                     int    k = 0;
 #pragma unroll
-                    for (int i = 0; i < (1 << (CANON >= 0 ? CANON : 0)); i++) {
-                        acc += eI[i] * xMI[i];
+                    for (int i = 0; i < kN; i++) {
+                        acc += ev[i] * xMI[i];
                         if ((mask >> i) & 1u) { mybins[k * kBlock] += c_tile * acc; acc = 0.0; k++; }
                     }
                 } else {
@@ -382,8 +422,8 @@ __global__ void __launch_bounds__ (kBlock, 3) k_enum (const EnumParams p) {
     }
 
     // ---- flush -------------------------------------------------------------------------------------------
-    double *out = p.T + (size_t) blockIdx.x * p.Nb * kBlock;
-    for (int e = tid; e < p.Nb * kBlock; e += kBlock) out[e] = bins[e];
+    double *out = p.T + (size_t) blockIdx.x * p.NbRel * kBlock;
+    for (int e = tid; e < p.NbRel * kBlock; e += kBlock) out[e] = bins[e];
 }
 
 // out[e] = sum over c < count of in[c * stride + e] for the slice of c owned by blockIdx.y (deterministic order);
@@ -405,15 +445,22 @@ __global__ void k_reduce_rows (const double *__restrict__ in, long long count, i
     out[(size_t) blockIdx.y * width + e] = (a0 + a1) + (a2 + a3);
 }
 
-// Ftab[chunk][n] = sum over threads of T[chunk][n][tid]; one warp per (chunk, n)
-__global__ void k_reduce_threads (const double *__restrict__ T, long long nchunks, int Nb, double *__restrict__ Ftab) {
+// Ftab[chunk][n] = sum over threads of T[chunk][n - nM(tid)][tid] (per-thread bins are relative to the protons of the
+// thread's M configuration); one warp per (chunk, n), lanes over threads in a fixed order
+__global__ void k_reduce_threads (const double *__restrict__ T, long long nchunks, int NbRel, int Nb, const int32_t *__restrict__ nMp,
+                                  double *__restrict__ Ftab) {
     const long long wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= nchunks * Nb) return;
-    const double *row = T + (size_t) wid * kBlock;
+    const long long chunk = wid / Nb;
+    const int n = (int) (wid - chunk * Nb);
+    const double *base = T + (size_t) chunk * NbRel * kBlock;
     double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < kBlock / 32; k++) acc += row[lane + 32 * k];
+    for (int k = 0; k < kBlock / 32; k++) {
+        const int t = lane + 32 * k, rel = n - nMp[t];
+        if (rel >= 0 && rel < NbRel) acc += base[(size_t) rel * kBlock + t];
+    }
     acc = pce::warp_sum (acc);
     if (lane == 0) Ftab[wid] = acc;
 }
@@ -422,7 +469,8 @@ __global__ void k_reduce_threads (const double *__restrict__ T, long long nchunk
 //   M site instance a: sum over tid with digit(tid) = a of Mtab[n][tid]
 //   F site instance a: sum over chunks with digit(chunk) = a of Ftab[chunk][n]
 struct MarginalParams {
-    int Nb, P_M, nM, nF, nO, write_z;
+    int Nb, NbRel, P_M, nM, nF, nO, write_z;
+    const int32_t *nMp;      // protons of each thread's M configuration
     long long chunk_begin, nchunks;
     int16_t siteM[kMaxM], radM[kMaxM], coverM[kMaxM];
     int16_t siteF[kMaxOuter], radF[kMaxOuter], coverF[kMaxOuter];
@@ -474,7 +522,11 @@ __global__ void __launch_bounds__ (kBlock) k_marginals (const MarginalParams p) 
         for (int k = 0; k < 64; k++) {
             if ((mask >> k) & 1ull) {
                 const long long e = tid + (long long) kBlock * k;
-                acc += kind == 2 ? p.Ftab[(size_t) e * p.Nb + n] : p.Mtab[(size_t) n * kBlock + e];
+                if (kind == 2) acc += p.Ftab[(size_t) e * p.Nb + n];
+                else {
+                    const int rel = n - p.nMp[e];
+                    if (rel >= 0 && rel < p.NbRel) acc += p.Mtab[(size_t) rel * kBlock + e];
+                }
             }
         }
         acc = pce::warp_sum (acc);
@@ -711,11 +763,23 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         }
         if (p.P_O > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many tiles per chunk");
         p.Nb = plan.Nb; p.beta = 1.0 / (PCE_R * m->temperature); p.gref = plan.gref;
+        {
+            int maxM = 0;
+            for (int i = 0; i < p.nM; i++) {
+                int best = 0;
+                for (int k = m->first[p.siteM[i]]; k <= m->last[p.siteM[i]]; k++) best = std::max (best, (int) m->protons[k]);
+                maxM += best;
+                if (p.radM[i] > 8) return fail (PCE_ERR_LIMIT, "sites with more than 8 instances are not supported by the enumeration kernel");
+            }
+            for (int i = 0; i < p.nI; i++) if (p.radI[i] > 8) return fail (PCE_ERR_LIMIT, "sites with more than 8 instances are not supported by the enumeration kernel");
+            p.NbRel = plan.Nb - maxM;
+            p.wstage = ((size_t) nMI * p.nOinst + (size_t) p.nOinst * p.nOinst) * 8 <= 16 * 1024 ? 1 : 0;
+        }
         // this shard's slice of the chunk range
         const long long c0 = pf * shard / nshards, c1 = pf * (shard + 1) / nshards;
         p.chunk_begin = c0; p.nchunks = c1 - c0;
         if (p.nchunks <= 0) continue;
-        const EnumLayout layout (plan.Nb, nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM, p.nI, p.nO, p.nOinst);
+        const EnumLayout layout (p.NbRel, nMI, p.P_lo, p.P_hi, p.P_I, p.nF, p.nM, p.nI, p.nO, p.nOinst, p.wstage);
         const size_t smem = layout.total;
         size_t limit = 0;
         {
@@ -724,7 +788,7 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
             limit = (size_t) value;
         }
         if (smem + 2 * 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
-        const int width = plan.Nb * kBlock;
+        const int width = p.NbRel * kBlock;
         const int per_segment = 64;
         const int nseg = (int) ((p.nchunks + per_segment - 1) / per_segment);
         PCE_CUDA (d_T.resize ((size_t) p.nchunks * width));
@@ -757,12 +821,12 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         {
             const long long warps = p.nchunks * plan.Nb;
             const long long blocks = (warps * 32 + 255) / 256;
-            k_reduce_threads<<<(unsigned) blocks, 256, 0, m->stream>>> (d_T.ptr, p.nchunks, plan.Nb, d_Ftab.ptr);
+            k_reduce_threads<<<(unsigned) blocks, 256, 0, m->stream>>> (d_T.ptr, p.nchunks, p.NbRel, plan.Nb, d_ms.ptr + 2 * kBlock, d_Ftab.ptr);
             PCE_CUDA (cudaGetLastError ());
         }
         MarginalParams mp;
         std::memset (&mp, 0, sizeof (mp));
-        mp.Nb = plan.Nb; mp.P_M = p.P_M; mp.nM = p.nM; mp.nF = p.nF; mp.nO = p.nO; mp.write_z = r == 0 ? 1 : 0;
+        mp.Nb = plan.Nb; mp.NbRel = p.NbRel; mp.nMp = d_ms.ptr + 2 * kBlock; mp.P_M = p.P_M; mp.nM = p.nM; mp.nF = p.nF; mp.nO = p.nO; mp.write_z = r == 0 ? 1 : 0;
         mp.chunk_begin = c0; mp.nchunks = p.nchunks;
         int rows = 1;
         for (int i = 0; i < p.nM; i++) { mp.siteM[i] = p.siteM[i]; mp.radM[i] = p.radM[i]; mp.coverM[i] = run.coverM[i]; rows += p.radM[i]; }
