@@ -511,33 +511,27 @@ __global__ void __launch_bounds__ (kBlock) k_marginals (const MarginalParams p) 
     }
     const long long count = kind == 2 ? p.nchunks : p.P_M;
     const unsigned  base  = kind == 2 ? (unsigned) p.chunk_begin : 0u;
-    // which of this thread's entries match (up to 64 entries per thread: 16384 chunks / 256 threads)
-    unsigned long long mask = 0ull;
+    // one bin per block (blockIdx.y); entries are spread over the 256 threads (entry e -> thread e % 256, up to 64 per
+    // thread: 16384 chunks / 256 threads) and combined in a fixed order
+    const int n = blockIdx.y;
+    double acc = 0.0;
     for (int k = 0; k < 64; k++) {
         const long long e = tid + (long long) kBlock * k;
-        if (e < count && (kind == 0 || ((base + (unsigned) e) / stride) % rad == digit)) mask |= 1ull << k;
-    }
-    for (int n = 0; n < p.Nb; n++) {
-        double acc = 0.0;
-        for (int k = 0; k < 64; k++) {
-            if ((mask >> k) & 1ull) {
-                const long long e = tid + (long long) kBlock * k;
-                if (kind == 2) acc += p.Ftab[(size_t) e * p.Nb + n];
-                else {
-                    const int rel = n - p.nMp[e];
-                    if (rel >= 0 && rel < p.NbRel) acc += p.Mtab[(size_t) rel * kBlock + e];
-                }
+        if (e < count && (kind == 0 || ((base + (unsigned) e) / stride) % rad == digit)) {
+            if (kind == 2) acc += p.Ftab[(size_t) e * p.Nb + n];
+            else {
+                const int rel = n - p.nMp[e];
+                if (rel >= 0 && rel < p.NbRel) acc += p.Mtab[(size_t) rel * kBlock + e];
             }
         }
-        acc = pce::warp_sum (acc);
-        if (lane == 0) s_part[warp] = acc;
-        __syncthreads ();
-        if (tid == 0) {
-            double total = 0.0;
-            for (int w = 0; w < kBlock / 32; w++) total += s_part[w];
-            p.bins[(size_t) row * p.Nb + n] += total;
-        }
-        __syncthreads ();
+    }
+    acc = pce::warp_sum (acc);
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads ();
+    if (tid == 0) {
+        double total = 0.0;
+        for (int w = 0; w < kBlock / 32; w++) total += s_part[w];
+        p.bins[(size_t) row * p.Nb + n] += total;
     }
 }
 
@@ -832,7 +826,7 @@ int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshar
         for (int i = 0; i < p.nM; i++) { mp.siteM[i] = p.siteM[i]; mp.radM[i] = p.radM[i]; mp.coverM[i] = run.coverM[i]; rows += p.radM[i]; }
         for (int j = 0; j < p.nF; j++) { mp.siteF[j] = p.siteOut[p.nO + j]; mp.radF[j] = p.radOut[p.nO + j]; mp.coverF[j] = run.coverF[j]; rows += mp.radF[j]; }
         mp.first = m->d_first.ptr; mp.Mtab = d_Mtab.ptr; mp.Ftab = d_Ftab.ptr; mp.bins = d_bins;
-        k_marginals<<<rows, kBlock, 0, m->stream>>> (mp);
+        k_marginals<<<dim3 (rows, plan.Nb), kBlock, 0, m->stream>>> (mp);
         PCE_CUDA (cudaGetLastError ());
         pce::count_launch (6);
     }

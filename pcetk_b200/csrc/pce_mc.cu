@@ -512,36 +512,53 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         return idx >= (uint32_t) nsites ? __ldg (p.pair_packed + (idx - nsites)) : (idx | (idx << 16));
     };
 
-    auto trial = [&] (const uint32_t w0, const uint32_t w1, const uint32_t pr) {
+    // A prepared proposal: everything that can be known before the Metropolis test -- sites, old and new instances,
+    // and the four pair cross-term values, whose L2 loads are issued at preparation time.  Proposals are prepared four
+    // trials ahead from the current state; an accepted move invalidates the ones prepared after it (they are prepared
+    // again), so the sequence of decisions is exactly that of one-at-a-time evaluation.
+    struct Prepared { uint32_t w1; int sa, sb, oa, ob, ia, ib; bool dbl, valid; double c0, c1, c2, c3; };
+    auto prepare = [&] (const uint32_t w0, const uint32_t w1, const uint32_t pr) -> Prepared {
+        Prepared P;
         const unsigned long long prod = (unsigned long long) w0 * nmoves;
         const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
-        const bool     dbl = idx >= (uint32_t) nsites;
-        const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
-        const uint32_t ia_info = s_site[sa];
-        const int na = (int) (ia_info >> 16), oa = state[sa];
-        bool valid = na >= 2;
+        P.w1 = w1;
+        P.dbl = idx >= (uint32_t) nsites;
+        P.sa = (int) (pr & 0xffffu); P.sb = (int) (pr >> 16);
+        const uint32_t ia_info = s_site[P.sa];
+        const int na = (int) (ia_info >> 16);
+        P.oa = state[P.sa];
+        P.valid = na >= 2;
         const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
-        int ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
-        if (ia >= oa) ia++;
-        if (!valid) ia = oa;
-        double x = __dsub_rn (h[ia], h[oa]);
-        int ib = 0, ob = 0;
-        if (dbl) {
-            const uint32_t ib_info = s_site[sb];
+        P.ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
+        if (P.ia >= P.oa) P.ia++;
+        if (!P.valid) P.ia = P.oa;
+        P.ib = 0; P.ob = 0; P.c0 = P.c1 = P.c2 = P.c3 = 0.0;
+        if (P.dbl) {
+            const uint32_t ib_info = s_site[P.sb];
             const int nb = (int) (ib_info >> 16);
-            ob = state[sb];
-            if (nb < 2) valid = false;
+            P.ob = state[P.sb];
+            if (nb < 2) P.valid = false;
             const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
-            ib = (int) (ib_info & 0xffffu) + (int) kb;
-            if (ib >= ob) ib++;
-            if (!valid) { ib = ob; ia = oa; }
-            const double *ra = p.wb + (size_t) ia * ldw, *ro = p.wb + (size_t) oa * ldw;
-            const double c0 = __ldg (ra + ib), c1 = __ldg (ra + ob), c2 = __ldg (ro + ib), c3 = __ldg (ro + ob);   // 4 loads in flight
-            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (c0, c1), c2), c3);
-            x = __dadd_rn (__dadd_rn (__dsub_rn (h[ia], h[oa]), __dsub_rn (h[ib], h[ob])), cross);
+            P.ib = (int) (ib_info & 0xffffu) + (int) kb;
+            if (P.ib >= P.ob) P.ib++;
+            if (!P.valid) { P.ib = P.ob; P.ia = P.oa; }
+            const double *ra = p.wb + (size_t) P.ia * ldw, *ro = p.wb + (size_t) P.oa * ldw;
+            P.c0 = __ldg (ra + P.ib); P.c1 = __ldg (ra + P.ob); P.c2 = __ldg (ro + P.ib); P.c3 = __ldg (ro + P.ob);
+        }
+        return P;
+    };
+
+    // Metropolis test and, when accepted, the field update and bookkeeping.  Returns whether the state changed.
+    auto evaluate = [&] (const Prepared &P) -> bool {
+        const int sa = P.sa, sb = P.sb, oa = P.oa, ob = P.ob, ia = P.ia, ib = P.ib;
+        const bool dbl = P.dbl;
+        double x = __dsub_rn (h[ia], h[oa]);
+        if (dbl) {
+            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (P.c0, P.c1), P.c2), P.c3);
+            x = __dadd_rn (__dadd_rn (x, __dsub_rn (h[ib], h[ob])), cross);
             if (production) c_flips++;
         }
-        const bool accept = valid && metropolis (x, w1);      // warp-uniform
+        const bool accept = P.valid && metropolis (x, P.w1);      // warp-uniform
         if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) { lg_f++; lg_fa += accept; } else { lg_m++; lg_ma += accept; } }
         if (accept) {
             // hb += wb[ia] - wb[oa] (+ wb[ib] - wb[ob]); rows are 32-byte aligned (ldw multiple of 4)
@@ -605,6 +622,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             production = scan >= p.nequil;
             tp = production ? (uint32_t) (scan - p.nequil) : 0u;
         }
+        return accept;
     };
 
     // Random numbers for 64 trials at a time: lane l generates Philox block b0 + l (two trials) and fetches the two
@@ -616,14 +634,21 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         const uint32_t t0 = target (r.x), t1 = target (r.z);
         const unsigned long long left = ntrials - 2ull * b0;
         const int nj = left < 64ull ? (int) left : 64;
-#pragma unroll 1
-        for (int j = 0; j < nj; j++) {
+        auto prepare_trial = [&] (int j) -> Prepared {
             const int  src = j >> 1;
             const bool odd = j & 1;
             const uint32_t w0 = __shfl_sync (0xffffffffu, odd ? r.z : r.x, src);
             const uint32_t w1 = __shfl_sync (0xffffffffu, odd ? r.w : r.y, src);
             const uint32_t pr = __shfl_sync (0xffffffffu, odd ? t1 : t0, src);
-            trial (w0, w1, pr);
+            return prepare (w0, w1, pr);
+        };
+#pragma unroll 1
+        for (int j = 0; j < nj; j += 4) {
+            Prepared P0 = prepare_trial (j), P1 = prepare_trial ((j + 1) & 63), P2 = prepare_trial ((j + 2) & 63), P3 = prepare_trial ((j + 3) & 63);
+            if (evaluate (P0)) { P1 = prepare_trial ((j + 1) & 63); P2 = prepare_trial ((j + 2) & 63); P3 = prepare_trial ((j + 3) & 63); }
+            if (j + 1 < nj && evaluate (P1)) { P2 = prepare_trial ((j + 2) & 63); P3 = prepare_trial ((j + 3) & 63); }
+            if (j + 2 < nj && evaluate (P2)) { P3 = prepare_trial ((j + 3) & 63); }
+            if (j + 3 < nj) evaluate (P3);
         }
     }
 
