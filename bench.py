@@ -388,6 +388,10 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if args.workload != "synthA":
+            c = d_counters.sum(dim=0).cpu().numpy().astype(float)       # production trials: moves, accepted, flips, accepted
+            line["config"]["acceptance"] = {"single": c[1] / max(c[0], 1.0), "double": c[3] / max(c[2], 1.0),
+                                            "overall": (c[1] + c[3]) / max(c[0] + c[2], 1.0)}
         if world == 1 and not args.no_cpu_baseline and args.workload in ("lysozyme", "ifp20", "defensin"):
             rate, seconds, kind = cpu_baseline(record, 500, 20000, grid_all, 1, repeats=3 if args.workload != "ifp20" else 1)
             line["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind,

@@ -137,7 +137,7 @@ int  pce_mc_npairs (const pce_mc *mc);
 int  pce_mc_get_pair (const pce_mc *mc, int index, int *site_a, int *site_b, double *wmax);   /* StateVector_GetPair */
 int  pce_mc_set_scans (pce_mc *mc, int nequil, int nprod);
 int  pce_mc_set_chains (pce_mc *mc, int nchains);
-int  pce_mc_set_kernel (pce_mc *mc, int kernel);   /* 0 = auto, 1 = chain-per-thread, 2 = chain-per-warp */
+int  pce_mc_set_kernel (pce_mc *mc, int kernel);   /* 0 = auto, 1 = chain per thread, 2 = chain per warp */
 int  pce_mc_get_info (const pce_mc *mc, int *kernel, int *nchains, int *nequil, int *nprod, long long *seed);
 /* launch geometry the sampler would use for nph pH values (any output may be NULL): chains_per_wave is the number of
  * chains resident on the whole device at once -- size nph*nchains as a multiple of it to run in full waves */

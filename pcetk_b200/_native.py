@@ -15,7 +15,7 @@ import numpy as np
 from .errors import CLibraryError, NativeLibraryMissing
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(HERE, "libpcetk_b200.so")
+LIBRARY_PATH = os.environ.get("PCETK_B200_LIBRARY") or os.path.join(HERE, "libpcetk_b200.so")      # override: tuning builds
 
 PCE_OK = 0
 PCE_ERR_ALLOC, PCE_ERR_INDEX, PCE_ERR_VALUE, PCE_ERR_SHAPE, PCE_ERR_STATE, PCE_ERR_CUDA, PCE_ERR_LIMIT = range(1, 8)

@@ -62,6 +62,7 @@ struct pce_model {
     std::vector<double>  wsym;                 // [ninst*ninst] full square of EnergyModel.h:48 "symmetricmatrix"
     bool   symmetrized = false;
     bool   dirty       = true;                 // host copy newer than device copy
+    int    generation  = 0;                    // bumped by every real upload (derived device tables key on it)
     cudaStream_t stream = nullptr;
 
     // device mirror

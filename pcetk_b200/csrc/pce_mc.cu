@@ -36,9 +36,15 @@ struct pce_mc {
     std::vector<double>  pair_wmax;
     pce::DeviceBuffer<int32_t> d_pair_a, d_pair_b;
     pce::DeviceBuffer<uint32_t> d_pair_packed;
+    pce::DeviceBuffer<float>    d_pair_bound;
+    int  bound_generation = -1;
     pce::DeviceBuffer<double>  d_ph, d_esum;
     pce::DeviceBuffer<unsigned long long> d_counts;
     pce::DeviceBuffer<long long> d_counters;
+    pce::DeviceBuffer<double>  d_dw;                 // difference rows wb[hi] - wb[lo] of every instance pair of a site
+    pce::DeviceBuffer<int32_t> d_dbase;              // first difference row of each site
+    int  dw_generation = -1, dw_ldd = 0;              // model generation / row stride the difference rows were built for
+    bool dw_valid = false;
     bool pairs_dirty = true;
 };
 
@@ -48,6 +54,7 @@ struct McParams {
     int nsites, ninst, npairs, ldw;
     const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
     const uint32_t *pair_packed;            // site a | site b << 16
+    const float    *pair_bound;             // upper bound of |cross term| of the pair in units of RT (k_mc_warp)
     const double  *gintr, *w, *wb, *ph;      // wb = beta * W (units of RT)
     int       nph, ph_index_offset, nchains, nequil, nprod;
     long long chain_offset;
@@ -65,6 +72,9 @@ struct McParams {
     long long *log_rows;            // [(nequil/f + nprod/f) * 5] scan, moves, accepted, flips, accepted per block of f scans (chain 0, pH 0)
     int        log_frequency;
     int        w_in_smem;
+    const double  *dw;              // warp kernels: difference rows [nrows][ldw] (nullptr: stream the W rows themselves)
+    const int32_t *dbase;           // [nsites] first difference row of the site
+    int            ldd;             // row stride of dw = padded field length of the launch
 };
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
@@ -414,35 +424,153 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_mc_warp: one chain per warp.  Every lane evaluates the (warp-uniform) proposal; accepted moves are
-// applied by all lanes with 128-bit loads of the beta-scaled W rows from L2.
-// Shared memory per warp: hb[ldh] doubles | since[nsites] u32 | state[nsites] u16
+// Applying an accepted move in the warp kernels: hb += wb[ia] - wb[oa] (+ wb[ib] - wb[ob]).
+// The row differences of all instance pairs of a site are precomputed (k_build_dw: D = wb[hi] - wb[lo], one rounding,
+// the same value the subtraction yields at run time; the opposite direction is its exact negation), which halves the
+// L2 traffic of an accepted move -- the roofline of the 1000-site model.  Loads are issued in fixed batches of U
+// predicated 128-bit loads per lane so that no serial remainder loop is left.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_build_dw (const double *__restrict__ wb, int ninst, int ldw, int ldd, const int32_t *__restrict__ row_lo,
+                            const int32_t *__restrict__ row_hi, double *__restrict__ dw) {
+    const int r = blockIdx.x;
+    const double *hi = wb + (size_t) row_hi[r] * ldw, *lo = wb + (size_t) row_lo[r] * ldw;
+    for (int k = threadIdx.x; k < ldd; k += blockDim.x) dw[(size_t) r * ldd + k] = k < ninst ? __dsub_rn (hi[k], lo[k]) : 0.0;     // zero padding
+}
+
+// difference row and direction (sign-bit mask) of the move oa -> ia on a site whose first instance is `first`
+__device__ __forceinline__ void diff_row (const McParams &p, int site, int first, int ia, int oa, const double2 **row, uint32_t *flip) {
+    const int a = ia - first, o = oa - first;
+    const int mx = a > o ? a : o, mn = a > o ? o : a;
+    const int r = __ldg (p.dbase + site) + ((mx * (mx - 1)) >> 1) + mn;
+    *row  = (const double2 *) (p.dw + (size_t) r * p.ldd);
+    *flip = a < o ? 0x80000000u : 0u;
+}
+
+__device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
+    return __hiloint2double (__double2hiint (v) ^ (int) mask, __double2loint (v));
+}
+
+// hb += (+-)D1 (+ (+-)D2): n2 (the padded field length in double2) is a multiple of 32 * U, so every batch is U
+// unpredicated 128-bit loads per lane and row, all issued before the first use
+template <int U>
+__device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, const double2 *r1, uint32_t f1, const double2 *r2, uint32_t f2, bool two) {
+    if (!two) {
+        for (int k0 = lane; k0 < n2; k0 += 32 * U) {
+            double2 a[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) a[u] = __ldg (r1 + k0 + 32 * u);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                double2 v = h2[k0 + 32 * u];
+                v.x = __dadd_rn (v.x, flip_sign (a[u].x, f1));
+                v.y = __dadd_rn (v.y, flip_sign (a[u].y, f1));
+                h2[k0 + 32 * u] = v;
+            }
+        }
+    } else {
+        for (int k0 = lane; k0 < n2; k0 += 32 * U) {
+            double2 a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { a[u] = __ldg (r1 + k0 + 32 * u); b[u] = __ldg (r2 + k0 + 32 * u); }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                double2 v = h2[k0 + 32 * u];
+                v.x = __dadd_rn (__dadd_rn (v.x, flip_sign (a[u].x, f1)), flip_sign (b[u].x, f2));
+                v.y = __dadd_rn (__dadd_rn (v.y, flip_sign (a[u].y, f1)), flip_sign (b[u].y, f2));
+                h2[k0 + 32 * u] = v;
+            }
+        }
+    }
+}
+
+// the same from the W rows themselves (models whose difference rows exceed the memory budget); nw2 = ldw / 2
+template <int U>
+__device__ __forceinline__ void apply_w_rows (double2 *h2, int nw2, int lane, const double2 *rna, const double2 *roa, const double2 *rnb, const double2 *rob, bool two) {
+    if (!two) {
+#pragma unroll (U)
+        for (int k = lane; k < nw2; k += 32) {
+            const double2 a = __ldg (rna + k), b = __ldg (roa + k);
+            double2 v = h2[k];
+            v.x = __dadd_rn (v.x, __dsub_rn (a.x, b.x));
+            v.y = __dadd_rn (v.y, __dsub_rn (a.y, b.y));
+            h2[k] = v;
+        }
+    } else {
+#pragma unroll (U / 2 > 0 ? U / 2 : 1)
+        for (int k = lane; k < nw2; k += 32) {
+            const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
+            double2 v = h2[k];
+            v.x = __dadd_rn (__dadd_rn (v.x, __dsub_rn (a.x, b.x)), __dsub_rn (c.x, d.x));
+            v.y = __dadd_rn (__dadd_rn (v.y, __dsub_rn (a.y, b.y)), __dsub_rn (c.y, d.y));
+            h2[k] = v;
+        }
+    }
+}
+
+template <int U>
+__device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s_site, double *h, int ldh, int ldw, int lane,
+                                            int sa, int sb, int ia, int oa, int ib, int ob, bool dbl) {
+    double2 *h2 = (double2 *) h;
+    if (p.dw != nullptr) {
+        const double2 *r1, *r2 = nullptr;
+        uint32_t f1, f2 = 0u;
+        diff_row (p, sa, (int) (s_site[sa] & 0xffffu), ia, oa, &r1, &f1);
+        if (dbl) diff_row (p, sb, (int) (s_site[sb] & 0xffffu), ib, ob, &r2, &f2);
+        apply_diff_rows<U> (h2, ldh >> 1, lane, r1, f1, r2, f2, dbl);
+    } else {
+        apply_w_rows<(U < 8 ? U : 8)> (h2, ldw >> 1, lane, (const double2 *) (p.wb + (size_t) ia * ldw), (const double2 *) (p.wb + (size_t) oa * ldw),
+                                      (const double2 *) (p.wb + (size_t) ib * ldw), (const double2 *) (p.wb + (size_t) ob * ldw), dbl);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_mc_warp: one chain per warp, trials evaluated SPECULATIVELY IN PARALLEL BY THE LANES.
+//
+// A trial's proposal and Metropolis test depend on the chain's state only; as long as no move is accepted the state
+// does not change, so the next 32*TPL trials can all be evaluated at once against the current state, one (or TPL) per
+// lane.  The first accepted trial (ballot + find-first-set) is applied; the trials before it were rightly rejected,
+// the ones after it are evaluated again in the next round.  The sequence of decisions is exactly that of one-at-a-time
+// evaluation (the chain specification), at 1/32 .. 1/64 of the instructions when acceptance is low, and the four
+// pair cross-term gathers of up to 64 trials are in flight together instead of one trial's.
+//
+// Random words live in a per-warp shared-memory ring (w0 | w1 | proposal target per trial), refilled 64 trials at a
+// time: lane l generates Philox block b + l (two trials) and fetches the two proposal targets (site, or packed pair
+// from the pair table -- state independent, so its L2 latency is paid long before the trial is evaluated).
+// A round never crosses the end of a scan, so the per-scan bookkeeping stays once per scan.
+// Accepted moves are applied by all lanes with 128-bit loads of the beta-scaled W rows from L2.
+// Shared memory per warp: hb[ldh] doubles | since[nsites] u32 | state[nsites] u16 | ring[4][RING] u32
 // ---------------------------------------------------------------------------------------------------
 struct WarpLayout {
-    size_t off_site, off_h, off_since, off_state, per_warp, shared_bytes;
-    int    ldh;
-    __host__ __device__ WarpLayout (int nsites, int ninst) {
-        ldh = (ninst + 3) & ~3;
+    size_t off_site, off_h, off_since, off_state, off_ring, per_warp, shared_bytes;
+    int    ldh, ring;
+    __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd) {
+        ldh  = (ninst + 64 * upd - 1) / (64 * upd) * (64 * upd);        // whole batches of the field update (apply_diff_rows)
+        ring = tpl <= 2 ? 128 : 256;
         shared_bytes = ((size_t) nsites * 4 + 15) & ~(size_t) 15;     // packed site table, one copy per CTA
         off_site = 0;
         size_t o = 0;
         off_h = o;     o += (size_t) ldh * 8;
         off_since = o; o += (size_t) nsites * 4;
         off_state = o; o += (size_t) nsites * 2;
+        o = (o + 7) & ~(size_t) 7;
+        off_ring = o;  o += (size_t) ring * 16;
         per_warp = (o + 15) & ~(size_t) 15;
     }
 };
 
-template <bool PER_CHAIN, int MIN_CTAS>
+template <bool PER_CHAIN, int MIN_CTAS, int TPL>
 __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const WarpLayout L (p.nsites, p.ninst);
+    constexpr int RING = TPL <= 2 ? 128 : 256;
+    constexpr int UPD  = MIN_CTAS == 1 ? 16 : 4;      // 128-bit loads per lane, row and batch when a move is applied
+    const WarpLayout L (p.nsites, p.ninst, TPL, UPD);
     uint32_t      *s_site = (uint32_t *) smem;                        // first | ninst << 16 per site (CTA-wide)
     unsigned char *base   = smem + L.shared_bytes + (size_t) wib * L.per_warp;
     double        *h      = (double *) (base + L.off_h);
     uint32_t      *since  = (uint32_t *) (base + L.off_since);
     uint16_t      *state  = (uint16_t *) (base + L.off_state);
+    uint32_t      *ring   = (uint32_t *) (base + L.off_ring);          // [0,RING) w0 | w1 | target | bound of the pair cross term
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
     for (int i = threadIdx.x; i < nsites; i += blockDim.x) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
@@ -463,35 +591,57 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     __syncwarp ();
     const double mu   = ph_to_mu (p.temperature, p.ph[q]);
     const double beta = 1.0 / (PCE_R * p.temperature);
-    // fused fields: lanes over k, j sequential (spec order); wb[k][a_j] gathers, once per chain
-    for (int k = lane; k < L.ldh; k += 32) {
-        double acc = 0.0;
-        if (k < ninst) {
-            const double *row = p.wb + (size_t) k * ldw;
-            acc = __dmul_rn (beta, __dsub_rn (__ldg (p.gintr + k), __dmul_rn ((double) __ldg (p.protons + k), mu)));
-            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, __ldg (row + state[j]));
+    auto gtb = [&] (int k) -> double {       // intrinsic term of instance k in units of RT
+        return __dmul_rn (beta, __dsub_rn (__ldg (p.gintr + k), __dmul_rn ((double) __ldg (p.protons + k), mu)));
+    };
+    // fused fields hb[k] = gtb[k] + sum_j wb[k][a_j], j sequential (spec order).  W is bitwise symmetric, so the
+    // gathers wb[k][a_j] are taken as the coalesced row reads wb[a_j][k]: a chunk of 256 consecutive k per pass
+    // (each lane owns 4 double2), every row of the state streamed once per chunk with 128-bit loads.
+    {
+        constexpr int CH = 4;
+        const int n2 = L.ldh >> 1, nw2 = ldw >> 1;
+        for (int c0 = 0; c0 < n2; c0 += 32 * CH) {
+            double2 acc[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int k2 = c0 + c * 32 + lane, k = 2 * k2;
+                acc[c].x = k < ninst ? gtb (k) : 0.0;
+                acc[c].y = k + 1 < ninst ? gtb (k + 1) : 0.0;
+            }
+#pragma unroll 2
+            for (int j = 0; j < nsites; j++) {
+                const double2 *row = (const double2 *) (p.wb + (size_t) state[j] * ldw);
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int k2 = c0 + c * 32 + lane;
+                    if (k2 < nw2) {
+                        const double2 v = __ldg (row + k2);
+                        acc[c].x = __dadd_rn (acc[c].x, v.x);
+                        acc[c].y = __dadd_rn (acc[c].y, v.y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int k2 = c0 + c * 32 + lane;
+                if (k2 < n2) ((double2 *) h)[k2] = acc[c];
+            }
         }
-        h[k] = acc;
     }
     __syncwarp ();
 
-    // initial energy.  The reference order (EnergyModel.c:204-224) is a serial sum over i then j < i; here
-    // lanes take rows i = lane, lane+32, ... and the partial sums are combined, so the value may differ
-    // from the serial sum in the last bits.  It only seeds the tracked energy (informational output).
+    // initial energy in units of RT.  sum_i hb[a_i] counts every pair interaction twice and the intrinsic terms once,
+    // so G/RT = (sum_i hb[a_i] + sum_i gtb[a_i]) / 2: O(nsites) instead of the O(nsites^2) gathers of
+    // EnergyModel.c:204-224.  Equal to the reference-order value to rounding (~1e-13 relative); it only seeds the
+    // tracked energy (informational output).
     double grt;
     {
-        double gi = 0.0, ws = 0.0;
-        int    np = 0;
+        double s = 0.0;
         for (int i = lane; i < nsites; i += 32) {
             const int ai = state[i];
-            gi += __ldg (p.gintr + ai);
-            np += __ldg (p.protons + ai);
-            const double *row = p.w + (size_t) ai * ldw;
-            for (int j = 0; j < i; j++) ws += __ldg (row + state[j]);
+            s += h[ai] + gtb (ai);
         }
-        gi = pce::warp_sum (gi); ws = pce::warp_sum (ws);
-        for (int o = 16; o > 0; o >>= 1) np += __shfl_xor_sync (0xffffffffu, np, o);
-        grt = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
+        grt = 0.5 * pce::warp_sum (s);
     }
 
     const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
@@ -505,86 +655,132 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                                            : p.counts + (size_t) q * ninst;
     uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
 
-    // proposal target of a random word: site (single move) or packed pair, fetched one Philox block ahead of its use
-    // because it does not depend on the chain's state (hides the L2 latency of the pair table)
+    // proposal target of a random word: site (single move, b = a) or packed pair
     auto target = [&] (const uint32_t w0) -> uint32_t {
         const uint32_t idx = __umulhi (w0, nmoves);
         return idx >= (uint32_t) nsites ? __ldg (p.pair_packed + (idx - nsites)) : (idx | (idx << 16));
     };
 
-    // A prepared proposal: everything that can be known before the Metropolis test -- sites, old and new instances,
-    // and the four pair cross-term values, whose L2 loads are issued at preparation time.  Proposals are prepared four
-    // trials ahead from the current state; an accepted move invalidates the ones prepared after it (they are prepared
-    // again), so the sequence of decisions is exactly that of one-at-a-time evaluation.
-    struct Prepared { uint32_t w1; int sa, sb, oa, ob, ia, ib; bool dbl, valid; double c0, c1, c2, c3; };
-    auto prepare = [&] (const uint32_t w0, const uint32_t w1, const uint32_t pr) -> Prepared {
-        Prepared P;
-        const unsigned long long prod = (unsigned long long) w0 * nmoves;
-        const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
-        P.w1 = w1;
-        P.dbl = idx >= (uint32_t) nsites;
-        P.sa = (int) (pr & 0xffffu); P.sb = (int) (pr >> 16);
-        const uint32_t ia_info = s_site[P.sa];
-        const int na = (int) (ia_info >> 16);
-        P.oa = state[P.sa];
-        P.valid = na >= 2;
-        const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
-        P.ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
-        if (P.ia >= P.oa) P.ia++;
-        if (!P.valid) P.ia = P.oa;
-        P.ib = 0; P.ob = 0; P.c0 = P.c1 = P.c2 = P.c3 = 0.0;
-        if (P.dbl) {
-            const uint32_t ib_info = s_site[P.sb];
-            const int nb = (int) (ib_info >> 16);
-            P.ob = state[P.sb];
-            if (nb < 2) P.valid = false;
-            const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
-            P.ib = (int) (ib_info & 0xffffu) + (int) kb;
-            if (P.ib >= P.ob) P.ib++;
-            if (!P.valid) { P.ib = P.ob; P.ia = P.oa; }
-            const double *ra = p.wb + (size_t) P.ia * ldw, *ro = p.wb + (size_t) P.oa * ldw;
-            P.c0 = __ldg (ra + P.ib); P.c1 = __ldg (ra + P.ob); P.c2 = __ldg (ro + P.ib); P.c3 = __ldg (ro + P.ob);
-        }
-        return P;
+    auto bound = [&] (const uint32_t w0) -> float {
+        const uint32_t idx = __umulhi (w0, nmoves);
+        return idx >= (uint32_t) nsites ? __ldg (p.pair_bound + (idx - nsites)) : 0.0f;
     };
 
-    // Metropolis test and, when accepted, the field update and bookkeeping.  Returns whether the state changed.
-    auto evaluate = [&] (const Prepared &P) -> bool {
-        const int sa = P.sa, sb = P.sb, oa = P.oa, ob = P.ob, ia = P.ia, ib = P.ib;
-        const bool dbl = P.dbl;
-        double x = __dsub_rn (h[ia], h[oa]);
-        if (dbl) {
-            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (P.c0, P.c1), P.c2), P.c3);
-            x = __dadd_rn (__dadd_rn (x, __dsub_rn (h[ib], h[ob])), cross);
-            if (production) c_flips++;
+    unsigned long long tcur = 0, tfill = 0;        // next trial to decide; trials [tcur, tfill) are in the ring
+    while (tcur < ntrials) {
+        while (tfill - tcur < (unsigned long long) (32 * TPL)) {
+            const unsigned long long bl = (tfill >> 1) + (unsigned long long) lane;
+            const pce::Philox4 r = pce::philox4x32_10 ((uint32_t) bl, (uint32_t) (bl >> 32), chain, phidx, p.k0, p.k1);
+            const uint32_t slot = ((uint32_t) tfill & (uint32_t) (RING - 1)) + 2u * (uint32_t) lane;
+            *(uint2 *) (ring + slot)            = make_uint2 (r.x, r.z);
+            *(uint2 *) (ring + RING + slot)     = make_uint2 (r.y, r.w);
+            *(uint2 *) (ring + 2 * RING + slot) = make_uint2 (target (r.x), target (r.z));
+            *(float2 *) (ring + 3 * RING + slot) = make_float2 (bound (r.x), bound (r.z));
+            tfill += 64ull;
         }
-        const bool accept = P.valid && metropolis (x, P.w1);      // warp-uniform
-        if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) { lg_f++; lg_fa += accept; } else { lg_m++; lg_ma += accept; } }
-        if (accept) {
-            // hb += wb[ia] - wb[oa] (+ wb[ib] - wb[ob]); rows are 32-byte aligned (ldw multiple of 4)
-            const double2 *rna = (const double2 *) (p.wb + (size_t) ia * ldw), *roa = (const double2 *) (p.wb + (size_t) oa * ldw);
-            const double2 *rnb = (const double2 *) (p.wb + (size_t) ib * ldw), *rob = (const double2 *) (p.wb + (size_t) ob * ldw);
-            double2       *h2  = (double2 *) h;
-            const int      n2  = L.ldh >> 1;
-            if (!dbl) {
-#pragma unroll 8
-                for (int k = lane; k < n2; k += 32) {
-                    const double2 a = __ldg (rna + k), b = __ldg (roa + k);
-                    double2 v = h2[k];
-                    v.x = __dadd_rn (v.x, __dsub_rn (a.x, b.x));
-                    v.y = __dadd_rn (v.y, __dsub_rn (a.y, b.y));
-                    h2[k] = v;
+        __syncwarp ();
+
+        // ---- evaluate 32*TPL trials against the current state ----
+        const uint32_t left_in_scan = nmoves - mv;
+        const uint32_t n_act = left_in_scan < (uint32_t) (32 * TPL) ? left_in_scan : (uint32_t) (32 * TPL);
+        uint32_t e_pr[TPL], e_a[TPL], e_b[TPL], e_w1[TPL];     // sa | sb << 16,  ia | oa << 16,  ib | ob << 16
+        double   e_x[TPL], e_c[TPL][4];
+        bool     e_dbl[TPL], e_need[TPL];
+        unsigned accm[TPL], dblm[TPL];
+        // phase 1: decode every trial of the round, form the field part of the energy change, and issue the pair
+        // cross-term gathers (all in flight together) -- except for double moves that are CERTAINLY rejected whatever
+        // their cross term is: x >= x0 - B with B the pair's bound, so u > exp (-(x0 - B)) (fp32, directed rounding,
+        // 1e-3 margin) decides without touching W.  Most double moves end here: 4 L2 sectors saved each.
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+            const uint32_t off  = (uint32_t) (u * 32 + lane);
+            const uint32_t slot = ((uint32_t) tcur + off) & (uint32_t) (RING - 1);
+            const uint32_t w0 = ring[slot], pr = ring[2 * RING + slot];
+            e_w1[u] = ring[RING + slot];
+            const float pbound = __uint_as_float (ring[3 * RING + slot]);
+            const bool act = off < n_act;
+            const unsigned long long prod = (unsigned long long) w0 * nmoves;
+            const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
+            const bool dbl = idx >= (uint32_t) nsites;
+            const int  sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
+            const uint32_t ia_info = s_site[sa];
+            const int na = (int) (ia_info >> 16), oa = state[sa];
+            bool valid = na >= 2;
+            const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
+            int ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
+            if (ia >= oa) ia++;
+            if (!valid) ia = oa;
+            int ib = 0, ob = 0;
+            e_c[u][0] = e_c[u][1] = e_c[u][2] = e_c[u][3] = 0.0;
+            e_need[u] = false;
+            double x = 0.0;
+            if (dbl) {
+                const uint32_t ib_info = s_site[sb];
+                const int nb = (int) (ib_info >> 16);
+                ob = state[sb];
+                if (nb < 2) valid = false;
+                const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
+                ib = (int) (ib_info & 0xffffu) + (int) kb;
+                if (ib >= ob) ib++;
+                if (!valid) { ib = ob; ia = oa; }
+                x = __dadd_rn (__dsub_rn (h[ia], h[oa]), __dsub_rn (h[ib], h[ob]));
+                const float xlow = __fsub_rd (__double2float_rd (x), pbound);            // <= x0 - B <= x
+                const float ulow = __uint2float_rd (e_w1[u]) * 2.3283064365386963e-10f;  // <= u
+                const bool certain = xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
+                if (act && valid && !certain) {
+                    const double *ra = p.wb + (size_t) ia * ldw, *ro = p.wb + (size_t) oa * ldw;
+                    e_c[u][0] = __ldg (ra + ib); e_c[u][1] = __ldg (ra + ob); e_c[u][2] = __ldg (ro + ib); e_c[u][3] = __ldg (ro + ob);
+                    e_need[u] = true;
                 }
             } else {
-#pragma unroll 4
-                for (int k = lane; k < n2; k += 32) {
-                    const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
-                    double2 v = h2[k];
-                    v.x = __dadd_rn (__dadd_rn (v.x, __dsub_rn (a.x, b.x)), __dsub_rn (c.x, d.x));
-                    v.y = __dadd_rn (__dadd_rn (v.y, __dsub_rn (a.y, b.y)), __dsub_rn (c.y, d.y));
-                    h2[k] = v;
-                }
+                x = __dsub_rn (h[ia], h[oa]);
+                e_need[u] = act && valid;
             }
+            e_dbl[u] = dbl; e_x[u] = x;
+            dblm[u] = __ballot_sync (0xffffffffu, act && dbl);
+            e_pr[u] = pr; e_a[u] = (uint32_t) ia | ((uint32_t) oa << 16); e_b[u] = (uint32_t) ib | ((uint32_t) ob << 16);
+        }
+        // phase 2: cross terms and Metropolis tests
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+            double x = e_x[u];
+            if (e_dbl[u]) x = __dadd_rn (x, __dadd_rn (__dsub_rn (__dsub_rn (e_c[u][0], e_c[u][1]), e_c[u][2]), e_c[u][3]));
+            const bool accept = metropolis (x, e_w1[u]) && e_need[u];
+            accm[u] = __ballot_sync (0xffffffffu, accept);
+            e_x[u] = x;
+        }
+
+        // ---- the first accepted trial ends the round ----
+        int ustar = -1, lstar = 0;
+#pragma unroll
+        for (int u = TPL - 1; u >= 0; u--) if (accm[u]) { ustar = u; lstar = __ffs (accm[u]) - 1; }
+        const uint32_t consumed = ustar >= 0 ? (uint32_t) (ustar * 32 + lstar + 1) : n_act;
+        uint32_t ndbl = 0;
+#pragma unroll
+        for (int u = 0; u < TPL; u++) {
+            const int c = (int) consumed - u * 32;
+            const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
+            ndbl += (uint32_t) __popc (dblm[u] & m);
+        }
+        if (production) c_flips += ndbl;
+        if (PER_CHAIN && p.log_rows != nullptr) { lg_f += ndbl; lg_m += consumed - ndbl; }
+
+        if (ustar >= 0) {
+            uint32_t s_pr = 0, s_a = 0, s_b = 0;
+            double   s_x = 0.0;
+#pragma unroll
+            for (int u = 0; u < TPL; u++) if (u == ustar) { s_pr = e_pr[u]; s_a = e_a[u]; s_b = e_b[u]; s_x = e_x[u]; }
+            s_pr = __shfl_sync (0xffffffffu, s_pr, lstar);
+            s_a  = __shfl_sync (0xffffffffu, s_a, lstar);
+            s_b  = __shfl_sync (0xffffffffu, s_b, lstar);
+            const double x = __shfl_sync (0xffffffffu, s_x, lstar);
+            bool dbl = false;
+#pragma unroll
+            for (int u = 0; u < TPL; u++) if (u == ustar) dbl = (dblm[u] >> lstar) & 1u;
+            const int sa = (int) (s_pr & 0xffffu), sb = (int) (s_pr >> 16);
+            const int ia = (int) (s_a & 0xffffu), oa = (int) (s_a >> 16), ib = (int) (s_b & 0xffffu), ob = (int) (s_b >> 16);
+            if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) lg_fa++; else lg_ma++; }
+            apply_move<UPD> (p, s_site, h, L.ldh, ldw, lane, sa, sb, ia, oa, ib, ob, dbl);
             grt = __dadd_rn (grt, x);
             if (lane == 0) {
                 const uint32_t since_a = since[sa];
@@ -599,9 +795,12 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 }
             }
             if (production) { if (dbl) c_facc++; else c_macc++; }
-            __syncwarp ();
         }
-        if (++mv == nmoves) {
+        __syncwarp ();       // state, stamps and fields of this round are visible to every lane before the next one
+
+        mv += consumed;
+        tcur += (unsigned long long) consumed;
+        if (mv == nmoves) {     // scan bookkeeping (MCModelDefault.c:298-312)
             mv = 0;
             if (production) {
                 esum += grt;
@@ -621,34 +820,6 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             scan++;
             production = scan >= p.nequil;
             tp = production ? (uint32_t) (scan - p.nequil) : 0u;
-        }
-        return accept;
-    };
-
-    // Random numbers for 64 trials at a time: lane l generates Philox block b0 + l (two trials) and fetches the two
-    // proposal targets; each trial then takes its words from the owning lane by shuffle.  Same stream as one block per
-    // two trials generated in order, at 1/32 of the instruction cost, and the pair-table loads run far ahead of their use.
-    for (unsigned long long b0 = 0; 2ull * b0 < ntrials; b0 += 32) {
-        const unsigned long long bl = b0 + (unsigned long long) lane;
-        const pce::Philox4 r = pce::philox4x32_10 ((uint32_t) bl, (uint32_t) (bl >> 32), chain, phidx, p.k0, p.k1);
-        const uint32_t t0 = target (r.x), t1 = target (r.z);
-        const unsigned long long left = ntrials - 2ull * b0;
-        const int nj = left < 64ull ? (int) left : 64;
-        auto prepare_trial = [&] (int j) -> Prepared {
-            const int  src = j >> 1;
-            const bool odd = j & 1;
-            const uint32_t w0 = __shfl_sync (0xffffffffu, odd ? r.z : r.x, src);
-            const uint32_t w1 = __shfl_sync (0xffffffffu, odd ? r.w : r.y, src);
-            const uint32_t pr = __shfl_sync (0xffffffffu, odd ? t1 : t0, src);
-            return prepare (w0, w1, pr);
-        };
-#pragma unroll 1
-        for (int j = 0; j < nj; j += 4) {
-            Prepared P0 = prepare_trial (j), P1 = prepare_trial ((j + 1) & 63), P2 = prepare_trial ((j + 2) & 63), P3 = prepare_trial ((j + 3) & 63);
-            if (evaluate (P0)) { P1 = prepare_trial ((j + 1) & 63); P2 = prepare_trial ((j + 2) & 63); P3 = prepare_trial ((j + 3) & 63); }
-            if (j + 1 < nj && evaluate (P1)) { P2 = prepare_trial ((j + 2) & 63); P3 = prepare_trial ((j + 3) & 63); }
-            if (j + 2 < nj && evaluate (P2)) { P3 = prepare_trial ((j + 3) & 63); }
-            if (j + 3 < nj) evaluate (P3);
         }
     }
 
@@ -681,7 +852,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 // ---------------------------------------------------------------------------------------------------
 // launch planning
 // ---------------------------------------------------------------------------------------------------
-struct Plan { int kernel, block, w_in_smem; size_t smem; int ctas_per_sm; };
+struct Plan { int kernel, block, w_in_smem; size_t smem; int ctas_per_sm; int tpl; int upd; };      // upd: 128-bit loads per lane and batch of the field update
 
 int smem_limit (int device, size_t *limit) {
     int value = 0;
@@ -717,16 +888,32 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     return best_warps >= 2;
 }
 
+// trials evaluated per lane and round by the chain-per-warp kernel: 1 (default; measured best on every model, the kernel
+// being bound by the L1TEX/LSU wavefront rate, not by the latency of a round) or 2 (PCE_MC_TPL=2, tuning aid)
+int warp_tpl () {
+    const char *forced = std::getenv ("PCE_MC_TPL");
+    return forced && std::atoi (forced) == 2 ? 2 : 1;
+}
+
 bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
     const pce_model *m = mc->model;
     if (m->ninst > 65535 || m->nsites > 65535) return false;
-    WarpLayout L (m->nsites, m->ninst);
-    if (L.per_warp + L.shared_bytes > limit) return false;
-    int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);   // up to 8 warps per block (255 registers each)
-    plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = L.shared_bytes + (size_t) warps * L.per_warp;
-    plan->ctas_per_sm = (int) std::max<size_t> (1, std::min<size_t> ((228 * 1024) / (plan->smem + 1024), (size_t) (2048 / plan->block)));
-    plan->ctas_per_sm = std::min (plan->ctas_per_sm, 2);          // the 2-CTA variant is compiled for 128 registers per thread
-    return true;
+    const int tpl = warp_tpl ();
+    // two variants: 128 registers and 4-deep update batches (taken when two CTAs of 8 warps fit on an SM, or when the
+    // 16-deep padding does not fit at all), else 255 registers and 16-deep batches with one resident CTA
+    for (int pass = 0; pass < 3; pass++) {
+        const int upd = pass == 1 ? 16 : 4;
+        WarpLayout L (m->nsites, m->ninst, tpl, upd);
+        if (L.per_warp + L.shared_bytes > limit) continue;
+        const int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);
+        const size_t smem = L.shared_bytes + (size_t) warps * L.per_warp;
+        const int ctas = (int) std::min<size_t> ((228 * 1024) / (smem + 1024), (size_t) (2048 / (warps * 32)));
+        if (pass == 0 && ctas < 2) continue;
+        plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = smem;
+        plan->ctas_per_sm = pass == 0 ? 2 : 1; plan->tpl = tpl; plan->upd = upd;
+        return true;
+    }
+    return false;
 }
 
 }  // namespace
@@ -776,8 +963,8 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
-    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_ph.release (); mc->d_esum.release ();
-    mc->d_counts.release (); mc->d_counters.release ();
+    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_pair_bound.release (); mc->d_ph.release (); mc->d_esum.release ();
+    mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release ();
     delete mc;
 }
 
@@ -828,7 +1015,11 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
     bool ok = false;
     if (mc->kernel == 1) ok = plan_thread (mc, limit, nph, plan);
     else if (mc->kernel == 2) ok = plan_warp (mc, limit, plan);
-    else ok = plan_thread (mc, limit, nph, plan) || plan_warp (mc, limit, plan);
+    else {
+        // auto: chain per thread while W fits in shared memory next to enough chains; else chain per warp
+        ok = plan_thread (mc, limit, nph, plan) && plan->w_in_smem;
+        if (!ok) ok = plan_warp (mc, limit, plan) || plan_thread (mc, limit, nph, plan);
+    }
     if (!ok) return fail (PCE_ERR_LIMIT, "model too large for the selected Monte Carlo kernel");
     return PCE_OK;
 }
@@ -836,7 +1027,7 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
 extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm, int *chains_per_wave, long long *smem_bytes) {
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
     PCE_CUDA (cudaSetDevice (mc->model->device));
-    Plan plan = { 0, 0, 0, 0, 1 };
+    Plan plan = { 0, 0, 0, 0, 1, 1, 4 };
     int status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
     int sms = 0;
@@ -846,6 +1037,43 @@ extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *c
     if (ctas_per_sm) *ctas_per_sm = plan.ctas_per_sm;
     if (chains_per_wave) *chains_per_wave = sms * plan.ctas_per_sm * (plan.kernel == 1 ? plan.block : plan.block / 32);
     if (smem_bytes) *smem_bytes = (long long) plan.smem;
+    return PCE_OK;
+}
+
+// Difference rows D[site][(lo, hi)] = wb[hi] - wb[lo] for every instance pair of every site, built on the device from
+// the uploaded beta-scaled W whenever the model was uploaded again.  Skipped (the kernels then stream the W rows) when
+// the table would exceed PCE_DW_BUDGET_MB (default 100 MB: it should stay L2-resident next to the hot part of W).
+static int build_difference_rows (pce_mc *mc, int ldd) {
+    pce_model *m = mc->model;
+    if (mc->dw_generation == m->generation && mc->dw_ldd == ldd) return PCE_OK;
+    mc->dw_generation = m->generation;
+    mc->dw_ldd = ldd;
+    mc->dw_valid = false;
+    std::vector<int32_t> base ((size_t) m->nsites), lo, hi;
+    for (int i = 0; i < m->nsites; i++) {
+        base[i] = (int32_t) lo.size ();
+        const int n = m->last[i] - m->first[i] + 1;
+        for (int mx = 1; mx < n; mx++)
+            for (int mn = 0; mn < mx; mn++) { lo.push_back (m->first[i] + mn); hi.push_back (m->first[i] + mx); }
+    }
+    const char *budget_env = std::getenv ("PCE_DW_BUDGET_MB");
+    const double budget = (budget_env ? std::atof (budget_env) : 100.0) * 1024.0 * 1024.0;
+    const size_t nrows = lo.size ();
+    if (nrows == 0 || (double) nrows * ldd * sizeof (double) > budget) return PCE_OK;
+    pce::DeviceBuffer<int32_t> d_lo, d_hi;
+    PCE_CUDA (d_lo.resize (nrows)); PCE_CUDA (d_hi.resize (nrows));
+    PCE_CUDA (mc->d_dbase.resize ((size_t) m->nsites));
+    PCE_CUDA (mc->d_dw.resize (nrows * (size_t) ldd));
+    PCE_CUDA (cudaMemcpyAsync (d_lo.ptr, lo.data (), nrows * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+    PCE_CUDA (cudaMemcpyAsync (d_hi.ptr, hi.data (), nrows * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+    PCE_CUDA (cudaMemcpyAsync (mc->d_dbase.ptr, base.data (), (size_t) m->nsites * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+    k_build_dw<<<(unsigned) nrows, 256, 0, m->stream>>> (m->d_wb.ptr, m->ninst, m->ldw, ldd, d_lo.ptr, d_hi.ptr, mc->d_dw.ptr);
+    pce::count_launch ();
+    cudaError_t err = cudaGetLastError ();
+    if (err == cudaSuccess) err = cudaStreamSynchronize (m->stream);     // the staging vectors and index buffers die with this scope
+    d_lo.release (); d_hi.release ();
+    if (err != cudaSuccess) return fail (PCE_ERR_CUDA, std::string ("difference rows: ") + cudaGetErrorString (err));
+    mc->dw_valid = true;
     return PCE_OK;
 }
 
@@ -873,16 +1101,45 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         }
         mc->pairs_dirty = false;
     }
+    if (mc->bound_generation != m->generation) {
+        // Upper bound of |wb[ia][ib] - wb[ia][ob] - wb[oa][ib] + wb[oa][ob]| per pair over all instance combinations,
+        // evaluated with the kernels' operation order on the same beta-scaled values, then rounded up to float with a
+        // margin: the warp kernel rejects a double move without reading W when the bound already decides it.
+        const double beta = 1.0 / (PCE_R * m->temperature);
+        const size_t n = (size_t) m->ninst;
+        std::vector<float> bound ((size_t) (npairs > 0 ? npairs : 1), 0.0f);
+        for (int k = 0; k < npairs; k++) {
+            const int sa = mc->pair_a[k], sb = mc->pair_b[k];
+            double worst = 0.0;
+            for (int ia = m->first[sa]; ia <= m->last[sa]; ia++)
+                for (int oa = m->first[sa]; oa <= m->last[sa]; oa++) {
+                    if (ia == oa) continue;
+                    for (int ib = m->first[sb]; ib <= m->last[sb]; ib++)
+                        for (int ob = m->first[sb]; ob <= m->last[sb]; ob++) {
+                            if (ib == ob) continue;
+                            const double c0 = beta * m->wsym[ia * n + ib], c1 = beta * m->wsym[ia * n + ob];
+                            const double c2 = beta * m->wsym[oa * n + ib], c3 = beta * m->wsym[oa * n + ob];
+                            const double cross = ((c0 - c1) - c2) + c3;
+                            worst = std::max (worst, std::fabs (cross));
+                        }
+                }
+            bound[k] = std::nextafter ((float) (worst * (1.0 + 1e-6) + 1e-30), INFINITY);
+        }
+        PCE_CUDA (mc->d_pair_bound.resize (bound.size ()));
+        PCE_CUDA (cudaMemcpyAsync (mc->d_pair_bound.ptr, bound.data (), bound.size () * sizeof (float), cudaMemcpyHostToDevice, m->stream));
+        PCE_CUDA (cudaStreamSynchronize (m->stream));
+        mc->bound_generation = m->generation;
+    }
     PCE_CUDA (mc->d_ph.resize (nph));
     PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
 
-    Plan plan = { 0, 0, 0, 0, 1 };
+    Plan plan = { 0, 0, 0, 0, 1, 1, 4 };
     status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
 
     p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
     p.first = m->d_first.ptr; p.nsi = m->d_nsite_inst.ptr; p.protons = m->d_protons.ptr;
-    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr; p.pair_packed = mc->d_pair_packed.ptr;
+    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr; p.pair_packed = mc->d_pair_packed.ptr; p.pair_bound = mc->d_pair_bound.ptr;
     p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.wb = m->d_wb.ptr; p.ph = mc->d_ph.ptr;
     p.nph = nph; p.ph_index_offset = ph_index_offset; p.nchains = mc->nchains; p.nequil = mc->nequil; p.nprod = mc->nprod;
     p.chain_offset = chain_offset;
@@ -890,6 +1147,15 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     p.temperature = m->temperature;
     p.w_in_smem = plan.w_in_smem;
 
+    if (plan.kernel != 1) {
+        // padded field length of this launch = row stride of the difference rows
+        const int ldd = WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd).ldh;
+        status = build_difference_rows (mc, ldd);
+        if (status != PCE_OK) return status;
+        p.dw = mc->dw_valid ? mc->d_dw.ptr : nullptr;
+        p.dbase = mc->d_dbase.ptr;
+        p.ldd = ldd;
+    }
     long long blocks;
     if (plan.kernel == 1) blocks = ((long long) nph * mc->nchains + plan.block - 1) / plan.block;     // chain-major linear grid
     else blocks = ((long long) nph * mc->nchains + plan.block / 32 - 1) / (plan.block / 32);
@@ -905,9 +1171,13 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     } else {
-        // one resident CTA (large fields): up to 255 registers, deep unrolling of the row updates; otherwise 128
-        auto kernel = plan.ctas_per_sm >= 2 ? (per_chain ? k_mc_warp<true, 2> : k_mc_warp<false, 2>)
-                                            : (per_chain ? k_mc_warp<true, 1> : k_mc_warp<false, 1>);
+        // one resident CTA (large fields): up to 255 registers; two: 128
+        void (*kernel) (const McParams);
+#define PCE_WARP_KERNEL(TPL_) (plan.upd == 4 ? (per_chain ? k_mc_warp<true, 2, TPL_> : k_mc_warp<false, 2, TPL_>) \
+                                                      : (per_chain ? k_mc_warp<true, 1, TPL_> : k_mc_warp<false, 1, TPL_>))
+        if (plan.tpl == 2) kernel = PCE_WARP_KERNEL (2);
+        else kernel = PCE_WARP_KERNEL (1);
+#undef PCE_WARP_KERNEL
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     }

@@ -309,6 +309,7 @@ int pce_model::upload () {
     }
     PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors above die with this scope
     dirty = false;
+    generation++;
     return PCE_OK;
 }
 

@@ -127,14 +127,19 @@ def test_energy_large_model_bit_exact(port):
         assert energies[s, 1] == port.energy(rec, wsym, states[s], 13.0)
 
 
-def test_warp_kernel_on_the_1000_site_model_matches_specification(port):
+@pytest.mark.parametrize("tpl,budget", [("1", None), ("2", None), ("1", "0")])
+def test_warp_kernel_on_the_1000_site_model_matches_specification(port, monkeypatch, tpl, budget):
     """BASELINE config 5 shape (1000 sites / 3000 instances, W = 72 MB): two short chains, count for count."""
     rec = synth_m(1000)
     model = P.MEADModel(rec, log=None)
     wsym = port.symmetrize(rec.interactions)
     sampler = P.MCModelDefault(nequil=1, nprod=3, randomSeed=2024, nchains=2)
     model.DefineMCModel(sampler, log=None)
-    assert sampler.LaunchPlan(1)["kernel"] == 2
+    # trials per lane and round (1, 2) and the two ways of applying an accepted move (difference rows / W rows)
+    monkeypatch.setenv("PCE_MC_TPL", tpl)
+    if budget is not None:
+        monkeypatch.setenv("PCE_DW_BUDGET_MB", budget)
+    assert sampler.LaunchPlan(1)["kernel"] == 2          # auto: W (72 MB) is not on chip -> chain per warp
     pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
     out = sampler.RunChains([7.0])
     for chain in (0, 1):

@@ -48,7 +48,7 @@ def test_chains_equal_specification(port, name, nequil, nprod, kernel):
             if kernel == 1:
                 assert out["energy"][q, chain] == spec["energy"]
                 assert out["esum"][q, chain] == spec["esum"]
-            else:   # the warp kernel seeds the tracked energy from a lane-parallel sum
+            else:   # the warp kernels seed the tracked energy from a lane-parallel sum
                 assert abs(out["energy"][q, chain] - spec["energy"]) < 1e-9
     # the aggregate entry point must equal the sum of its chains
     counts, counters, esum = sampler.RunCounts([2.0, 7.5], phIndexOffset=3)
