@@ -363,7 +363,8 @@ def main():
             with open(os.path.join(ROOT, "profiles", "r01_summary.json")) as handle:
                 summary = json.load(handle)
             key = "k_enum" if args.workload == "synthA" else ("k_mc_warp" if launch_info.get("kernel") == 2 else "k_mc_thread")
-            on_chip = dict(summary[key], kernel=key)
+            entry = key + "_ifp20" if key == "k_mc_warp" and args.workload != "synthM" else key
+            on_chip = dict(summary[entry], kernel=key)
         except (OSError, ValueError, KeyError):
             pass
         roofline = {
@@ -378,6 +379,21 @@ def main():
             "reference_algorithm_effective_gbs": algo_bytes_per_unit * value / world / 1e9,
             "kernel_ms_per_launch": kernel_ms,
         }
+        if args.workload != "synthA" and launch_info.get("kernel") == 2 and on_chip is not None:
+            # chain-per-warp kernel: the W / difference rows are served by L2.  Algorithmic L2 bytes of one launch = one
+            # difference row per changed site of every accepted move + the four W entries of every double-move proposal
+            # + the rows read by the field initialisation; accepted moves are counted in production scans only and
+            # scaled to all scans.  The denominator is measured here with a streaming read of an L2-resident buffer.
+            c = d_counters.sum(dim=0).cpu().numpy().astype(float)
+            scale = float(nequil + nprod) / float(nprod)
+            row_bytes = record.ninstances * 8.0
+            l2_bytes = scale * ((c[1] + 2.0 * c[3]) * row_bytes + c[2] * 32.0) + float(len(grid_all)) * chains * record.nsites * row_bytes
+            peak = C.c_double(0.0)
+            _native.check(lib.pce_probe_read_bandwidth(local_rank, 48 * 1024 * 1024, 40, C.byref(peak)))
+            on_chip["l2_algorithmic_bytes_per_launch"] = l2_bytes
+            on_chip["l2_algorithmic_gbs"] = l2_bytes / (kernel_ms * 1e-3) / 1e9
+            on_chip["l2_read_peak_gbs_measured"] = peak.value
+            on_chip["l2_frac"] = on_chip["l2_algorithmic_gbs"] / max(peak.value, 1e-9)
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak" if args.workload != "synthA" else "strong",

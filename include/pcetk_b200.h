@@ -49,6 +49,9 @@ int pce_set_stream (pce_model *model, void *cuda_stream);       /* cudaStream_t;
 int pce_synchronize (pce_model *model);
 /* launch counter: kernels launched by this library since the last reset (bench.py's gpu_launches) */
 long long pce_launch_count (int reset);
+/* measurement hook (no reference counterpart): streaming read bandwidth in GB/s of a zero-filled buffer of `bytes`
+ * read `passes` times with 128-bit loads -- L2 bandwidth for buffers well below the L2 size, HBM for large ones */
+int pce_probe_read_bandwidth (int device, long long bytes, int passes, double *gb_per_s);
 
 /* ---- model: allocation (EnergyModel_Allocate / _Deallocate, EnergyModel.h:64-65) ---------------- */
 int  pce_model_create (int nsites, int ninstances, double temperature, int device, pce_model **out);

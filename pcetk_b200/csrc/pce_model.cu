@@ -426,3 +426,49 @@ extern "C" int pce_test_philox (int device, const uint32_t *ctr, int nblocks, co
     d_ctr.release (); d_out.release ();
     return PCE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// measurement hook: streaming read bandwidth of a buffer of `bytes` (L2-resident when it is well below the 126 MB
+// L2, HBM when it is several times larger), 128-bit loads from every SM.  bench.py uses it as the measured
+// denominator of the L2 roofline of the chain-per-warp kernel (MEASURED_PEAKS.json only holds the HBM figure).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (512) k_probe_read (const double2 *__restrict__ data, size_t n2, int passes, double *sink) {
+    double acc = 0.0;
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    for (int pass = 0; pass < passes; pass++) {
+        size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n2; i += 4 * stride) {
+            const double2 a = __ldcg (data + i), b = __ldcg (data + i + stride), c = __ldcg (data + i + 2 * stride), d = __ldcg (data + i + 3 * stride);
+            acc += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+        }
+        for (; i < n2; i += stride) { const double2 a = __ldcg (data + i); acc += a.x + a.y; }
+    }
+    if (acc == 123.456) *sink = acc;       // keeps the loads alive
+}
+
+extern "C" int pce_probe_read_bandwidth (int device, long long bytes, int passes, double *gb_per_s) {
+    if (bytes < 4096 || passes < 1 || gb_per_s == nullptr) return fail (PCE_ERR_VALUE, "invalid probe size");
+    PCE_CUDA (cudaSetDevice (device));
+    int sms = 0;
+    PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device));
+    pce::DeviceBuffer<double2> buffer;
+    pce::DeviceBuffer<double>  sink;
+    const size_t n2 = (size_t) bytes / sizeof (double2);
+    PCE_CUDA (buffer.resize (n2)); PCE_CUDA (sink.resize (1));
+    PCE_CUDA (cudaMemset (buffer.ptr, 0, n2 * sizeof (double2)));
+    cudaEvent_t start, stop;
+    PCE_CUDA (cudaEventCreate (&start)); PCE_CUDA (cudaEventCreate (&stop));
+    k_probe_read<<<sms * 4, 512>>> (buffer.ptr, n2, 2, sink.ptr);              // warm-up: brings the buffer into L2
+    PCE_CUDA (cudaEventRecord (start));
+    k_probe_read<<<sms * 4, 512>>> (buffer.ptr, n2, passes, sink.ptr);
+    PCE_CUDA (cudaEventRecord (stop));
+    pce::count_launch (2);
+    cudaError_t err = cudaEventSynchronize (stop);
+    float ms = 0.0f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime (&ms, start, stop);
+    cudaEventDestroy (start); cudaEventDestroy (stop);
+    buffer.release (); sink.release ();
+    if (err != cudaSuccess) return fail (PCE_ERR_CUDA, std::string ("bandwidth probe: ") + cudaGetErrorString (err));
+    *gb_per_s = (double) n2 * sizeof (double2) * passes / (ms * 1e-3) / 1e9;
+    return PCE_OK;
+}
