@@ -36,7 +36,9 @@ struct pce_mc {
     std::vector<double>  pair_wmax;
     pce::DeviceBuffer<int32_t> d_pair_a, d_pair_b;
     pce::DeviceBuffer<uint32_t> d_pair_packed;
-    pce::DeviceBuffer<float>    d_pair_bound;
+    pce::DeviceBuffer<uint32_t> d_pair_x;
+    pce::DeviceBuffer<double>   d_cross;
+    bool cross_valid = false, cross_overflow = false;   // overflow: the table exceeds 2^24 entries -> 255-register variant only
     int  bound_generation = -1;
     pce::DeviceBuffer<double>  d_ph, d_esum;
     pce::DeviceBuffer<unsigned long long> d_counts;
@@ -54,7 +56,8 @@ struct McParams {
     int nsites, ninst, npairs, ldw;
     const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
     const uint32_t *pair_packed;            // site a | site b << 16
-    const float    *pair_bound;             // upper bound of |cross term| of the pair in units of RT (k_mc_warp)
+    const uint32_t *pair_x;                 // k_mc_warp: cross-table base of the pair | ceil (4 * bound of |cross term|) << 24
+    const double   *cross;                  // k_mc_warp: precomputed pair cross terms (nullptr: gather the four W entries)
     const double  *gintr, *w, *wb, *ph;      // wb = beta * W (units of RT)
     int       nph, ph_index_offset, nchains, nequil, nprod;
     long long chain_offset;
@@ -564,13 +567,14 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
     constexpr int RING = TPL <= 2 ? 128 : 256;
     constexpr int UPD  = MIN_CTAS == 1 ? 16 : 4;      // 128-bit loads per lane, row and batch when a move is applied
+    constexpr bool FALLBACK = MIN_CTAS == 1;          // only the 255-register variant carries the four-gather cross-term path
     const WarpLayout L (p.nsites, p.ninst, TPL, UPD);
     uint32_t      *s_site = (uint32_t *) smem;                        // first | ninst << 16 per site (CTA-wide)
     unsigned char *base   = smem + L.shared_bytes + (size_t) wib * L.per_warp;
     double        *h      = (double *) (base + L.off_h);
     uint32_t      *since  = (uint32_t *) (base + L.off_since);
     uint16_t      *state  = (uint16_t *) (base + L.off_state);
-    uint32_t      *ring   = (uint32_t *) (base + L.off_ring);          // [0,RING) w0 | w1 | target | bound of the pair cross term
+    uint32_t      *ring   = (uint32_t *) (base + L.off_ring);          // [0,RING) w0 | w1 | target | cross-table base and bound of the pair
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
     for (int i = threadIdx.x; i < nsites; i += blockDim.x) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
@@ -661,11 +665,12 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         return idx >= (uint32_t) nsites ? __ldg (p.pair_packed + (idx - nsites)) : (idx | (idx << 16));
     };
 
-    auto bound = [&] (const uint32_t w0) -> float {
+    auto pair_extra = [&] (const uint32_t w0) -> uint32_t {       // cross-table base | quantised bound of the pair
         const uint32_t idx = __umulhi (w0, nmoves);
-        return idx >= (uint32_t) nsites ? __ldg (p.pair_bound + (idx - nsites)) : 0.0f;
+        return idx >= (uint32_t) nsites ? __ldg (p.pair_x + (idx - nsites)) : 0u;
     };
 
+    const bool use_cross = p.cross != nullptr;
     unsigned long long tcur = 0, tfill = 0;        // next trial to decide; trials [tcur, tfill) are in the ring
     while (tcur < ntrials) {
         while (tfill - tcur < (unsigned long long) (32 * TPL)) {
@@ -675,7 +680,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             *(uint2 *) (ring + slot)            = make_uint2 (r.x, r.z);
             *(uint2 *) (ring + RING + slot)     = make_uint2 (r.y, r.w);
             *(uint2 *) (ring + 2 * RING + slot) = make_uint2 (target (r.x), target (r.z));
-            *(float2 *) (ring + 3 * RING + slot) = make_float2 (bound (r.x), bound (r.z));
+            *(uint2 *) (ring + 3 * RING + slot) = make_uint2 (pair_extra (r.x), pair_extra (r.z));
             tfill += 64ull;
         }
         __syncwarp ();
@@ -697,7 +702,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             const uint32_t slot = ((uint32_t) tcur + off) & (uint32_t) (RING - 1);
             const uint32_t w0 = ring[slot], pr = ring[2 * RING + slot];
             e_w1[u] = ring[RING + slot];
-            const float pbound = __uint_as_float (ring[3 * RING + slot]);
+            const uint32_t px = ring[3 * RING + slot];
+            const float pbound = 0.25f * (float) (px >> 24);                     // the pair's bound, quantised upwards (0: none)
             const bool act = off < n_act;
             const unsigned long long prod = (unsigned long long) w0 * nmoves;
             const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
@@ -707,7 +713,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             const int na = (int) (ia_info >> 16), oa = state[sa];
             bool valid = na >= 2;
             const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
-            int ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
+            const int ka = (int) (proda >> 32);
+            int ia = (int) (ia_info & 0xffffu) + ka;
             if (ia >= oa) ia++;
             if (!valid) ia = oa;
             int ib = 0, ob = 0;
@@ -719,17 +726,24 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 const int nb = (int) (ib_info >> 16);
                 ob = state[sb];
                 if (nb < 2) valid = false;
-                const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
-                ib = (int) (ib_info & 0xffffu) + (int) kb;
+                const int kb = (int) __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
+                ib = (int) (ib_info & 0xffffu) + kb;
                 if (ib >= ob) ib++;
                 if (!valid) { ib = ob; ia = oa; }
                 x = __dadd_rn (__dsub_rn (h[ia], h[oa]), __dsub_rn (h[ib], h[ob]));
                 const float xlow = __fsub_rd (__double2float_rd (x), pbound);            // <= x0 - B <= x
                 const float ulow = __uint2float_rd (e_w1[u]) * 2.3283064365386963e-10f;  // <= u
-                const bool certain = xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
+                const bool certain = (px >> 24) != 0u && xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
                 if (act && valid && !certain) {
-                    const double *ra = p.wb + (size_t) ia * ldw, *ro = p.wb + (size_t) oa * ldw;
-                    e_c[u][0] = __ldg (ra + ib); e_c[u][1] = __ldg (ra + ob); e_c[u][2] = __ldg (ro + ib); e_c[u][3] = __ldg (ro + ob);
+                    if (!FALLBACK || use_cross) {
+                        // one gather: the cross term of (old a, draw a, old b, draw b), precomputed with the same operations
+                        const int la = oa - (int) (ia_info & 0xffffu), lb = ob - (int) (ib_info & 0xffffu);
+                        const uint32_t e = (px & 0xffffffu) + (uint32_t) ((la * (na - 1) + ka) * (nb * (nb - 1)) + lb * (nb - 1) + kb);
+                        e_c[u][0] = __ldg (p.cross + e);
+                    } else {
+                        const double *ra = p.wb + (size_t) ia * ldw, *ro = p.wb + (size_t) oa * ldw;
+                        e_c[u][0] = __ldg (ra + ib); e_c[u][1] = __ldg (ra + ob); e_c[u][2] = __ldg (ro + ib); e_c[u][3] = __ldg (ro + ob);
+                    }
                     e_need[u] = true;
                 }
             } else {
@@ -744,7 +758,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 #pragma unroll
         for (int u = 0; u < TPL; u++) {
             double x = e_x[u];
-            if (e_dbl[u]) x = __dadd_rn (x, __dadd_rn (__dsub_rn (__dsub_rn (e_c[u][0], e_c[u][1]), e_c[u][2]), e_c[u][3]));
+            if (e_dbl[u]) x = __dadd_rn (x, (!FALLBACK || use_cross) ? e_c[u][0] : __dadd_rn (__dsub_rn (__dsub_rn (e_c[u][0], e_c[u][1]), e_c[u][2]), e_c[u][3]));
             const bool accept = metropolis (x, e_w1[u]) && e_need[u];
             accm[u] = __ballot_sync (0xffffffffu, accept);
             e_x[u] = x;
@@ -905,10 +919,12 @@ bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
         const int upd = pass == 1 ? 16 : 4;
         WarpLayout L (m->nsites, m->ninst, tpl, upd);
         if (L.per_warp + L.shared_bytes > limit) continue;
-        const int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);
+        int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);
+        if (const char *cap = std::getenv ("PCE_MC_WARPS")) warps = std::max (1, std::min (warps, std::atoi (cap)));      // tuning aid
         const size_t smem = L.shared_bytes + (size_t) warps * L.per_warp;
         const int ctas = (int) std::min<size_t> ((228 * 1024) / (smem + 1024), (size_t) (2048 / (warps * 32)));
-        if (pass == 0 && ctas < 2) continue;
+        if (pass == 0 && (ctas < 2 || mc->cross_overflow)) continue;
+        if (pass == 2 && mc->cross_overflow) continue;      // only the one-CTA 255-register variant gathers W itself
         const char *forced = std::getenv ("PCE_MC_CTAS");       // tuning aid: resident CTAs per SM of the small-field variant (2..4)
         const int  most = forced ? std::max (2, std::min (4, std::atoi (forced))) : 4;
         plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = smem;
@@ -965,7 +981,7 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
-    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_pair_bound.release (); mc->d_ph.release (); mc->d_esum.release ();
+    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_pair_x.release (); mc->d_cross.release (); mc->d_ph.release (); mc->d_esum.release ();
     mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release ();
     delete mc;
 }
@@ -1104,31 +1120,46 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         mc->pairs_dirty = false;
     }
     if (mc->bound_generation != m->generation) {
-        // Upper bound of |wb[ia][ib] - wb[ia][ob] - wb[oa][ib] + wb[oa][ob]| per pair over all instance combinations,
-        // evaluated with the kernels' operation order on the same beta-scaled values, then rounded up to float with a
-        // margin: the warp kernel rejects a double move without reading W when the bound already decides it.
+        // Per pair: every cross term wb[ia][ib] - wb[ia][ob] - wb[oa][ib] + wb[oa][ob], indexed by (old a, draw a, old b,
+        // draw b) and evaluated with the kernels' operation order on the same beta-scaled values (one gather instead of
+        // four in k_mc_warp), and an upper bound of its magnitude, quantised upwards to 1/4 RT: the warp kernel rejects a
+        // double move without reading anything when the bound already decides it.
         const double beta = 1.0 / (PCE_R * m->temperature);
         const size_t n = (size_t) m->ninst;
-        std::vector<float> bound ((size_t) (npairs > 0 ? npairs : 1), 0.0f);
+        std::vector<uint32_t> extra ((size_t) (npairs > 0 ? npairs : 1), 0u);
+        std::vector<double>   table;
+        bool fits = true;
         for (int k = 0; k < npairs; k++) {
             const int sa = mc->pair_a[k], sb = mc->pair_b[k];
+            const int fa = m->first[sa], fb = m->first[sb], na = m->last[sa] - fa + 1, nb = m->last[sb] - fb + 1;
+            const size_t base = table.size ();
             double worst = 0.0;
-            for (int ia = m->first[sa]; ia <= m->last[sa]; ia++)
-                for (int oa = m->first[sa]; oa <= m->last[sa]; oa++) {
-                    if (ia == oa) continue;
-                    for (int ib = m->first[sb]; ib <= m->last[sb]; ib++)
-                        for (int ob = m->first[sb]; ob <= m->last[sb]; ob++) {
-                            if (ib == ob) continue;
-                            const double c0 = beta * m->wsym[ia * n + ib], c1 = beta * m->wsym[ia * n + ob];
-                            const double c2 = beta * m->wsym[oa * n + ib], c3 = beta * m->wsym[oa * n + ob];
-                            const double cross = ((c0 - c1) - c2) + c3;
+            for (int la = 0; la < na; la++)
+                for (int ka = 0; ka < na - 1; ka++)
+                    for (int lb = 0; lb < nb; lb++)
+                        for (int kb = 0; kb < nb - 1; kb++) {
+                            const int oa = fa + la, ob = fb + lb, ia = fa + ka + (fa + ka >= oa ? 1 : 0), ib = fb + kb + (fb + kb >= ob ? 1 : 0);
+                            // volatile: every product and difference is rounded on its own (no host-side contraction)
+                            volatile double c0 = beta * m->wsym[ia * n + ib], c1 = beta * m->wsym[ia * n + ob];
+                            volatile double c2 = beta * m->wsym[oa * n + ib], c3 = beta * m->wsym[oa * n + ob];
+                            volatile double t1 = c0 - c1, t2 = t1 - c2;
+                            const double cross = t2 + c3;
+                            table.push_back (cross);
                             worst = std::max (worst, std::fabs (cross));
                         }
-                }
-            bound[k] = std::nextafter ((float) (worst * (1.0 + 1e-6) + 1e-30), INFINITY);
+            const double q = std::ceil (worst * (1.0 + 1e-6) * 4.0 + 1e-9);       // >= 1; 0 is reserved for "no shortcut"
+            if (base >= (1u << 24)) fits = false;
+            extra[k] = (uint32_t) (base & 0xffffffu) | ((q <= 255.0 ? (uint32_t) q : 0u) << 24);
         }
-        PCE_CUDA (mc->d_pair_bound.resize (bound.size ()));
-        PCE_CUDA (cudaMemcpyAsync (mc->d_pair_bound.ptr, bound.data (), bound.size () * sizeof (float), cudaMemcpyHostToDevice, m->stream));
+        const char *table_env = std::getenv ("PCE_CROSS_TABLE");          // 0: gather the four W entries instead (test hook)
+        mc->cross_valid = fits && npairs > 0 && !(table_env && std::atoi (table_env) == 0);
+        mc->cross_overflow = npairs > 0 && !mc->cross_valid;
+        PCE_CUDA (mc->d_pair_x.resize (extra.size ()));
+        PCE_CUDA (cudaMemcpyAsync (mc->d_pair_x.ptr, extra.data (), extra.size () * sizeof (uint32_t), cudaMemcpyHostToDevice, m->stream));
+        if (mc->cross_valid) {
+            PCE_CUDA (mc->d_cross.resize (table.size ()));
+            PCE_CUDA (cudaMemcpyAsync (mc->d_cross.ptr, table.data (), table.size () * sizeof (double), cudaMemcpyHostToDevice, m->stream));
+        }
         PCE_CUDA (cudaStreamSynchronize (m->stream));
         mc->bound_generation = m->generation;
     }
@@ -1141,7 +1172,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
 
     p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
     p.first = m->d_first.ptr; p.nsi = m->d_nsite_inst.ptr; p.protons = m->d_protons.ptr;
-    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr; p.pair_packed = mc->d_pair_packed.ptr; p.pair_bound = mc->d_pair_bound.ptr;
+    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr; p.pair_packed = mc->d_pair_packed.ptr; p.pair_x = mc->d_pair_x.ptr; p.cross = mc->cross_valid ? mc->d_cross.ptr : nullptr;
     p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.wb = m->d_wb.ptr; p.ph = mc->d_ph.ptr;
     p.nph = nph; p.ph_index_offset = ph_index_offset; p.nchains = mc->nchains; p.nequil = mc->nequil; p.nprod = mc->nprod;
     p.chain_offset = chain_offset;

@@ -2,6 +2,4 @@ cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 B="python bench.py --no-cpu-baseline --no-e2e"
 run() { name=$1; shift; timeout 300 "$@" > gpurun_out/$name.log 2>&1; echo "$name: $(grep '^{' gpurun_out/$name.log | cut -c1-90)"; }
-for c in 2 3 4; do PCE_MC_CTAS=$c run z_i_c$c $B --workload ifp20 --steps 2 --warmup 1; done
-for c in 2 4; do PCE_MC_CTAS=$c run z_l_c$c $B --workload lysozyme --kernel 2 --steps 2 --warmup 1 --nprod 4000; done
-PCE_MC_CTAS=4 timeout 600 python -m pytest tests/test_gpu_mc.py tests/test_gpu_edge.py -q --timeout 300 -p no:cacheprovider -x 2>&1 | tail -2
+for w in 7 6 5 4 2; do PCE_MC_WARPS=$w run w_$w $B --workload synthM --steps 2 --warmup 1 --chains $((w*7)) --nprod 400 --nequil 100; done

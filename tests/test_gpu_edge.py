@@ -127,8 +127,8 @@ def test_energy_large_model_bit_exact(port):
         assert energies[s, 1] == port.energy(rec, wsym, states[s], 13.0)
 
 
-@pytest.mark.parametrize("tpl,budget", [("1", None), ("2", None), ("1", "0")])
-def test_warp_kernel_on_the_1000_site_model_matches_specification(port, monkeypatch, tpl, budget):
+@pytest.mark.parametrize("tpl,budget,cross", [("1", None, None), ("2", None, None), ("1", "0", None), ("1", None, "0")])
+def test_warp_kernel_on_the_1000_site_model_matches_specification(port, monkeypatch, tpl, budget, cross):
     """BASELINE config 5 shape (1000 sites / 3000 instances, W = 72 MB): two short chains, count for count."""
     rec = synth_m(1000)
     model = P.MEADModel(rec, log=None)
@@ -139,6 +139,8 @@ def test_warp_kernel_on_the_1000_site_model_matches_specification(port, monkeypa
     monkeypatch.setenv("PCE_MC_TPL", tpl)
     if budget is not None:
         monkeypatch.setenv("PCE_DW_BUDGET_MB", budget)
+    if cross is not None:
+        monkeypatch.setenv("PCE_CROSS_TABLE", cross)         # gather the four W entries instead of the precomputed cross term
     assert sampler.LaunchPlan(1)["kernel"] == 2          # auto: W (72 MB) is not on chip -> chain per warp
     pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
     out = sampler.RunChains([7.0])
