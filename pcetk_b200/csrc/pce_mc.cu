@@ -15,8 +15,10 @@
 //   k_mc_thread  one chain per THREAD, model + per-chain state in shared memory.  For fixture-sized
 //                models (ninst <= 256).  Accepted moves are applied warp-cooperatively so that the
 //                axpy never runs with 1/32 lanes.
-//   k_mc_warp    one chain per WARP, fields in shared memory, W rows streamed from L2 with 128-bit
-//                loads.  For models whose W does not fit on chip (the 1000-site synthetic: 72 MB).
+//   k_mc_warp    one chain per WARP, fields in shared memory; the lanes evaluate 32 consecutive trials
+//                speculatively in parallel, the first accepted one ends the round.  Difference rows of W
+//                streamed from L2 with 128-bit loads.  For models whose W does not fit on chip (ifp20,
+//                the 1000-site synthetic: 72 MB).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
