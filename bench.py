@@ -408,11 +408,29 @@ def main():
             c = d_counters.sum(dim=0).cpu().numpy().astype(float)       # production trials: moves, accepted, flips, accepted
             line["config"]["acceptance"] = {"single": c[1] / max(c[0], 1.0), "double": c[3] / max(c[2], 1.0),
                                             "overall": (c[1] + c[3]) / max(c[0] + c[2], 1.0)}
+        if world == 1 and not args.no_e2e and args.workload in ("lysozyme", "ifp20", "defensin"):
+            # BASELINE's third metric: wall time of ONE titration curve through the public API (TitrationCurves), host
+            # arrays in, curves out.  (a) the reference's statistical effort per pH value (20000 production scans) split
+            # over 64 chains; (b) the package defaults (64 chains x 20000 scans = 64x the reference's samples).
+            curve = {}
+            for label, nch, npr in (("reference_effort", 64, 313), ("defaults", 64, 20000 if args.workload != "ifp20" else 2000)):
+                cm = P.MEADModel(record, log=None, device=local_rank)
+                cm.DefineMCModel(P.MCModelDefault(nequil=500, nprod=npr, randomSeed=7, nchains=nch), log=None)
+                P.TitrationCurves(cm, log=None, curveSampling=0.5, curveStart=0.0, curveStop=20.0).CalculateCurves(log=None)     # warm-up
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tc = P.TitrationCurves(cm, log=None, curveSampling=0.5, curveStart=0.0, curveStop=20.0)
+                tc.CalculateCurves(log=None)
+                tc.CalculateHalfpKs()
+                curve[label] = {"wall_ms": 1000.0 * (time.perf_counter() - t0), "chains": nch, "nequil": 500, "nprod_per_chain": npr, "ph_points": tc.nsteps}
+            line["titration_curve"] = curve
         if world == 1 and not args.no_cpu_baseline and args.workload in ("lysozyme", "ifp20", "defensin"):
             rate, seconds, kind = cpu_baseline(record, 500, 20000, grid_all, 1, repeats=3 if args.workload != "ifp20" else 1)
             line["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind,
                                     "sample": "%d single-chain %s curve(s) (41 pH, 500+20000 scans, MT19937), %.1f s on one host core" % (
                                         3 if args.workload != "ifp20" else 1, record.name, seconds)}
+            if "titration_curve" in line:
+                line["titration_curve"]["reference_one_core_wall_ms"] = 1000.0 * seconds / (3 if args.workload != "ifp20" else 1)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

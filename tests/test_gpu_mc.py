@@ -57,11 +57,12 @@ def test_chains_equal_specification(port, name, nequil, nprod, kernel):
     assert np.abs(esum / out["esum"].sum(axis=1) - 1.0).max() < 1e-12
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("name,grid", [("twosites", [2.0, 4.0, 6.0, 7.0, 9.0]), ("defensin", [2.0, 7.0, 12.5]), ("lysozyme", [3.0, 6.0, 7.0, 10.0])])
-def test_ensemble_vs_exact_probabilities(port, name, grid):
+def test_ensemble_vs_exact_probabilities(port, name, grid, kernel):
     """256 chains x 20000 production scans per pH value (5.1e6 scans): |dp| <= 0.01 and a 5-sigma z-score bound using
-    the reference's measured seed-to-seed sigma (<= 0.0079 per 20000 scans)."""
-    rec, _gold, model, sampler = make(name, nequil=500, nprod=20000, randomSeed=20240611, nchains=256)
+    the reference's measured seed-to-seed sigma (<= 0.0079 per 20000 scans).  Both kernels."""
+    rec, _gold, model, sampler = make(name, nequil=500, nprod=20000, randomSeed=20240611, nchains=256, kernel=kernel)
     wsym = port.symmetrize(rec.interactions)
     p = model.CalculateProbabilitiesBatch(grid)
     for row, ph in zip(p, grid):
