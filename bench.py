@@ -16,7 +16,9 @@ metric = MC trial moves per second (whole job).  Prints ONE JSON line (rank 0).
           container) on all host threads, one independent single-chain curve per thread per step.
 
 Other workloads (`ifp20`, `synthM` = 1000 sites MC, `synthA` = 2^32-state enumeration) report their own metric and are
-extra evidence, not the headline line.
+extra evidence, not the headline line.  synthM defaults to two waves of resident chains (50 per pH value), 100 + 400 scans
+(0.35 s per curve on one B200); BASELINE's full shape is `--chains 65536 --nequil 500 --nprod N` (2.7e6 chains: about
+8 minutes per step on one GPU at 1.9e10 moves/s for N = 50).
 """
 
 import argparse
@@ -176,7 +178,7 @@ def main():
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--workload", default="lysozyme", choices=["lysozyme", "ifp20", "defensin", "synthM", "synthA"])
     parser.add_argument("--chains", type=int, default=0, help="chains per pH value per GPU (default depends on the workload)")
-    parser.add_argument("--nprod", type=int, default=0, help="production scans per chain (default: reference's 20000; synthM: 20)")
+    parser.add_argument("--nprod", type=int, default=0, help="production scans per chain (default: reference's 20000; ifp20 2000; synthM 400)")
     parser.add_argument("--nequil", type=int, default=-1)
     parser.add_argument("--waves", type=int, default=2, help="when --chains is not given: chains = waves x (chains resident on the GPU) / 41")
     parser.add_argument("--kernel", type=int, default=0, help="MC kernel: 0 auto, 1 chain-per-thread, 2 chain-per-warp")
@@ -253,7 +255,7 @@ def main():
         d2h = int(nbins) * 8 * len(groups)
         algo_bytes_per_unit = 0.0
     else:
-        defaults = {"lysozyme": (1024, 20000, 500), "defensin": (1024, 20000, 500), "ifp20": (256, 2000, 500), "synthM": (8, 10, 10)}
+        defaults = {"lysozyme": (1024, 20000, 500), "defensin": (1024, 20000, 500), "ifp20": (256, 2000, 500), "synthM": (50, 400, 100)}
         chains, nprod, nequil = defaults[args.workload]
         chains = args.chains or chains
         nprod = args.nprod or nprod
