@@ -141,6 +141,26 @@ def test_titration_curve_lysozyme_ph0_20(port):
     assert len(curves.halves[his][0]) >= 1
 
 
+@pytest.mark.parametrize("name,keys", [("twosites", ["golden_curve_mc_curves_analytic"]), ("defensin", ["golden_curve_mc_curves_custom", "golden_curve_mc_curves_gmct"]),
+                                       ("lysozyme_full_test", ["golden_curve_mc_curves_custom", "golden_curve_mc_curves_gmct"]),
+                                       ("rubredoxin", ["golden_curve_mc_curves_custom", "golden_curve_mc_curves_gmct"]), ("ifp20", ["golden_curve_mc_curves"])])
+def test_titration_curves_vs_the_reference_mc_curve_files(name, keys):
+    """Every Monte Carlo curve file of the reference's fixtures (its own MCModelDefault: curves_mc / curves_custom /
+    curves; GMCT: curves_gmct; 29 pH values each; single chains that differ from the exact curves by up to 0.018,
+    SURVEY.md appendix C) against 128 chains x 4000 scans per pH value here: |dp| <= 0.03, RMS <= 0.005.  twosites'
+    `curves_analytic` directory holds the MC curves (the reference's directories are swapped).  ifp20 (171 instances,
+    49 pairs) runs on the chain-per-warp kernel."""
+    rec, gold, model, sampler = make(name, nequil=500, nprod=4000, randomSeed=4242, nchains=128)
+    curves = P.TitrationCurves(model, log=None)            # the reference's defaults: pH 0..14 step 0.5
+    curves.CalculateCurves(log=None)
+    assert curves.nsteps == 29 and np.allclose(curves.pHValues(), gold["golden_curve_ph"])
+    mc = np.array([[p for site in step for p in site] for step in curves.steps])
+    for key in keys:
+        diff = mc - gold[key]
+        assert np.abs(diff).max() <= 0.03, (key, np.abs(diff).max())
+        assert np.sqrt((diff ** 2).mean()) <= 0.005, (key, np.sqrt((diff ** 2).mean()))
+
+
 def test_logging_branch_counter_table_vs_lyso_mc_traj():
     """lyso_mc_traj.out: per-500-scan rows (scan, moves, accepted, flips, accepted) of the reference's logging branch."""
     import io
