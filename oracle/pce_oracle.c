@@ -339,10 +339,17 @@ static uint32_t mulhi32 (uint32_t a, uint32_t b, uint32_t *lo) {
  *              :97: a uniform type draw followed by an independent uniform site draw); the new
  *              instance is uniform over the *other* instances (k in [0,n-1), skip current) instead of
  *              the reference's rejection loop (MCModelDefault.c:99-101) -- same distribution.
- *   energy   : everything in units of RT.  wb = beta*W, gtb[k] = beta*(Gintr[k] - protons[k]*mu(pH)); every chain
- *              caches the fused fields hb[k] = gtb[k] + sum_j wb[k][a_j].  A single move then has
- *              dG/RT = hb[new] - hb[old]; a double move adds the second site and the pair cross term.  Equal in
- *              exact arithmetic to MCModelDefault.c:103-117 and :146-164 (same-site W is zero by construction).
+ *   energy   : everything in units of RT.  wb = beta*W, gtb[k] = beta*(Gintr[k] - protons[k]*mu(pH)).  Only energy
+ *              DIFFERENCES between instances of one site ever enter a decision, so every chain caches the fused
+ *              fields RELATIVE TO THE FIRST INSTANCE OF THE SITE: for instance k of site s with first instance f,
+ *              g[r(k)] = (gtb[k] - gtb[f]) + sum_j wr[a_j][r(k)],  wr[a][r(k)] = wb[a][k] - wb[a][f]  (one rounding),
+ *              r(k) = k - s - 1 (the first instances are not stored: their relative field is 0) -- ninst - nsites
+ *              values per chain instead of ninst.  With G(k) = 0 for a first instance and g[r(k)] otherwise, a single
+ *              move has dG/RT = G(new) - G(old); a double move adds the second site and the pair cross term
+ *              wb[ia][ib] - wb[ia][ob] - wb[oa][ib] + wb[oa][ob].  An accepted move old -> new adds the difference row
+ *              E[r] = wr[new][r] - wr[old][r] (one rounding; stored once per instance pair lo < hi of a site, the
+ *              opposite direction is its exact negation) to every g[r].  Equal in exact arithmetic to
+ *              MCModelDefault.c:103-117 and :146-164 (same-site W is zero by construction).
  *   accept   : MCModelDefault_Metropolis (MCModelDefault.c:71-85) with u = w1 * 2^-32.
  *   counting : residence times, equal to adding 1 to the active instance of every site after every
  *              production scan (MCModelDefault.c:215-226, :306-309).
@@ -359,12 +366,23 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
     const size_t n = (size_t) ninst;
     int       *state = (int *) malloc (sizeof (int) * (size_t) nsites);
     long long *since = (long long *) calloc ((size_t) nsites, sizeof (long long));
-    double    *hb    = (double *) malloc (sizeof (double) * n);
     double    *wb    = (double *) malloc (sizeof (double) * n * n);
     uint32_t   word[4];
     const double mu   = mu_of (temperature, pH);
     const double beta = 1.0 / (PCE_R * temperature);
     for (size_t e = 0; e < n * n; e++) wb[e] = beta * w[e];
+    /* relative fields: site of every instance, r(k), and wr[a][r] = wb[a][k] - wb[a][first of k's site] */
+    const size_t nr = n - (size_t) nsites;
+    int    *site_of = (int *) malloc (sizeof (int) * n);
+    double *g       = (double *) malloc (sizeof (double) * (nr > 0 ? nr : 1));
+    double *wr      = (double *) malloc (sizeof (double) * n * (nr > 0 ? nr : 1));
+    for (int i = 0; i < nsites; i++) for (int k = first[i]; k <= last[i]; k++) site_of[k] = i;
+    for (size_t a = 0; a < n; a++)
+        for (size_t k = 0; k < n; k++) {
+            const int sk = site_of[k], f = first[sk];
+            if ((int) k != f) wr[a * nr + (k - (size_t) sk - 1)] = wb[a * n + k] - wb[a * n + (size_t) f];
+        }
+#define RELG(k_) ((k_) == first[site_of[(k_)]] ? 0.0 : g[(size_t) (k_) - (size_t) site_of[(k_)] - 1])
     /* initial state */
     for (int i = 0; i < nsites; i++) {
         if ((i & 3) == 0 || i == 0) {
@@ -374,9 +392,13 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
         state[i] = first[i] + (int) mulhi32 (word[i & 3], (uint32_t) (last[i] - first[i] + 1), NULL);
     }
     for (size_t k = 0; k < n; k++) {
-        double acc = beta * (gintr[k] - (double) protons[k] * mu);
-        for (int j = 0; j < nsites; j++) acc += wb[k * n + (size_t) state[j]];
-        hb[k] = acc;
+        const int sk = site_of[k], f = first[sk];
+        if ((int) k == f) continue;
+        const size_t r = k - (size_t) sk - 1;
+        const double gk = beta * (gintr[k] - (double) protons[k] * mu), gf = beta * (gintr[f] - (double) protons[f] * mu);
+        double acc = gk - gf;
+        for (int j = 0; j < nsites; j++) acc += wr[(size_t) state[j] * nr + r];
+        g[r] = acc;
     }
     double grt = beta * energy_folded (&m, state, pH);
     const uint32_t nmoves = (uint32_t) (nsites + npairs);
@@ -412,10 +434,10 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
             }
             if (production) counters[sb >= 0 ? 2 : 0]++;
             if (!valid) continue;
-            double x = hb[ia] - hb[oa];
+            double x = RELG (ia) - RELG (oa);
             if (sb >= 0) {
                 double cross = wb[(size_t) ia * n + ib] - wb[(size_t) ia * n + ob] - wb[(size_t) oa * n + ib] + wb[(size_t) oa * n + ob];
-                x = (x + (hb[ib] - hb[ob])) + cross;
+                x = (x + (RELG (ib) - RELG (ob))) + cross;
             }
             int accept;
             if (x < 0.0) accept = 1;
@@ -425,10 +447,17 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
             if (production) counters[sb >= 0 ? 3 : 1]++;
             counts[oa] += tp - since[sa]; since[sa] = tp; state[sa] = ia;
             if (sb >= 0) { counts[ob] += tp - since[sb]; since[sb] = tp; state[sb] = ib; }
-            for (size_t k = 0; k < n; k++) {
-                double v = hb[k] + (wb[(size_t) ia * n + k] - wb[(size_t) oa * n + k]);
-                if (sb >= 0) v = v + (wb[(size_t) ib * n + k] - wb[(size_t) ob * n + k]);
-                hb[k] = v;
+            for (size_t r = 0; r < nr; r++) {
+                /* E = wr[hi] - wr[lo] of the instance pair, added with the sign of the direction */
+                const int hia = ia > oa ? ia : oa, loa = ia > oa ? oa : ia;
+                const double ea = wr[(size_t) hia * nr + r] - wr[(size_t) loa * nr + r];
+                double v = ia > oa ? g[r] + ea : g[r] - ea;
+                if (sb >= 0) {
+                    const int hib = ib > ob ? ib : ob, lob = ib > ob ? ob : ib;
+                    const double eb = wr[(size_t) hib * nr + r] - wr[(size_t) lob * nr + r];
+                    v = ib > ob ? v + eb : v - eb;
+                }
+                g[r] = v;
             }
             grt = grt + x;
         }
@@ -438,6 +467,7 @@ int oracle_mc_philox_chain (int nsites, int ninst, double temperature, const int
     if (esum) *esum = es / beta;
     if (final_state) for (int i = 0; i < nsites; i++) final_state[i] = state[i];
     if (final_energy) *final_energy = grt / beta;
-    free (state); free (since); free (hb); free (wb);
+#undef RELG
+    free (state); free (since); free (g); free (wr); free (site_of); free (wb);
     return 0;
 }

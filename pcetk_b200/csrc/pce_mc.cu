@@ -4,9 +4,11 @@
 // UpdateProbabilities :215-226, FindPairs :231-288, Production/Equilibration :298-327).
 //
 // Algorithm (specified operation for operation by oracle_mc_philox_chain in oracle/pce_oracle.c):
-//   * every chain keeps cached fields h[k] = sum_j W[k][a_j]; a proposal costs O(1) (dW = h[new]-h[old]),
-//     an accepted move costs one coalesced axpy over two rows of W -- instead of the reference's 2*nsites
-//     strided gathers per trial (MCModelDefault.c:109-111);
+//   * every chain keeps cached fields RELATIVE TO THE FIRST INSTANCE OF EACH SITE, g[r(k)] = h[k] - h[first], with
+//     h[k] = Gintr'[k] + sum_j W[k][a_j] (only differences between instances of one site ever enter a decision):
+//     ninst - nsites values per chain; a proposal costs O(1) (dG = G(new) - G(old)), an accepted move one coalesced
+//     add of a precomputed difference row E = wr[hi] - wr[lo] -- instead of the reference's 2*nsites strided
+//     gathers per trial (MCModelDefault.c:109-111);
 //   * random numbers are Philox4x32-10 blocks addressed by (seed, pH index, chain, trial), two trials
 //     per block, so any chain can be replayed in isolation and nothing has to be checkpointed;
 //   * occupancies are residence times (scan of last change per site) instead of nsites increments per scan.
@@ -45,10 +47,16 @@ struct pce_mc {
     pce::DeviceBuffer<double>  d_ph, d_esum;
     pce::DeviceBuffer<unsigned long long> d_counts;
     pce::DeviceBuffer<long long> d_counters;
-    pce::DeviceBuffer<double>  d_dw;                 // difference rows wb[hi] - wb[lo] of every instance pair of a site
+    // tables of the relative-field formulation, built on the device from the uploaded beta-scaled W
+    pce::DeviceBuffer<double>  d_wr;                 // wr[a][r(k)] = wb[a][k] - wb[a][first of k's site]   [ninst][ldr]
+    pce::DeviceBuffer<double>  d_dw;                 // difference rows E = wr[hi] - wr[lo] of every instance pair of a site [nrows][ldd]
     pce::DeviceBuffer<int32_t> d_dbase;              // first difference row of each site
-    int  dw_generation = -1, dw_ldd = 0;              // model generation / row stride the difference rows were built for
-    bool dw_valid = false;
+    pce::DeviceBuffer<int32_t> d_rk, d_rf;           // instance / first instance of the site of relative slot r
+    int  nrel = 0, ldr = 0, nrows = 0;
+    int  rel_generation = -1;                         // model generation d_wr, d_rk, d_rf were built from
+    int  dw_generation = -1, dw_ldd = 0;              // model generation / row stride / slot layout the difference rows were built for
+    bool dw_abs = false, dw_valid = false;
+    size_t ncross = 0;
     bool pairs_dirty = true;
 };
 
@@ -58,8 +66,8 @@ struct McParams {
     int nsites, ninst, npairs, ldw;
     const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
     const uint32_t *pair_packed;            // site a | site b << 16
-    const uint32_t *pair_x;                 // k_mc_warp: cross-table base of the pair | ceil (4 * bound of |cross term|) << 24
-    const double   *cross;                  // k_mc_warp: precomputed pair cross terms (nullptr: gather the four W entries)
+    const uint32_t *pair_x;                 // cross-table base of the pair | ceil (4 * bound of |cross term|) << 24
+    const double   *cross;                  // precomputed pair cross terms (k_mc_warp: nullptr = gather the four W entries)
     const double  *gintr, *w, *wb, *ph;      // wb = beta * W (units of RT)
     int       nph, ph_index_offset, nchains, nequil, nprod;
     long long chain_offset;
@@ -77,29 +85,37 @@ struct McParams {
     long long *log_rows;            // [(nequil/f + nprod/f) * 5] scan, moves, accepted, flips, accepted per block of f scans (chain 0, pH 0)
     int        log_frequency;
     int        w_in_smem;
-    const double  *dw;              // warp kernels: difference rows [nrows][ldw] (nullptr: stream the W rows themselves)
+    // relative fields (see the file header): nrel = ninst - nsites slots per chain
+    int            nrel, ldr, nrows, ncross;
+    const double  *wr;              // [ninst][ldr] wr[a][r(k)] = wb[a][k] - wb[a][first of k's site]
+    const int32_t *rk, *rf;         // [nrel] instance of slot r / first instance of its site
+    const int32_t *site_of;         // [ninst] site of every instance
+    const double  *dw;              // difference rows E = wr[hi] - wr[lo] [nrows][ldd] (nullptr: stream the two wr rows themselves)
     const int32_t *dbase;           // [nsites] first difference row of the site
-    int            ldd;             // row stride of dw = padded field length of the launch
+    int            ldd;             // row stride of dw (warp kernel: the padded field length of the launch)
 };
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
 struct ThreadLayout {
-    size_t off_w, off_h, off_counts, off_since, off_site, off_pair, off_state, total;
-    int    hstride, ldws, kslots;
-    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int block, int w_in_smem, int nchains, int nph, int since_bytes) {
-        hstride = ninst | 1;                       // odd: lanes of a warp fall on distinct bank pairs
-        ldws    = ninst | 1;
+    size_t off_e, off_cross, off_h, off_counts, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
+    int    hstride, estride, kslots;
+    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes) {
+        hstride = (nrel > 0 ? nrel : 1) | 1;       // odd: lanes of a warp fall on distinct bank pairs
+        estride = nrel > 0 ? nrel : 1;
         // a block covers `block` consecutive (pH, chain) pairs of the chain-major grid: at most kslots pH values
         kslots = (block - 1) / (nchains > 0 ? nchains : 1) + 2;
         if (kslots > nph) kslots = nph;
         size_t o = 0;
-        off_w = o;      o += w_in_smem ? (size_t) ninst * ldws * 8 : 0;
-        off_h = o;      o += (size_t) block * hstride * 8;
+        off_e = o;      o += (size_t) (nrows > 0 ? nrows : 1) * estride * 8;      // difference rows E
+        off_cross = o;  o += (size_t) (ncross > 0 ? ncross : 1) * 8;              // pair cross terms
+        off_h = o;      o += (size_t) block * hstride * 8;                        // relative fields, one row per chain
         off_counts = o; o += (size_t) kslots * ninst * 4;     // u32: block * nprod < 2^32 is checked on the host
         off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
         o = (o + 3) & ~(size_t) 3;
         off_site = o;   o += (size_t) nsites * 4;
         off_pair = o;   o += (size_t) (npairs > 0 ? npairs : 1) * 4;
+        off_pairx = o;  o += (size_t) (npairs > 0 ? npairs : 1) * 4;
+        off_erow = o;   o += (size_t) nsites * 4;
         off_state = o;  o += (size_t) nsites * block;
         total = (o + 15) & ~(size_t) 15;
     }
@@ -138,28 +154,41 @@ __device__ __forceinline__ double lds_f64 (uint32_t address) {
 __device__ __forceinline__ void sts_f64 (uint32_t address, double v) {
     asm volatile ("st.shared.f64 [%0], %1;" : : "r"(address), "d"(v) : "memory");
 }
+__device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
+    return __hiloint2double (__double2hiint (v) ^ (int) mask, __double2loint (v));
+}
 
 // ---------------------------------------------------------------------------------------------------
 // k_mc_thread.  The (pH, chain) grid is linearised chain-major (g = q*nchains + chain) and cut into blocks
 // of blockDim.x threads, so the grid can be sized to whole waves whatever nchains is; every thread carries
-// its own pH.  Energies are in units of RT and the intrinsic term is fused into the cached fields, so a
-// proposal is two shared-memory loads and one subtraction.  Trials are processed two per Philox block, with
-// the next block generated ahead of the dependent proposal -> accept -> update chain.
+// its own pH.  Energies are in units of RT, the intrinsic term is fused into the cached fields and the fields
+// are relative to the first instance of each site, so a single-move proposal is at most two shared-memory
+// loads and one subtraction.  Trials are processed two per Philox block, with the next block generated ahead of
+// the dependent proposal -> accept -> update chain.  The model lives in shared memory as the difference rows E
+// (one per instance pair of a site) and the pair cross-term table: W itself is never read by the trial loop.
 // ---------------------------------------------------------------------------------------------------
-template <bool PER_CHAIN, bool W_SMEM, typename SinceT>
-__global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
+// Register budgets: every SM sub-partition holds 16384 registers and a quarter of the block's warps, so a block of
+// 512 / 640 / 768 / 896 / 1024 threads may use 128 / 96 / 80 / 72 / 64 registers per thread (__launch_bounds__ would round
+// the block up to the next multiple of 256 threads and allow fewer).  The kernel wants 83 (allocated as 88): below that
+// ptxas rematerialises addresses and constants (13.5 instead of 9.2 warp-instructions per trial at 64), so blocks of
+// up to 640 threads run the 83-register build and the planner prefers them.
+template <bool PER_CHAIN, typename SinceT, int MAX_REGS>
+__global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
-    const ThreadLayout L (p.nsites, p.ninst, p.npairs, B, W_SMEM ? 1 : 0, p.nchains, p.nph, (int) sizeof (SinceT));
-    double             *s_w      = (double *) (smem + L.off_w);
+    const ThreadLayout L (p.nsites, p.ninst, p.npairs, p.nrel, p.nrows, p.ncross, B, p.nchains, p.nph, (int) sizeof (SinceT));
+    double             *s_e      = (double *) (smem + L.off_e);
+    double             *s_cross  = (double *) (smem + L.off_cross);
     double             *s_h      = (double *) (smem + L.off_h);
     uint32_t           *s_counts = (uint32_t *) (smem + L.off_counts);
     SinceT             *s_since  = (SinceT *) (smem + L.off_since);
     uint32_t           *s_site   = (uint32_t *) (smem + L.off_site);      // first | ninst << 16
     uint32_t           *s_pair   = (uint32_t *) (smem + L.off_pair);      // site a | site b << 16
+    uint32_t           *s_pairx  = (uint32_t *) (smem + L.off_pairx);     // base of the pair in the cross-term table
+    uint32_t           *s_erow   = (uint32_t *) (smem + L.off_erow);      // first difference row of the site
     uint8_t            *s_state  = smem + L.off_state;
 
-    const int nsites = p.nsites, ninst = p.ninst;
+    const int nsites = p.nsites, ninst = p.ninst, nrel = p.nrel;
     const long long total = (long long) p.nph * p.nchains;
     const long long g0    = (long long) blockIdx.x * B;             // first (pH, chain) pair of this block
     const long long gidx  = g0 + tid;
@@ -175,14 +204,12 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     SinceT   *my_since = s_since + tid;
     long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
 
-    // stage the model: beta-scaled W, packed site and pair tables
-    if (W_SMEM)
-        for (int e = tid; e < ninst * ninst; e += B) s_w[(e / ninst) * L.ldws + (e % ninst)] = p.wb[(size_t) (e / ninst) * p.ldw + (e % ninst)];
-    const double *wbase = W_SMEM ? s_w : p.wb;
-    const int     wld   = W_SMEM ? L.ldws : p.ldw;
+    // stage the model: difference rows, cross terms, packed site and pair tables
+    for (int e = tid; e < p.nrows * nrel; e += B) s_e[(e / nrel) * L.estride + (e % nrel)] = p.dw[(size_t) (e / nrel) * p.ldd + (e % nrel)];
+    for (int e = tid; e < p.ncross; e += B) s_cross[e] = p.cross[e];
     for (int k = tid; k < L.kslots * ninst; k += B) s_counts[k] = 0u;
-    for (int i = tid; i < nsites; i += B) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
-    for (int i = tid; i < p.npairs; i += B) s_pair[i] = (uint32_t) p.pair_a[i] | ((uint32_t) p.pair_b[i] << 16);
+    for (int i = tid; i < nsites; i += B) { s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16); s_erow[i] = (uint32_t) p.dbase[i]; }
+    for (int i = tid; i < p.npairs; i += B) { s_pair[i] = (uint32_t) p.pair_a[i] | ((uint32_t) p.pair_b[i] << 16); s_pairx[i] = p.pair_x[i] & 0xffffffu; }
 
     // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i)
     {
@@ -199,21 +226,23 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
     const double mu   = ph_to_mu (p.temperature, p.ph[q]);
     const double beta = 1.0 / (PCE_R * p.temperature);
 
-    // fused fields, cooperatively: for each chain c of this warp, lanes over k; hb[k] = gtb[k] + sum_j wb[k][a_j]
-    // with j sequential (spec order).  mu differs per chain (per-thread pH): broadcast it.
+    // relative fields, cooperatively: for each chain c of this warp, lanes over the slots r;
+    // g[r] = (gtb[k] - gtb[f]) + sum_j wr[a_j][r] with j sequential (spec order).  mu differs per chain: broadcast it.
     for (int c = 0; c < 32; c++) {
         const double mu_c = __shfl_sync (0xffffffffu, mu, c);
         double *hc = s_h + (size_t) (warp_base + c) * L.hstride;
         const uint8_t *sc = s_state + warp_base + c;
-        for (int k = lane; k < ninst; k += 32) {
-            const double *row = wbase + (size_t) k * wld;
-            double acc = __dmul_rn (beta, __dsub_rn (p.gintr[k], __dmul_rn ((double) p.protons[k], mu_c)));
-            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, row[sc[j * B]]);
-            hc[k] = acc;
+        for (int r = lane; r < nrel; r += 32) {
+            const int k = p.rk[r], f = p.rf[r];
+            const double gk = __dmul_rn (beta, __dsub_rn (p.gintr[k], __dmul_rn ((double) p.protons[k], mu_c)));
+            const double gf = __dmul_rn (beta, __dsub_rn (p.gintr[f], __dmul_rn ((double) p.protons[f], mu_c)));
+            double acc = __dsub_rn (gk, gf);
+            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, p.wr[(size_t) sc[j * B] * p.ldr + r]);
+            hc[r] = acc;
         }
     }
     __syncwarp ();
-    double *myh = s_h + (size_t) tid * L.hstride;
+    const double *myg = s_h + (size_t) tid * L.hstride;
 
     // initial energy in the reference's order (EnergyModel.c:204-224), then to units of RT
     double grt;
@@ -241,7 +270,7 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
 
     // one trial: proposal from (w0), Metropolis with (w1), cooperative application of accepted moves
     const bool has_pairs = p.npairs > 0;
-    const uint32_t h_addr = (uint32_t) __cvta_generic_to_shared (s_h), w_addr = (uint32_t) __cvta_generic_to_shared (s_w);
+    const uint32_t h_addr = (uint32_t) __cvta_generic_to_shared (s_h), e_addr = (uint32_t) __cvta_generic_to_shared (s_e);
     auto trial = [&] (const uint32_t w0, const uint32_t w1) {
         const unsigned long long prod = (unsigned long long) w0 * nmoves;
         const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
@@ -249,46 +278,59 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
         const uint32_t pr  = dbl ? s_pair[idx - nsites] : (idx | (idx << 16));     // single move: site b = site a
         const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
         const uint32_t ia_info = s_site[sa];
-        const int na = (int) (ia_info >> 16), oa = my_state[sa * B];
+        const int fa = (int) (ia_info & 0xffffu), na = (int) (ia_info >> 16), oa = my_state[sa * B];
         bool valid = active && na >= 2;
         const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
-        int ia = (int) (ia_info & 0xffffu) + (int) (proda >> 32);
+        const int ka = (int) (proda >> 32);
+        int ia = fa + ka;
         if (ia >= oa) ia++;
         int ib = 0, ob = 0;
         double x;
-        if (has_pairs && (W_SMEM || dbl)) {
-            // W on chip: evaluated for every lane (a warp almost always holds a double move; no divergent branch); for
-            // single moves ib == ob and the extra terms are exactly zero, so the value equals the single-move formula
-            // bit for bit.  W in global memory: only lanes with a double move pay for the four cross-term loads.
+        // G(k) = relative field of instance k: 0 for the first instance of its site, else g[k - site - 1]
+        if (has_pairs) {
+            // evaluated for every lane (a warp almost always holds a double move; no divergent branch); for single
+            // moves ib == ob and the cross term is zero, so the value equals the single-move formula bit for bit
             const uint32_t ib_info = s_site[sb];
-            const int nb = (int) (ib_info >> 16);
+            const int fb = (int) (ib_info & 0xffffu), nb = (int) (ib_info >> 16);
             ob = my_state[sb * B];
-            const uint32_t kb = __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
-            ib = (int) (ib_info & 0xffffu) + (int) kb;
+            const int kb = (int) __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
+            ib = fb + kb;
             if (ib >= ob) ib++;
             if (dbl && nb < 2) valid = false;
             if (!dbl) ib = ob;
             if (!valid) { ia = oa; ib = ob; }
-            const double *ra = wbase + ia * wld, *ro = wbase + oa * wld;
-            const double c0 = ra[ib], c1 = ra[ob], c2 = ro[ib], c3 = ro[ob];
-            const double cross = __dadd_rn (__dsub_rn (__dsub_rn (c0, c1), c2), c3);
-            x = __dadd_rn (__dadd_rn (__dsub_rn (myh[ia], myh[oa]), __dsub_rn (myh[ib], myh[ob])), cross);
+            double cross = 0.0;
+            if (dbl && valid) cross = s_cross[s_pairx[idx - nsites] + (uint32_t) (((oa - fa) * (na - 1) + ka) * (nb * (nb - 1)) + (ob - fb) * (nb - 1) + kb)];
+            const double gan = ia != fa ? myg[ia - sa - 1] : 0.0, gao = oa != fa ? myg[oa - sa - 1] : 0.0;
+            const double gbn = ib != fb ? myg[ib - sb - 1] : 0.0, gbo = ob != fb ? myg[ob - sb - 1] : 0.0;
+            x = __dadd_rn (__dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo)), cross);
             if (production && dbl) c_flips++;
         } else {
             if (!valid) ia = oa;
-            x = __dsub_rn (myh[ia], myh[oa]);
+            const double gan = ia != fa ? myg[ia - sa - 1] : 0.0, gao = oa != fa ? myg[oa - sa - 1] : 0.0;
+            x = __dsub_rn (gan, gao);
         }
         const bool accept = valid && metropolis (x, w1);
         if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) { lg_f++; lg_fa += accept; } else { lg_m++; lg_ma += accept; } }
 
-        // apply accepted moves: two accepting chains per round, one per half-warp; each lane updates entries
-        // k = sub, sub+16, sub+32, ... of its chain's field vector (hb += wb[new] - wb[old] for one or two sites)
+        // apply accepted moves: two accepting chains per round, one per half-warp; each lane updates slots
+        // r = sub, sub+16, sub+32, ... of its chain's field vector: g[r] += (+-)E_a[r] (+ (+-)E_b[r])
         unsigned pending = __ballot_sync (0xffffffffu, accept);
         if (pending) {
-            const unsigned dblmask = __ballot_sync (0xffffffffu, accept && dbl);
-            const uint32_t packed = (uint32_t) ia | ((uint32_t) oa << 8) | ((uint32_t) ib << 16) | ((uint32_t) ob << 24);
+            // difference row and direction of each changed site: row | reverse << 14, site b in the upper half, double << 30
+            uint32_t packed = 0u;
+            if (accept) {
+                const int la = ia - fa, lo_a = oa - fa;
+                const int mxa = la > lo_a ? la : lo_a, mna = la > lo_a ? lo_a : la;
+                packed = (s_erow[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) | (la < lo_a ? 1u << 14 : 0u);
+                if (dbl) {
+                    const int fb = (int) (s_site[sb] & 0xffffu), lb = ib - fb, lo_b = ob - fb;
+                    const int mxb = lb > lo_b ? lb : lo_b, mnb = lb > lo_b ? lo_b : lb;
+                    packed |= ((s_erow[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) << 15) | (lb < lo_b ? 1u << 29 : 0u) | (1u << 30);
+                }
+            }
             // small field vectors: two chains per round (16 lanes each); larger ones: one chain per round (32 lanes)
-            const int  lpc  = ninst > 64 ? 32 : 16;
+            const int  lpc  = nrel > 48 ? 32 : 16;
             const int  half = lpc == 16 ? lane >> 4 : 0, sub = lane & (lpc - 1);
             do {
                 const int s0 = __ffs (pending) - 1;
@@ -299,40 +341,23 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
                 const bool work = src >= 0;
                 const uint32_t y = __shfl_sync (0xffffffffu, packed, src & 31);
                 if (work) {
-                    const bool two_sites = (dblmask >> src) & 1u;
-                    const int na_ = (int) (y & 255u), oa_ = (int) ((y >> 8) & 255u), nb_ = (int) ((y >> 16) & 255u), ob_ = (int) (y >> 24);
-                    if (W_SMEM) {
-                        const uint32_t hrow = h_addr + (uint32_t) ((warp_base + src) * L.hstride) * 8u;
-                        const uint32_t ra = w_addr + (uint32_t) (na_ * wld) * 8u, ro = w_addr + (uint32_t) (oa_ * wld) * 8u;
-                        const uint32_t rb = w_addr + (uint32_t) (nb_ * wld) * 8u, rp = w_addr + (uint32_t) (ob_ * wld) * 8u;
+                    const bool two_sites = (y >> 30) & 1u;
+                    const uint32_t fa_ = (y >> 14) & 1u ? 0x80000000u : 0u, fb_ = (y >> 29) & 1u ? 0x80000000u : 0u;
+                    const uint32_t hrow = h_addr + (uint32_t) ((warp_base + src) * L.hstride) * 8u;
+                    const uint32_t ra = e_addr + (uint32_t) ((y & 0x3fffu) * L.estride) * 8u, rb = e_addr + (uint32_t) (((y >> 15) & 0x3fffu) * L.estride) * 8u;
 #pragma unroll 1
-                        for (int k = sub; k < ninst; k += 3 * lpc) {
-                            const uint32_t o0 = (uint32_t) k * 8u, o1 = o0 + (uint32_t) lpc * 8u, o2 = o1 + (uint32_t) lpc * 8u;
-                            const bool p1 = k + lpc < ninst, p2 = k + 2 * lpc < ninst;
-                            double h0 = lds_f64 (hrow + o0), a0 = lds_f64 (ra + o0), b0 = lds_f64 (ro + o0);
-                            double h1 = 0.0, a1 = 0.0, b1 = 0.0, h2 = 0.0, a2 = 0.0, b2 = 0.0;
-                            if (p1) { h1 = lds_f64 (hrow + o1); a1 = lds_f64 (ra + o1); b1 = lds_f64 (ro + o1); }
-                            if (p2) { h2 = lds_f64 (hrow + o2); a2 = lds_f64 (ra + o2); b2 = lds_f64 (ro + o2); }
-                            h0 = __dadd_rn (h0, __dsub_rn (a0, b0)); h1 = __dadd_rn (h1, __dsub_rn (a1, b1)); h2 = __dadd_rn (h2, __dsub_rn (a2, b2));
-                            if (two_sites) {
-                                h0 = __dadd_rn (h0, __dsub_rn (lds_f64 (rb + o0), lds_f64 (rp + o0)));
-                                if (p1) h1 = __dadd_rn (h1, __dsub_rn (lds_f64 (rb + o1), lds_f64 (rp + o1)));
-                                if (p2) h2 = __dadd_rn (h2, __dsub_rn (lds_f64 (rb + o2), lds_f64 (rp + o2)));
-                            }
-                            sts_f64 (hrow + o0, h0);
-                            if (p1) sts_f64 (hrow + o1, h1);
-                            if (p2) sts_f64 (hrow + o2, h2);
+                    for (int r = sub; r < nrel; r += 2 * lpc) {
+                        const uint32_t o0 = (uint32_t) r * 8u, o1 = o0 + (uint32_t) lpc * 8u;
+                        const bool p1 = r + lpc < nrel;
+                        double h0 = lds_f64 (hrow + o0), a0 = lds_f64 (ra + o0), h1 = 0.0, a1 = 0.0;
+                        if (p1) { h1 = lds_f64 (hrow + o1); a1 = lds_f64 (ra + o1); }
+                        h0 = __dadd_rn (h0, flip_sign (a0, fa_)); h1 = __dadd_rn (h1, flip_sign (a1, fa_));
+                        if (two_sites) {
+                            h0 = __dadd_rn (h0, flip_sign (lds_f64 (rb + o0), fb_));
+                            if (p1) h1 = __dadd_rn (h1, flip_sign (lds_f64 (rb + o1), fb_));
                         }
-                    } else {
-                        double       *hc  = s_h + (warp_base + src) * L.hstride;
-                        const double *rna = p.wb + (size_t) na_ * wld, *roa = p.wb + (size_t) oa_ * wld;
-                        const double *rnb = p.wb + (size_t) nb_ * wld, *rob = p.wb + (size_t) ob_ * wld;
-#pragma unroll 2
-                        for (int k = sub; k < ninst; k += lpc) {
-                            double v = __dadd_rn (hc[k], __dsub_rn (__ldg (rna + k), __ldg (roa + k)));
-                            if (two_sites) v = __dadd_rn (v, __dsub_rn (__ldg (rnb + k), __ldg (rob + k)));
-                            hc[k] = v;
-                        }
+                        sts_f64 (hrow + o0, h0);
+                        if (p1) sts_f64 (hrow + o1, h1);
                     }
                 }
             } while (pending);
@@ -429,33 +454,39 @@ __global__ void __launch_bounds__ (512, 1) k_mc_thread (const McParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Applying an accepted move in the warp kernels: hb += wb[ia] - wb[oa] (+ wb[ib] - wb[ob]).
-// The row differences of all instance pairs of a site are precomputed (k_build_dw: D = wb[hi] - wb[lo], one rounding,
-// the same value the subtraction yields at run time; the opposite direction is its exact negation), which halves the
-// L2 traffic of an accepted move -- the roofline of the 1000-site model.  Loads are issued in fixed batches of U
-// predicated 128-bit loads per lane so that no serial remainder loop is left.
+// Tables of the relative-field formulation and the application of an accepted move in the warp kernel.
+//   wr[a][r(k)] = wb[a][k] - wb[a][first of k's site]     (k_build_wr; rows of it initialise the fields)
+//   E[row][r]   = wr[hi][r] - wr[lo][r]                   (k_build_dw; one row per instance pair lo < hi of a site)
+// An accepted move old -> new adds (+-)E of its instance pair to every field slot (the opposite direction is the exact
+// negation): one row of L2 traffic per changed site.  Loads are issued in fixed batches of U unpredicated 128-bit loads per
+// lane over a field vector padded to whole batches, so that no serial remainder loop is left.
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_build_dw (const double *__restrict__ wb, int ninst, int ldw, int ldd, const int32_t *__restrict__ row_lo,
-                            const int32_t *__restrict__ row_hi, double *__restrict__ dw) {
-    const int r = blockIdx.x;
-    const double *hi = wb + (size_t) row_hi[r] * ldw, *lo = wb + (size_t) row_lo[r] * ldw;
-    for (int k = threadIdx.x; k < ldd; k += blockDim.x) dw[(size_t) r * ldd + k] = k < ninst ? __dsub_rn (hi[k], lo[k]) : 0.0;     // zero padding
+__global__ void k_build_wr (const double *__restrict__ wb, int ldw, int nrel, int ldr, const int32_t *__restrict__ rk, const int32_t *__restrict__ rf,
+                            double *__restrict__ wr) {
+    const double *row = wb + (size_t) blockIdx.x * ldw;
+    for (int r = threadIdx.x; r < ldr; r += blockDim.x) wr[(size_t) blockIdx.x * ldr + r] = r < nrel ? __dsub_rn (row[rk[r]], row[rf[r]]) : 0.0;
 }
 
-// difference row and direction (sign-bit mask) of the move oa -> ia on a site whose first instance is `first`
-__device__ __forceinline__ void diff_row (const McParams &p, int site, int first, int ia, int oa, const double2 **row, uint32_t *flip) {
-    const int a = ia - first, o = oa - first;
-    const int mx = a > o ? a : o, mn = a > o ? o : a;
-    const int r = __ldg (p.dbase + site) + ((mx * (mx - 1)) >> 1) + mn;
-    *row  = (const double2 *) (p.dw + (size_t) r * p.ldd);
-    *flip = a < o ? 0x80000000u : 0u;
+__global__ void k_build_dw (const double *__restrict__ wr, int nrel, int ldr, int ldd, const int32_t *__restrict__ row_lo,
+                            const int32_t *__restrict__ row_hi, double *__restrict__ dw, int abs, int ninst,
+                            const int32_t *__restrict__ site_of, const int32_t *__restrict__ first) {
+    const int e = blockIdx.x;
+    const double *hi = wr + (size_t) row_hi[e] * ldr, *lo = wr + (size_t) row_lo[e] * ldr;
+    if (!abs) {     // compact slots
+        for (int r = threadIdx.x; r < ldd; r += blockDim.x) dw[(size_t) e * ldd + r] = r < nrel ? __dsub_rn (hi[r], lo[r]) : 0.0;     // zero padding
+    } else {        // instance-indexed slots: zero at the first instance of every site
+        for (int k = threadIdx.x; k < ldd; k += blockDim.x) {
+            double v = 0.0;
+            if (k < ninst) {
+                const int site = site_of[k];
+                if (k != first[site]) v = __dsub_rn (hi[k - site - 1], lo[k - site - 1]);
+            }
+            dw[(size_t) e * ldd + k] = v;
+        }
+    }
 }
 
-__device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
-    return __hiloint2double (__double2hiint (v) ^ (int) mask, __double2loint (v));
-}
-
-// hb += (+-)D1 (+ (+-)D2): n2 (the padded field length in double2) is a multiple of 32 * U, so every batch is U
+// g += (+-)E1 (+ (+-)E2): n2 (the padded field length in double2) is a multiple of 32 * U, so every batch is U
 // unpredicated 128-bit loads per lane and row, all issued before the first use
 template <int U>
 __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, const double2 *r1, uint32_t f1, const double2 *r2, uint32_t f2, bool two) {
@@ -488,43 +519,54 @@ __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, 
     }
 }
 
-// the same from the W rows themselves (models whose difference rows exceed the memory budget); nw2 = ldw / 2
+// the same from the two wr rows of each instance pair (models whose difference rows exceed the memory budget); nr2 = ldr / 2
 template <int U>
-__device__ __forceinline__ void apply_w_rows (double2 *h2, int nw2, int lane, const double2 *rna, const double2 *roa, const double2 *rnb, const double2 *rob, bool two) {
+__device__ __forceinline__ void apply_wr_rows (double2 *h2, int nr2, int lane, const double2 *ahi, const double2 *alo, uint32_t f1,
+                                               const double2 *bhi, const double2 *blo, uint32_t f2, bool two) {
     if (!two) {
 #pragma unroll (U)
-        for (int k = lane; k < nw2; k += 32) {
-            const double2 a = __ldg (rna + k), b = __ldg (roa + k);
+        for (int k = lane; k < nr2; k += 32) {
+            const double2 a = __ldg (ahi + k), b = __ldg (alo + k);
             double2 v = h2[k];
-            v.x = __dadd_rn (v.x, __dsub_rn (a.x, b.x));
-            v.y = __dadd_rn (v.y, __dsub_rn (a.y, b.y));
+            v.x = __dadd_rn (v.x, flip_sign (__dsub_rn (a.x, b.x), f1));
+            v.y = __dadd_rn (v.y, flip_sign (__dsub_rn (a.y, b.y), f1));
             h2[k] = v;
         }
     } else {
 #pragma unroll (U / 2 > 0 ? U / 2 : 1)
-        for (int k = lane; k < nw2; k += 32) {
-            const double2 a = __ldg (rna + k), b = __ldg (roa + k), c = __ldg (rnb + k), d = __ldg (rob + k);
+        for (int k = lane; k < nr2; k += 32) {
+            const double2 a = __ldg (ahi + k), b = __ldg (alo + k), c = __ldg (bhi + k), d = __ldg (blo + k);
             double2 v = h2[k];
-            v.x = __dadd_rn (__dadd_rn (v.x, __dsub_rn (a.x, b.x)), __dsub_rn (c.x, d.x));
-            v.y = __dadd_rn (__dadd_rn (v.y, __dsub_rn (a.y, b.y)), __dsub_rn (c.y, d.y));
+            v.x = __dadd_rn (__dadd_rn (v.x, flip_sign (__dsub_rn (a.x, b.x), f1)), flip_sign (__dsub_rn (c.x, d.x), f2));
+            v.y = __dadd_rn (__dadd_rn (v.y, flip_sign (__dsub_rn (a.y, b.y), f1)), flip_sign (__dsub_rn (c.y, d.y), f2));
             h2[k] = v;
         }
     }
 }
 
-template <int U>
-__device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s_site, double *h, int ldh, int ldw, int lane,
+template <int U, bool ROWS_ONLY>
+__device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s_site, double *h, int ldh, int lane,
                                             int sa, int sb, int ia, int oa, int ib, int ob, bool dbl) {
     double2 *h2 = (double2 *) h;
-    if (p.dw != nullptr) {
-        const double2 *r1, *r2 = nullptr;
-        uint32_t f1, f2 = 0u;
-        diff_row (p, sa, (int) (s_site[sa] & 0xffffu), ia, oa, &r1, &f1);
-        if (dbl) diff_row (p, sb, (int) (s_site[sb] & 0xffffu), ib, ob, &r2, &f2);
+    // instance pair (lo < hi, local indices) and direction of each changed site
+    const int fa = (int) (s_site[sa] & 0xffffu), la = ia - fa, pa = oa - fa;
+    const int mxa = la > pa ? la : pa, mna = la > pa ? pa : la;
+    const uint32_t f1 = la < pa ? 0x80000000u : 0u;
+    int fb = 0, mxb = 1, mnb = 0;
+    uint32_t f2 = 0u;
+    if (dbl) {
+        fb = (int) (s_site[sb] & 0xffffu);
+        const int lb = ib - fb, pb = ob - fb;
+        mxb = lb > pb ? lb : pb; mnb = lb > pb ? pb : lb;
+        f2 = lb < pb ? 0x80000000u : 0u;
+    }
+    if (ROWS_ONLY || p.dw != nullptr) {
+        const double2 *r1 = (const double2 *) (p.dw + (size_t) (__ldg (p.dbase + sa) + ((mxa * (mxa - 1)) >> 1) + mna) * p.ldd), *r2 = r1;
+        if (dbl) r2 = (const double2 *) (p.dw + (size_t) (__ldg (p.dbase + sb) + ((mxb * (mxb - 1)) >> 1) + mnb) * p.ldd);
         apply_diff_rows<U> (h2, ldh >> 1, lane, r1, f1, r2, f2, dbl);
     } else {
-        apply_w_rows<(U < 8 ? U : 8)> (h2, ldw >> 1, lane, (const double2 *) (p.wb + (size_t) ia * ldw), (const double2 *) (p.wb + (size_t) oa * ldw),
-                                      (const double2 *) (p.wb + (size_t) ib * ldw), (const double2 *) (p.wb + (size_t) ob * ldw), dbl);
+        apply_wr_rows<(U < 8 ? U : 8)> (h2, p.ldr >> 1, lane, (const double2 *) (p.wr + (size_t) (fa + mxa) * p.ldr), (const double2 *) (p.wr + (size_t) (fa + mna) * p.ldr), f1,
+                                       (const double2 *) (p.wr + (size_t) (fb + mxb) * p.ldr), (const double2 *) (p.wr + (size_t) (fb + mnb) * p.ldr), f2, dbl);
     }
 }
 
@@ -543,13 +585,16 @@ __device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s
 // from the pair table -- state independent, so its L2 latency is paid long before the trial is evaluated).
 // A round never crosses the end of a scan, so the per-scan bookkeeping stays once per scan.
 // Accepted moves are applied by all lanes with 128-bit loads of the beta-scaled W rows from L2.
-// Shared memory per warp: hb[ldh] doubles | since[nsites] u32 | state[nsites] u16 | ring[4][RING] u32
+// Shared memory per warp: g[ldh] doubles (relative fields) | since[nsites] u32 | state[nsites] u16 | ring[4][RING] u32
 // ---------------------------------------------------------------------------------------------------
 struct WarpLayout {
     size_t off_site, off_h, off_since, off_state, off_ring, per_warp, shared_bytes;
     int    ldh, ring;
-    __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd) {
-        ldh  = (ninst + 64 * upd - 1) / (64 * upd) * (64 * upd);        // whole batches of the field update (apply_diff_rows)
+    // abs: the relative fields are stored at the instance's own index with a zero at every first instance (small models:
+    // no index arithmetic in the proposal); else compactly, without the first instances (large models: ninst - nsites slots)
+    __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd, bool abs) {
+        const int nfield = abs ? ninst : (ninst > nsites ? ninst - nsites : 1);
+        ldh  = (nfield + 64 * upd - 1) / (64 * upd) * (64 * upd);       // whole batches of the field update (apply_diff_rows)
         ring = tpl <= 2 ? 128 : 256;
         shared_bytes = ((size_t) nsites * 4 + 15) & ~(size_t) 15;     // packed site table, one copy per CTA
         off_site = 0;
@@ -563,6 +608,10 @@ struct WarpLayout {
     }
 };
 
+// Register budgets (16384 registers per SM sub-partition, a quarter of the resident warps each): 1 CTA of 8 warps 255,
+// 2 CTAs 128, 3 CTAs 80, 4 CTAs 64.  Measured on ifp20: 3.4e10 / 3.8e10 / 3.7e10 moves/s for 2 / 3 / 4 CTAs -- at 64
+// registers ptxas moves the warp-uniform bookkeeping off the uniform datapath (12 % more instructions), so three CTAs
+// are the default for small fields (PCE_MC_CTAS overrides).
 template <bool PER_CHAIN, int MIN_CTAS, int TPL>
 __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
@@ -570,7 +619,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     constexpr int RING = TPL <= 2 ? 128 : 256;
     constexpr int UPD  = MIN_CTAS == 1 ? 16 : 4;      // 128-bit loads per lane, row and batch when a move is applied
     constexpr bool FALLBACK = MIN_CTAS == 1;          // only the 255-register variant carries the four-gather cross-term path
-    const WarpLayout L (p.nsites, p.ninst, TPL, UPD);
+    constexpr bool ABS = MIN_CTAS != 1;               // small fields: instance-indexed slots (see WarpLayout)
+    const WarpLayout L (p.nsites, p.ninst, TPL, UPD, ABS);
     uint32_t      *s_site = (uint32_t *) smem;                        // first | ninst << 16 per site (CTA-wide)
     unsigned char *base   = smem + L.shared_bytes + (size_t) wib * L.per_warp;
     double        *h      = (double *) (base + L.off_h);
@@ -600,27 +650,41 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     auto gtb = [&] (int k) -> double {       // intrinsic term of instance k in units of RT
         return __dmul_rn (beta, __dsub_rn (__ldg (p.gintr + k), __dmul_rn ((double) __ldg (p.protons + k), mu)));
     };
-    // fused fields hb[k] = gtb[k] + sum_j wb[k][a_j], j sequential (spec order).  W is bitwise symmetric, so the
-    // gathers wb[k][a_j] are taken as the coalesced row reads wb[a_j][k]: a chunk of 256 consecutive k per pass
-    // (each lane owns 4 double2), every row of the state streamed once per chunk with 128-bit loads.
-    {
+    // relative fields g[r] = (gtb[k] - gtb[f]) + sum_j wr[a_j][r], j sequential (spec order)
+    if (ABS) {
+        // instance-indexed slots: lanes over the instances, zero at the first instance of every site
+        for (int k = lane; k < L.ldh; k += 32) {
+            double acc = 0.0;
+            if (k < ninst) {
+                const int site = __ldg (p.site_of + k), f = __ldg (p.first + site);
+                if (k != f) {
+                    const double *col = p.wr + (k - site - 1);
+                    acc = __dsub_rn (gtb (k), gtb (f));
+                    for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, __ldg (col + (size_t) state[j] * p.ldr));
+                }
+            }
+            h[k] = acc;
+        }
+    } else {
+        // compact slots: a chunk of 256 consecutive slots per pass (each lane owns 4 double2), every wr row of the state
+        // streamed once per chunk with 128-bit loads
         constexpr int CH = 4;
-        const int n2 = L.ldh >> 1, nw2 = ldw >> 1;
+        const int n2 = L.ldh >> 1, nr2 = p.ldr >> 1, nrel = p.nrel;
         for (int c0 = 0; c0 < n2; c0 += 32 * CH) {
             double2 acc[CH];
 #pragma unroll
             for (int c = 0; c < CH; c++) {
-                const int k2 = c0 + c * 32 + lane, k = 2 * k2;
-                acc[c].x = k < ninst ? gtb (k) : 0.0;
-                acc[c].y = k + 1 < ninst ? gtb (k + 1) : 0.0;
+                const int r = 2 * (c0 + c * 32 + lane);
+                acc[c].x = r < nrel ? __dsub_rn (gtb (__ldg (p.rk + r)), gtb (__ldg (p.rf + r))) : 0.0;
+                acc[c].y = r + 1 < nrel ? __dsub_rn (gtb (__ldg (p.rk + r + 1)), gtb (__ldg (p.rf + r + 1))) : 0.0;
             }
 #pragma unroll 2
             for (int j = 0; j < nsites; j++) {
-                const double2 *row = (const double2 *) (p.wb + (size_t) state[j] * ldw);
+                const double2 *row = (const double2 *) (p.wr + (size_t) state[j] * p.ldr);
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
                     const int k2 = c0 + c * 32 + lane;
-                    if (k2 < nw2) {
+                    if (k2 < nr2) {
                         const double2 v = __ldg (row + k2);
                         acc[c].x = __dadd_rn (acc[c].x, v.x);
                         acc[c].y = __dadd_rn (acc[c].y, v.y);
@@ -636,18 +700,25 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     }
     __syncwarp ();
 
-    // initial energy in units of RT.  sum_i hb[a_i] counts every pair interaction twice and the intrinsic terms once,
-    // so G/RT = (sum_i hb[a_i] + sum_i gtb[a_i]) / 2: O(nsites) instead of the O(nsites^2) gathers of
-    // EnergyModel.c:204-224.  Equal to the reference-order value to rounding (~1e-13 relative); it only seeds the
-    // tracked energy (informational output).
+    // initial energy in units of RT: sum_i gtb[a_i] + sum_{i > j} wb[a_i][a_j], lanes over i and the partial sums combined, so
+    // the value may differ from the serial reference-order sum (EnergyModel.c:204-224) in the last bits.  It only seeds
+    // the tracked energy (informational output).
     double grt;
     {
-        double s = 0.0;
-        for (int i = lane; i < nsites; i += 32) {
-            const int ai = state[i];
-            s += h[ai] + gtb (ai);
+        double gi = 0.0, ws = 0.0;
+        for (int i0 = 0; i0 < nsites; i0 += 32) {          // trip counts are warp-uniform (keeps the whole kernel on the uniform datapath)
+            const int  i  = i0 + lane;
+            const bool in = i < nsites;
+            const int  ai = in ? state[i] : 0;
+            if (in) gi += gtb (ai);
+            const double *row = p.wb + (size_t) ai * ldw;
+            const int jend = i0 + 32 < nsites ? i0 + 32 : nsites;
+            for (int j = 0; j < jend; j++) {
+                const double v = __ldg (row + state[j]);
+                if (in && j < i) ws += v;
+            }
         }
-        grt = 0.5 * pce::warp_sum (s);
+        grt = pce::warp_sum (gi) + pce::warp_sum (ws);
     }
 
     const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
@@ -732,7 +803,11 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 ib = (int) (ib_info & 0xffffu) + kb;
                 if (ib >= ob) ib++;
                 if (!valid) { ib = ob; ia = oa; }
-                x = __dadd_rn (__dsub_rn (h[ia], h[oa]), __dsub_rn (h[ib], h[ob]));
+                const int fa = (int) (ia_info & 0xffffu), fb = (int) (ib_info & 0xffffu);
+                // relative fields: 0 for a first instance (stored as such in the instance-indexed layout)
+                const double gan = ABS ? h[ia] : ia != fa ? h[ia - sa - 1] : 0.0, gao = ABS ? h[oa] : oa != fa ? h[oa - sa - 1] : 0.0;
+                const double gbn = ABS ? h[ib] : ib != fb ? h[ib - sb - 1] : 0.0, gbo = ABS ? h[ob] : ob != fb ? h[ob - sb - 1] : 0.0;
+                x = __dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo));
                 const float xlow = __fsub_rd (__double2float_rd (x), pbound);            // <= x0 - B <= x
                 const float ulow = __uint2float_rd (e_w1[u]) * 2.3283064365386963e-10f;  // <= u
                 const bool certain = (px >> 24) != 0u && xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
@@ -749,7 +824,9 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                     e_need[u] = true;
                 }
             } else {
-                x = __dsub_rn (h[ia], h[oa]);
+                const int fa = (int) (ia_info & 0xffffu);
+                const double gan = ABS ? h[ia] : ia != fa ? h[ia - sa - 1] : 0.0, gao = ABS ? h[oa] : oa != fa ? h[oa - sa - 1] : 0.0;
+                x = __dsub_rn (gan, gao);
                 e_need[u] = act && valid;
             }
             e_dbl[u] = dbl; e_x[u] = x;
@@ -796,7 +873,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             const int sa = (int) (s_pr & 0xffffu), sb = (int) (s_pr >> 16);
             const int ia = (int) (s_a & 0xffffu), oa = (int) (s_a >> 16), ib = (int) (s_b & 0xffffu), ob = (int) (s_b >> 16);
             if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) lg_fa++; else lg_ma++; }
-            apply_move<UPD> (p, s_site, h, L.ldh, ldw, lane, sa, sb, ia, oa, ib, ob, dbl);
+            apply_move<UPD, ABS> (p, s_site, h, L.ldh, lane, sa, sb, ia, oa, ib, ob, dbl);
             grt = __dadd_rn (grt, x);
             if (lane == 0) {
                 const uint32_t since_a = since[sa];
@@ -879,29 +956,43 @@ int smem_limit (int device, size_t *limit) {
 
 // chain-per-thread plan: W in shared memory when it fits, and the block size (multiple of 32, <= 512) that puts the
 // most warps on an SM; ties go to the smaller block (finer-grained waves).
+// sizes of the relative-field tables of a model: slots per chain, difference rows, cross-table entries
+struct TableSizes { int nrel, nrows; size_t ncross; };
+TableSizes table_sizes (const pce_mc *mc) {
+    const pce_model *m = mc->model;
+    TableSizes t = { m->ninst - m->nsites, 0, 0 };
+    for (int i = 0; i < m->nsites; i++) { const int n = m->last[i] - m->first[i] + 1; t.nrows += n * (n - 1) / 2; }
+    for (size_t k = 0; k < mc->pair_a.size (); k++) {
+        const int na = m->last[mc->pair_a[k]] - m->first[mc->pair_a[k]] + 1, nb = m->last[mc->pair_b[k]] - m->first[mc->pair_b[k]] + 1;
+        t.ncross += (size_t) na * (na - 1) * nb * (nb - 1);
+    }
+    return t;
+}
+
+// chain-per-thread plan: the difference rows and the cross-term table must fit in shared memory next to enough chains;
+// the block size (multiple of 32, one resident CTA, up to 1024 threads: 128 / 80 / 64 registers for <= 512 / 768 / 1024)
+// is the one that puts the most warps on an SM; ties go to the smaller block (finer-grained waves).
 bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     const pce_model *m = mc->model;
-    if (m->ninst > 256) return false;
-    const size_t per_sm = 228 * 1024;
+    const TableSizes t = table_sizes (mc);
+    if (m->ninst > 256 || t.nrows > 16383 || t.ncross >= (1u << 24)) return false;
     int best_warps = 0;
     const char *forced = std::getenv ("PCE_MC_BLOCK");      // tuning aid: force the block size
     const int forced_block = forced ? std::atoi (forced) : 0;
-    for (int w_in = 1; w_in >= 0; w_in--) {
-        for (int block = 32; block <= 512; block += 32) {
-            if (forced_block && block != forced_block) continue;
-            ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), block, w_in, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
-            if (L.total > limit) continue;
-            if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
-            int ctas = (int) std::min<size_t> (per_sm / (L.total + 1024), (size_t) (2048 / block));
-            ctas = std::min (ctas, 32);
-            const int warps = ctas * block / 32;
-            if (warps > best_warps) {
-                best_warps = warps; plan->kernel = 1; plan->block = block; plan->w_in_smem = w_in; plan->smem = L.total; plan->ctas_per_sm = ctas;
-            }
+    // measured on lysozyme: 512 threads 6.85e10, 640 (the largest block that still gets the 83-register build) 7.73e10,
+    // 768 / 896 with the 69- and 64-register builds 5.9e10 / 6.0e10 -- so blocks beyond 640 are only taken when forced
+    for (int block = 32; block <= (forced_block ? 1024 : 640); block += 32) {
+        if (forced_block && block != forced_block) continue;
+        ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
+        if (L.total > limit) continue;
+        if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
+        const int warps = block / 32;
+        if (warps > best_warps) {
+            best_warps = warps; plan->kernel = 1; plan->block = block; plan->w_in_smem = 1; plan->smem = L.total; plan->ctas_per_sm = 1;
         }
-        if (best_warps >= 4) break;     // W on chip with at least 4 warps/SM: take it
     }
-    return best_warps >= 2;
+    // auto mode: with fewer than 8 resident warps the chain-per-warp kernel does better; a forced choice runs with what fits
+    return best_warps >= (mc->kernel == 1 ? 1 : 8);
 }
 
 // trials evaluated per lane and round by the chain-per-warp kernel: 1 (default; measured best on every model, the kernel
@@ -915,20 +1006,20 @@ bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
     const pce_model *m = mc->model;
     if (m->ninst > 65535 || m->nsites > 65535) return false;
     const int tpl = warp_tpl ();
-    // small fields: 4-deep update batches and two to four resident CTAs of 8 warps (128 / 80 / 64 registers; ifp20 gains
-    // 27 % from 16 -> 32 warps per SM); large fields (one CTA fits): 255 registers and 16-deep batches
+    // small fields: 4-deep update batches and two or three resident CTAs of 8 warps (128 / 80 registers); large fields
+    // (one CTA fits): 255 registers and 16-deep batches
     for (int pass = 0; pass < 3; pass++) {
         const int upd = pass == 1 ? 16 : 4;
-        WarpLayout L (m->nsites, m->ninst, tpl, upd);
+        WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1);
         if (L.per_warp + L.shared_bytes > limit) continue;
         int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);
         if (const char *cap = std::getenv ("PCE_MC_WARPS")) warps = std::max (1, std::min (warps, std::atoi (cap)));      // tuning aid
         const size_t smem = L.shared_bytes + (size_t) warps * L.per_warp;
         const int ctas = (int) std::min<size_t> ((228 * 1024) / (smem + 1024), (size_t) (2048 / (warps * 32)));
+        const char *forced = std::getenv ("PCE_MC_CTAS");       // tuning aid: resident CTAs per SM of the small-field variant (2..4)
+        const int  most = forced ? std::max (2, std::min (4, std::atoi (forced))) : 3;
         if (pass == 0 && (ctas < 2 || mc->cross_overflow)) continue;
         if (pass == 2 && mc->cross_overflow) continue;      // only the one-CTA 255-register variant gathers W itself
-        const char *forced = std::getenv ("PCE_MC_CTAS");       // tuning aid: resident CTAs per SM of the small-field variant (2..4)
-        const int  most = forced ? std::max (2, std::min (4, std::atoi (forced))) : 4;
         plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = smem;
         plan->ctas_per_sm = pass == 0 ? std::min (ctas, most) : 1; plan->tpl = tpl; plan->upd = upd;
         return true;
@@ -984,7 +1075,7 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
     mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_pair_x.release (); mc->d_cross.release (); mc->d_ph.release (); mc->d_esum.release ();
-    mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release ();
+    mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release (); mc->d_wr.release (); mc->d_rk.release (); mc->d_rf.release ();
     delete mc;
 }
 
@@ -1037,8 +1128,7 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
     else if (mc->kernel == 2) ok = plan_warp (mc, limit, plan);
     else {
         // auto: chain per thread while W fits in shared memory next to enough chains; else chain per warp
-        ok = plan_thread (mc, limit, nph, plan) && plan->w_in_smem;
-        if (!ok) ok = plan_warp (mc, limit, plan) || plan_thread (mc, limit, nph, plan);
+        ok = plan_thread (mc, limit, nph, plan) || plan_warp (mc, limit, plan);
     }
     if (!ok) return fail (PCE_ERR_LIMIT, "model too large for the selected Monte Carlo kernel");
     return PCE_OK;
@@ -1060,14 +1150,34 @@ extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *c
     return PCE_OK;
 }
 
-// Difference rows D[site][(lo, hi)] = wb[hi] - wb[lo] for every instance pair of every site, built on the device from
-// the uploaded beta-scaled W whenever the model was uploaded again.  Skipped (the kernels then stream the W rows) when
-// the table would exceed PCE_DW_BUDGET_MB (default 100 MB: it should stay L2-resident next to the hot part of W).
-static int build_difference_rows (pce_mc *mc, int ldd) {
+// Tables of the relative-field formulation, built on the device from the uploaded beta-scaled W whenever the model was
+// uploaded again: wr (ninst rows of nrel slots) and the difference rows E[site][(lo, hi)] = wr[hi] - wr[lo] of every
+// instance pair of every site, with row stride ldd.  The difference rows are skipped (the warp kernel then streams the two
+// wr rows) when they would exceed PCE_DW_BUDGET_MB (default 100 MB: they should stay L2-resident).
+static int build_relative_tables (pce_mc *mc, int ldd, bool abs) {
     pce_model *m = mc->model;
-    if (mc->dw_generation == m->generation && mc->dw_ldd == ldd) return PCE_OK;
+    if (mc->rel_generation != m->generation) {
+        const int nrel = m->ninst - m->nsites;
+        std::vector<int32_t> rk ((size_t) std::max (nrel, 1), 0), rf ((size_t) std::max (nrel, 1), 0);
+        for (int i = 0; i < m->nsites; i++)
+            for (int k = m->first[i] + 1; k <= m->last[i]; k++) { rk[(size_t) (k - i - 1)] = k; rf[(size_t) (k - i - 1)] = m->first[i]; }
+        mc->nrel = nrel;
+        mc->ldr  = (std::max (nrel, 1) + 3) & ~3;
+        PCE_CUDA (mc->d_rk.resize (rk.size ())); PCE_CUDA (mc->d_rf.resize (rf.size ()));
+        PCE_CUDA (mc->d_wr.resize ((size_t) m->ninst * mc->ldr));
+        PCE_CUDA (cudaMemcpyAsync (mc->d_rk.ptr, rk.data (), rk.size () * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+        PCE_CUDA (cudaMemcpyAsync (mc->d_rf.ptr, rf.data (), rf.size () * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+        k_build_wr<<<(unsigned) m->ninst, 256, 0, m->stream>>> (m->d_wb.ptr, m->ldw, nrel, mc->ldr, mc->d_rk.ptr, mc->d_rf.ptr, mc->d_wr.ptr);
+        pce::count_launch ();
+        PCE_CUDA (cudaGetLastError ());
+        PCE_CUDA (cudaStreamSynchronize (m->stream));        // the staging vectors die with this scope
+        mc->rel_generation = m->generation;
+        mc->dw_generation = -1;
+    }
+    if (mc->dw_generation == m->generation && mc->dw_ldd == ldd && mc->dw_abs == abs) return PCE_OK;
     mc->dw_generation = m->generation;
     mc->dw_ldd = ldd;
+    mc->dw_abs = abs;
     mc->dw_valid = false;
     std::vector<int32_t> base ((size_t) m->nsites), lo, hi;
     for (int i = 0; i < m->nsites; i++) {
@@ -1076,18 +1186,21 @@ static int build_difference_rows (pce_mc *mc, int ldd) {
         for (int mx = 1; mx < n; mx++)
             for (int mn = 0; mn < mx; mn++) { lo.push_back (m->first[i] + mn); hi.push_back (m->first[i] + mx); }
     }
+    PCE_CUDA (mc->d_dbase.resize ((size_t) m->nsites));
+    PCE_CUDA (cudaMemcpyAsync (mc->d_dbase.ptr, base.data (), (size_t) m->nsites * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
+    PCE_CUDA (cudaStreamSynchronize (m->stream));
     const char *budget_env = std::getenv ("PCE_DW_BUDGET_MB");
     const double budget = (budget_env ? std::atof (budget_env) : 100.0) * 1024.0 * 1024.0;
     const size_t nrows = lo.size ();
+    mc->nrows = (int) nrows;
     if (nrows == 0 || (double) nrows * ldd * sizeof (double) > budget) return PCE_OK;
     pce::DeviceBuffer<int32_t> d_lo, d_hi;
     PCE_CUDA (d_lo.resize (nrows)); PCE_CUDA (d_hi.resize (nrows));
-    PCE_CUDA (mc->d_dbase.resize ((size_t) m->nsites));
     PCE_CUDA (mc->d_dw.resize (nrows * (size_t) ldd));
     PCE_CUDA (cudaMemcpyAsync (d_lo.ptr, lo.data (), nrows * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
     PCE_CUDA (cudaMemcpyAsync (d_hi.ptr, hi.data (), nrows * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
-    PCE_CUDA (cudaMemcpyAsync (mc->d_dbase.ptr, base.data (), (size_t) m->nsites * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
-    k_build_dw<<<(unsigned) nrows, 256, 0, m->stream>>> (m->d_wb.ptr, m->ninst, m->ldw, ldd, d_lo.ptr, d_hi.ptr, mc->d_dw.ptr);
+    k_build_dw<<<(unsigned) nrows, 256, 0, m->stream>>> (mc->d_wr.ptr, mc->nrel, mc->ldr, ldd, d_lo.ptr, d_hi.ptr, mc->d_dw.ptr, abs ? 1 : 0, m->ninst,
+                                                         m->d_site_of_inst.ptr, m->d_first.ptr);
     pce::count_launch ();
     cudaError_t err = cudaGetLastError ();
     if (err == cudaSuccess) err = cudaStreamSynchronize (m->stream);     // the staging vectors and index buffers die with this scope
@@ -1160,6 +1273,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         PCE_CUDA (cudaMemcpyAsync (mc->d_pair_x.ptr, extra.data (), extra.size () * sizeof (uint32_t), cudaMemcpyHostToDevice, m->stream));
         if (mc->cross_valid) {
             PCE_CUDA (mc->d_cross.resize (table.size ()));
+            mc->ncross = table.size ();
             PCE_CUDA (cudaMemcpyAsync (mc->d_cross.ptr, table.data (), table.size () * sizeof (double), cudaMemcpyHostToDevice, m->stream));
         }
         PCE_CUDA (cudaStreamSynchronize (m->stream));
@@ -1182,11 +1296,18 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     p.temperature = m->temperature;
     p.w_in_smem = plan.w_in_smem;
 
-    if (plan.kernel != 1) {
-        // padded field length of this launch = row stride of the difference rows
-        const int ldd = WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd).ldh;
-        status = build_difference_rows (mc, ldd);
+    {
+        // row stride of the difference rows: the padded field length of a chain-per-warp launch, else the slot count
+        const int nrel = std::max (m->ninst - m->nsites, 1);
+        const bool abs = plan.kernel == 2 && plan.upd != 16;         // small-field variants of the warp kernel: instance-indexed slots
+        const int ldd = plan.kernel == 2 ? WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd, abs).ldh : ((nrel + 3) & ~3);
+        status = build_relative_tables (mc, ldd, abs);
         if (status != PCE_OK) return status;
+        if (plan.kernel == 1 && (!mc->dw_valid || (npairs > 0 && !mc->cross_valid)))
+            return fail (PCE_ERR_LIMIT, "the chain-per-thread kernel needs the difference rows and the cross-term table");
+        if (abs && !mc->dw_valid) return fail (PCE_ERR_LIMIT, "the small-field chain-per-warp kernel needs the difference rows");
+        p.nrel = mc->nrel; p.ldr = mc->ldr; p.nrows = mc->nrows; p.ncross = (int) mc->ncross;
+        p.wr = mc->d_wr.ptr; p.rk = mc->d_rk.ptr; p.rf = mc->d_rf.ptr; p.site_of = m->d_site_of_inst.ptr;
         p.dw = mc->dw_valid ? mc->d_dw.ptr : nullptr;
         p.dbase = mc->d_dbase.ptr;
         p.ldd = ldd;
@@ -1197,12 +1318,13 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
     if (plan.kernel == 1) {
         void (*kernel) (const McParams);
-        if (mc->nprod < 65536)
-            kernel = per_chain ? (plan.w_in_smem ? k_mc_thread<true, true, uint16_t> : k_mc_thread<true, false, uint16_t>)
-                               : (plan.w_in_smem ? k_mc_thread<false, true, uint16_t> : k_mc_thread<false, false, uint16_t>);
-        else
-            kernel = per_chain ? (plan.w_in_smem ? k_mc_thread<true, true, uint32_t> : k_mc_thread<true, false, uint32_t>)
-                               : (plan.w_in_smem ? k_mc_thread<false, true, uint32_t> : k_mc_thread<false, false, uint32_t>);
+#define PCE_THREAD_KERNEL(S_) (plan.block <= 640 ? (per_chain ? k_mc_thread<true, S_, 128> : k_mc_thread<false, S_, 128>) \
+                              : plan.block <= 768 ? (per_chain ? k_mc_thread<true, S_, 80> : k_mc_thread<false, S_, 80>) \
+                              : plan.block <= 896 ? (per_chain ? k_mc_thread<true, S_, 72> : k_mc_thread<false, S_, 72>) \
+                                                  : (per_chain ? k_mc_thread<true, S_, 64> : k_mc_thread<false, S_, 64>))
+        if (mc->nprod < 65536) kernel = PCE_THREAD_KERNEL (uint16_t);
+        else kernel = PCE_THREAD_KERNEL (uint32_t);
+#undef PCE_THREAD_KERNEL
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     } else {
@@ -1216,6 +1338,10 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         else kernel = PCE_WARP_KERNEL (1);
 #undef PCE_WARP_KERNEL
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
+        // shared-memory carveout for exactly the planned number of resident CTAs (the rest of the 228 KB stays L1 for the
+        // difference rows and the cross-term table); without __launch_bounds__ the driver has no occupancy hint of its own
+        const int carveout = (int) std::min<size_t> (100, ((size_t) plan.ctas_per_sm * (plan.smem + 1024) * 100) / (228 * 1024) + 1);
+        PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     }
     pce::count_launch ();
