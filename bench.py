@@ -382,13 +382,13 @@ def main():
             "kernel_ms_per_launch": kernel_ms,
         }
         if args.workload != "synthA" and launch_info.get("kernel") == 2 and on_chip is not None:
-            # chain-per-warp kernel: the W / difference rows are served by L2.  Algorithmic L2 bytes of one launch = one
+            # chain-per-warp kernel: the difference rows are served by L2.  Algorithmic L2 bytes of one launch = one
             # difference row per changed site of every accepted move + the four W entries of every double-move proposal
             # + the rows read by the field initialisation; accepted moves are counted in production scans only and
             # scaled to all scans.  The denominator is measured here with a streaming read of an L2-resident buffer.
             c = d_counters.sum(dim=0).cpu().numpy().astype(float)
             scale = float(nequil + nprod) / float(nprod)
-            row_bytes = record.ninstances * 8.0
+            row_bytes = (record.ninstances - record.nsites) * 8.0          # fields relative to the first instance of each site
             l2_bytes = scale * ((c[1] + 2.0 * c[3]) * row_bytes + c[2] * 32.0) + float(len(grid_all)) * chains * record.nsites * row_bytes
             peak = C.c_double(0.0)
             _native.check(lib.pce_probe_read_bandwidth(local_rank, 48 * 1024 * 1024, 40, C.byref(peak)))
