@@ -427,12 +427,13 @@ def main():
                 curve[label] = {"wall_ms": 1000.0 * (time.perf_counter() - t0), "chains": nch, "nequil": 500, "nprod_per_chain": npr, "ph_points": tc.nsteps}
             line["titration_curve"] = curve
         if world == 1 and not args.no_cpu_baseline and args.workload in ("lysozyme", "ifp20", "defensin"):
-            rate, seconds, kind = cpu_baseline(record, 500, 20000, grid_all, 1, repeats=3 if args.workload != "ifp20" else 1)
+            ncurves = 6 if args.workload != "ifp20" else 1            # 10-20 s of one host core
+            rate, seconds, kind = cpu_baseline(record, 500, 20000, grid_all, 1, repeats=ncurves)
             line["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind,
                                     "sample": "%d single-chain %s curve(s) (41 pH, 500+20000 scans, MT19937), %.1f s on one host core" % (
-                                        3 if args.workload != "ifp20" else 1, record.name, seconds)}
+                                        ncurves, record.name, seconds)}
             if "titration_curve" in line:
-                line["titration_curve"]["reference_one_core_wall_ms"] = 1000.0 * seconds / (3 if args.workload != "ifp20" else 1)
+                line["titration_curve"]["reference_one_core_wall_ms"] = 1000.0 * seconds / ncurves
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
