@@ -93,11 +93,17 @@ struct McParams {
     const double  *dw;              // difference rows E = wr[hi] - wr[lo] [nrows][ldd] (nullptr: stream the two wr rows themselves)
     const int32_t *dbase;           // [nsites] first difference row of the site
     int            ldd;             // row stride of dw (warp kernel: the padded field length of the launch)
+    // chain-per-thread kernel: the shared-memory layout, computed on the host (ThreadLayout) so that the kernel can
+    // re-read an offset from the constant bank instead of keeping it in a register or recomputing it
+    uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
+    int            tl_hstride, tl_estride, tl_kslots;
+    uint32_t       nmoves;          // nsites + npairs
+    unsigned long long ntrials;     // (nequil + nprod) * nmoves
 };
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
 struct ThreadLayout {
-    size_t off_e, off_cross, off_h, off_counts, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
+    size_t off_e, off_cross, off_h, off_eng, off_counts, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
     int    hstride, estride, kslots;
     __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes) {
         hstride = (nrel > 0 ? nrel : 1) | 1;       // odd: lanes of a warp fall on distinct bank pairs
@@ -109,6 +115,7 @@ struct ThreadLayout {
         off_e = o;      o += (size_t) (nrows > 0 ? nrows : 1) * estride * 8;      // difference rows E
         off_cross = o;  o += (size_t) (ncross > 0 ? ncross : 1) * 8;              // pair cross terms
         off_h = o;      o += (size_t) block * hstride * 8;                        // relative fields, one row per chain
+        off_eng = o;    o += (size_t) block * 16;                                  // tracked energy and its sum over production scans, per chain
         off_counts = o; o += (size_t) kslots * ninst * 4;     // u32: block * nprod < 2^32 is checked on the host
         off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
         o = (o + 3) & ~(size_t) 3;
@@ -169,24 +176,27 @@ __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
 // ---------------------------------------------------------------------------------------------------
 // Register budgets: every SM sub-partition holds 16384 registers and a quarter of the block's warps, so a block of
 // 512 / 640 / 768 / 896 / 1024 threads may use 128 / 96 / 80 / 72 / 64 registers per thread (__launch_bounds__ would round
-// the block up to the next multiple of 256 threads and allow fewer).  The kernel wants 83 (allocated as 88): below that
-// ptxas rematerialises addresses and constants (13.5 instead of 9.2 warp-instructions per trial at 64), so blocks of
-// up to 640 threads run the 83-register build and the planner prefers them.
+// the block up to the next multiple of 256 threads and allow fewer).  Uncapped, the kernel takes 79 (8.9 warp-instructions
+// per trial); capped below that ptxas rematerialises loop invariants inside the trial loop (10.6 at 72, 13 at 64), so
+// the planner stops at 768 threads.  To get there the loop state was put on a diet: no Philox prefetch, 32-bit scan
+// counter instead of 64-bit trial counters, tracked energy and its sum in shared memory, 32-bit shared-memory offsets
+// instead of generic pointers, the shared-memory layout passed in the kernel parameters.
 template <bool PER_CHAIN, typename SinceT, int MAX_REGS>
 __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
-    const ThreadLayout L (p.nsites, p.ninst, p.npairs, p.nrel, p.nrows, p.ncross, B, p.nchains, p.nph, (int) sizeof (SinceT));
-    double             *s_e      = (double *) (smem + L.off_e);
-    double             *s_cross  = (double *) (smem + L.off_cross);
-    double             *s_h      = (double *) (smem + L.off_h);
-    uint32_t           *s_counts = (uint32_t *) (smem + L.off_counts);
-    SinceT             *s_since  = (SinceT *) (smem + L.off_since);
-    uint32_t           *s_site   = (uint32_t *) (smem + L.off_site);      // first | ninst << 16
-    uint32_t           *s_pair   = (uint32_t *) (smem + L.off_pair);      // site a | site b << 16
-    uint32_t           *s_pairx  = (uint32_t *) (smem + L.off_pairx);     // base of the pair in the cross-term table
-    uint32_t           *s_erow   = (uint32_t *) (smem + L.off_erow);      // first difference row of the site
-    uint8_t            *s_state  = smem + L.off_state;
+    double             *s_e      = (double *) (smem + p.tl_e);
+    double             *s_cross  = (double *) (smem + p.tl_cross);
+    double             *s_h      = (double *) (smem + p.tl_h);
+    double             *my_eng   = (double *) (smem + p.tl_eng) + threadIdx.x;      // [0]: tracked energy G/RT, [B]: its sum over production scans
+    uint32_t           *s_counts = (uint32_t *) (smem + p.tl_counts);
+    SinceT             *s_since  = (SinceT *) (smem + p.tl_since);
+    uint32_t           *s_site   = (uint32_t *) (smem + p.tl_site);       // first | ninst << 16
+    uint32_t           *s_pair   = (uint32_t *) (smem + p.tl_pair);       // site a | site b << 16
+    uint32_t           *s_pairx  = (uint32_t *) (smem + p.tl_pairx);      // base of the pair in the cross-term table
+    uint32_t           *s_erow   = (uint32_t *) (smem + p.tl_erow);       // first difference row of the site
+    uint8_t            *s_state  = smem + p.tl_state;
+    struct { int hstride, estride, kslots; } L = { p.tl_hstride, p.tl_estride, p.tl_kslots };
 
     const int nsites = p.nsites, ninst = p.ninst, nrel = p.nrel;
     const long long total = (long long) p.nph * p.nchains;
@@ -200,8 +210,10 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
     uint32_t *my_counts = s_counts + (size_t) (q - q_base) * ninst;
-    uint8_t  *my_state = s_state + tid;
-    SinceT   *my_since = s_since + tid;
+    // per-thread arrays as 32-bit offsets into the dynamic shared memory (one register each instead of a 64-bit pointer)
+    const uint32_t o_state = p.tl_state + (uint32_t) tid, o_since = p.tl_since + (uint32_t) tid * (uint32_t) sizeof (SinceT);
+#define my_state(i_) smem[o_state + (uint32_t) (i_)]
+#define my_since(i_) (*(SinceT *) (smem + o_since + (uint32_t) (i_) * (uint32_t) sizeof (SinceT)))
     long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
 
     // stage the model: difference rows, cross terms, packed site and pair tables
@@ -217,8 +229,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         for (int i = 0; i < nsites; i++) {
             if ((i & 3) == 0) r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
             const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-            my_state[i * B] = (uint8_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
-            my_since[i * B] = (SinceT) 0;
+            my_state (i * B) = (uint8_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
+            my_since (i * B) = (SinceT) 0;
         }
     }
     __syncthreads ();
@@ -242,31 +254,29 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         }
     }
     __syncwarp ();
-    const double *myg = s_h + (size_t) tid * L.hstride;
+    const uint32_t o_g = p.tl_h + (uint32_t) (tid * L.hstride) * 8u;
+#define myg(i_) (*(const double *) (smem + o_g + (uint32_t) (i_) * 8u))
 
     // initial energy in the reference's order (EnergyModel.c:204-224), then to units of RT
-    double grt;
     {
         double gi = 0.0, ws = 0.0;
         int    np = 0;
         for (int i = 0; i < nsites; i++) {
-            const int ai = my_state[i * B];
+            const int ai = my_state (i * B);
             gi = __dadd_rn (gi, p.gintr[ai]);
             np += p.protons[ai];
             const double *row = p.w + (size_t) ai * p.ldw;
-            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[my_state[j * B]]);
+            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[my_state (j * B)]);
         }
-        grt = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
+        my_eng[0] = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
+        my_eng[B] = 0.0;
     }
 
-    const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
-    const unsigned long long ntrials = (unsigned long long) ((long long) p.nequil + p.nprod) * nmoves;
+    const uint32_t nmoves = p.nmoves;
+    const uint32_t nscans = (uint32_t) p.nequil + (uint32_t) p.nprod;
     uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
     uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
-    double   esum = 0.0;
-    long long scan = 0;
-    uint32_t  mv = 0, tp = 0;
-    bool      production = p.nequil == 0;
+    uint32_t scan = 0, mv = 0;            // production <=> scan >= nequil; production scan index tp = scan - nequil
 
     // one trial: proposal from (w0), Metropolis with (w1), cooperative application of accepted moves
     const bool has_pairs = p.npairs > 0;
@@ -278,7 +288,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         const uint32_t pr  = dbl ? s_pair[idx - nsites] : (idx | (idx << 16));     // single move: site b = site a
         const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
         const uint32_t ia_info = s_site[sa];
-        const int fa = (int) (ia_info & 0xffffu), na = (int) (ia_info >> 16), oa = my_state[sa * B];
+        const int fa = (int) (ia_info & 0xffffu), na = (int) (ia_info >> 16), oa = my_state (sa * B);
         bool valid = active && na >= 2;
         const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
         const int ka = (int) (proda >> 32);
@@ -292,7 +302,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             // moves ib == ob and the cross term is zero, so the value equals the single-move formula bit for bit
             const uint32_t ib_info = s_site[sb];
             const int fb = (int) (ib_info & 0xffffu), nb = (int) (ib_info >> 16);
-            ob = my_state[sb * B];
+            ob = my_state (sb * B);
             const int kb = (int) __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
             ib = fb + kb;
             if (ib >= ob) ib++;
@@ -301,13 +311,13 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             if (!valid) { ia = oa; ib = ob; }
             double cross = 0.0;
             if (dbl && valid) cross = s_cross[s_pairx[idx - nsites] + (uint32_t) (((oa - fa) * (na - 1) + ka) * (nb * (nb - 1)) + (ob - fb) * (nb - 1) + kb)];
-            const double gan = ia != fa ? myg[ia - sa - 1] : 0.0, gao = oa != fa ? myg[oa - sa - 1] : 0.0;
-            const double gbn = ib != fb ? myg[ib - sb - 1] : 0.0, gbo = ob != fb ? myg[ob - sb - 1] : 0.0;
+            const double gan = ia != fa ? myg (ia - sa - 1) : 0.0, gao = oa != fa ? myg (oa - sa - 1) : 0.0;
+            const double gbn = ib != fb ? myg (ib - sb - 1) : 0.0, gbo = ob != fb ? myg (ob - sb - 1) : 0.0;
             x = __dadd_rn (__dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo)), cross);
-            if (production && dbl) c_flips++;
+            if (scan >= (uint32_t) p.nequil && dbl) c_flips++;
         } else {
             if (!valid) ia = oa;
-            const double gan = ia != fa ? myg[ia - sa - 1] : 0.0, gao = oa != fa ? myg[oa - sa - 1] : 0.0;
+            const double gan = ia != fa ? myg (ia - sa - 1) : 0.0, gao = oa != fa ? myg (oa - sa - 1) : 0.0;
             x = __dsub_rn (gan, gao);
         }
         const bool accept = valid && metropolis (x, w1);
@@ -363,18 +373,20 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             } while (pending);
             __syncwarp ();
             if (accept) {
-                grt = __dadd_rn (grt, x);
-                const uint32_t since_a = my_since[sa * B];
+                const bool production = scan >= (uint32_t) p.nequil;
+                const uint32_t tp = production ? scan - (uint32_t) p.nequil : 0u;
+                my_eng[0] = __dadd_rn (my_eng[0], x);
+                const uint32_t since_a = my_since (sa * B);
                 if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
                 else if (tp != since_a) atomicAdd (&my_counts[oa], tp - since_a);
-                my_since[sa * B] = (SinceT) tp;
-                my_state[sa * B] = (uint8_t) ia;
+                my_since (sa * B) = (SinceT) tp;
+                my_state (sa * B) = (uint8_t) ia;
                 if (dbl) {
-                    const uint32_t since_b = my_since[sb * B];
+                    const uint32_t since_b = my_since (sb * B);
                     if (PER_CHAIN) my_chain_counts[ob] += (long long) (tp - since_b);
                     else if (tp != since_b) atomicAdd (&my_counts[ob], tp - since_b);
-                    my_since[sb * B] = (SinceT) tp;
-                    my_state[sb * B] = (uint8_t) ib;
+                    my_since (sb * B) = (SinceT) tp;
+                    my_state (sb * B) = (uint8_t) ib;
                     if (production) c_facc++;
                 } else if (production) c_macc++;
             }
@@ -382,12 +394,14 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         // scan bookkeeping (MCModelDefault.c:298-312): after the last trial of a production scan the energy is recorded
         if (++mv == nmoves) {
             mv = 0;
+            const bool production = scan >= (uint32_t) p.nequil;
             if (production) {
-                esum += grt;
-                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && active) p.trajectory[scan - p.nequil] = grt / beta;
+                const double grt = my_eng[0];
+                my_eng[B] += grt;
+                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && active) p.trajectory[scan - (uint32_t) p.nequil] = grt / beta;
             }
             if (PER_CHAIN && p.log_rows != nullptr) {        // the per-block counter table of MCModelDefault.pyx:85-151
-                const long long done = (production ? scan - p.nequil : scan) + 1;
+                const long long done = (long long) (production ? scan - (uint32_t) p.nequil : scan) + 1;
                 if (done % p.log_frequency == 0) {
                     if (q == 0 && local == 0 && active) {
                         long long *row = p.log_rows + 5 * ((production ? p.nequil / p.log_frequency : 0) + done / p.log_frequency - 1);
@@ -395,22 +409,17 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                     }
                     lg_m = lg_ma = lg_f = lg_fa = 0;
                 }
-                if (!production && scan + 1 == p.nequil) lg_m = lg_ma = lg_f = lg_fa = 0;
+                if (!production && scan + 1 == (uint32_t) p.nequil) lg_m = lg_ma = lg_f = lg_fa = 0;
             }
             scan++;
-            production = scan >= p.nequil;
-            tp = production ? (uint32_t) (scan - p.nequil) : 0u;
         }
     };
 
-    pce::Philox4 rnext = pce::philox4x32_10 (0u, 0u, chain, phidx, p.k0, p.k1);
-    for (unsigned long long b = 0; 2ull * b < ntrials; b++) {
-        const pce::Philox4 r = rnext;
-        const unsigned long long bn = b + 1;
-        rnext = pce::philox4x32_10 ((uint32_t) bn, (uint32_t) (bn >> 32), chain, phidx, p.k0, p.k1);   // ahead of its use
+    for (unsigned long long b = 0; scan < nscans; b++) {
+        const pce::Philox4 r = pce::philox4x32_10 ((uint32_t) b, (uint32_t) (b >> 32), chain, phidx, p.k0, p.k1);
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {          // one copy of the trial body in the instruction cache
-            if (half && 2ull * b + 1ull >= ntrials) break;
+            if (half && scan >= nscans) break;           // odd number of trials: the last block serves one
             trial (half ? r.z : r.x, half ? r.w : r.y);
         }
     }
@@ -419,16 +428,16 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (active) {
         for (int i = 0; i < nsites; i++) {
-            const int      a = my_state[i * B];
-            const uint32_t d = (uint32_t) p.nprod - my_since[i * B];
+            const int      a = my_state (i * B);
+            const uint32_t d = (uint32_t) p.nprod - my_since (i * B);
             if (PER_CHAIN) my_chain_counts[a] += (long long) d;
             else if (d) atomicAdd (&my_counts[a], d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
-            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = my_state[i * B];
-            p.chain_energy[c] = grt / beta;
-            p.chain_esum[c]   = esum / beta;
+            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = my_state (i * B);
+            p.chain_energy[c] = my_eng[0] / beta;
+            p.chain_esum[c]   = my_eng[B] / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
             p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
         }
@@ -442,7 +451,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             }
         // counters and energy sums: one atomic per thread (pH values may differ within a warp)
         if (active) {
-            if (p.esum != nullptr) atomicAdd (&p.esum[q], esum / beta);
+            if (p.esum != nullptr) atomicAdd (&p.esum[q], my_eng[B] / beta);
             if (p.counters != nullptr) {
                 atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
                 atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
@@ -452,6 +461,9 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         }
     }
 }
+#undef my_state
+#undef my_since
+#undef myg
 
 // ---------------------------------------------------------------------------------------------------
 // Tables of the relative-field formulation and the application of an accepted move in the warp kernel.
@@ -979,9 +991,9 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     int best_warps = 0;
     const char *forced = std::getenv ("PCE_MC_BLOCK");      // tuning aid: force the block size
     const int forced_block = forced ? std::atoi (forced) : 0;
-    // measured on lysozyme: 512 threads 6.85e10, 640 (the largest block that still gets the 83-register build) 7.73e10,
-    // 768 / 896 with the 69- and 64-register builds 5.9e10 / 6.0e10 -- so blocks beyond 640 are only taken when forced
-    for (int block = 32; block <= (forced_block ? 1024 : 640); block += 32) {
+    // measured on lysozyme (moves/s): 640 threads 7.6e10, 768 (the largest block the uncapped 79-register build fits) 8.5e10,
+    // 832 / 896 with the 72-register build 7.1e10 / 7.3e10 -- so blocks beyond 768 are only taken when forced
+    for (int block = 32; block <= (forced_block ? 1024 : 768); block += 32) {
         if (forced_block && block != forced_block) continue;
         ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
         if (L.total > limit) continue;
@@ -1316,14 +1328,32 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     if (plan.kernel == 1) blocks = ((long long) nph * mc->nchains + plan.block - 1) / plan.block;     // chain-major linear grid
     else blocks = ((long long) nph * mc->nchains + plan.block / 32 - 1) / (plan.block / 32);
     if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
+    p.nmoves = (uint32_t) (m->nsites + npairs);
+    p.ntrials = (unsigned long long) ((long long) mc->nequil + mc->nprod) * p.nmoves;
+    if (plan.kernel == 1) {
+        const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
+        p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_eng = (uint32_t) TL.off_eng; p.tl_counts = (uint32_t) TL.off_counts;
+        p.tl_since = (uint32_t) TL.off_since; p.tl_site = (uint32_t) TL.off_site; p.tl_pair = (uint32_t) TL.off_pair; p.tl_pairx = (uint32_t) TL.off_pairx;
+        p.tl_erow = (uint32_t) TL.off_erow; p.tl_state = (uint32_t) TL.off_state;
+        p.tl_hstride = TL.hstride; p.tl_estride = TL.estride; p.tl_kslots = TL.kslots;
+        if (TL.total != plan.smem) return fail (PCE_ERR_STATE, "shared-memory layout of the chain-per-thread kernel changed between planning and launch");
+    }
     if (plan.kernel == 1) {
         void (*kernel) (const McParams);
-#define PCE_THREAD_KERNEL(S_) (plan.block <= 640 ? (per_chain ? k_mc_thread<true, S_, 128> : k_mc_thread<false, S_, 128>) \
-                              : plan.block <= 768 ? (per_chain ? k_mc_thread<true, S_, 80> : k_mc_thread<false, S_, 80>) \
-                              : plan.block <= 896 ? (per_chain ? k_mc_thread<true, S_, 72> : k_mc_thread<false, S_, 72>) \
-                                                  : (per_chain ? k_mc_thread<true, S_, 64> : k_mc_thread<false, S_, 64>))
-        if (mc->nprod < 65536) kernel = PCE_THREAD_KERNEL (uint16_t);
-        else kernel = PCE_THREAD_KERNEL (uint32_t);
+        // the first build (fewest instructions first) whose registers fit: a quarter of the block's warps share the 16384
+        // registers of an SM sub-partition, allocated in units of 8 per thread
+        auto fits = [&] (void (*candidate) (const McParams)) -> bool {
+            cudaFuncAttributes attributes;
+            if (cudaFuncGetAttributes (&attributes, candidate) != cudaSuccess) return false;
+            const int allocated = (attributes.numRegs + 7) & ~7, warps_per_partition = (plan.block / 32 + 3) / 4;
+            return warps_per_partition * allocated * 32 <= 16384;
+        };
+#define PCE_THREAD_KERNEL(S_, R_) (per_chain ? k_mc_thread<true, S_, R_> : k_mc_thread<false, S_, R_>)
+#define PCE_THREAD_PICK(S_) (fits (PCE_THREAD_KERNEL (S_, 128)) ? PCE_THREAD_KERNEL (S_, 128) : fits (PCE_THREAD_KERNEL (S_, 80)) ? PCE_THREAD_KERNEL (S_, 80) \
+                             : fits (PCE_THREAD_KERNEL (S_, 72)) ? PCE_THREAD_KERNEL (S_, 72) : PCE_THREAD_KERNEL (S_, 64))
+        if (mc->nprod < 65536) kernel = PCE_THREAD_PICK (uint16_t);
+        else kernel = PCE_THREAD_PICK (uint32_t);
+#undef PCE_THREAD_PICK
 #undef PCE_THREAD_KERNEL
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
