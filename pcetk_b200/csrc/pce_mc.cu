@@ -38,7 +38,6 @@ struct pce_mc {
     uint64_t   seed = 1;
     std::vector<int32_t> pair_a, pair_b;
     std::vector<double>  pair_wmax;
-    pce::DeviceBuffer<int32_t> d_pair_a, d_pair_b;
     pce::DeviceBuffer<uint32_t> d_pair_packed;
     pce::DeviceBuffer<uint32_t> d_pair_x;
     pce::DeviceBuffer<double>   d_cross;
@@ -64,7 +63,7 @@ namespace {
 
 struct McParams {
     int nsites, ninst, npairs, ldw;
-    const int32_t *first, *nsi, *protons, *pair_a, *pair_b;
+    const int32_t *first, *nsi, *protons;
     const uint32_t *pair_packed;            // site a | site b << 16
     const uint32_t *pair_x;                 // cross-table base of the pair | ceil (4 * bound of |cross term|) << 24
     const double   *cross;                  // precomputed pair cross terms (k_mc_warp: nullptr = gather the four W entries)
@@ -84,7 +83,6 @@ struct McParams {
     double    *trajectory;          // [nprod] energies of chain 0 of pH 0
     long long *log_rows;            // [(nequil/f + nprod/f) * 5] scan, moves, accepted, flips, accepted per block of f scans (chain 0, pH 0)
     int        log_frequency;
-    int        w_in_smem;
     // relative fields (see the file header): nrel = ninst - nsites slots per chain
     int            nrel, ldr, nrows, ncross;
     const double  *wr;              // [ninst][ldr] wr[a][r(k)] = wb[a][k] - wb[a][first of k's site]
@@ -221,7 +219,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     for (int e = tid; e < p.ncross; e += B) s_cross[e] = p.cross[e];
     for (int k = tid; k < L.kslots * ninst; k += B) s_counts[k] = 0u;
     for (int i = tid; i < nsites; i += B) { s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16); s_erow[i] = (uint32_t) p.dbase[i]; }
-    for (int i = tid; i < p.npairs; i += B) { s_pair[i] = (uint32_t) p.pair_a[i] | ((uint32_t) p.pair_b[i] << 16); s_pairx[i] = p.pair_x[i] & 0xffffffu; }
+    for (int i = tid; i < p.npairs; i += B) { s_pair[i] = p.pair_packed[i]; s_pairx[i] = p.pair_x[i] & 0xffffffu; }
 
     // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i)
     {
@@ -957,7 +955,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 // ---------------------------------------------------------------------------------------------------
 // launch planning
 // ---------------------------------------------------------------------------------------------------
-struct Plan { int kernel, block, w_in_smem; size_t smem; int ctas_per_sm; int tpl; int upd; };      // upd: 128-bit loads per lane and batch of the field update
+struct Plan { int kernel, block; size_t smem; int ctas_per_sm; int tpl; int upd; };      // upd: 128-bit loads per lane and batch of the field update
 
 int smem_limit (int device, size_t *limit) {
     int value = 0;
@@ -1000,7 +998,7 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
         if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
         const int warps = block / 32;
         if (warps > best_warps) {
-            best_warps = warps; plan->kernel = 1; plan->block = block; plan->w_in_smem = 1; plan->smem = L.total; plan->ctas_per_sm = 1;
+            best_warps = warps; plan->kernel = 1; plan->block = block; plan->smem = L.total; plan->ctas_per_sm = 1;
         }
     }
     // auto mode: with fewer than 8 resident warps the chain-per-warp kernel does better; a forced choice runs with what fits
@@ -1032,7 +1030,7 @@ bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
         const int  most = forced ? std::max (2, std::min (4, std::atoi (forced))) : 3;
         if (pass == 0 && (ctas < 2 || mc->cross_overflow)) continue;
         if (pass == 2 && mc->cross_overflow) continue;      // only the one-CTA 255-register variant gathers W itself
-        plan->kernel = 2; plan->block = warps * 32; plan->w_in_smem = 0; plan->smem = smem;
+        plan->kernel = 2; plan->block = warps * 32; plan->smem = smem;
         plan->ctas_per_sm = pass == 0 ? std::min (ctas, most) : 1; plan->tpl = tpl; plan->upd = upd;
         return true;
     }
@@ -1086,7 +1084,7 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
-    mc->d_pair_a.release (); mc->d_pair_b.release (); mc->d_pair_packed.release (); mc->d_pair_x.release (); mc->d_cross.release (); mc->d_ph.release (); mc->d_esum.release ();
+    mc->d_pair_packed.release (); mc->d_pair_x.release (); mc->d_cross.release (); mc->d_ph.release (); mc->d_esum.release ();
     mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release (); mc->d_wr.release (); mc->d_rk.release (); mc->d_rf.release ();
     delete mc;
 }
@@ -1149,7 +1147,7 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
 extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm, int *chains_per_wave, long long *smem_bytes) {
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
     PCE_CUDA (cudaSetDevice (mc->model->device));
-    Plan plan = { 0, 0, 0, 0, 1, 1, 4 };
+    Plan plan = { 0, 0, 0, 1, 1, 4 };
     int status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
     int sms = 0;
@@ -1232,18 +1230,11 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     // behaviour (pairs are fixed at Initialize, MCModelDefault.pyx:37-54) and only upload them once
     const int npairs = (int) mc->pair_a.size ();
     if (mc->pairs_dirty) {
-        PCE_CUDA (mc->d_pair_a.resize (npairs > 0 ? npairs : 1));
-        PCE_CUDA (mc->d_pair_b.resize (npairs > 0 ? npairs : 1));
         PCE_CUDA (mc->d_pair_packed.resize (npairs > 0 ? npairs : 1));
         std::vector<uint32_t> packed ((size_t) (npairs > 0 ? npairs : 1), 0u);
         for (int k = 0; k < npairs; k++) packed[k] = (uint32_t) mc->pair_a[k] | ((uint32_t) mc->pair_b[k] << 16);
         PCE_CUDA (cudaMemcpyAsync (mc->d_pair_packed.ptr, packed.data (), packed.size () * sizeof (uint32_t), cudaMemcpyHostToDevice, m->stream));
         PCE_CUDA (cudaStreamSynchronize (m->stream));
-        if (npairs > 0) {
-            PCE_CUDA (cudaMemcpyAsync (mc->d_pair_a.ptr, mc->pair_a.data (), npairs * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
-            PCE_CUDA (cudaMemcpyAsync (mc->d_pair_b.ptr, mc->pair_b.data (), npairs * sizeof (int32_t), cudaMemcpyHostToDevice, m->stream));
-            PCE_CUDA (cudaStreamSynchronize (m->stream));
-        }
         mc->pairs_dirty = false;
     }
     if (mc->bound_generation != m->generation) {
@@ -1294,19 +1285,18 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     PCE_CUDA (mc->d_ph.resize (nph));
     PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
 
-    Plan plan = { 0, 0, 0, 0, 1, 1, 4 };
+    Plan plan = { 0, 0, 0, 1, 1, 4 };
     status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
 
     p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
     p.first = m->d_first.ptr; p.nsi = m->d_nsite_inst.ptr; p.protons = m->d_protons.ptr;
-    p.pair_a = mc->d_pair_a.ptr; p.pair_b = mc->d_pair_b.ptr; p.pair_packed = mc->d_pair_packed.ptr; p.pair_x = mc->d_pair_x.ptr; p.cross = mc->cross_valid ? mc->d_cross.ptr : nullptr;
+    p.pair_packed = mc->d_pair_packed.ptr; p.pair_x = mc->d_pair_x.ptr; p.cross = mc->cross_valid ? mc->d_cross.ptr : nullptr;
     p.gintr = m->d_gintr.ptr; p.w = m->d_w.ptr; p.wb = m->d_wb.ptr; p.ph = mc->d_ph.ptr;
     p.nph = nph; p.ph_index_offset = ph_index_offset; p.nchains = mc->nchains; p.nequil = mc->nequil; p.nprod = mc->nprod;
     p.chain_offset = chain_offset;
     p.k0 = (uint32_t) mc->seed; p.k1 = (uint32_t) (mc->seed >> 32);
     p.temperature = m->temperature;
-    p.w_in_smem = plan.w_in_smem;
 
     {
         // row stride of the difference rows: the padded field length of a chain-per-warp launch, else the slot count
