@@ -95,6 +95,9 @@ struct McParams {
     // re-read an offset from the constant bank instead of keeping it in a register or recomputing it
     uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
     int            tl_hstride, tl_estride, tl_kslots;
+    // chain-per-warp kernel: the shared-memory layout (WarpLayout), likewise
+    uint32_t       wl_shared, wl_per_warp, wl_since, wl_state, wl_ring;
+    int            wl_ldh;
     uint32_t       nmoves;          // nsites + npairs
     unsigned long long ntrials;     // (nequil + nprod) * nmoves
 };
@@ -630,16 +633,17 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     constexpr int UPD  = MIN_CTAS == 1 ? 16 : 4;      // 128-bit loads per lane, row and batch when a move is applied
     constexpr bool FALLBACK = MIN_CTAS == 1;          // only the 255-register variant carries the four-gather cross-term path
     constexpr bool ABS = MIN_CTAS != 1;               // small fields: instance-indexed slots (see WarpLayout)
-    const WarpLayout L (p.nsites, p.ninst, TPL, UPD, ABS);
-    uint32_t      *s_site = (uint32_t *) smem;                        // first | ninst << 16 per site (CTA-wide)
-    unsigned char *base   = smem + L.shared_bytes + (size_t) wib * L.per_warp;
-    double        *h      = (double *) (base + L.off_h);
-    uint32_t      *since  = (uint32_t *) (base + L.off_since);
-    uint16_t      *state  = (uint16_t *) (base + L.off_state);
-    uint32_t      *ring   = (uint32_t *) (base + L.off_ring);          // [0,RING) w0 | w1 | target | cross-table base and bound of the pair
+    // The shared-memory layout (WarpLayout) comes from the host in the kernel parameters and every array is addressed by a
+    // 32-bit offset: nothing of it has to stay live across the round loop or be recomputed inside it.
+    const uint32_t o_warp = p.wl_shared + (uint32_t) wib * p.wl_per_warp;          // this warp's slice; fields first
+#define s_site(i_) (*(uint32_t *) (smem + 4u * (uint32_t) (i_)))                     /* first | ninst << 16 per site (CTA-wide) */
+#define h(i_)      (*(double *)   (smem + o_warp + 8u * (uint32_t) (i_)))
+#define since(i_)  (*(uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) (i_)))
+#define state(i_)  (*(uint16_t *) (smem + o_warp + p.wl_state + 2u * (uint32_t) (i_)))
+#define ring(i_)   (*(uint32_t *) (smem + o_warp + p.wl_ring + 4u * (uint32_t) (i_)))   /* [0,RING) w0 | w1 | target | cross-table base and bound */
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
-    for (int i = threadIdx.x; i < nsites; i += blockDim.x) s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
+    for (int i = threadIdx.x; i < nsites; i += blockDim.x) s_site (i) = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
     __syncthreads ();
     const long long gidx = (long long) blockIdx.x * warps + wib;       // chain-major linear (pH, chain) index
     if (gidx >= (long long) p.nph * p.nchains) return;              // whole warp leaves together (no later block barrier)
@@ -651,8 +655,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     for (int i = lane; i < nsites; i += 32) {
         pce::Philox4 r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
         const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-        state[i] = (uint16_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
-        since[i] = 0u;
+        state (i) = (uint16_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
+        since (i) = 0u;
     }
     __syncwarp ();
     const double mu   = ph_to_mu (p.temperature, p.ph[q]);
@@ -663,23 +667,23 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     // relative fields g[r] = (gtb[k] - gtb[f]) + sum_j wr[a_j][r], j sequential (spec order)
     if (ABS) {
         // instance-indexed slots: lanes over the instances, zero at the first instance of every site
-        for (int k = lane; k < L.ldh; k += 32) {
+        for (int k = lane; k < p.wl_ldh; k += 32) {
             double acc = 0.0;
             if (k < ninst) {
                 const int site = __ldg (p.site_of + k), f = __ldg (p.first + site);
                 if (k != f) {
                     const double *col = p.wr + (k - site - 1);
                     acc = __dsub_rn (gtb (k), gtb (f));
-                    for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, __ldg (col + (size_t) state[j] * p.ldr));
+                    for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, __ldg (col + (size_t) state (j) * p.ldr));
                 }
             }
-            h[k] = acc;
+            h (k) = acc;
         }
     } else {
         // compact slots: a chunk of 256 consecutive slots per pass (each lane owns 4 double2), every wr row of the state
         // streamed once per chunk with 128-bit loads
         constexpr int CH = 4;
-        const int n2 = L.ldh >> 1, nr2 = p.ldr >> 1, nrel = p.nrel;
+        const int n2 = p.wl_ldh >> 1, nr2 = p.ldr >> 1, nrel = p.nrel;
         for (int c0 = 0; c0 < n2; c0 += 32 * CH) {
             double2 acc[CH];
 #pragma unroll
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             }
 #pragma unroll 2
             for (int j = 0; j < nsites; j++) {
-                const double2 *row = (const double2 *) (p.wr + (size_t) state[j] * p.ldr);
+                const double2 *row = (const double2 *) (p.wr + (size_t) state (j) * p.ldr);
 #pragma unroll
                 for (int c = 0; c < CH; c++) {
                     const int k2 = c0 + c * 32 + lane;
@@ -704,7 +708,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 #pragma unroll
             for (int c = 0; c < CH; c++) {
                 const int k2 = c0 + c * 32 + lane;
-                if (k2 < n2) ((double2 *) h)[k2] = acc[c];
+                if (k2 < n2) ((double2 *) &h (0))[k2] = acc[c];
             }
         }
     }
@@ -719,20 +723,20 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         for (int i0 = 0; i0 < nsites; i0 += 32) {          // trip counts are warp-uniform (keeps the whole kernel on the uniform datapath)
             const int  i  = i0 + lane;
             const bool in = i < nsites;
-            const int  ai = in ? state[i] : 0;
+            const int  ai = in ? state (i) : 0;
             if (in) gi += gtb (ai);
             const double *row = p.wb + (size_t) ai * ldw;
             const int jend = i0 + 32 < nsites ? i0 + 32 : nsites;
             for (int j = 0; j < jend; j++) {
-                const double v = __ldg (row + state[j]);
+                const double v = __ldg (row + state (j));
                 if (in && j < i) ws += v;
             }
         }
         grt = pce::warp_sum (gi) + pce::warp_sum (ws);
     }
 
-    const uint32_t nmoves = (uint32_t) (nsites + p.npairs);
-    const unsigned long long ntrials = (unsigned long long) ((long long) p.nequil + p.nprod) * nmoves;
+    const uint32_t nmoves = p.nmoves;
+    const unsigned long long ntrials = p.ntrials;
     uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
     double   esum = 0.0;
     long long scan = 0;
@@ -760,10 +764,10 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             const unsigned long long bl = (tfill >> 1) + (unsigned long long) lane;
             const pce::Philox4 r = pce::philox4x32_10 ((uint32_t) bl, (uint32_t) (bl >> 32), chain, phidx, p.k0, p.k1);
             const uint32_t slot = ((uint32_t) tfill & (uint32_t) (RING - 1)) + 2u * (uint32_t) lane;
-            *(uint2 *) (ring + slot)            = make_uint2 (r.x, r.z);
-            *(uint2 *) (ring + RING + slot)     = make_uint2 (r.y, r.w);
-            *(uint2 *) (ring + 2 * RING + slot) = make_uint2 (target (r.x), target (r.z));
-            *(uint2 *) (ring + 3 * RING + slot) = make_uint2 (pair_extra (r.x), pair_extra (r.z));
+            *(uint2 *) &ring (slot)            = make_uint2 (r.x, r.z);
+            *(uint2 *) &ring (RING + slot)     = make_uint2 (r.y, r.w);
+            *(uint2 *) &ring (2 * RING + slot) = make_uint2 (target (r.x), target (r.z));
+            *(uint2 *) &ring (3 * RING + slot) = make_uint2 (pair_extra (r.x), pair_extra (r.z));
             tfill += 64ull;
         }
         __syncwarp ();
@@ -783,17 +787,17 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         for (int u = 0; u < TPL; u++) {
             const uint32_t off  = (uint32_t) (u * 32 + lane);
             const uint32_t slot = ((uint32_t) tcur + off) & (uint32_t) (RING - 1);
-            const uint32_t w0 = ring[slot], pr = ring[2 * RING + slot];
-            e_w1[u] = ring[RING + slot];
-            const uint32_t px = ring[3 * RING + slot];
+            const uint32_t w0 = ring (slot), pr = ring (2 * RING + slot);
+            e_w1[u] = ring (RING + slot);
+            const uint32_t px = ring (3 * RING + slot);
             const float pbound = 0.25f * (float) (px >> 24);                     // the pair's bound, quantised upwards (0: none)
             const bool act = off < n_act;
             const unsigned long long prod = (unsigned long long) w0 * nmoves;
             const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
             const bool dbl = idx >= (uint32_t) nsites;
             const int  sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
-            const uint32_t ia_info = s_site[sa];
-            const int na = (int) (ia_info >> 16), oa = state[sa];
+            const uint32_t ia_info = s_site (sa);
+            const int na = (int) (ia_info >> 16), oa = state (sa);
             bool valid = na >= 2;
             const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
             const int ka = (int) (proda >> 32);
@@ -805,9 +809,9 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             e_need[u] = false;
             double x = 0.0;
             if (dbl) {
-                const uint32_t ib_info = s_site[sb];
+                const uint32_t ib_info = s_site (sb);
                 const int nb = (int) (ib_info >> 16);
-                ob = state[sb];
+                ob = state (sb);
                 if (nb < 2) valid = false;
                 const int kb = (int) __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
                 ib = (int) (ib_info & 0xffffu) + kb;
@@ -815,8 +819,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 if (!valid) { ib = ob; ia = oa; }
                 const int fa = (int) (ia_info & 0xffffu), fb = (int) (ib_info & 0xffffu);
                 // relative fields: 0 for a first instance (stored as such in the instance-indexed layout)
-                const double gan = ABS ? h[ia] : ia != fa ? h[ia - sa - 1] : 0.0, gao = ABS ? h[oa] : oa != fa ? h[oa - sa - 1] : 0.0;
-                const double gbn = ABS ? h[ib] : ib != fb ? h[ib - sb - 1] : 0.0, gbo = ABS ? h[ob] : ob != fb ? h[ob - sb - 1] : 0.0;
+                const double gan = ABS ? h (ia) : ia != fa ? h (ia - sa - 1) : 0.0, gao = ABS ? h (oa) : oa != fa ? h (oa - sa - 1) : 0.0;
+                const double gbn = ABS ? h (ib) : ib != fb ? h (ib - sb - 1) : 0.0, gbo = ABS ? h (ob) : ob != fb ? h (ob - sb - 1) : 0.0;
                 x = __dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo));
                 const float xlow = __fsub_rd (__double2float_rd (x), pbound);            // <= x0 - B <= x
                 const float ulow = __uint2float_rd (e_w1[u]) * 2.3283064365386963e-10f;  // <= u
@@ -835,7 +839,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 }
             } else {
                 const int fa = (int) (ia_info & 0xffffu);
-                const double gan = ABS ? h[ia] : ia != fa ? h[ia - sa - 1] : 0.0, gao = ABS ? h[oa] : oa != fa ? h[oa - sa - 1] : 0.0;
+                const double gan = ABS ? h (ia) : ia != fa ? h (ia - sa - 1) : 0.0, gao = ABS ? h (oa) : oa != fa ? h (oa - sa - 1) : 0.0;
                 x = __dsub_rn (gan, gao);
                 e_need[u] = act && valid;
             }
@@ -883,18 +887,18 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             const int sa = (int) (s_pr & 0xffffu), sb = (int) (s_pr >> 16);
             const int ia = (int) (s_a & 0xffffu), oa = (int) (s_a >> 16), ib = (int) (s_b & 0xffffu), ob = (int) (s_b >> 16);
             if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) lg_fa++; else lg_ma++; }
-            apply_move<UPD, ABS> (p, s_site, h, L.ldh, lane, sa, sb, ia, oa, ib, ob, dbl);
+            apply_move<UPD, ABS> (p, (const uint32_t *) smem, &h (0), p.wl_ldh, lane, sa, sb, ia, oa, ib, ob, dbl);
             grt = __dadd_rn (grt, x);
             if (lane == 0) {
-                const uint32_t since_a = since[sa];
+                const uint32_t since_a = since (sa);
                 if (tp != since_a) atomicAdd (&counts[oa], (unsigned long long) (tp - since_a));
-                since[sa] = tp;
-                state[sa] = (uint16_t) ia;
+                since (sa) = tp;
+                state (sa) = (uint16_t) ia;
                 if (dbl) {
-                    const uint32_t since_b = since[sb];
+                    const uint32_t since_b = since (sb);
                     if (tp != since_b) atomicAdd (&counts[ob], (unsigned long long) (tp - since_b));
-                    since[sb] = tp;
-                    state[sb] = (uint16_t) ib;
+                    since (sb) = tp;
+                    state (sb) = (uint16_t) ib;
                 }
             }
             if (production) { if (dbl) c_facc++; else c_macc++; }
@@ -928,13 +932,13 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 
     __syncwarp ();
     for (int i = lane; i < nsites; i += 32) {
-        const uint32_t d = (uint32_t) p.nprod - since[i];
-        if (d) atomicAdd (&counts[state[i]], (unsigned long long) d);
+        const uint32_t d = (uint32_t) p.nprod - since (i);
+        if (d) atomicAdd (&counts[state (i)], (unsigned long long) d);
     }
     const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (PER_CHAIN) {
         const size_t c = (size_t) q * p.nchains + local;
-        for (int i = lane; i < nsites; i += 32) p.chain_state[c * nsites + i] = state[i];
+        for (int i = lane; i < nsites; i += 32) p.chain_state[c * nsites + i] = state (i);
         if (lane == 0) {
             p.chain_energy[c] = grt / beta;
             p.chain_esum[c]   = esum / beta;
@@ -951,6 +955,11 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         }
     }
 }
+#undef s_site
+#undef h
+#undef since
+#undef state
+#undef ring
 
 // ---------------------------------------------------------------------------------------------------
 // launch planning
@@ -1320,6 +1329,11 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
     p.nmoves = (uint32_t) (m->nsites + npairs);
     p.ntrials = (unsigned long long) ((long long) mc->nequil + mc->nprod) * p.nmoves;
+    if (plan.kernel == 2) {
+        const WarpLayout WL (m->nsites, m->ninst, plan.tpl, plan.upd, plan.upd != 16);
+        p.wl_shared = (uint32_t) WL.shared_bytes; p.wl_per_warp = (uint32_t) WL.per_warp; p.wl_since = (uint32_t) WL.off_since;
+        p.wl_state = (uint32_t) WL.off_state; p.wl_ring = (uint32_t) WL.off_ring; p.wl_ldh = WL.ldh;
+    }
     if (plan.kernel == 1) {
         const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
         p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_eng = (uint32_t) TL.off_eng; p.tl_counts = (uint32_t) TL.off_counts;
