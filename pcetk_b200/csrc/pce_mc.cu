@@ -824,7 +824,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 x = __dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo));
                 const float xlow = __fsub_rd (__double2float_rd (x), pbound);            // <= x0 - B <= x
                 const float ulow = __uint2float_rd (e_w1[u]) * 2.3283064365386963e-10f;  // <= u
-                const bool certain = (px >> 24) != 0u && xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
+                // (small fields: the cross-term table is cache-resident, the gather is cheaper than the test)
+                const bool certain = !ABS && (px >> 24) != 0u && xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
                 if (act && valid && !certain) {
                     if (!FALLBACK || use_cross) {
                         // one gather: the cross term of (old a, draw a, old b, draw b), precomputed with the same operations
