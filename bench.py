@@ -377,6 +377,10 @@ def main():
             "note": "HBM is not the limiter of this path (working set in shared memory / L2): `achieved` counts the bytes this algorithm "
                     "actually moves at HBM per launch, so `frac` is ~0 by design; the real limiter and its ncu-measured utilisation are in "
                     "`on_chip`.  reference_algorithm_effective_gbs = the reference algorithm's gather traffic (SURVEY.md 8d) replaced by this run.",
+            # the binding on-chip resource and its measured utilisation (ncu, profiles/): issue slots for the chain-per-thread
+            # and enumeration kernels, the L1TEX/LSU wavefront pipe for the chain-per-warp kernel on large models
+            "limiter": (on_chip or {}).get("limiter"),
+            "limiter_frac": (on_chip or {}).get("l1tex_throughput_frac" if launch_info.get("kernel") == 2 and args.workload == "synthM" else "issue_active_frac"),
             "reference_algorithm_bytes_per_unit": algo_bytes_per_unit,
             "reference_algorithm_effective_gbs": algo_bytes_per_unit * value / world / 1e9,
             "kernel_ms_per_launch": kernel_ms,
