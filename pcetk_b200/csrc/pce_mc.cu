@@ -14,13 +14,14 @@
 //   * occupancies are residence times (scan of last change per site) instead of nsites increments per scan.
 //
 // Two kernels:
-//   k_mc_thread  one chain per THREAD, model + per-chain state in shared memory.  For fixture-sized
-//                models (ninst <= 256).  Accepted moves are applied warp-cooperatively so that the
-//                axpy never runs with 1/32 lanes.
+//   k_mc_thread  one chain per THREAD; difference rows, cross-term table and per-chain state in shared
+//                memory.  For models whose tables fit on chip next to >= 8 warps of chains (lysozyme,
+//                defensin, ...).  Accepted moves are applied warp-cooperatively so that the row add
+//                never runs with 1/32 lanes.
 //   k_mc_warp    one chain per WARP, fields in shared memory; the lanes evaluate 32 consecutive trials
-//                speculatively in parallel, the first accepted one ends the round.  Difference rows of W
-//                streamed from L2 with 128-bit loads.  For models whose W does not fit on chip (ifp20,
-//                the 1000-site synthetic: 72 MB).
+//                speculatively in parallel, the first accepted one ends the round.  Difference rows
+//                streamed from L1/L2 with 128-bit loads.  For everything else (ifp20; the 1000-site
+//                synthetic, whose 60 MB of difference rows are L2-resident).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
