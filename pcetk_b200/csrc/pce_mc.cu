@@ -1214,7 +1214,12 @@ static int build_relative_tables (pce_mc *mc, int ldd, bool abs) {
     const double budget = (budget_env ? std::atof (budget_env) : 100.0) * 1024.0 * 1024.0;
     const size_t nrows = lo.size ();
     mc->nrows = (int) nrows;
-    if (nrows == 0 || (double) nrows * ldd * sizeof (double) > budget) return PCE_OK;
+    if (nrows == 0) {        // every site has a single instance: nothing can move, an empty table is a valid one
+        PCE_CUDA (mc->d_dw.resize (1));
+        mc->dw_valid = true;
+        return PCE_OK;
+    }
+    if ((double) nrows * ldd * sizeof (double) > budget) return PCE_OK;
     pce::DeviceBuffer<int32_t> d_lo, d_hi;
     PCE_CUDA (d_lo.resize (nrows)); PCE_CUDA (d_hi.resize (nrows));
     PCE_CUDA (mc->d_dw.resize (nrows * (size_t) ldd));

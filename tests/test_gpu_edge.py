@@ -84,6 +84,28 @@ def test_mc_single_instance_site_and_ragged(port, kernel):
         assert np.array_equal(counts, out["counts"].sum(axis=1))
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_mc_model_without_any_choice(port, kernel):
+    """Every site has a single instance: nothing can move (the reference's sampler would spin forever); every trial is a
+    counted no-op and the single microstate has probability 1."""
+    base = synth_a(4)
+    keep = [0, 2, 4, 6]
+    first = np.arange(4, dtype=np.int32)
+    rec = ModelRecord("frozen", first, first.copy(), base.protons[keep], base.gmodel[keep], base.gintr[keep],
+                      base.interactions[np.ix_(keep, keep)], 300.0, [("SYN", "SIT", k + 1) for k in range(4)], ["i%d" % k for k in range(4)])
+    model = P.MEADModel(rec, log=None)
+    sampler = P.MCModelDefault(nequil=5, nprod=50, randomSeed=3, nchains=33, kernel=kernel, doubleFlip=0.0)
+    model.DefineMCModel(sampler, log=None)
+    counts, counters, _esum = sampler.RunCounts([7.0])
+    assert counts[0].tolist() == [33 * 50] * 4
+    assert counters[0][1] == 0 and counters[0][3] == 0 and counters[0][0] + counters[0][2] == 33 * 50 * (4 + sampler.npairs)
+    wsym = port.symmetrize(rec.interactions)
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    out = sampler.RunChains([7.0])
+    spec = port.mc_philox_chain(rec, wsym, pairs, 5, 50, sampler.seed, 7, 0, 7.0)
+    assert np.array_equal(out["counts"][0, 7], spec["counts"]) and out["counters"][0, 7].tolist() == spec["counters"].tolist()
+
+
 def test_mc_no_pairs_and_all_pairs(port):
     rec = ragged_model(8)
     wsym = port.symmetrize(rec.interactions)
