@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import pcetk_b200 as P
+from conftest import load_fixture
 from pcetk_b200.formats import ModelRecord
 from pcetk_b200.synthetic import synth_a, synth_m
 
@@ -104,6 +105,20 @@ def test_mc_model_without_any_choice(port, kernel):
     out = sampler.RunChains([7.0])
     spec = port.mc_philox_chain(rec, wsym, pairs, 5, 50, sampler.seed, 7, 0, 7.0)
     assert np.array_equal(out["counts"][0, 7], spec["counts"]) and out["counters"][0, 7].tolist() == spec["counters"].tolist()
+
+
+def test_mc_long_runs_use_32_bit_residence_stamps(port):
+    """nprod >= 65536 switches the chain-per-thread kernel from 16-bit to 32-bit residence stamps: same chain, count for count."""
+    rec, _gold = load_fixture("twosites")
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    sampler = P.MCModelDefault(nequil=10, nprod=70000, randomSeed=99, nchains=3, kernel=1)
+    model.DefineMCModel(sampler, log=None)
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    out = sampler.RunChains([6.5])
+    spec = port.mc_philox_chain(rec, wsym, pairs, 10, 70000, sampler.seed, 2, 0, 6.5)
+    assert np.array_equal(out["counts"][0, 2], spec["counts"]) and out["counters"][0, 2].tolist() == spec["counters"].tolist()
+    assert out["counts"][0, 2].sum() == 70000 * rec.nsites and out["esum"][0, 2] == spec["esum"]
 
 
 def test_mc_no_pairs_and_all_pairs(port):
