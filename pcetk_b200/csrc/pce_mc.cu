@@ -96,6 +96,8 @@ struct McParams {
     // re-read an offset from the constant bank instead of keeping it in a register or recomputing it
     uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
     int            tl_hstride, tl_estride, tl_kslots;
+    int            ph_minor;        // linearisation of the (pH, chain) grid: 1 = g = chain * nph + q (consecutive threads take consecutive pH
+                                    // values, so every warp and block carries the same mix of cheap and expensive pH values), 0 = g = q * nchains + chain
     // chain-per-warp kernel: the shared-memory layout (WarpLayout), likewise
     uint32_t       wl_shared, wl_per_warp, wl_since, wl_state, wl_ring;
     int            wl_ldh;
@@ -107,11 +109,13 @@ struct McParams {
 struct ThreadLayout {
     size_t off_e, off_cross, off_h, off_eng, off_counts, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
     int    hstride, estride, kslots;
-    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes) {
+    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes, bool ph_minor) {
         hstride = (nrel > 0 ? nrel : 1) | 1;       // odd: lanes of a warp fall on distinct bank pairs
         estride = nrel > 0 ? nrel : 1;
-        // a block covers `block` consecutive (pH, chain) pairs of the chain-major grid: at most kslots pH values
-        kslots = (block - 1) / (nchains > 0 ? nchains : 1) + 2;
+        // occupancy counters per pH value a block can meet: a block covers `block` consecutive (pH, chain) pairs of the
+        // linear grid -- pH-minor (g = chain * nph + q): min (block, nph) values; chain-major (g = q * nchains + chain):
+        // at most (block - 1) / nchains + 2
+        kslots = ph_minor ? block : (block - 1) / (nchains > 0 ? nchains : 1) + 2;
         if (kslots > nph) kslots = nph;
         size_t o = 0;
         off_e = o;      o += (size_t) (nrows > 0 ? nrows : 1) * estride * 8;      // difference rows E
@@ -206,12 +210,13 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const long long gidx  = g0 + tid;
     const bool active = gidx < total;
     const long long gclamped = active ? gidx : total - 1;
-    const int q      = (int) (gclamped / p.nchains);                 // pH point of this thread
-    const int local  = (int) (gclamped % p.nchains);                 // chain within this launch
-    const int q_base = (int) (g0 / p.nchains);
+    const int q      = (int) (p.ph_minor ? gclamped % p.nph : gclamped / p.nchains);      // pH point of this thread
+    const int local  = (int) (p.ph_minor ? gclamped / p.nph : gclamped % p.nchains);      // chain within this launch
+    // first pH value of the block's counter slots (pH-minor: the values wrap around, all of them when the block is large)
+    const int q_base = p.ph_minor ? (B >= p.nph ? 0 : (int) (g0 % p.nph)) : (int) (g0 / p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
-    uint32_t *my_counts = s_counts + (size_t) (q - q_base) * ninst;
+    uint32_t *my_counts = s_counts + (size_t) (q - q_base + (q < q_base ? p.nph : 0)) * ninst;
     // per-thread arrays as 32-bit offsets into the dynamic shared memory (one register each instead of a 64-bit pointer)
     const uint32_t o_state = p.tl_state + (uint32_t) tid, o_since = p.tl_since + (uint32_t) tid * (uint32_t) sizeof (SinceT);
 #define my_state(i_) smem[o_state + (uint32_t) (i_)]
@@ -448,7 +453,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         __syncthreads ();
         if (p.counts != nullptr)
             for (int k = tid; k < L.kslots * ninst; k += B) {
-                const int qq = q_base + k / ninst;
+                int qq = q_base + k / ninst;
+                if (p.ph_minor && qq >= p.nph) qq -= p.nph;
                 if (qq < p.nph && s_counts[k]) atomicAdd (&p.counts[(size_t) qq * ninst + (k % ninst)], (unsigned long long) s_counts[k]);
             }
         // counters and energy sums: one atomic per thread (pH values may differ within a warp)
@@ -648,6 +654,9 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     __syncthreads ();
     const long long gidx = (long long) blockIdx.x * warps + wib;       // chain-major linear (pH, chain) index
     if (gidx >= (long long) p.nph * p.nchains) return;              // whole warp leaves together (no later block barrier)
+    // chain-major on purpose: the warps of a CTA work at the same pH value and therefore on the same few difference rows
+    // (L1 hits; the pH-minor order the chain-per-thread kernel uses for load balance costs ifp20 30 % here), and CTAs of
+    // 8 chains are fine-grained enough for the block scheduler to balance cheap and expensive pH values
     const int q     = (int) (gidx / p.nchains);
     const int local = (int) (gidx % p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
@@ -966,7 +975,7 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 // ---------------------------------------------------------------------------------------------------
 // launch planning
 // ---------------------------------------------------------------------------------------------------
-struct Plan { int kernel, block; size_t smem; int ctas_per_sm; int tpl; int upd; };      // upd: 128-bit loads per lane and batch of the field update
+struct Plan { int kernel, block; size_t smem; int ctas_per_sm; int tpl; int upd; int ph_minor; };      // upd: 128-bit loads per lane and batch of the field update
 
 int smem_limit (int device, size_t *limit) {
     int value = 0;
@@ -1002,14 +1011,17 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     const int forced_block = forced ? std::atoi (forced) : 0;
     // measured on lysozyme (moves/s): 640 threads 7.6e10, 768 (the largest block the uncapped 79-register build fits) 8.5e10,
     // 832 / 896 with the 72-register build 7.1e10 / 7.3e10 -- so blocks beyond 768 are only taken when forced
+    // pH-minor linearisation (load balance: acceptance, hence cost, varies 10x over a titration curve) unless the per-block
+    // occupancy counters of all pH values would take more than 48 KB of shared memory
+    const bool ph_minor = (size_t) std::min (nph, 768) * m->ninst * 4 <= 48 * 1024 && std::getenv ("PCE_MC_CHAIN_MAJOR") == nullptr;
     for (int block = 32; block <= (forced_block ? 1024 : 768); block += 32) {
         if (forced_block && block != forced_block) continue;
-        ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
+        ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, ph_minor);
         if (L.total > limit) continue;
         if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
         const int warps = block / 32;
         if (warps > best_warps) {
-            best_warps = warps; plan->kernel = 1; plan->block = block; plan->smem = L.total; plan->ctas_per_sm = 1;
+            best_warps = warps; plan->kernel = 1; plan->block = block; plan->smem = L.total; plan->ctas_per_sm = 1; plan->ph_minor = ph_minor ? 1 : 0;
         }
     }
     // auto mode: with fewer than 8 resident warps the chain-per-warp kernel does better; a forced choice runs with what fits
@@ -1158,7 +1170,7 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
 extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm, int *chains_per_wave, long long *smem_bytes) {
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
     PCE_CUDA (cudaSetDevice (mc->model->device));
-    Plan plan = { 0, 0, 0, 1, 1, 4 };
+    Plan plan = { 0, 0, 0, 1, 1, 4, 1 };
     int status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
     int sms = 0;
@@ -1301,7 +1313,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     PCE_CUDA (mc->d_ph.resize (nph));
     PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
 
-    Plan plan = { 0, 0, 0, 1, 1, 4 };
+    Plan plan = { 0, 0, 0, 1, 1, 4, 1 };
     status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
 
@@ -1342,7 +1354,8 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         p.wl_state = (uint32_t) WL.off_state; p.wl_ring = (uint32_t) WL.off_ring; p.wl_ldh = WL.ldh;
     }
     if (plan.kernel == 1) {
-        const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4);
+        const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, plan.ph_minor != 0);
+        p.ph_minor = plan.ph_minor;
         p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_eng = (uint32_t) TL.off_eng; p.tl_counts = (uint32_t) TL.off_counts;
         p.tl_since = (uint32_t) TL.off_since; p.tl_site = (uint32_t) TL.off_site; p.tl_pair = (uint32_t) TL.off_pair; p.tl_pairx = (uint32_t) TL.off_pairx;
         p.tl_erow = (uint32_t) TL.off_erow; p.tl_state = (uint32_t) TL.off_state;
