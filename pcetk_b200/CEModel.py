@@ -2,8 +2,8 @@
 
 Keeps the call surface of ``ContinuumElectrostatics/CEModel.py`` that the hot path touches --
 ``nsites``/``ninstances`` (:52-66), ``DefineMCModel`` (:442-456), ``CalculateMicrostateEnergy`` (:460-462),
-``CalculateProbabilities`` (:466-499), ``SummaryProbabilities`` (:220-274), ``WriteW``/``WriteGintr``
-(:363-438) -- with ``Site`` and ``Instance`` objects carrying the same attributes (``Site.py``,
+``CalculateProbabilities`` (:466-499), ``SummarySites`` / ``SummaryProbabilities`` (:192-274),
+``SedScript_FromProbabilities`` (:278-331), ``PrintInteractions`` (:335-359), ``WriteW``/``WriteGintr`` (:363-438) -- with ``Site`` and ``Instance`` objects carrying the same attributes (``Site.py``,
 ``Instance.py:37-75``).
 
 The reference builds a model from a pDynamo ``System`` and runs MEAD; both are out of scope (SURVEY.md
@@ -256,6 +256,67 @@ class CEModel(object):
                 rows.append(row)
             width = max(len(r) for r in rows) if rows else 0
             log.Table([r + [""] * (width - len(r)) for r in rows], title="Probabilities of instances")
+
+    def SummarySites(self, log=logFile):
+        """List titratable sites (CEModel.py:192-216).  The Center columns need atomic coordinates, which the
+        precomputed-energy input does not carry; they are printed only when the record supplies ``site_centers``."""
+        if LogFileActive(log) and self.isInitialized:
+            centers = getattr(self.record, "site_centers", None)
+            rows = [["SiteID", "Segment", "Residue", "Serial", "Instances"] + (["x", "y", "z"] if centers is not None else [])]
+            for site in self.sites:
+                row = ["%d" % (site.siteIndex + 1), "%s" % site.segName, "%s" % site.resName, "%d" % site.resSerial, "%d" % site.ninstances]
+                if centers is not None:
+                    row.extend("%10.3f" % c for c in centers[site.siteIndex])
+                rows.append(row)
+            log.Table(rows, title="Titratable sites")
+
+    def PrintInteractions(self, log=logFile):
+        """Print the symmetrised interaction matrix in a readable form (CEModel.py:335-359); readable only for a
+        few sites with two instances each, as the reference says."""
+        if self.isCalculated and LogFileActive(log):
+            wsym = self.energyModel.GetSymmetricMatrix()
+            log.Text("%16s" % "" + "".join("%16s" % site.label.center(8) for site in self.sites) + "\n")
+            log.Text("%16s" % "" + "".join("%8s" % instance.label.center(8) for site in self.sites for instance in site.instances) + "\n")
+            for site in self.sites:
+                for instance in site.instances:
+                    row = wsym[instance._instIndexGlobal]
+                    log.Text("%16s" % (site.label + " " + instance.label) + "".join("%8.2f" % w for w in row) + "\n")
+
+    def SedScript_FromProbabilities(self, filename="his_repl.sed", overwrite=False, putPath=False, log=logFile):
+        """Write a sed script that renames histidines in a PDB file to their most probable tautomer, with CHARMM
+        patch hints for unusual protonations (CEModel.py:278-331; same line formats)."""
+        if not self.isProbability:
+            raise ContinuumElectrostaticsError("First calculate probabilities.")
+        if not overwrite and os.path.exists(filename):
+            if LogFileActive(log):
+                log.Text("\nFile %s already exists, skipping.\n" % filename)
+            return
+        unusualProtonations = {"ARG": ("d", ), "ASP": ("p", ), "CYS": ("d", ), "GLU": ("p", ), "LYS": ("d", ), "TYR": ("d", )}
+        translateLabels = {"p": "protonated", "d": "deprotonated"}
+        lines = ["# %s\n" % os.path.abspath(filename)] if putPath else []
+        warnings = []
+        histidines = ("HIS", "HSP")
+        for site in self.sites:
+            if site.resName in histidines:
+                value, _index, label = site.GetMostProbableInstance()
+                lines.append("/H.. .%4d/  s/H../%3s/  # %.4f\n" % (site.resSerial, label, value))
+        for site in self.sites:
+            if site.resName in histidines:
+                continue
+            value, _index, label = site.GetMostProbableInstance()
+            if site.resName not in unusualProtonations:
+                warnings.append("# Unknown residue: %4s %3s %4d (most probable instance is \"%s\" with probability of %.4f)\n" % (
+                    site.segName, site.resName, site.resSerial, label, value))
+            elif label in unusualProtonations[site.resName]:
+                if site.resName in ("ASP", "GLU"):
+                    lines.append("# patch %sP %4s %4d setup  ! %.4f\n" % (site.resName, site.segName, site.resSerial, value))
+                else:
+                    warnings.append("# Warning: %4s %3s %4d is %s with probability of %.4f\n" % (
+                        site.segName, site.resName, site.resSerial, translateLabels[label], value))
+        with open(filename, "w") as handle:
+            handle.writelines(lines + warnings)
+        if LogFileActive(log):
+            log.Text("\nWrote file: %s\n" % filename)
 
     def _InstanceRows(self):
         return [(site.siteIndex, instance.instIndex, instance.label) for site in self.sites for instance in site.instances]

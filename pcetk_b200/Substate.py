@@ -98,6 +98,34 @@ class Substate(object):
             log.Table(rows, title=title or None)
 
 
+    def Summary_ToLatex(self, filename="table.tex", relativeEnergy=True, includeSegment=False, translateToLatex=None):
+        """Write the substate table as a LaTeX ``tabular`` (Substate.py:171-220; same columns and cell formats)."""
+        symbols = {"ASP": {"p": "0", "d": "($-$)"},
+                   "GLU": {"p": "0", "d": "($-$)"},
+                   "HIS": {"HSP": "$\\epsilon$, $\\delta$(+)", "HSE": "$\\epsilon$", "HSD": "$\\delta$", "fd": "($-$)"}}
+        if translateToLatex:
+            symbols.update(translateToLatex)
+        if not self.isCalculated:
+            return
+        sites = [self.owner.sites[siteIndex] for siteIndex in self.indicesOfSites]
+        titles = ["%s%s%d" % ((site.segName + " ") if includeSegment else "", site.resName.capitalize(), site.resSerial) for site in sites]
+        lines = ["\\begin{tabular}{@{\\extracolsep{2mm}}cc%sc}" % ("l" * len(sites)),
+                 "State & $\\Delta E$ (kcal/mol) & " + "".join(" %s &" % title for title in titles) + " No. of protons \\\\",
+                 "\\hline\\noalign{\\smallskip}"]
+        for count, (energy, indicesOfInstances) in enumerate(self.substates, 1):
+            if relativeEnergy:
+                energy = energy - self.zeroEnergy
+            cells, nprotons = [], 0
+            for site, instanceIndex in zip(sites, indicesOfInstances):
+                instance = site.instances[instanceIndex]
+                cells.append("  %-26s &" % symbols.get(site.resName, {}).get(instance.label, instance.label))
+                nprotons += instance.protons
+            lines.append("%3d & %5.1f & " % (count, energy) + "".join(cells) + "  %1d \\\\" % nprotons)
+        lines.extend(["\\hline\\noalign{\\smallskip}", "\\end{tabular}"])
+        with open(filename, "w") as handle:
+            handle.write("\n".join(lines) + "\n")
+
+
 class MEADSubstate(Substate):
     """A class to maintain backward compatibility (Substate.py:224-226)."""
     pass

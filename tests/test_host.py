@@ -168,3 +168,75 @@ def test_synthetic_generators_are_frozen():
     sampler = P.MCModelDefault(nprod=10)
     model.DefineMCModel(sampler, log=None)
     assert sampler.npairs > 1000
+
+
+def test_reports_sites_interactions_sed_script_latex(tmp_path):
+    """SummarySites / PrintInteractions / SedScript_FromProbabilities (CEModel.py:192-216, 278-359) and
+    Substate.Summary_ToLatex (Substate.py:171-220) on the lysozyme fixture with probabilities set by hand."""
+    from pcetk_b200.log import TextLog
+    from pcetk_b200.Substate import Substate
+
+    rec, _ = load_fixture("lysozyme")
+    model = P.MEADModel(rec, log=None)
+    with pytest.raises(P.ContinuumElectrostaticsError, match="First calculate probabilities"):
+        model.SedScript_FromProbabilities(filename=str(tmp_path / "x.sed"), log=None)
+    out = io.StringIO()
+    model.SummarySites(log=TextLog(out))
+    text = out.getvalue().splitlines()
+    assert sum(1 for line in text if " HIS " in line or " GLU " in line or " ASP " in line) >= 10
+    assert len([line for line in text if line.split() and line.split()[0].isdigit()]) == model.nsites
+
+    # probabilities by hand: every site in its last instance except HIS15 (HSD) and GLU35 (protonated)
+    for site in model.sites:
+        for instance in site.instances:
+            instance.probability = 0.0
+        site.instances[-1].probability = 0.9
+        site.instances[0].probability = 0.1
+    his = [s for s in model.sites if s.resName == "HIS"][0]
+    glu = [s for s in model.sites if s.resName == "GLU" and s.resSerial == 35][0]
+    labels = [i.label for i in his.instances]
+    for instance in his.instances:
+        instance.probability = 0.7 if instance.label == "HSD" else 0.1
+    for instance in glu.instances:
+        instance.probability = 0.8 if instance.label == "p" else 0.2
+    model.isProbability = True
+    sed = str(tmp_path / "his_repl.sed")
+    model.SedScript_FromProbabilities(filename=sed, putPath=True, log=None)
+    with open(sed) as handle:
+        lines = handle.readlines()
+    assert lines[0] == "# %s\n" % os.path.abspath(sed)
+    assert "HSD" in labels and lines[1] == "/H.. .%4d/  s/H../HSD/  # 0.7000\n" % his.resSerial
+    assert "# patch GLUP %4s %4d setup  ! 0.8000\n" % (glu.segName, 35) in lines
+    assert not any("patch ASPP" in line for line in lines)            # aspartates are deprotonated here: usual
+    # existing file is kept unless overwrite is set
+    with open(sed, "w") as handle:
+        handle.write("keep\n")
+    out = io.StringIO()
+    model.SedScript_FromProbabilities(filename=sed, log=TextLog(out))
+    assert "already exists" in out.getvalue() and open(sed).read() == "keep\n"
+    model.SedScript_FromProbabilities(filename=sed, overwrite=True, log=None)
+    assert open(sed).read() != "keep\n"
+
+    two, _ = load_fixture("twosites")
+    small = P.MEADModel(two, log=None)
+    out = io.StringIO()
+    small.PrintInteractions(log=TextLog(out))
+    rows = out.getvalue().splitlines()
+    assert len(rows) == 2 + small.ninstances
+    wsym = small.energyModel.GetSymmetricMatrix()
+    assert rows[2 + 4].split()[-small.ninstances:] == ["%.2f" % w for w in wsym[4]]
+
+    # LaTeX table from a substate whose energies are filled in by hand (the GPU path is tests/test_gpu_energy.py)
+    sub = Substate.__new__(Substate)
+    sub.owner, sub.indicesOfSites, sub.isCalculated = model, [his.siteIndex, glu.siteIndex], True
+    sub.substates = [[-3.0, [labels.index("HSD"), 0]], [-1.75, [labels.index("HSP"), 1]]]
+    sub.zeroEnergy = -3.0
+    tex = str(tmp_path / "table.tex")
+    sub.Summary_ToLatex(filename=tex)
+    with open(tex) as handle:
+        lines = handle.read().splitlines()
+    assert lines[0] == "\\begin{tabular}{@{\\extracolsep{2mm}}ccllc}"
+    assert lines[1] == "State & $\\Delta E$ (kcal/mol) &  His%d & Glu35 & No. of protons \\\\" % his.resSerial
+    assert lines[3] == "  1 &   0.0 &   %-26s &  %-26s &  %1d \\\\" % ("$\\delta$", "0", 2)
+    assert lines[4].startswith("  2 &   1.2 &   $\\epsilon$, $\\delta$(+)") or lines[4].startswith("  2 &   1.3 &")
+    assert lines[-1] == "\\end{tabular}"
