@@ -35,6 +35,10 @@ template <typename T>
 struct DeviceBuffer {
     T     *ptr   = nullptr;
     size_t count = 0;
+    DeviceBuffer () = default;
+    DeviceBuffer (const DeviceBuffer &) = delete;
+    DeviceBuffer &operator= (const DeviceBuffer &) = delete;
+    ~DeviceBuffer () { release (); }           // error returns between resize and release do not leak
     cudaError_t resize (size_t n) {
         if (n <= count && ptr != nullptr) return cudaSuccess;
         release ();

@@ -187,7 +187,7 @@ __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
 // the planner stops at 768 threads.  To get there the loop state was put on a diet: no Philox prefetch, 32-bit scan
 // counter instead of 64-bit trial counters, tracked energy and its sum in shared memory, 32-bit shared-memory offsets
 // instead of generic pointers, the shared-memory layout passed in the kernel parameters.
-template <bool PER_CHAIN, typename SinceT, int MAX_REGS>
+template <bool PER_CHAIN, typename SinceT, int MAX_REGS, bool SHORT_FIELDS>
 __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
@@ -334,6 +334,50 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         // r = sub, sub+16, sub+32, ... of its chain's field vector: g[r] += (+-)E_a[r] (+ (+-)E_b[r])
         unsigned pending = __ballot_sync (0xffffffffu, accept);
         if (pending) {
+            if (SHORT_FIELDS) {
+                // nrel <= 32 (compile-time variant, chosen at launch) -- short field vectors (the fixtures: lysozyme 23 slots,
+                // defensin 15): every lane owns ONE slot, so a round is straight-line code -- one chain per round on all 32
+                // lanes, or two chains (one per half-warp) when the vector fits 16 lanes.  The issue slots, not the lanes,
+                // bound this kernel: 1.9 accepting chains per warp-step x ~20 instructions instead of 1.2 rounds x ~60 of
+                // the strided loop below.  The accepting lane hands out the shared-memory ADDRESS of its difference row with
+                // the direction in the sign bit (and bit 30 = a second site follows: double moves are accepted 3e-5 of
+                // the time, so their second row takes a separate, warp-uniform pass).
+                uint32_t pa = 0u, pb = 0u;
+                if (accept) {
+                    const int la = ia - fa, lo_a = oa - fa;
+                    const int mxa = la > lo_a ? la : lo_a, mna = la > lo_a ? lo_a : la;
+                    pa = (e_addr + (s_erow[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) * (uint32_t) (L.estride * 8)) | (la < lo_a ? 0x80000000u : 0u);
+                    if (dbl) {
+                        const int fb = (int) (s_site[sb] & 0xffffu), lb = ib - fb, lo_b = ob - fb;
+                        const int mxb = lb > lo_b ? lb : lo_b, mnb = lb > lo_b ? lo_b : lb;
+                        pb = (e_addr + (s_erow[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) * (uint32_t) (L.estride * 8)) | (lb < lo_b ? 0x80000000u : 0u);
+                        pa |= 0x40000000u;
+                    }
+                }
+                const bool     second   = __any_sync (0xffffffffu, accept && dbl);
+                const bool     pairwise = nrel <= 16;
+                const int      sub   = pairwise ? (lane & 15) : lane;
+                const bool     mine  = sub < nrel;
+                const uint32_t o     = (uint32_t) sub * 8u;
+                const uint32_t hs8   = (uint32_t) L.hstride * 8u, hbase = h_addr + (uint32_t) warp_base * hs8 + o;
+                do {
+                    int src = __ffs (pending) - 1;
+                    pending &= pending - 1;
+                    if (pairwise) {
+                        const int s1 = __ffs (pending) - 1;      // -1 when no second chain is waiting
+                        pending &= pending - 1;                  // (0 stays 0)
+                        if (lane >> 4) src = s1;
+                    }
+                    const uint32_t y = __shfl_sync (0xffffffffu, pa, src);       // (the source lane is taken modulo 32: -1 reads lane 31, unused)
+                    const bool     work = mine && src >= 0;
+                    const uint32_t hslot = hbase + (uint32_t) src * hs8;
+                    if (work) sts_f64 (hslot, __dadd_rn (lds_f64 (hslot), flip_sign (lds_f64 ((y & 0x3fffffffu) + o), y & 0x80000000u)));
+                    if (second) {        // warp-uniform and rare
+                        const uint32_t yb = __shfl_sync (0xffffffffu, pb, src);
+                        if (work && (y & 0x40000000u)) sts_f64 (hslot, __dadd_rn (lds_f64 (hslot), flip_sign (lds_f64 ((yb & 0x3fffffffu) + o), yb & 0x80000000u)));
+                    }
+                } while (pending);
+            } else {
             // difference row and direction of each changed site: row | reverse << 14, site b in the upper half, double << 30
             uint32_t packed = 0u;
             if (accept) {
@@ -346,7 +390,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                     packed |= ((s_erow[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) << 15) | (lb < lo_b ? 1u << 29 : 0u) | (1u << 30);
                 }
             }
-            // small field vectors: two chains per round (16 lanes each); larger ones: one chain per round (32 lanes)
+            // longer field vectors: two chains per round (16 lanes each) up to 48 slots, else one chain per round (32 lanes)
             const int  lpc  = nrel > 48 ? 32 : 16;
             const int  half = lpc == 16 ? lane >> 4 : 0, sub = lane & (lpc - 1);
             do {
@@ -378,6 +422,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                     }
                 }
             } while (pending);
+            }
             __syncwarp ();
             if (accept) {
                 const bool production = scan >= (uint32_t) p.nequil;
@@ -1014,8 +1059,21 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
     // pH-minor linearisation (load balance: acceptance, hence cost, varies 10x over a titration curve) unless the per-block
     // occupancy counters of all pH values would take more than 48 KB of shared memory
     const bool ph_minor = (size_t) std::min (nph, 768) * m->ninst * 4 <= 48 * 1024 && std::getenv ("PCE_MC_CHAIN_MAJOR") == nullptr;
-    for (int block = 32; block <= (forced_block ? 1024 : 768); block += 32) {
+    // Short field vectors (nrel <= 32, SHORT_FIELDS build): the uncapped build takes 72 registers, which fits 896 threads
+    // (7 warps per sub-partition x 72 x 32 = 16128 registers) -- taken when the chains also fit in shared memory
+    // (defensin: 1.10e11 -> 1.17e11 moves/s; lysozyme's 263 B per chain stop at 832, whose uneven 7/7/6/6 warps do not pay).
+    int most = 768;
+    if (t.nrel <= 32) {
+        cudaFuncAttributes attributes;
+        const bool narrow = mc->nprod < 65536;
+        const cudaError_t err = narrow ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, true>)
+                                       : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, true>);
+        if (err == cudaSuccess && ((attributes.numRegs + 7) & ~7) * 32 * 7 <= 16384) most = 896;
+        else if (err != cudaSuccess) (void) cudaGetLastError ();
+    }
+    for (int block = 32; block <= (forced_block ? 1024 : most); block += 32) {
         if (forced_block && block != forced_block) continue;
+        if (!forced_block && block > 768 && block % 128 != 0) continue;       // beyond 768 only whole warps per sub-partition
         ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, ph_minor);
         if (L.total > limit) continue;
         if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
@@ -1364,6 +1422,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     }
     if (plan.kernel == 1) {
         void (*kernel) (const McParams);
+        const bool short_fields = p.nrel <= 32;      // one field slot per lane when an accepted move is applied
         // the first build (fewest instructions first) whose registers fit: a quarter of the block's warps share the 16384
         // registers of an SM sub-partition, allocated in units of 8 per thread
         auto fits = [&] (void (*candidate) (const McParams)) -> bool {
@@ -1372,7 +1431,8 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
             const int allocated = (attributes.numRegs + 7) & ~7, warps_per_partition = (plan.block / 32 + 3) / 4;
             return warps_per_partition * allocated * 32 <= 16384;
         };
-#define PCE_THREAD_KERNEL(S_, R_) (per_chain ? k_mc_thread<true, S_, R_> : k_mc_thread<false, S_, R_>)
+#define PCE_THREAD_KERNEL(S_, R_) (short_fields ? (per_chain ? k_mc_thread<true, S_, R_, true> : k_mc_thread<false, S_, R_, true>) \
+                                                : (per_chain ? k_mc_thread<true, S_, R_, false> : k_mc_thread<false, S_, R_, false>))
 #define PCE_THREAD_PICK(S_) (fits (PCE_THREAD_KERNEL (S_, 128)) ? PCE_THREAD_KERNEL (S_, 128) : fits (PCE_THREAD_KERNEL (S_, 80)) ? PCE_THREAD_KERNEL (S_, 80) \
                              : fits (PCE_THREAD_KERNEL (S_, 72)) ? PCE_THREAD_KERNEL (S_, 72) : PCE_THREAD_KERNEL (S_, 64))
         if (mc->nprod < 65536) kernel = PCE_THREAD_PICK (uint16_t);
