@@ -685,8 +685,7 @@ int make_plan (const pce_model *m, const double *ph, int nph, int unfolded, Plan
     return PCE_OK;
 }
 
-// scratch buffers kept per model would complicate the model struct; they are allocated per call (the
-// enumeration is milliseconds to seconds, the allocations are microseconds)
+// One enumeration per planned run (roles rotated so that every site is covered), accumulated into d_bins.
 int run_plan (pce_model *m, const Plan &plan, int unfolded, int shard, int nshards, double *d_bins) {
     const size_t nbins_total = (size_t) (1 + m->ninst) * plan.Nb;
     PCE_CUDA (cudaMemsetAsync (d_bins, 0, nbins_total * sizeof (double), m->stream));
