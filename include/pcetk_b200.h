@@ -28,6 +28,7 @@ extern "C" {
 
 typedef struct pce_model pce_model; /* replaces EnergyModel + its private StateVector (EnergyModel.h:39-60) */
 typedef struct pce_mc    pce_mc;    /* replaces MCModelDefault (MCModelDefault.h:41-54) */
+typedef struct pce_state pce_state; /* replaces StateVector (StateVector.h:26-50); its pair list lives in pce_mc */
 
 typedef enum {
     PCE_OK            = 0,
@@ -99,6 +100,44 @@ int pce_model_state_from_probabilities (const pce_model *model, int32_t *state_g
 
 /* copy the model to its device (done implicitly by compute calls when the host copy changed) */
 int pce_model_upload (pce_model *model);
+
+/* ---- state vector (StateVector.h:53-84; host object, bound by ContinuumElectrostatics.StateVector.pyx) ----------------
+ * One active instance per site, as GLOBAL instance indices; `local` = index within the site.  Getters write -1 and return
+ * PCE_ERR_INDEX for a site out of range (the reference returns -1 and sets Status_IndexOutOfRange, StateVector.c:236-292);
+ * setters return PCE_ERR_VALUE for an instance outside the site ("Invalid value (%d).", Status_ValueError).
+ * pce_state_active() is the int32 row pce_energy / pce_mc_run_chains exchange: no conversion between the two. */
+int  pce_state_create (int nsites, pce_state **out);                                   /* StateVector_Allocate :53 */
+int  pce_state_create_for_model (const pce_model *model, pce_state **out);             /* Allocate + SetSite per site, StateVector.pyx:80-103 */
+void pce_state_destroy (pce_state *state);                                             /* StateVector_Deallocate :57 */
+int  pce_state_clone (const pce_state *state, pce_state **out);                        /* StateVector_Clone :60 */
+int  pce_state_copy_to (const pce_state *state, pce_state *other);                     /* StateVector_CopyTo :61 (lengths are checked here) */
+int  pce_state_nsites (const pce_state *state);
+int  pce_state_nsubstate (const pce_state *state);
+int  pce_state_reset (pce_state *state);                                               /* StateVector_Reset :64 */
+int  pce_state_reset_substate (pce_state *state);                                      /* StateVector_ResetSubstate :65 */
+int  pce_state_reset_to_maximum (pce_state *state);                                    /* StateVector_ResetToMaximum :66 */
+int  pce_state_randomize (pce_state *state, unsigned long long seed);                  /* StateVector_Randomize :67 (Philox words instead of MT19937) */
+int  pce_state_set_site (pce_state *state, int site, int first, int last);             /* StateVector_SetSite :70 */
+int  pce_state_get_site (const pce_state *state, int site, int *first, int *last);
+int  pce_state_is_substate (const pce_state *state, int site, int *flag);              /* StateVector_IsSubstate :73 */
+int  pce_state_get_item (const pce_state *state, int site, int *local);                /* StateVector_GetItem :74 */
+int  pce_state_set_item (pce_state *state, int site, int local);                       /* StateVector_SetItem :75 */
+int  pce_state_get_actual_item (const pce_state *state, int site, int *global);        /* StateVector_GetActualItem :76 */
+int  pce_state_set_actual_item (pce_state *state, int site, int global);               /* StateVector_SetActualItem :77 */
+int  pce_state_allocate_substate (pce_state *state, int nssites);                      /* StateVector_AllocateSubstate :54 (a second call fails) */
+int  pce_state_get_substate_item (const pce_state *state, int index, int *site);       /* StateVector_GetSubstateItem :78 */
+int  pce_state_set_substate_item (pce_state *state, int selected_site, int index);     /* StateVector_SetSubstateItem :79 */
+int  pce_state_increment (pce_state *state, int *more);                                /* StateVector_Increment :82: *more = 0 and the all-first state after the last state */
+int  pce_state_increment_substate (pce_state *state, int *more);                       /* StateVector_IncrementSubstate :83 */
+/* bulk forms (no reference counterpart) */
+const int32_t *pce_state_active (const pce_state *state);                              /* the row of global indices, valid until the vector is destroyed */
+int  pce_state_get_active (const pce_state *state, int32_t *out);
+int  pce_state_set_active (pce_state *state, const int32_t *in);                       /* validated against the site ranges */
+int  pce_state_set_index (pce_state *state, long long index);                          /* mixed-radix decode: the state `index` increments after the all-first state */
+int  pce_state_get_index (const pce_state *state, long long *index);
+/* every state of the substate in IncrementSubstate order (the loop of Substate.py:99-108) as rows of nsites global indices:
+ * one batch for pce_energy.  states == NULL: only *count.  Leaves the substate at its first state. */
+int  pce_state_enumerate_substate (pce_state *state, long long capacity, int32_t *states, long long *count);
 
 /* ---- kernel 1: microstate energies --------------------------------------------------------------
  * EnergyModel_CalculateMicrostateEnergy[Unfolded] (EnergyModel.h:75-76), batched: `states` holds

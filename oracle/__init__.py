@@ -186,6 +186,19 @@ class Ref:
         lib.ref_mc_get_pair.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
         lib.ref_mc_run.argtypes = [C.c_void_p, C.c_double, _f64p]
         lib.ref_mc_run_trajectory.argtypes = [C.c_void_p, C.c_double, _f64p, C.c_void_p, C.c_void_p]
+        pint = C.POINTER(C.c_int)
+        for name, argtypes in (("ref_vector_nsites", []), ("ref_vector_increment", []), ("ref_vector_increment_substate", []),
+                               ("ref_vector_get_item", [C.c_int, pint]), ("ref_vector_set_item", [C.c_int, C.c_int]),
+                               ("ref_vector_get_actual_item", [C.c_int, pint]), ("ref_vector_set_actual_item", [C.c_int, C.c_int]),
+                               ("ref_vector_is_substate", [C.c_int, pint]), ("ref_vector_allocate_substate", [C.c_int]),
+                               ("ref_vector_set_substate_item", [C.c_int, C.c_int]), ("ref_vector_get_substate_item", [C.c_int, pint])):
+            getattr(lib, name).restype = C.c_int
+            getattr(lib, name).argtypes = [C.c_void_p] + argtypes
+        for name in ("ref_vector_reset", "ref_vector_reset_to_maximum", "ref_vector_reset_substate"):
+            getattr(lib, name).restype = None
+            getattr(lib, name).argtypes = [C.c_void_p]
+        lib.ref_vector_state.restype = None
+        lib.ref_vector_state.argtypes = [C.c_void_p, _i32p]
         self.lib = lib
         self.rec = rec
         self.handle = lib.ref_model_create(
@@ -211,6 +224,23 @@ class Ref:
             self.close()
         except Exception:
             pass
+
+    # ---- the reference's StateVector, function by function (StateVector.h:53-84) -> (status, value) ----
+    STATUS_NAMES = ("Continue", "ArrayNonConformableSizes", "IndexOutOfRange", "MemoryAllocationFailure", "ValueError")
+
+    def vector_call(self, name, *args):
+        """Call ``ref_vector_<name>``; functions with an out-parameter return ``(status, value)``, the others their result."""
+        fn = getattr(self.lib, "ref_vector_" + name)
+        if name in ("get_item", "get_actual_item", "is_substate", "get_substate_item"):
+            value = C.c_int(0)
+            status = fn(self.handle, *args, C.byref(value))
+            return status, value.value
+        return fn(self.handle, *args)
+
+    def vector_state(self):
+        out = np.zeros(self.lib.ref_vector_nsites(self.handle), dtype=np.int32)
+        self.lib.ref_vector_state(self.handle, out)
+        return out
 
     def check_symmetric(self, tolerance=0.05):
         dev = C.c_double(0.0)

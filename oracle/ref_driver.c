@@ -148,3 +148,58 @@ int ref_mc_run_trajectory (void *handle, double pH, double *out_p, double *energ
     if (counters != NULL) { counters[0] = moves; counters[1] = movesAcc; counters[2] = flips; counters[3] = flipsAcc; }
     return 0;
 }
+
+/* ---- the caller-visible StateVector, function by function (StateVector.h:53-84): what the Cython class
+ * ContinuumElectrostatics.StateVector.pyx forwards to.  Every wrapper returns the Status the reference set
+ * (0 = Status_Continue) and hands values back through out-parameters. ---- */
+int ref_vector_nsites (void *handle) { return ((RefModel *) handle)->vector->nsites; }
+void ref_vector_reset (void *handle) { StateVector_Reset (((RefModel *) handle)->vector); }
+void ref_vector_reset_to_maximum (void *handle) { StateVector_ResetToMaximum (((RefModel *) handle)->vector); }
+void ref_vector_reset_substate (void *handle) { StateVector_ResetSubstate (((RefModel *) handle)->vector); }
+int ref_vector_increment (void *handle) { return StateVector_Increment (((RefModel *) handle)->vector) ? 1 : 0; }
+int ref_vector_increment_substate (void *handle) { return StateVector_IncrementSubstate (((RefModel *) handle)->vector) ? 1 : 0; }
+int ref_vector_get_item (void *handle, int site, int *value) {
+    Status status = Status_Continue;
+    *value = StateVector_GetItem (((RefModel *) handle)->vector, site, &status);
+    return (int) status;
+}
+int ref_vector_set_item (void *handle, int site, int local) {
+    Status status = Status_Continue;
+    StateVector_SetItem (((RefModel *) handle)->vector, site, local, &status);
+    return (int) status;
+}
+int ref_vector_get_actual_item (void *handle, int site, int *value) {
+    Status status = Status_Continue;
+    *value = StateVector_GetActualItem (((RefModel *) handle)->vector, site, &status);
+    return (int) status;
+}
+int ref_vector_set_actual_item (void *handle, int site, int global) {
+    Status status = Status_Continue;
+    StateVector_SetActualItem (((RefModel *) handle)->vector, site, global, &status);
+    return (int) status;
+}
+int ref_vector_is_substate (void *handle, int site, int *flag) {
+    Status status = Status_Continue;
+    *flag = StateVector_IsSubstate (((RefModel *) handle)->vector, site, &status) ? 1 : 0;
+    return (int) status;
+}
+int ref_vector_allocate_substate (void *handle, int nssites) {
+    Status status = Status_Continue;
+    StateVector_AllocateSubstate (((RefModel *) handle)->vector, nssites, &status);
+    return (int) status;
+}
+int ref_vector_set_substate_item (void *handle, int selected_site, int index) {
+    Status status = Status_Continue;
+    StateVector_SetSubstateItem (((RefModel *) handle)->vector, selected_site, index, &status);
+    return (int) status;
+}
+int ref_vector_get_substate_item (void *handle, int index, int *site) {
+    Status status = Status_Continue;
+    *site = StateVector_GetSubstateItem (((RefModel *) handle)->vector, index, &status);
+    return (int) status;
+}
+void ref_vector_state (void *handle, int *out) {
+    StateVector *vector = ((RefModel *) handle)->vector;
+    int i;
+    for (i = 0; i < vector->nsites; i++) out[i] = vector->sites[i].indexActive;
+}

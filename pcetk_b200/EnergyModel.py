@@ -271,6 +271,5 @@ class EnergyModel(object):
         vector = StateVector(self.owner)
         state = np.zeros(len(vector), dtype=np.int32)
         _native.check(self._lib.pce_model_state_from_probabilities(self._handle, state))
-        for index, value in enumerate(state):
-            vector.SetActualItem(index, int(value))
+        vector.SetGlobalIndices(state)
         return vector

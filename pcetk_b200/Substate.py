@@ -59,17 +59,14 @@ class Substate(object):
         return vector
 
     def CalculateSubstateEnergies(self, log=logFile):
-        """Enumerate the substate with IncrementSubstate and evaluate all of it in one batch (Substate.py:91-119)."""
+        """Enumerate the substate (the IncrementSubstate loop of Substate.py:99-108, run natively) and evaluate all of it in
+        one kernel-1 batch (Substate.py:91-119)."""
         if not self.isCalculated:
-            vector = self.vector
-            vector.ResetSubstate()
-            states, locals_ = [], []
-            increment = True
-            while increment:
-                states.append(vector.GlobalIndices())
-                locals_.append([vector[siteIndex] for siteIndex in self.indicesOfSites])
-                increment = vector.IncrementSubstate()
-            energies = self.owner.energyModel.CalculateMicrostateEnergies(np.stack(states), pH=float(self.pH))
+            # every substate as a row of global instance indices, in IncrementSubstate order (native odometer)
+            states = self.vector.SubstateRows()
+            firsts = np.array([self.owner.sites[siteIndex].instances[0]._instIndexGlobal for siteIndex in self.indicesOfSites], dtype=np.int32)
+            locals_ = (states[:, self.indicesOfSites] - firsts).tolist()
+            energies = self.owner.energyModel.CalculateMicrostateEnergies(states, pH=float(self.pH))
             substates = [[float(energy), indices] for energy, indices in zip(energies, locals_)]
             substates.sort()
             self.substates = substates

@@ -69,6 +69,35 @@ SIGNATURES = {
     "pce_model_scale_interactions": (_int, [_void, _dbl]),
     "pce_model_state_from_probabilities": (_int, [_void, _i32p]),
     "pce_model_upload": (_int, [_void]),
+    "pce_state_create": (_int, [_int, C.POINTER(_void)]),
+    "pce_state_create_for_model": (_int, [_void, C.POINTER(_void)]),
+    "pce_state_destroy": (None, [_void]),
+    "pce_state_clone": (_int, [_void, C.POINTER(_void)]),
+    "pce_state_copy_to": (_int, [_void, _void]),
+    "pce_state_nsites": (_int, [_void]),
+    "pce_state_nsubstate": (_int, [_void]),
+    "pce_state_reset": (_int, [_void]),
+    "pce_state_reset_substate": (_int, [_void]),
+    "pce_state_reset_to_maximum": (_int, [_void]),
+    "pce_state_randomize": (_int, [_void, C.c_ulonglong]),
+    "pce_state_set_site": (_int, [_void, _int, _int, _int]),
+    "pce_state_get_site": (_int, [_void, _int, _pint, _pint]),
+    "pce_state_is_substate": (_int, [_void, _int, _pint]),
+    "pce_state_get_item": (_int, [_void, _int, _pint]),
+    "pce_state_set_item": (_int, [_void, _int, _int]),
+    "pce_state_get_actual_item": (_int, [_void, _int, _pint]),
+    "pce_state_set_actual_item": (_int, [_void, _int, _int]),
+    "pce_state_allocate_substate": (_int, [_void, _int]),
+    "pce_state_get_substate_item": (_int, [_void, _int, _pint]),
+    "pce_state_set_substate_item": (_int, [_void, _int, _int]),
+    "pce_state_increment": (_int, [_void, _pint]),
+    "pce_state_increment_substate": (_int, [_void, _pint]),
+    "pce_state_active": (C.POINTER(C.c_int32), [_void]),
+    "pce_state_get_active": (_int, [_void, _i32p]),
+    "pce_state_set_active": (_int, [_void, _i32p]),
+    "pce_state_set_index": (_int, [_void, _ll]),
+    "pce_state_get_index": (_int, [_void, _pll]),
+    "pce_state_enumerate_substate": (_int, [_void, _ll, _void, _pll]),
     "pce_energy": (_int, [_void, _i32p, _ll, _f64p, _int, _int, _f64p]),
     "pce_energy_device": (_int, [_void, _void, _ll, _void, _int, _int, _void]),
     "pce_analytic_bins_size": (_ll, [_void]),
