@@ -155,6 +155,62 @@ def parse_halfpk_table(log_text, record):
     return None
 
 
+def parse_comparison_table(log_text, record, column):
+    """The 'Comparison between previous and present results' table of lysozyme_compare (lysozyme.py:62-82 prints the first
+    pK1/2 of every instance for both structures, 1 decimal, 'n/a' where a curve never crosses 0.5) -> pK1/2 per instance of
+    ``column`` (0 = pKold, 1 = pKnew), NaN for n/a."""
+    lines = log_text.splitlines()
+    start = [i for i, line in enumerate(lines) if "Comparison between previous and present results" in line][0]
+    out = np.full(record.ninstances, np.nan)
+    site_index = {(res, serial): k for k, (_seg, res, serial) in enumerate(record.site_labels)}
+    for row in lines[start + 4:]:
+        if row.startswith("---"):
+            break
+        t = row.split()
+        k = site_index[(t[0], int(t[1]))]
+        ninst = int(record.site_last[k]) - int(record.site_first[k]) + 1
+        pairs = t[5:]                                    # label value label value ... (old), then the same for new
+        assert len(pairs) == 4 * ninst, row
+        chosen = pairs[2 * ninst * column:2 * ninst * (column + 1)]
+        for q in range(ninst):
+            label, value = chosen[2 * q], chosen[2 * q + 1]
+            assert label == record.inst_labels[int(record.site_first[k]) + q], (row, label)
+            if value != "n/a":
+                out[int(record.site_first[k]) + q] = float(value)
+    return out
+
+
+def extract_lysozyme_compare(parameters):
+    """tests/lysozyme_compare: two lysozyme structures (7LYZ of 1977, 2LZT of 1990) in one run -- two models, two sets of
+    MCModelDefault curves, and a table of the first pK1/2 of every instance for both."""
+    name = "lysozyme_compare"
+    with tempfile.TemporaryDirectory() as tmp:
+        with tarfile.open(os.path.join(REFERENCE, "tests", name, "results.tgz")) as tar:
+            tar.extractall(tmp)
+        results = os.path.join(tmp, "results")
+        with open(os.path.join(results, "lysozyme.out")) as handle:
+            log_text = handle.read()
+        marks = [m.start() for m in re.finditer(r"\*\*\* Now calculating:", log_text)]
+        parts = [log_text[marks[0]:marks[1]], log_text[marks[1]:]]
+        for column, (label, part) in enumerate(zip(("7LYZ", "2LZT"), parts)):
+            record = formats.model_from_mead_directory("%s_%s" % (name, label), part, os.path.join(results, "mead", label), parameters)
+            payload = record.to_npz_dict()
+            payload["golden_gintr_4dp"] = np.array([r[-1] for r in formats.parse_instance_table(part)])
+            pairs = parse_pairs(part)
+            site_index = {s: k for k, s in enumerate(record.site_labels)}
+            payload["golden_pairs"] = np.array([[site_index[a], site_index[b]] for a, b, _w in pairs], dtype=np.int32).reshape(-1, 2)
+            payload["golden_pairs_wmax"] = np.array([w for _a, _b, w in pairs], dtype=np.float64)
+            ph, p = formats.read_curves_directory(os.path.join(results, "curves", label), record)
+            payload["golden_curve_ph"] = ph
+            payload["golden_curve_mc_curves"] = p
+            payload["golden_halfpk"] = parse_comparison_table(log_text, record, column)
+            path = os.path.join(OUT, "%s_%s.npz" % (name, label))
+            np.savez_compressed(path, **payload)
+            print("%-20s nsites=%3d ninst=%3d nstates=%.4g pairs=%d halfpk=%d -> %s (%d KB)" % (
+                name + "/" + label, record.nsites, record.ninstances, float(record.nstates), len(pairs),
+                int(np.isfinite(payload["golden_halfpk"]).sum()), os.path.basename(path), os.path.getsize(path) // 1024))
+
+
 def main():
     parameters_dir = os.path.join(REFERENCE, "parameters", "sites")
     est = [os.path.join(REFERENCE, "tests", "ifp20", n) for n in ("BLF.est", "ACB.est", "ACC.est")]
@@ -238,6 +294,8 @@ def main():
             np.savez_compressed(path, **payload)
             print("%-20s nsites=%3d ninst=%3d nstates=%.4g gmicro=%d pairs=%d -> %s (%d KB)" % (
                 name, record.nsites, record.ninstances, float(record.nstates), len(gm), len(pairs), os.path.basename(path), os.path.getsize(path) // 1024))
+
+    extract_lysozyme_compare(parameters)
 
     # lysozyme_traj: per-scan MC energies at pH 7 (stat_mc.dat) and move counters; same model as 'lysozyme'
     with tempfile.TemporaryDirectory() as tmp:

@@ -199,3 +199,33 @@ def test_reference_mc_mean_energy_matches_stat_mc_fixture(port):
     assert abs(energies.mean() - gold["stat_mc"].mean()) < 0.05
     assert abs(energies.min() - gold["stat_mc"].min()) < 1e-5
     ref.close()
+
+
+COMPARE_FIXTURES = ["lysozyme_compare_7LYZ", "lysozyme_compare_2LZT"]
+
+
+@pytest.mark.parametrize("name", COMPARE_FIXTURES)
+def test_lysozyme_compare_models_are_pinned(port, name):
+    """tests/lysozyme_compare (two lysozyme structures in one run): the models rebuilt from its MEAD logs reproduce the
+    Gintr table, the symmetry verdict and the pair list of its log, and the exact probabilities of the oracle lie within
+    single-run Monte Carlo noise of the reference's own curve files (two 20000-scan runs of one model differ by 0.021)."""
+    rec, gold = load_fixture(name)
+    assert np.abs(np.round(rec.gintr, 4) - gold["golden_gintr_4dp"]).max() < 1e-9
+    ok, _dev = port.check_symmetric(rec.interactions, 0.05)
+    assert ok
+    wsym = port.symmetrize(rec.interactions)
+    a, b, wmax = port.find_pairs(rec, wsym, 2.0)
+    assert np.stack([a, b], axis=1).tolist() == gold["golden_pairs"].tolist()
+    assert np.abs(wmax - gold["golden_pairs_wmax"]).max() <= 5.1e-7
+    for pick in (4, 13, 22):
+        p, _z, _g = port.analytic(rec, wsym, float(gold["golden_curve_ph"][pick]))
+        assert np.abs(p - gold["golden_curve_mc_curves"][pick]).max() <= 0.03
+
+
+def test_two_reference_runs_of_one_model_size_the_mc_tolerance():
+    """lysozyme/curves_mc and lysozyme_compare/curves/7LYZ are two runs of the reference's sampler on the SAME model (same
+    MEAD outputs, clock-seeded generator): their largest difference is what 'statistical parity' with one reference run means."""
+    (rec_a, gold_a), (rec_b, gold_b) = load_fixture("lysozyme"), load_fixture("lysozyme_compare_7LYZ")
+    assert np.array_equal(rec_a.gintr, rec_b.gintr) and np.array_equal(rec_a.interactions, rec_b.interactions)
+    diff = np.abs(gold_a["golden_curve_mc_curves_mc"] - gold_b["golden_curve_mc_curves"])
+    assert 0.015 < diff.max() < 0.03 and np.sqrt((diff ** 2).mean()) < 0.004
