@@ -141,6 +141,28 @@ def cpu_baseline(record, nequil, nprod, grid, threads, repeats=1):
     return total / elapsed, elapsed, ("reference" if use_ref else "port")
 
 
+def cpu_baseline_analytic(nsites=24, ph=7.0):
+    """Exhaustive enumeration of the reference (EnergyModel_CalculateProbabilitiesAnalytically) on one host core for the
+    `nsites`-site variant of the synth-A generator: the reference cannot run 2^32 states (2^26 cap, a 32 GiB array), so
+    the largest case that stays within ~10 s is timed.  Returns (states/s, seconds, kind, nstates)."""
+    import oracle
+    from pcetk_b200 import synthetic
+
+    record = synthetic.synth_a(nsites)
+    use_ref = oracle.have_ref()
+    start = time.perf_counter()
+    if use_ref:
+        ref = oracle.Ref(record)
+        ref.analytic(float(ph))
+        ref.close()
+    else:
+        oracle.build()
+        port = oracle.Port()
+        port.analytic(record, port.symmetrize(record.interactions), float(ph))
+    elapsed = time.perf_counter() - start
+    return record.nstates / elapsed, elapsed, ("reference" if use_ref else "port"), record.nstates
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -430,6 +452,21 @@ def main():
                 tc.CalculateHalfpKs()
                 curve[label] = {"wall_ms": 1000.0 * (time.perf_counter() - t0), "chains": nch, "nequil": 500, "nprod_per_chain": npr, "ph_points": tc.nsteps}
             line["titration_curve"] = curve
+        if world == 1 and not args.no_cpu_baseline and args.workload == "synthA":
+            # the reference cannot run this workload at all; its per-state cost is nsites (nsites - 1) / 2 gathers + one exp per
+            # pH value, so the 24-site rate is an UPPER bound of what it would do on 32 sites (276 against 496 gathers)
+            rate, seconds, kind, nstates = cpu_baseline_analytic(24, 7.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "states/s", "cores": 1, "kind": kind,
+                                    "sample": "24-site variant of the same generator, 2^24 states at ONE pH value, %.1f s on one host core; the "
+                                              "reference caps exhaustive enumeration at 2^26 states and needs one pass per pH value "
+                                              "(x 41 for this curve), so 2^32 x 41 pH extrapolates to >= %.0f core-hours" % (
+                                                  seconds, 2.0 ** 32 * 41 / rate / 3600.0)}
+        if world == 1 and not args.no_cpu_baseline and args.workload == "synthM":
+            # 20 + 100 scans of one chain at pH 7: ~8e5 trial moves, 5-10 s on one host core
+            rate, seconds, kind = cpu_baseline(record, 20, 100, grid_all[14:15], 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind,
+                                    "sample": "one single-chain run at pH 7 (20 + 100 scans of %d trial moves, MT19937), %.1f s on one host core" % (
+                                        nmoves, seconds)}
         if world == 1 and not args.no_cpu_baseline and args.workload in ("lysozyme", "ifp20", "defensin"):
             ncurves = 6 if args.workload != "ifp20" else 1            # 10-20 s of one host core
             rate, seconds, kind = cpu_baseline(record, 500, 20000, grid_all, 1, repeats=ncurves)
