@@ -287,6 +287,7 @@ def main():
         model.DefineMCModel(sampler, log=None)
         if not args.chains:
             # size the ensemble to whole waves of the launch geometry (chain-major linear grid)
+            sampler.nchains = 1 << 20          # the launch geometry of a saturating ensemble (the planner sizes blocks by the ensemble)
             plan = sampler.LaunchPlan(len(grid_all))
             chains = max(1, (args.waves * plan["chains_per_wave"]) // len(grid_all))
             sampler.nchains = chains

@@ -795,8 +795,9 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
     uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
     double   esum = 0.0;
     long long scan = 0;
-    uint32_t  mv = 0, tp = 0;
+    uint32_t  mv = 0;
     bool      production = p.nequil == 0;
+    const bool per_scan = PER_CHAIN && (p.log_rows != nullptr || p.trajectory != nullptr);
     unsigned long long *counts = PER_CHAIN ? (unsigned long long *) (p.chain_counts + ((size_t) q * p.nchains + local) * ninst)
                                            : p.counts + (size_t) q * ninst;
     uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
@@ -828,8 +829,11 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
         __syncwarp ();
 
         // ---- evaluate 32*TPL trials against the current state ----
-        const uint32_t left_in_scan = nmoves - mv;
-        const uint32_t n_act = left_in_scan < (uint32_t) (32 * TPL) ? left_in_scan : (uint32_t) (32 * TPL);
+        // A round may run across scan ends (a scan of a small model is shorter than a round: lysozyme 24 trials); only the
+        // logging / trajectory mode, which reports per scan, keeps its rounds within one scan.
+        const unsigned long long left_total = ntrials - tcur;
+        uint32_t n_act = left_total < (unsigned long long) (32 * TPL) ? (uint32_t) left_total : (uint32_t) (32 * TPL);
+        if (per_scan && nmoves - mv < n_act) n_act = nmoves - mv;
         uint32_t e_pr[TPL], e_a[TPL], e_b[TPL], e_w1[TPL];     // sa | sb << 16,  ia | oa << 16,  ib | ob << 16
         double   e_x[TPL], e_c[TPL][4];
         bool     e_dbl[TPL], e_need[TPL];
@@ -918,15 +922,34 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 #pragma unroll
         for (int u = TPL - 1; u >= 0; u--) if (accm[u]) { ustar = u; lstar = __ffs (accm[u]) - 1; }
         const uint32_t consumed = ustar >= 0 ? (uint32_t) (ustar * 32 + lstar + 1) : n_act;
-        uint32_t ndbl = 0;
+        // scan ends inside the consumed trials: k_before of them lie before the last consumed trial (they see the energy as
+        // it was), k_total counts the one right after it as well (it sees the energy after an accepted move)
+        uint32_t k_before = 0, k_total = 0;
+        if (mv + consumed >= nmoves) { k_before = (mv + consumed - 1) / nmoves; k_total = (mv + consumed) / nmoves; }
+        // first consumed trial that belongs to the production phase
+        uint32_t j_prod = 0;
+        if (!production) {
+            const long long wait = (long long) (p.nequil - scan) * (long long) nmoves - (long long) mv;
+            j_prod = wait > (long long) (32 * TPL) ? (uint32_t) (32 * TPL) : (uint32_t) wait;
+        }
+        uint32_t ndbl = 0, ndbl_prod = 0;
 #pragma unroll
         for (int u = 0; u < TPL; u++) {
-            const int c = (int) consumed - u * 32;
+            const int c = (int) consumed - u * 32, c0 = (int) j_prod - u * 32;
             const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
+            const unsigned m0 = c0 >= 32 ? 0xffffffffu : c0 <= 0 ? 0u : ((1u << c0) - 1u);
             ndbl += (uint32_t) __popc (dblm[u] & m);
+            ndbl_prod += (uint32_t) __popc (dblm[u] & m & ~m0);
         }
-        if (production) c_flips += ndbl;
+        c_flips += ndbl_prod;
         if (PER_CHAIN && p.log_rows != nullptr) { lg_f += ndbl; lg_m += consumed - ndbl; }
+        // energy of the production scans that ended before the last consumed trial
+        for (uint32_t k = 0; k < k_before; k++) {
+            if (scan + (long long) k >= (long long) p.nequil) {
+                esum += grt;
+                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan + k - p.nequil] = grt / beta;
+            }
+        }
 
         if (ustar >= 0) {
             uint32_t s_pr = 0, s_a = 0, s_b = 0;
@@ -945,31 +968,35 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
             if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) lg_fa++; else lg_ma++; }
             apply_move<UPD, ABS> (p, (const uint32_t *) smem, &h (0), p.wl_ldh, lane, sa, sb, ia, oa, ib, ob, dbl);
             grt = __dadd_rn (grt, x);
+            // the accepted trial lies in scan `scan + k_before`: production there decides the stamp and the counters
+            const long long scan_acc = scan + (long long) k_before;
+            const bool      prod_acc = scan_acc >= (long long) p.nequil;
+            const uint32_t  tp_acc = prod_acc ? (uint32_t) (scan_acc - p.nequil) : 0u;
             if (lane == 0) {
                 const uint32_t since_a = since (sa);
-                if (tp != since_a) atomicAdd (&counts[oa], (unsigned long long) (tp - since_a));
-                since (sa) = tp;
+                if (tp_acc != since_a) atomicAdd (&counts[oa], (unsigned long long) (tp_acc - since_a));
+                since (sa) = tp_acc;
                 state (sa) = (uint16_t) ia;
                 if (dbl) {
                     const uint32_t since_b = since (sb);
-                    if (tp != since_b) atomicAdd (&counts[ob], (unsigned long long) (tp - since_b));
-                    since (sb) = tp;
+                    if (tp_acc != since_b) atomicAdd (&counts[ob], (unsigned long long) (tp_acc - since_b));
+                    since (sb) = tp_acc;
                     state (sb) = (uint16_t) ib;
                 }
             }
-            if (production) { if (dbl) c_facc++; else c_macc++; }
+            if (prod_acc) { if (dbl) c_facc++; else c_macc++; }
         }
         __syncwarp ();       // state, stamps and fields of this round are visible to every lane before the next one
 
-        mv += consumed;
+        // the scan (if any) that ends right after the last consumed trial
+        if (k_total > k_before && scan + (long long) k_before >= (long long) p.nequil) {
+            esum += grt;
+            if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan + k_before - p.nequil] = grt / beta;
+        }
+        mv = mv + consumed - k_total * nmoves;
         tcur += (unsigned long long) consumed;
-        if (mv == nmoves) {     // scan bookkeeping (MCModelDefault.c:298-312)
-            mv = 0;
-            if (production) {
-                esum += grt;
-                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan - p.nequil] = grt / beta;
-            }
-            if (PER_CHAIN && p.log_rows != nullptr) {
+        if (k_total) {     // scan bookkeeping (MCModelDefault.c:298-312)
+            if (PER_CHAIN && p.log_rows != nullptr) {       // per_scan mode: k_total == 1
                 const long long done = (production ? scan - p.nequil : scan) + 1;
                 if (done % p.log_frequency == 0) {
                     if (q == 0 && local == 0 && lane == 0) {
@@ -980,9 +1007,8 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
                 }
                 if (!production && scan + 1 == p.nequil) lg_m = lg_ma = lg_f = lg_fa = 0;
             }
-            scan++;
+            scan += (long long) k_total;
             production = scan >= p.nequil;
-            tp = production ? (uint32_t) (scan - p.nequil) : 0u;
         }
     }
 
@@ -1020,7 +1046,9 @@ __global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
 // ---------------------------------------------------------------------------------------------------
 // launch planning
 // ---------------------------------------------------------------------------------------------------
-struct Plan { int kernel, block; size_t smem; int ctas_per_sm; int tpl; int upd; int ph_minor; };      // upd: 128-bit loads per lane and batch of the field update
+// upd: 128-bit loads per lane and batch of the field update; ctas_per_sm: the register budget (resident CTAs of 8 warps);
+// resident: CTAs of `block` threads that actually share an SM (more, smaller CTAs when a small ensemble is spread evenly)
+struct Plan { int kernel, block; size_t smem; int ctas_per_sm; int tpl; int upd; int ph_minor; int resident; };
 
 int smem_limit (int device, size_t *limit) {
     int value = 0;
@@ -1029,8 +1057,6 @@ int smem_limit (int device, size_t *limit) {
     return PCE_OK;
 }
 
-// chain-per-thread plan: W in shared memory when it fits, and the block size (multiple of 32, <= 512) that puts the
-// most warps on an SM; ties go to the smaller block (finer-grained waves).
 // sizes of the relative-field tables of a model: slots per chain, difference rows, cross-table entries
 struct TableSizes { int nrel, nrows; size_t ncross; };
 TableSizes table_sizes (const pce_mc *mc) {
@@ -1044,14 +1070,24 @@ TableSizes table_sizes (const pce_mc *mc) {
     return t;
 }
 
-// chain-per-thread plan: the difference rows and the cross-term table must fit in shared memory next to enough chains;
-// the block size (multiple of 32, one resident CTA, up to 1024 threads: 128 / 80 / 64 registers for <= 512 / 768 / 1024)
-// is the one that puts the most warps on an SM; ties go to the smaller block (finer-grained waves).
-bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
+// Cost model of one launch, in units of the time one warp of the chain-per-thread kernel needs when it has an SM to itself.
+// Measured on B200 (profiles/README.md, round 2, `scripts/r02/planner_sweep.py`: lysozyme and defensin, 41 pH values x
+// 1 .. 2772 chains): a warp-step of the chain-per-thread kernel is latency-bound at 1470 cycles alone and slows by 1.8 % per
+// co-resident warp (24 warps: x 1.43); the chain-per-warp kernel (speculative lanes) finishes a chain in 0.19 of that time and
+// a full grid of resident warps in 0.138, so it wins below ~8 waves of its own grid (~28 000 chains) and loses above.
+struct CostModel {
+    static constexpr double thread_per_warp = 0.018;     // slow-down of a chain-per-thread warp-step per co-resident warp
+    static constexpr double warp_floor = 0.19, warp_per_wave = 0.138, warp_fixed = 0.03;
+};
+
+// chain-per-thread plan: the difference rows and the cross-term table must fit in shared memory next to the chains.  Every
+// block size (multiple of 32, up to 768 threads -- 896 for short field vectors) that fits is priced with the cost model for
+// the `total` = nph x nchains chains of this launch: a small ensemble is spread over all SMs in small blocks (few warps per SM,
+// each running at its latency floor), a large one takes the block that puts the most warps on an SM.
+bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, double *cost_out) {
     const pce_model *m = mc->model;
     const TableSizes t = table_sizes (mc);
     if (m->ninst > 256 || t.nrows > 16383 || t.ncross >= (1u << 24)) return false;
-    int best_warps = 0;
     const char *forced = std::getenv ("PCE_MC_BLOCK");      // tuning aid: force the block size
     const int forced_block = forced ? std::atoi (forced) : 0;
     // measured on lysozyme (moves/s): 640 threads 7.6e10, 768 (the largest block the uncapped 79-register build fits) 8.5e10,
@@ -1071,17 +1107,32 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, Plan *plan) {
         if (err == cudaSuccess && ((attributes.numRegs + 7) & ~7) * 32 * 7 <= 16384) most = 896;
         else if (err != cudaSuccess) (void) cudaGetLastError ();
     }
+    const double total = (double) nph * (double) mc->nchains;
+    double best_cost = 0.0;
+    int    best_warps = 0;
     for (int block = 32; block <= (forced_block ? 1024 : most); block += 32) {
         if (forced_block && block != forced_block) continue;
         if (!forced_block && block > 768 && block % 128 != 0) continue;       // beyond 768 only whole warps per sub-partition
         ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, ph_minor);
         if (L.total > limit) continue;
         if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
-        const int warps = block / 32;
-        if (warps > best_warps) {
-            best_warps = warps; plan->kernel = 1; plan->block = block; plan->smem = L.total; plan->ctas_per_sm = 1; plan->ph_minor = ph_minor ? 1 : 0;
+        // resident CTAs: shared memory (1 KB reserved per CTA), threads, registers (88 allocated up to 640 threads, then 80 / 72)
+        const int regs = block <= 640 ? 88 : block <= 768 ? 80 : 72;
+        const int ctas = (int) std::max<size_t> (1, std::min<size_t> (std::min<size_t> ((228 * 1024) / (L.total + 1024), (size_t) (2048 / block)),
+                                                                      (size_t) (65536 / (regs * block))));
+        const int    warps_full = ctas * (block / 32);
+        const double capacity = (double) sms * ctas * block;
+        const double waves = std::ceil (total / capacity);
+        const double rest = total - (waves - 1.0) * capacity;                                  // chains of the last wave
+        const double warps_last = std::min ((double) warps_full, std::ceil (std::ceil (rest / block) / sms) * (block / 32));
+        const double cost = (waves - 1.0) * (1.0 + CostModel::thread_per_warp * warps_full) + (1.0 + CostModel::thread_per_warp * warps_last);
+        // ties go to the larger block (measured: 768 threads 64.4 ms against 2 x 384 threads 69.0 ms on a full lysozyme grid)
+        if (best_warps == 0 || cost <= best_cost + 1e-9) {
+            best_cost = cost; best_warps = warps_full;
+            plan->kernel = 1; plan->block = block; plan->smem = L.total; plan->ctas_per_sm = ctas; plan->ph_minor = ph_minor ? 1 : 0; plan->resident = ctas;
         }
     }
+    if (cost_out) *cost_out = best_cost;
     // auto mode: with fewer than 8 resident warps the chain-per-warp kernel does better; a forced choice runs with what fits
     return best_warps >= (mc->kernel == 1 ? 1 : 8);
 }
@@ -1093,7 +1144,7 @@ int warp_tpl () {
     return forced && std::atoi (forced) == 2 ? 2 : 1;
 }
 
-bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
+bool plan_warp (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, double *cost_out) {
     const pce_model *m = mc->model;
     if (m->ninst > 65535 || m->nsites > 65535) return false;
     const int tpl = warp_tpl ();
@@ -1113,6 +1164,27 @@ bool plan_warp (const pce_mc *mc, size_t limit, Plan *plan) {
         if (pass == 2 && mc->cross_overflow) continue;      // only the one-CTA 255-register variant gathers W itself
         plan->kernel = 2; plan->block = warps * 32; plan->smem = smem;
         plan->ctas_per_sm = pass == 0 ? std::min (ctas, most) : 1; plan->tpl = tpl; plan->upd = upd;
+        plan->resident = plan->ctas_per_sm;
+        // An ensemble of less than one wave: the SMs with the most warps set the time (328 CTAs of 8 warps on 148 SMs
+        // leave 32 SMs with 24 warps and 116 with 16), so cut the CTAs down to the size that levels the warps per SM
+        const long long total = (long long) nph * mc->nchains, per_sm = (long long) plan->ctas_per_sm * warps;
+        if (pass != 1 && total < (long long) sms * per_sm && std::getenv ("PCE_MC_WARPS") == nullptr) {
+            int best_wpc = warps;
+            long long best_load = ((total + warps - 1) / warps + sms - 1) / sms * warps;
+            for (int wpc = warps / 2; wpc >= 1; wpc /= 2) {
+                const long long load = ((total + wpc - 1) / wpc + sms - 1) / sms * wpc;
+                if (load < best_load) { best_load = load; best_wpc = wpc; }
+            }
+            if (best_wpc != warps) {
+                plan->block = best_wpc * 32;
+                plan->smem = L.shared_bytes + (size_t) best_wpc * L.per_warp;
+                plan->resident = (int) std::min<long long> (32, per_sm / best_wpc);
+            }
+        }
+        if (cost_out) {
+            const double waves = (double) nph * (double) mc->nchains / ((double) sms * plan->ctas_per_sm * warps);
+            *cost_out = std::max (CostModel::warp_floor, CostModel::warp_fixed + CostModel::warp_per_wave * waves);
+        }
         return true;
     }
     return false;
@@ -1214,12 +1286,20 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
     size_t limit = 0;
     int status = smem_limit (mc->model->device, &limit);
     if (status != PCE_OK) return status;
+    int sms = 0;
+    PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, mc->model->device));
     bool ok = false;
-    if (mc->kernel == 1) ok = plan_thread (mc, limit, nph, plan);
-    else if (mc->kernel == 2) ok = plan_warp (mc, limit, plan);
+    if (mc->kernel == 1) ok = plan_thread (mc, limit, nph, sms, plan, nullptr);
+    else if (mc->kernel == 2) ok = plan_warp (mc, limit, nph, sms, plan, nullptr);
     else {
-        // auto: chain per thread while W fits in shared memory next to enough chains; else chain per warp
-        ok = plan_thread (mc, limit, nph, plan) || plan_warp (mc, limit, plan);
+        // auto: price both kernels for this ensemble (CostModel) where both can run the model: the chain-per-thread kernel needs
+        // the tables in shared memory and wins on large ensembles, the chain-per-warp kernel finishes small ones 5x sooner
+        Plan thread_plan = *plan, warp_plan = *plan;
+        double thread_cost = 0.0, warp_cost = 0.0;
+        const bool thread_ok = plan_thread (mc, limit, nph, sms, &thread_plan, &thread_cost);
+        const bool warp_ok = plan_warp (mc, limit, nph, sms, &warp_plan, &warp_cost);
+        if (thread_ok && (!warp_ok || thread_cost <= warp_cost)) { *plan = thread_plan; ok = true; }
+        else if (warp_ok) { *plan = warp_plan; ok = true; }
     }
     if (!ok) return fail (PCE_ERR_LIMIT, "model too large for the selected Monte Carlo kernel");
     return PCE_OK;
@@ -1228,7 +1308,7 @@ static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
 extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm, int *chains_per_wave, long long *smem_bytes) {
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
     PCE_CUDA (cudaSetDevice (mc->model->device));
-    Plan plan = { 0, 0, 0, 1, 1, 4, 1 };
+    Plan plan = { 0, 0, 0, 1, 1, 4, 1, 1 };
     int status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
     int sms = 0;
@@ -1236,7 +1316,7 @@ extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *c
     if (kernel) *kernel = plan.kernel;
     if (block) *block = plan.block;
     if (ctas_per_sm) *ctas_per_sm = plan.ctas_per_sm;
-    if (chains_per_wave) *chains_per_wave = sms * plan.ctas_per_sm * (plan.kernel == 1 ? plan.block : plan.block / 32);
+    if (chains_per_wave) *chains_per_wave = sms * plan.resident * (plan.kernel == 1 ? plan.block : plan.block / 32);
     if (smem_bytes) *smem_bytes = (long long) plan.smem;
     return PCE_OK;
 }
@@ -1371,7 +1451,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     PCE_CUDA (mc->d_ph.resize (nph));
     PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
 
-    Plan plan = { 0, 0, 0, 1, 1, 4, 1 };
+    Plan plan = { 0, 0, 0, 1, 1, 4, 1, 1 };
     status = make_mc_plan (mc, nph, &plan);
     if (status != PCE_OK) return status;
 
@@ -1454,7 +1534,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         // shared-memory carveout for exactly the planned number of resident CTAs (the rest of the 228 KB stays L1 for the
         // difference rows and the cross-term table); without __launch_bounds__ the driver has no occupancy hint of its own
-        const int carveout = (int) std::min<size_t> (100, ((size_t) plan.ctas_per_sm * (plan.smem + 1024) * 100) / (228 * 1024) + 1);
+        const int carveout = (int) std::min<size_t> (100, ((size_t) plan.resident * (plan.smem + 1024) * 100) / (228 * 1024) + 1);
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     }
