@@ -154,7 +154,10 @@ int pce_energy_device (pce_model *model, const int32_t *d_states, long long nsta
  * pce_analytic_bins_size: number of doubles in a bins buffer for this model.
  * pce_analytic_bins     : enumerate shard `shard` of `nshards` (equal slices of the outer state index)
  *                         into d_bins (device, zeroed by the call).  Bins of different shards ADD, which
- *                         is the only multi-GPU exchange the path needs (one all-reduce(sum)).
+ *                         is the only multi-GPU exchange the path needs (one all-reduce(sum)).  Bin n of
+ *                         row r is stored scaled by exp(sigma[n]) (pce_analytic_bin_scales): the scales
+ *                         depend on the model and the pH list only, so every shard uses the same ones.
+ * pce_analytic_bin_scales: (host) sigma[0 .. bins_size / (1 + ninst)) for this pH list.
  * pce_analytic_finish   : (host) turn summed bins into probabilities for each pH: out_p[q*ninst + k];
  *                         out_lnz[q] = ln sum_s exp(-(G_s(pH_q) - gzero)/RT) (may be NULL); also stores
  *                         the last pH's probabilities in the model.
@@ -164,6 +167,7 @@ long long pce_analytic_bins_size (const pce_model *model);
 int pce_analytic_bins (pce_model *model, const double *ph, int nph, int unfolded, int shard, int nshards, double max_states, double *d_bins);
 int pce_analytic_finish (pce_model *model, const double *bins /* host */, const double *ph, int nph, int unfolded, double gzero,
                          double *out_p, double *out_lnz);
+int pce_analytic_bin_scales (pce_model *model, const double *ph, int nph, int unfolded, double *sigma);
 int pce_analytic (pce_model *model, const double *ph, int nph, int unfolded, double gzero, double max_states, double *out_p, double *out_lnz);
 /* exact minimum microstate energy at one pH (the shift the reference applies, EnergyModel.c:262-275):
  * with it, Z as returned by EnergyModel_CalculateZfolded is exp(lnz + Gmin/RT). */
@@ -201,12 +205,14 @@ int pce_mc_run_device (pce_mc *mc, const double *ph /* host */, int nph, int ph_
  * chain_counts[nph*nchains*ninst], chain_state[nph*nchains*nsites], chain_energy[nph*nchains] */
 int pce_mc_run_chains (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
                        long long *chain_counts, int32_t *chain_state, double *chain_energy, double *chain_esum, long long *chain_counters);
-/* MCModelDefault.pyx:79-159 trajectory mode: energies[nprod] of chain 0 after every production scan */
-int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, long long *counts, long long *counters);
+/* MCModelDefault.pyx:79-159 trajectory mode: energies[nprod] of chain 0 after every production scan; the chain draws
+ * the random stream (seed, pH index ph_index_offset, chain 0) */
+int pce_mc_run_trajectory (pce_mc *mc, double ph, int ph_index_offset, double *energies, long long *counts, long long *counters);
 /* the same with the per-block counter table of the logging branch: log_rows[(nequil/f + nprod/f) * 5] holds, per block of
  * f = log_frequency scans (equilibration blocks first), {scans done in the phase, moves, moves accepted, double moves,
  * double moves accepted} -- the rows MCModelDefault.pyx:85-151 prints */
-int pce_mc_run_logged (pce_mc *mc, double ph, int log_frequency, double *energies, long long *counts, long long *counters, long long *log_rows);
+int pce_mc_run_logged (pce_mc *mc, double ph, int ph_index_offset, int log_frequency, double *energies, long long *counts, long long *counters,
+                       long long *log_rows);
 
 /* ---- test hooks ----------------------------------------------------------------------------------- */
 /* Philox4x32-10 blocks computed ON THE DEVICE: out[4*i..] for counters ctr[4*i..], one key */

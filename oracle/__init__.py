@@ -73,6 +73,8 @@ class Port:
         lib.oracle_energy.argtypes = _MODEL_SIG + [_i32p, C.c_double, C.c_int]
         lib.oracle_analytic.argtypes = _MODEL_SIG + [C.c_double, C.c_double, C.c_int, C.c_longlong, C.c_void_p,
                                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        lib.oracle_analytic_compensated.argtypes = _MODEL_SIG + [C.c_double, C.c_double, C.c_int, C.c_longlong, C.c_int, C.c_void_p,
+                                                                 C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.oracle_enumerate_energies.argtypes = _MODEL_SIG + [C.c_double, C.c_longlong, _f64p]
         lib.oracle_find_pairs.argtypes = [C.c_int, C.c_int, _i32p, _i32p, _f64p, C.c_double, C.c_int, _i32p, _i32p, _f64p]
         lib.oracle_mc_mt.argtypes = _MODEL_SIG + [C.c_int, _i32p, _i32p, C.c_int, C.c_int, C.c_uint32, C.c_int, _f64p,
@@ -112,6 +114,17 @@ class Port:
                                           p.ctypes.data if want_p else None, C.byref(z), C.byref(gmin))
         if status != 0:
             raise MemoryError("cannot allocate Boltzmann factors")
+        return p, z.value, gmin.value
+
+    def analytic_compensated(self, rec, wsym, pH=7.0, unfolded=False, gzero=0.0, threads=0):
+        """-> (p[ninst], Z, Gmin): the reference's algorithm (EnergyModel.c:252-354) with long-double sums, state range split
+        over ``threads`` host threads (default: all).  For state counts where the reference's serial double sum is the noise."""
+        p = np.empty(rec.ninstances, dtype=np.float64)
+        z, gmin = C.c_double(0.0), C.c_double(0.0)
+        status = self.lib.oracle_analytic_compensated(*_model_args(rec, wsym), pH, gzero, int(unfolded), rec.nstates,
+                                                      int(threads or os.cpu_count() or 1), p.ctypes.data, C.byref(z), C.byref(gmin))
+        if status != 0:
+            raise MemoryError("cannot allocate accumulators")
         return p, z.value, gmin.value
 
     def find_pairs(self, rec, wsym, limit=2.0):

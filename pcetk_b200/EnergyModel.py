@@ -189,9 +189,11 @@ class EnergyModel(object):
 
     @staticmethod
     def _phGroups(ph, max_protons):
-        """Split a pH list into groups narrow enough for one enumeration pass (kernel 2)."""
+        """Split a pH list into groups one enumeration pass can serve (kernel 2).  Every proton-count bin carries
+        its own scale, so only the protons of a partial sum (at most 16) see the half-width of a group: pH 0..20 is one
+        group for any model; a grid wider than ~32 pH units is split."""
         order = np.argsort(ph, kind="stable")
-        halfwidth = 590.0 / (2.302585092994 * max(max_protons, 1))
+        halfwidth = 590.0 / (2.302585092994 * max(min(max_protons, 16), 1))
         groups, current = [], []
         for index in order:
             if current and ph[index] - ph[current[0]] > 2.0 * halfwidth:

@@ -42,6 +42,12 @@ class MCModelDefault(object):
         self.lastCounters = None
         self.lastEnergySums = None
         self.lastLogRows = None
+        # Random streams are addressed by (seed, pH index, chain, trial).  The reference's Mersenne Twister keeps advancing from
+        # call to call; here every call of the reference-compatible entry points takes the next unused pH indices, so that
+        # repeated calls (and the pH points of a serial titration loop) draw independent samples.  ``lastPhIndexOffset`` is the
+        # first index the last call used: pass it as ``phIndexOffset`` to replay that call exactly.
+        self._nextStream = 0
+        self.lastPhIndexOffset = 0
 
     def __del__(self):
         handle = getattr(self, "_handle", None)
@@ -119,9 +125,19 @@ class MCModelDefault(object):
         self.lastEnergySums = esum
         return counts, counters, esum
 
-    def CalculateOwnerProbabilitiesBatch(self, pHs, phIndexOffset=0):
-        """Probabilities for a list of pH values in one launch -> p[npH, ninst]; the model keeps the last row."""
-        counts, _counters, _esum = self.RunCounts(pHs, phIndexOffset)
+    def _takeStreams(self, count, phIndexOffset=None):
+        """First pH index of a call over ``count`` pH values: the next unused ones, or the explicit (replayable) offset."""
+        if phIndexOffset is None:
+            phIndexOffset = self._nextStream
+            self._nextStream += int(count)
+        self.lastPhIndexOffset = int(phIndexOffset)
+        return int(phIndexOffset)
+
+    def CalculateOwnerProbabilitiesBatch(self, pHs, phIndexOffset=None):
+        """Probabilities for a list of pH values in one launch -> p[npH, ninst]; the model keeps the last row.
+        Successive calls draw fresh random streams unless ``phIndexOffset`` addresses them explicitly."""
+        count = len(np.atleast_1d(pHs))
+        counts, _counters, _esum = self.RunCounts(pHs, self._takeStreams(count, phIndexOffset))
         return counts / float(self.nchains * self.nprod)
 
     def CalculateOwnerProbabilities(self, pH=7.0, logFrequency=0, trajectoryFilename="", log=logFile):
@@ -140,8 +156,8 @@ class MCModelDefault(object):
             counters = np.zeros(4, dtype=np.int64)
             nrows = (self.nequil // logFrequency + self.nprod // logFrequency) if logFrequency > 0 else 0
             rows = np.zeros((max(nrows, 1), 5), dtype=np.int64)
-            _native.check(self._lib.pce_mc_run_logged(self._handle, float(pH), int(max(logFrequency, 0)), _native.ptr(energies), _native.ptr(counts),
-                                                      _native.ptr(counters), _native.ptr(rows) if nrows else None))
+            _native.check(self._lib.pce_mc_run_logged(self._handle, float(pH), self._takeStreams(1), int(max(logFrequency, 0)), _native.ptr(energies),
+                                                      _native.ptr(counts), _native.ptr(counters), _native.ptr(rows) if nrows else None))
             if trajectoryFilename != "":
                 with open(trajectoryFilename, "w") as output:
                     for value in energies:

@@ -103,6 +103,7 @@ SIGNATURES = {
     "pce_analytic_bins_size": (_ll, [_void]),
     "pce_analytic_bins": (_int, [_void, _f64p, _int, _int, _int, _int, _dbl, _void]),
     "pce_analytic_finish": (_int, [_void, _f64p, _f64p, _int, _int, _dbl, _void, _void]),
+    "pce_analytic_bin_scales": (_int, [_void, _f64p, _int, _int, _f64p]),
     "pce_analytic": (_int, [_void, _f64p, _int, _int, _dbl, _dbl, _void, _void]),
     "pce_analytic_gmin": (_int, [_void, _dbl, _int, _dbl, _pdbl]),
     "pce_mc_create": (_int, [_void, _dbl, _int, _int, _ll, _int, C.POINTER(_void)]),
@@ -117,8 +118,8 @@ SIGNATURES = {
     "pce_mc_run": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void]),
     "pce_mc_run_device": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void]),
     "pce_mc_run_chains": (_int, [_void, _f64p, _int, _int, _ll, _void, _void, _void, _void, _void]),
-    "pce_mc_run_trajectory": (_int, [_void, _dbl, _void, _void, _void]),
-    "pce_mc_run_logged": (_int, [_void, _dbl, _int, _void, _void, _void, _void]),
+    "pce_mc_run_trajectory": (_int, [_void, _dbl, _int, _void, _void, _void]),
+    "pce_mc_run_logged": (_int, [_void, _dbl, _int, _int, _void, _void, _void, _void]),
     "pce_test_philox": (_int, [_int, _u32p, _int, _u32p, _u32p]),
 }
 

@@ -54,6 +54,8 @@ struct DeviceBuffer {
 
 }  // namespace pce
 
+struct pce_enum_cache;     // plan and tables of the last enumeration (pce_analytic.cu)
+
 // The model: host copy (authoritative for setters/getters) + device mirror.
 struct pce_model {
     int    nsites = 0, ninst = 0, device = 0;
@@ -77,6 +79,10 @@ struct pce_model {
     // scratch of the enumeration kernel (grow-only)
     pce::DeviceBuffer<double>  s_gt, s_T, s_Mtab, s_Ftab, s_seg, s_xs;
     pce::DeviceBuffer<int32_t> s_ms;
+    pce::DeviceBuffer<unsigned> s_cnt;         // block counters of the reduction (zero between launches)
+
+    pce_enum_cache *enum_cache = nullptr;
+    void (*enum_cache_free) (pce_enum_cache *) = nullptr;
 
     int  sites_ok () const;                    // PCE_OK when every site is set, contiguous and ascending
     int  upload ();

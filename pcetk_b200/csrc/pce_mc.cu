@@ -1611,11 +1611,12 @@ extern "C" int pce_mc_run_chains (pce_mc *mc, const double *ph, int nph, int ph_
     return status;
 }
 
-extern "C" int pce_mc_run_trajectory (pce_mc *mc, double ph, double *energies, long long *counts, long long *counters) {
-    return pce_mc_run_logged (mc, ph, 0, energies, counts, counters, nullptr);
+extern "C" int pce_mc_run_trajectory (pce_mc *mc, double ph, int ph_index_offset, double *energies, long long *counts, long long *counters) {
+    return pce_mc_run_logged (mc, ph, ph_index_offset, 0, energies, counts, counters, nullptr);
 }
 
-extern "C" int pce_mc_run_logged (pce_mc *mc, double ph, int log_frequency, double *energies, long long *counts, long long *counters, long long *log_rows) {
+extern "C" int pce_mc_run_logged (pce_mc *mc, double ph, int ph_index_offset, int log_frequency, double *energies, long long *counts, long long *counters,
+                                  long long *log_rows) {
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
     if (log_rows != nullptr && log_frequency < 1) return fail (PCE_ERR_VALUE, "logFrequency must be positive");
     pce_model *m = mc->model;
@@ -1643,7 +1644,7 @@ extern "C" int pce_mc_run_logged (pce_mc *mc, double ph, int log_frequency, doub
         p.chain_counts = d_counts.ptr; p.chain_state = d_state.ptr; p.chain_energy = d_energy.ptr; p.chain_esum = d_esum.ptr;
         p.chain_counters = d_counters.ptr; p.trajectory = d_traj.ptr;
         if (log_rows) { p.log_rows = d_log.ptr; p.log_frequency = log_frequency; }
-        status = launch_mc (mc, &ph, 1, 0, 0, true, p);
+        status = launch_mc (mc, &ph, 1, ph_index_offset, 0, true, p);
         if (status != PCE_OK) break;
         err = cudaStreamSynchronize (m->stream);
         if (err == cudaSuccess && energies) err = cudaMemcpy (energies, d_traj.ptr, mc->nprod * sizeof (double), cudaMemcpyDeviceToHost);

@@ -78,6 +78,7 @@ extern "C" void pce_model_destroy (pce_model *m) {
         m->s_gt.release (); m->s_T.release (); m->s_Mtab.release (); m->s_Ftab.release (); m->s_seg.release (); m->s_xs.release (); m->s_ms.release ();
         cudaSetDevice (current);
     }
+    if (m->enum_cache != nullptr && m->enum_cache_free != nullptr) m->enum_cache_free (m->enum_cache);
     delete m;
 }
 

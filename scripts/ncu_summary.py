@@ -60,7 +60,10 @@ def main():
             if not tokens:
                 continue
             op = tokens[1] if tokens[0].startswith("@") and len(tokens) > 1 else tokens[0]
-            count = int(record[index["Instructions Executed"]] or 0)
+            try:
+                count = int(record[index["Instructions Executed"]] or 0)
+            except ValueError:       # a report with several kernels repeats the header rows
+                continue
             ops[op.split(".")[0]] += count
             total += count
         lines.append("  executed warp instructions by opcode (total %d, %d SASS lines):" % (total, len(rows) - 2))
