@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- the hot path of efliks/pcetk on B200, measured on the metric BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lysozyme|ifp20|synthM|synthA] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload lysozyme|ifp20|defensin|synthM|synthA|synthA36] [--impl b200|reference]
 
-Default workload = BASELINE.json configs[1]: the lysozyme fixture (21 sites / 44 instances / 3 double-move pairs),
+Headline (default) workload = BASELINE.json configs[1]: the lysozyme fixture (21 sites / 44 instances / 3 double-move pairs),
 Metropolis MC titration curve pH 0..20 step 0.5 (41 points), 500 equilibration + 20000 production scans per chain
 (the reference's defaults), `--chains` chains per pH value per GPU.  One "step" = one whole titration curve.
 metric = MC trial moves per second (whole job).  Prints ONE JSON line (rank 0).
 
   value : device-resident model, kernel + (N>1) the one NCCL all-reduce of the occupancy counts; CUDA events.
-  e2e   : the same curve through the public API (CEModel.CalculateProbabilitiesBatch) from HOST arrays: the model is
-          re-loaded, symmetrised and uploaded, the kernel runs, and counts come back to the host, every step; wall clock
-          around a device synchronise.
+  e2e   : the same curve through the public API from HOST arrays: the model is re-loaded, symmetrised and uploaded, the
+          kernel runs, and counts come back to the host, every step; wall clock around a device synchronise.  One GPU:
+          CEModel.CalculateProbabilitiesBatch; several: pcetk_b200.distributed (chains / chunk range sharded, ONE all-reduce).
+  roofline : the resource that bounds the dominant kernel, measured in the same run: issue slots (chain-per-thread and small
+          chain-per-warp Monte Carlo: warp-instructions per trial from the committed ncu digest x trials/s, against an
+          issue-rate probe), L2 read bandwidth (1000-site Monte Carlo: bytes from the kernel's own move counters, against a
+          streaming-read probe), FP64 (enumeration: one DFMA per state and role rotation, against a DFMA probe).
+  workloads : the other BASELINE configs in the same invocation (short runs): synthA = 2^32-state analytic enumeration
+          (states/s; strong scaling over GPUs), synthM = 1000 sites / 3000 instances Monte Carlo (a slice of the
+          65536 chains x 41 pH shape: `chains` per pH value per GPU, nequil 500), ifp20, defensin.  Each carries its own
+          ms_per_step, e2e, roofline and (one GPU) cpu_baseline.  `--workload X` makes X the headline instead and skips the rest.
   --impl reference : the reference's own C (oracle/_ref, compiled unmodified from /root/reference in the build
           container) on all host threads, one independent single-chain curve per thread per step.
-
-Other workloads (`ifp20`, `synthM` = 1000 sites MC, `synthA` = 2^32-state enumeration) report their own metric and are
-extra evidence, not the headline line.  synthM defaults to two waves of resident chains (50 per pH value), 100 + 400 scans
-(0.35 s per curve on one B200); BASELINE's full shape is `--chains 65536 --nequil 500 --nprod N` (2.7e6 chains: about
-8 minutes per step on one GPU at 1.9e10 moves/s for N = 50).
 """
 
 import argparse
@@ -49,6 +52,8 @@ def load_record(workload):
         return synthetic.synth_m(1000)
     if workload == "synthA":
         return synthetic.synth_a(32)
+    if workload == "synthA36":
+        return synthetic.synth_a(36)
     raise SystemExit("unknown workload " + workload)
 
 
@@ -192,15 +197,330 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+MC_DEFAULTS = {   # chains per pH per GPU (0 = whole waves of the saturating launch geometry), nprod, nequil
+    "lysozyme": (0, 20000, 500), "defensin": (0, 20000, 500), "ifp20": (256, 2000, 500), "synthM": (0, 100, 500)}
+
+
+class Context(object):
+    """Device, process group, launch stream and the measured peaks of this run."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        import pcetk_b200 as P
+        from pcetk_b200 import _native
+
+        self.torch, self.dist, self.P, self.native = torch, dist, P, _native
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        self.stream = torch.cuda.current_stream()
+        self.lib = _native.library()
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.device)      # > 126 MB L2
+        self.peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as handle:
+                self.peaks = json.load(handle)
+        except (OSError, ValueError):
+            pass
+        self.digests = {}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_summary.json")) as handle:
+                self.digests = json.load(handle)
+        except (OSError, ValueError):
+            pass
+        self._probes = {}
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, value):
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def probe(self, kind):
+        """Measured on-chip peaks of this device: 'dfma' (1e9 DFMA/s), 'shared' (GB/s), 'issue' (1e9 warp-instr/s), 'l2' (GB/s)."""
+        import ctypes as C
+        if kind not in self._probes:
+            value = C.c_double(0.0)
+            if kind == "l2":
+                self.native.check(self.lib.pce_probe_read_bandwidth(self.local_rank, 48 * 1024 * 1024, 40, C.byref(value)))
+            else:
+                self.native.check(self.lib.pce_probe_on_chip(self.local_rank, {"dfma": 0, "shared": 1, "issue": 2}[kind], C.byref(value)))
+            self._probes[kind] = value.value
+        return self._probes[kind]
+
+    def timed(self, step, steps, warmup, clocks=False):
+        """W untimed steps, then K steps timed with CUDA events on the launch stream (L2 flushed between steps, outside the
+        events), barrier + synchronise on both sides, max over ranks.  -> (ms of all K steps, clock record, kernel launches)"""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        self.lib.pce_launch_count(1)
+        sampler = ClockSampler(self.local_rank) if clocks and self.rank == 0 else None
+        if sampler:
+            sampler.start()
+        events = []
+        for _ in range(steps):
+            self.flush.fill_(1)
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            start.record(self.stream)
+            step()
+            stop.record(self.stream)
+            events.append((start, stop))
+        self.barrier()
+        clock_info = sampler.stop() if sampler else None
+        launches = int(self.lib.pce_launch_count(0))
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in events)), clock_info, launches
+
+    def timed_wall(self, step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.torch.cuda.synchronize()
+        return self.max_over_ranks(time.perf_counter() - t0)
+
+
+def model_h2d_bytes(record, nph):
+    return record.ninstances * ((record.ninstances + 3) // 4 * 4) * 8 + record.ninstances * 20 + record.nsites * 8 + nph * 8
+
+
+def mc_workload(ctx, name, steps, warmup, chains=0, nprod=0, nequil=-1, waves=2, kernel=0, e2e=True, cpu=True, headline=False):
+    """Monte Carlo titration curve (41 pH values) of one model -> dict of the bench-line keys of this workload."""
+    import ctypes as C
+    P, lib, native, torch = ctx.P, ctx.lib, ctx.native, ctx.torch
+    record = load_record(name)
+    model = P.MEADModel(record, log=None, device=ctx.local_rank)
+    em = model.energyModel
+    em.SetStream(ctx.stream.cuda_stream)
+    default_chains, default_nprod, default_nequil = MC_DEFAULTS[name]
+    chains = chains or default_chains
+    nprod = nprod or default_nprod
+    nequil = nequil if nequil >= 0 else default_nequil
+    grid = ph_grid()
+    nph = len(grid)
+    sampler = P.MCModelDefault(nequil=nequil, nprod=nprod, randomSeed=20241019, nchains=max(chains, 1), kernel=kernel)
+    model.DefineMCModel(sampler, log=None)
+    if not chains:
+        sampler.nchains = 1 << 20          # the launch geometry of a saturating ensemble (the planner sizes blocks by the ensemble)
+        plan = sampler.LaunchPlan(nph)
+        chains = max(1, (waves * plan["chains_per_wave"]) // nph)
+        sampler.nchains = chains
+    plan = sampler.LaunchPlan(nph)
+    sampler.chainOffset = ctx.rank * chains
+    sampler._configure()
+    npairs = sampler.npairs
+    nmoves = record.nsites + npairs
+    d_counts = torch.zeros((nph, record.ninstances), dtype=torch.int64, device=ctx.device)
+    d_counters = torch.zeros((nph, 4), dtype=torch.int64, device=ctx.device)
+    d_esum = torch.zeros(nph, dtype=torch.float64, device=ctx.device)
+    em.Upload()
+
+    def step_device():
+        native.check(lib.pce_mc_run_device(sampler._handle, grid, nph, 0, ctx.rank * chains, C.c_void_p(d_counts.data_ptr()),
+                                           C.c_void_p(d_counters.data_ptr()), C.c_void_p(d_esum.data_ptr())))
+        if ctx.world > 1:
+            ctx.dist.all_reduce(d_counts)            # the path's only exchange: per-(pH, instance) occupancy counts
+
+    def step_e2e():
+        em.Load(gintr=record.gintr, gmodel=record.gmodel, protons=record.protons, interactions=record.interactions)
+        em.SymmetrizeInteractions(log=None)
+        if ctx.world > 1:
+            from pcetk_b200.distributed import mc_probabilities
+            return mc_probabilities(sampler, grid, total_chains=chains * ctx.world, rank=ctx.rank, world=ctx.world, device=ctx.device, phIndexOffset=0)[0]
+        return model.CalculateProbabilitiesBatch(grid)
+
+    units_per_step = float(nph) * chains * (nequil + nprod) * nmoves * ctx.world
+    elapsed_ms, clock_info, launches = ctx.timed(step_device, steps, warmup, clocks=headline)
+    value = units_per_step * steps / (elapsed_ms * 1e-3)
+    out = {
+        "metric": "mc_trial_moves_per_s", "value": value, "unit": "moves/s", "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / max(steps, 1),
+        "scaling": "weak", "dtype": "f64",
+        "data": "reference fixture model, synthetic chains" if name in ("lysozyme", "ifp20", "defensin") else "synthetic",
+        "config": {"workload": "%s (%d sites / %d instances / %d pairs) MC titration curve pH 0..20 step 0.5 (41 pts), nequil %d, nprod %d, %d chains per pH per GPU" % (
+                       record.name, record.nsites, record.ninstances, npairs, nequil, nprod, chains),
+                   "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": "chains sharded over %d GPU(s), one all-reduce of counts" % ctx.world, "launch": plan},
+        "gpu_launches": launches,
+    }
+    if name == "synthM":
+        out["config"]["shape"] = ("slice of BASELINE configs[4] (65536 chains x 41 pH, nequil 500): %d chains per pH value per GPU, the same per-chain work "
+                                  "(500 + %d scans); the full shape on 8 GPUs is recorded in profiles/r02_synthM_full_shape.json" % (chains, nprod))
+    if clock_info is not None:
+        out["clocks"] = clock_info
+    c = d_counters.sum(dim=0).cpu().numpy().astype(float)       # production trials of this rank: moves, accepted, double moves, accepted
+    out["config"]["acceptance"] = {"single": c[1] / max(c[0], 1.0), "double": c[3] / max(c[2], 1.0), "overall": (c[1] + c[3]) / max(c[0] + c[2], 1.0)}
+    if e2e:
+        e2e_s = ctx.timed_wall(step_e2e, steps, min(warmup, 2))
+        out["e2e"] = {"value": units_per_step * steps / e2e_s, "unit": "moves/s", "h2d_bytes_per_step": int(model_h2d_bytes(record, nph)),
+                      "d2h_bytes_per_step": int(nph * (record.ninstances * 8 + 4 * 8 + 8))}
+    if ctx.rank == 0:
+        out["roofline"] = mc_roofline(ctx, record, plan, name, value / ctx.world, out["ms_per_step"], c, chains, nequil, nprod, npairs)
+    if ctx.rank == 0 and ctx.world == 1 and e2e and headline and name in ("lysozyme", "ifp20", "defensin"):
+        # BASELINE's third metric: wall time of ONE titration curve through the public API (TitrationCurves), host
+        # arrays in, curves out.  (a) the reference's statistical effort per pH value (20000 production scans) split
+        # over 64 chains; (b) the package defaults (64 chains x 20000 scans = 64x the reference's samples).
+        curve = {}
+        for label, nch, npr in (("reference_effort", 64, 313), ("defaults", 64, 20000 if name != "ifp20" else 2000)):
+            cm = P.MEADModel(record, log=None, device=ctx.local_rank)
+            cm.DefineMCModel(P.MCModelDefault(nequil=500, nprod=npr, randomSeed=7, nchains=nch), log=None)
+            P.TitrationCurves(cm, log=None, curveSampling=0.5, curveStart=0.0, curveStop=20.0).CalculateCurves(log=None)     # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tc = P.TitrationCurves(cm, log=None, curveSampling=0.5, curveStart=0.0, curveStop=20.0)
+            tc.CalculateCurves(log=None)
+            tc.CalculateHalfpKs()
+            curve[label] = {"wall_ms": 1000.0 * (time.perf_counter() - t0), "chains": nch, "nequil": 500, "nprod_per_chain": npr, "ph_points": tc.nsteps,
+                            "launch": cm.sampler.LaunchPlan(tc.nsteps) if hasattr(cm, "sampler") and cm.sampler is not None else None}
+        out["titration_curve"] = curve
+    if ctx.rank == 0 and ctx.world == 1 and cpu:
+        if name == "synthM":
+            # 20 + 100 scans of one chain at pH 7: ~8e5 trial moves, 5-10 s on one host core
+            rate, seconds, kind = cpu_baseline(record, 20, 100, grid[14:15], 1)
+            sample = "one single-chain run at pH 7 (20 + 100 scans of %d trial moves, MT19937), %.1f s on one host core" % (nmoves, seconds)
+        elif name == "ifp20":
+            rate, seconds, kind = cpu_baseline(record, 500, 20000, grid[10:20], 1)
+            sample = "one single-chain run over 10 pH values (pH 5..9.5, 500+20000 scans, MT19937), %.1f s on one host core" % seconds
+        else:
+            ncurves = 6 if headline else 2
+            rate, seconds, kind = cpu_baseline(record, 500, 20000, grid, 1, repeats=ncurves)
+            sample = "%d single-chain %s curve(s) (41 pH, 500+20000 scans, MT19937), %.1f s on one host core" % (ncurves, record.name, seconds)
+            if "titration_curve" in out:
+                out["titration_curve"]["reference_one_core_wall_ms"] = 1000.0 * seconds / ncurves
+        out["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind, "sample": sample}
+    return out
+
+
+def mc_roofline(ctx, record, plan, name, value_per_gpu, ms_per_step, counters, chains, nequil, nprod, npairs):
+    """The binding on-chip resource of the Monte Carlo kernel that ran, with a denominator measured in this run."""
+    nmoves = record.nsites + npairs
+    reference_bytes = (record.nsites * 20.0 * record.nsites + npairs * 36.0 * record.nsites) / nmoves       # SURVEY.md 8d
+    common = {"kernel": "k_mc_thread" if plan["kernel"] == 1 else "k_mc_warp", "kernel_ms_per_launch": ms_per_step,
+              "hbm": "not the limiter: the working set is on chip (shared memory / L2); DRAM traffic per launch in profiles/",
+              "reference_algorithm_bytes_per_unit": reference_bytes, "reference_algorithm_effective_gbs": reference_bytes * value_per_gpu / 1e9}
+    if name == "synthM":
+        # chain-per-warp kernel on the 1000-site model: difference rows stream from L2.  Algorithmic L2 bytes of one launch = one
+        # difference row per changed site of every accepted move + one cross-term double per double-move proposal + the rows read
+        # by the field initialisation; accepted moves are counted in production scans and scaled to all scans.
+        nph = len(ph_grid())
+        scale = float(nequil + nprod) / float(nprod)
+        row_bytes = (record.ninstances - record.nsites) * 8.0
+        l2_bytes = scale * ((counters[1] + 2.0 * counters[3]) * row_bytes + counters[2] * 8.0) + float(nph) * chains * record.nsites * row_bytes
+        peak = ctx.probe("l2")
+        achieved = l2_bytes / (ms_per_step * 1e-3) / 1e9
+        return dict(common, bound="l2", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / max(peak, 1e-9), traffic=l2_bytes,
+                    peak_source="streaming 128-bit reads of an L2-resident 48 MiB buffer, measured in this run (pce_probe_read_bandwidth)",
+                    note="achieved = algorithmic L2 bytes from the kernel's own move counters / launch time; the kernel's limiter next to L2 is "
+                         "the L1TEX wavefront rate (profiles/README.md)")
+    digest = ctx.digests.get("k_mc_thread" if plan["kernel"] == 1 else "k_mc_warp_%s" % name, None)
+    if digest is None or not digest.get("warp_instructions_per_trial"):
+        return dict(common, bound="issue", achieved=None, peak=ctx.probe("issue"), unit="1e9 warp-instructions/s", frac=None, traffic=None,
+                    note="no ncu digest of this kernel build under profiles/ (r02_summary.json): instructions per trial unknown")
+    per_trial = float(digest["warp_instructions_per_trial"])
+    peak = ctx.probe("issue")
+    achieved = value_per_gpu * per_trial / 1e9
+    return dict(common, bound="issue", achieved=achieved, peak=peak, unit="1e9 warp-instructions/s", frac=achieved / max(peak, 1e-9),
+                traffic=digest.get("dram_bytes_per_launch"), warp_instructions_per_unit=per_trial, digest=digest.get("source"),
+                peak_source="independent FP32 FMAs on every SM (128 lanes: one warp-instruction per scheduler and clock), measured in this run (pce_probe_on_chip kind 2); nominal 148 SMs x 4 per clock",
+                note="achieved = trial moves/s of this run x warp-instructions per trial of the committed ncu digest of the same kernel")
+
+
+def analytic_workload(ctx, name, steps, warmup, e2e=True, cpu=True):
+    """Exhaustive enumeration over the 41-point pH grid: states/s, chunk range sharded over ranks (strong scaling)."""
+    import ctypes as C
+    P, lib, native, torch = ctx.P, ctx.lib, ctx.native, ctx.torch
+    record = load_record(name)
+    model = P.MEADModel(record, log=None, device=ctx.local_rank)
+    em = model.energyModel
+    em.SetStream(ctx.stream.cuda_stream)
+    em.analyticStatesLimit = 2 ** 44
+    grid = ph_grid()
+    nbins = int(lib.pce_analytic_bins_size(em._handle))
+    max_protons = nbins // (1 + record.ninstances) - 1
+    groups = em._phGroups(grid, max_protons)
+    bins = [torch.zeros(nbins, dtype=torch.float64, device=ctx.device) for _ in groups]
+    em.Upload()
+
+    def step_device():
+        for group, buf in zip(groups, bins):
+            sub = np.ascontiguousarray(grid[group])
+            native.check(lib.pce_analytic_bins(em._handle, sub, len(sub), 0, ctx.rank, ctx.world, float(em.analyticStatesLimit), C.c_void_p(buf.data_ptr())))
+            if ctx.world > 1:
+                ctx.dist.all_reduce(buf)
+
+    def step_e2e():
+        em.Load(gintr=record.gintr, gmodel=record.gmodel, protons=record.protons, interactions=record.interactions)
+        em.SymmetrizeInteractions(log=None)
+        if ctx.world > 1:
+            from pcetk_b200.distributed import analytic_probabilities
+            return analytic_probabilities(model, grid, rank=ctx.rank, world=ctx.world, device=ctx.device)
+        return model.CalculateProbabilitiesBatch(grid)
+
+    nstates = float(record.nstates)
+    elapsed_ms, _clock, launches = ctx.timed(step_device, steps, warmup)
+    value = nstates * steps / (elapsed_ms * 1e-3)
+    out = {
+        "metric": "analytic_microstates_per_s", "value": value, "unit": "states/s", "steps": steps, "warmup": warmup, "ms_per_step": elapsed_ms / max(steps, 1),
+        "scaling": "strong", "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic %d sites x 2 instances, 2^%d microstates, analytic probabilities of all instances on pH 0..20 step 0.5 (41 pts) per step" % (
+                       record.nsites, record.nsites),
+                   "l2": "flushed between timed steps (256 MiB write)", "enumeration_passes_per_curve": len(groups),
+                   "parallelism": "chunk range sharded over %d GPU(s), one all-reduce of the proton-count bins" % ctx.world},
+        "gpu_launches": launches,
+    }
+    if e2e:
+        e2e_s = ctx.timed_wall(step_e2e, steps, min(warmup, 2))
+        out["e2e"] = {"value": nstates * steps / e2e_s, "unit": "states/s", "h2d_bytes_per_step": int(model_h2d_bytes(record, len(grid))),
+                      "d2h_bytes_per_step": int(nbins * 8 * len(groups))}
+    if ctx.rank == 0:
+        # one DFMA per state and role rotation (two rotations cover all sites): algorithmic flops = 4 per state
+        peak = 2.0 * ctx.probe("dfma") / 1e3                     # TFLOP/s
+        achieved = 4.0 * value / ctx.world / 1e12
+        digest = ctx.digests.get("k_enum", {})
+        out["roofline"] = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / max(peak, 1e-9),
+                           "traffic": digest.get("dram_bytes_per_launch"), "kernel": "k_enum", "kernel_ms_per_launch": out["ms_per_step"] / (2.0 * len(groups)),
+                           "peak_source": "8 independent DFMA chains per thread on every SM, measured in this run (pce_probe_on_chip kind 0)",
+                           "shared_memory_peak_gbs": ctx.probe("shared"),
+                           "note": "algorithmic flops = 2 role rotations x 1 DFMA per state; the kernel's own limiter is the shared-memory broadcast of "
+                                   "the tile table (profiles/README.md); HBM traffic ~0 by construction",
+                           "reference_algorithm_bytes_per_unit": record.nsites * (record.nsites - 1) / 2 * 8.0}
+    if ctx.rank == 0 and ctx.world == 1 and cpu:
+        # the reference cannot run this workload at all (2^26 cap, an nstates-sized array); its per-state cost is nsites (nsites - 1) / 2
+        # gathers + one exp per pH value, so the 24-site rate is an UPPER bound of what it would do on 32 sites (276 against 496 gathers)
+        rate, seconds, kind, _n = cpu_baseline_analytic(24, 7.0)
+        out["cpu_baseline"] = {"value": rate, "unit": "states/s", "cores": 1, "kind": kind,
+                               "sample": "24-site variant of the same generator, 2^24 states at ONE pH value, %.1f s on one host core; the "
+                                         "reference caps exhaustive enumeration at 2^26 states and needs one pass per pH value "
+                                         "(x 41 for this curve), so this curve extrapolates to >= %.0f core-hours" % (seconds, nstates * 41 / rate / 3600.0)}
+    return out
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=5)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    parser.add_argument("--workload", default="lysozyme", choices=["lysozyme", "ifp20", "defensin", "synthM", "synthA"])
+    parser.add_argument("--workload", default="", choices=["", "lysozyme", "ifp20", "defensin", "synthM", "synthA", "synthA36"],
+                        help="make this workload the headline and skip the side workloads (default: lysozyme + all side workloads)")
     parser.add_argument("--chains", type=int, default=0, help="chains per pH value per GPU (default depends on the workload)")
-    parser.add_argument("--nprod", type=int, default=0, help="production scans per chain (default: reference's 20000; ifp20 2000; synthM 400)")
+    parser.add_argument("--nprod", type=int, default=0, help="production scans per chain (default: reference's 20000; ifp20 2000; synthM 100)")
     parser.add_argument("--nequil", type=int, default=-1)
     parser.add_argument("--waves", type=int, default=2, help="when --chains is not given: chains = waves x (chains resident on the GPU) / 41")
     parser.add_argument("--kernel", type=int, default=0, help="MC kernel: 0 auto, 1 chain-per-thread, 2 chain-per-warp")
@@ -208,277 +528,49 @@ def main():
     parser.add_argument("--cpu-nprod", type=int, default=20000)
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-e2e", action="store_true")
+    parser.add_argument("--no-side-workloads", action="store_true")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 0)
 
     if args.impl == "reference":
+        if not args.workload:
+            args.workload = "lysozyme"
         run_reference_arm(args)
         return
 
-    import torch
-    import torch.distributed as dist
-
-    import pcetk_b200 as P
-    from pcetk_b200 import _native
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-
-    record = load_record(args.workload)
-    model = P.MEADModel(record, log=None, device=local_rank)
-    em = model.energyModel
-    stream = torch.cuda.current_stream()
-    em.SetStream(stream.cuda_stream)
-    lib = _native.library()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)      # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    result = {}
-    if args.workload == "synthA":
-        # analytic enumeration: states/s over the 41-point grid, chunk range sharded over ranks
-        import ctypes as C
-        em.analyticStatesLimit = 2 ** 40
-        grid_all = ph_grid()
-        max_protons = int(lib.pce_analytic_bins_size(em._handle) // (1 + record.ninstances)) - 1
-        groups = em._phGroups(grid_all, max_protons)
-        nbins = lib.pce_analytic_bins_size(em._handle)
-        bins = [torch.zeros(nbins, dtype=torch.float64, device=device) for _ in groups]
-        em.Upload()
-
-        def step_device():
-            for group, buf in zip(groups, bins):
-                sub = np.ascontiguousarray(grid_all[group])
-                _native.check(lib.pce_analytic_bins(em._handle, sub, len(sub), 0, rank, world, 0.0, C.c_void_p(buf.data_ptr())))
-                if world > 1:
-                    dist.all_reduce(buf)
-
-        def step_e2e():
-            em.Load(gintr=record.gintr, gmodel=record.gmodel, protons=record.protons, interactions=record.interactions)
-            em.SymmetrizeInteractions(log=None)
-            return model.CalculateProbabilitiesBatch(grid_all)
-
-        units_per_step = float(record.nstates)          # microstates enumerated per curve (all 41 pH values served)
-        metric, unit = "analytic_microstates_per_s", "states/s"
-        launch_info = {"passes": len(groups)}
-        workload = "synthetic 32 sites x 2 instances, 2^32 microstates, analytic probabilities on pH 0..20 step 0.5 (41 pts) per step"
-        h2d = record.ninstances * ((record.ninstances + 3) // 4 * 4) * 8 + record.ninstances * 20 + record.nsites * 8
-        d2h = int(nbins) * 8 * len(groups)
-        algo_bytes_per_unit = 0.0
+    ctx = Context()
+    headline = args.workload or "lysozyme"
+    e2e, cpu = not args.no_e2e, not args.no_cpu_baseline
+    if headline.startswith("synthA"):
+        result = analytic_workload(ctx, headline, args.steps, args.warmup, e2e=e2e, cpu=cpu)
     else:
-        defaults = {"lysozyme": (1024, 20000, 500), "defensin": (1024, 20000, 500), "ifp20": (256, 2000, 500), "synthM": (50, 400, 100)}
-        chains, nprod, nequil = defaults[args.workload]
-        chains = args.chains or chains
-        nprod = args.nprod or nprod
-        nequil = args.nequil if args.nequil >= 0 else nequil
-        grid_all = ph_grid()
-        sampler = P.MCModelDefault(nequil=nequil, nprod=nprod, randomSeed=20241019, nchains=chains, kernel=args.kernel)
-        model.DefineMCModel(sampler, log=None)
-        if not args.chains:
-            # size the ensemble to whole waves of the launch geometry (chain-major linear grid)
-            sampler.nchains = 1 << 20          # the launch geometry of a saturating ensemble (the planner sizes blocks by the ensemble)
-            plan = sampler.LaunchPlan(len(grid_all))
-            chains = max(1, (args.waves * plan["chains_per_wave"]) // len(grid_all))
-            sampler.nchains = chains
-        plan = sampler.LaunchPlan(len(grid_all))
-        sampler.chainOffset = rank * chains
-        npairs = sampler.npairs
-        nmoves = record.nsites + npairs
-        sampler._configure()
-        d_counts = torch.zeros((len(grid_all), record.ninstances), dtype=torch.int64, device=device)
-        d_counters = torch.zeros((len(grid_all), 4), dtype=torch.int64, device=device)
-        d_esum = torch.zeros(len(grid_all), dtype=torch.float64, device=device)
-        em.Upload()
-        import ctypes as C
-
-        def step_device():
-            _native.check(lib.pce_mc_run_device(sampler._handle, grid_all, len(grid_all), 0, rank * chains, C.c_void_p(d_counts.data_ptr()),
-                                                C.c_void_p(d_counters.data_ptr()), C.c_void_p(d_esum.data_ptr())))
-            if world > 1:
-                dist.all_reduce(d_counts)            # the path's only exchange: per-(pH, instance) occupancy counts
-
-        def step_e2e():
-            em.Load(gintr=record.gintr, gmodel=record.gmodel, protons=record.protons, interactions=record.interactions)
-            em.SymmetrizeInteractions(log=None)
-            p = model.CalculateProbabilitiesBatch(grid_all)
-            if world > 1:
-                t = torch.from_numpy(p).to(device)
-                dist.all_reduce(t)
-                p = (t / world).cpu().numpy()
-            return p
-
-        units_per_step = float(len(grid_all)) * chains * (nequil + nprod) * nmoves
-        metric, unit = "mc_trial_moves_per_s", "moves/s"
-        launch_info = plan
-        workload = "%s (%d sites / %d instances / %d pairs) MC titration curve pH 0..20 step 0.5 (41 pts), nequil %d, nprod %d, %d chains per pH per GPU" % (
-            record.name, record.nsites, record.ninstances, npairs, nequil, nprod, chains)
-        h2d = record.ninstances * ((record.ninstances + 3) // 4 * 4) * 8 + record.ninstances * 20 + record.nsites * 8 + len(grid_all) * 8
-        d2h = len(grid_all) * (record.ninstances * 8 + 4 * 8 + 8)
-        # reference algorithm: nsites single moves cost 20*nsites bytes, npairs double moves 36*nsites
-        algo_bytes_per_unit = (record.nsites * 20.0 * record.nsites + npairs * 36.0 * record.nsites) / nmoves
-
-    # ---- value: device-resident ----------------------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    lib.pce_launch_count(1)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    events = []
-    for _ in range(args.steps):
-        flush.fill_(1)                                # L2 flush between timed steps (outside the timed events)
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record(stream)
-        step_device()
-        stop.record(stream)
-        events.append((start, stop))
-    barrier()
-    clock_info = clocks.stop() if rank == 0 else None
-    launches = int(lib.pce_launch_count(0))
-    elapsed_ms = sum(a.elapsed_time(b) for a, b in events)
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    total_units = units_per_step * args.steps * (world if args.workload != "synthA" else 1)
-    value = total_units / (elapsed_ms * 1e-3)
-
-    # ---- e2e: public API from host buffers -----------------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(min(args.warmup, 2)):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_units / float(t.item()), "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
-
-    if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as handle:
-                peaks = json.load(handle)
-        except (OSError, ValueError):
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        kernel_ms = elapsed_ms / max(args.steps, 1)
-        # bytes this algorithm actually moves at HBM per launch: the model staged once per CTA wave (L2 serves the
-        # repeats) plus the outputs; the working set lives in shared memory (fixtures) or L2 (synthM)
-        actual_bytes = float(h2d + d2h)
-        on_chip = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_summary.json")) as handle:
-                summary = json.load(handle)
-            key = "k_enum" if args.workload == "synthA" else ("k_mc_warp" if launch_info.get("kernel") == 2 else "k_mc_thread")
-            entry = key + "_ifp20" if key == "k_mc_warp" and args.workload != "synthM" else key
-            on_chip = dict(summary[entry], kernel=key)
-        except (OSError, ValueError, KeyError):
-            pass
-        roofline = {
-            "bound": "hbm", "achieved": actual_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": actual_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "traffic": (on_chip or {}).get("dram_bytes_per_launch"),
-            "on_chip": on_chip,
-            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-            "note": "HBM is not the limiter of this path (working set in shared memory / L2): `achieved` counts the bytes this algorithm "
-                    "actually moves at HBM per launch, so `frac` is ~0 by design; the real limiter and its ncu-measured utilisation are in "
-                    "`on_chip`.  reference_algorithm_effective_gbs = the reference algorithm's gather traffic (SURVEY.md 8d) replaced by this run.",
-            # the binding on-chip resource and its measured utilisation (ncu, profiles/): issue slots for the chain-per-thread
-            # and enumeration kernels, the L1TEX/LSU wavefront pipe for the chain-per-warp kernel on large models
-            "limiter": (on_chip or {}).get("limiter"),
-            "limiter_frac": (on_chip or {}).get("l1tex_throughput_frac" if launch_info.get("kernel") == 2 and args.workload == "synthM" else "issue_active_frac"),
-            "reference_algorithm_bytes_per_unit": algo_bytes_per_unit,
-            "reference_algorithm_effective_gbs": algo_bytes_per_unit * value / world / 1e9,
-            "kernel_ms_per_launch": kernel_ms,
-        }
-        if args.workload != "synthA" and launch_info.get("kernel") == 2 and on_chip is not None:
-            # chain-per-warp kernel: the difference rows are served by L2.  Algorithmic L2 bytes of one launch = one
-            # difference row per changed site of every accepted move + the four W entries of every double-move proposal
-            # + the rows read by the field initialisation; accepted moves are counted in production scans only and
-            # scaled to all scans.  The denominator is measured here with a streaming read of an L2-resident buffer.
-            c = d_counters.sum(dim=0).cpu().numpy().astype(float)
-            scale = float(nequil + nprod) / float(nprod)
-            row_bytes = (record.ninstances - record.nsites) * 8.0          # fields relative to the first instance of each site
-            l2_bytes = scale * ((c[1] + 2.0 * c[3]) * row_bytes + c[2] * 32.0) + float(len(grid_all)) * chains * record.nsites * row_bytes
-            peak = C.c_double(0.0)
-            _native.check(lib.pce_probe_read_bandwidth(local_rank, 48 * 1024 * 1024, 40, C.byref(peak)))
-            on_chip["l2_algorithmic_bytes_per_launch"] = l2_bytes
-            on_chip["l2_algorithmic_gbs"] = l2_bytes / (kernel_ms * 1e-3) / 1e9
-            on_chip["l2_read_peak_gbs_measured"] = peak.value
-            on_chip["l2_frac"] = on_chip["l2_algorithmic_gbs"] / max(peak.value, 1e-9)
-        line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak" if args.workload != "synthA" else "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "reference fixture model, synthetic chains" if args.workload in ("lysozyme", "ifp20", "defensin") else "synthetic",
-            "config": {"workload": workload, "l2": "flushed between timed steps (256 MiB write)", "parallelism": "chains sharded over %d GPU(s), one all-reduce of counts" % world,
-                       "launch": launch_info},
-            "clocks": clock_info, "gpu_launches": launches, "roofline": roofline,
-        }
-        if e2e is not None:
-            line["e2e"] = e2e
-        if args.workload != "synthA":
-            c = d_counters.sum(dim=0).cpu().numpy().astype(float)       # production trials: moves, accepted, flips, accepted
-            line["config"]["acceptance"] = {"single": c[1] / max(c[0], 1.0), "double": c[3] / max(c[2], 1.0),
-                                            "overall": (c[1] + c[3]) / max(c[0] + c[2], 1.0)}
-        if world == 1 and not args.no_e2e and args.workload in ("lysozyme", "ifp20", "defensin"):
-            # BASELINE's third metric: wall time of ONE titration curve through the public API (TitrationCurves), host
-            # arrays in, curves out.  (a) the reference's statistical effort per pH value (20000 production scans) split
-            # over 64 chains; (b) the package defaults (64 chains x 20000 scans = 64x the reference's samples).
-            curve = {}
-            for label, nch, npr in (("reference_effort", 64, 313), ("defaults", 64, 20000 if args.workload != "ifp20" else 2000)):
-                cm = P.MEADModel(record, log=None, device=local_rank)
-                cm.DefineMCModel(P.MCModelDefault(nequil=500, nprod=npr, randomSeed=7, nchains=nch), log=None)
-                P.TitrationCurves(cm, log=None, curveSampling=0.5, curveStart=0.0, curveStop=20.0).CalculateCurves(log=None)     # warm-up
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                tc = P.TitrationCurves(cm, log=None, curveSampling=0.5, curveStart=0.0, curveStop=20.0)
-                tc.CalculateCurves(log=None)
-                tc.CalculateHalfpKs()
-                curve[label] = {"wall_ms": 1000.0 * (time.perf_counter() - t0), "chains": nch, "nequil": 500, "nprod_per_chain": npr, "ph_points": tc.nsteps}
-            line["titration_curve"] = curve
-        if world == 1 and not args.no_cpu_baseline and args.workload == "synthA":
-            # the reference cannot run this workload at all; its per-state cost is nsites (nsites - 1) / 2 gathers + one exp per
-            # pH value, so the 24-site rate is an UPPER bound of what it would do on 32 sites (276 against 496 gathers)
-            rate, seconds, kind, nstates = cpu_baseline_analytic(24, 7.0)
-            line["cpu_baseline"] = {"value": rate, "unit": "states/s", "cores": 1, "kind": kind,
-                                    "sample": "24-site variant of the same generator, 2^24 states at ONE pH value, %.1f s on one host core; the "
-                                              "reference caps exhaustive enumeration at 2^26 states and needs one pass per pH value "
-                                              "(x 41 for this curve), so 2^32 x 41 pH extrapolates to >= %.0f core-hours" % (
-                                                  seconds, 2.0 ** 32 * 41 / rate / 3600.0)}
-        if world == 1 and not args.no_cpu_baseline and args.workload == "synthM":
-            # 20 + 100 scans of one chain at pH 7: ~8e5 trial moves, 5-10 s on one host core
-            rate, seconds, kind = cpu_baseline(record, 20, 100, grid_all[14:15], 1)
-            line["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind,
-                                    "sample": "one single-chain run at pH 7 (20 + 100 scans of %d trial moves, MT19937), %.1f s on one host core" % (
-                                        nmoves, seconds)}
-        if world == 1 and not args.no_cpu_baseline and args.workload in ("lysozyme", "ifp20", "defensin"):
-            ncurves = 6 if args.workload != "ifp20" else 1            # 10-20 s of one host core
-            rate, seconds, kind = cpu_baseline(record, 500, 20000, grid_all, 1, repeats=ncurves)
-            line["cpu_baseline"] = {"value": rate, "unit": "moves/s", "cores": 1, "kind": kind,
-                                    "sample": "%d single-chain %s curve(s) (41 pH, 500+20000 scans, MT19937), %.1f s on one host core" % (
-                                        ncurves, record.name, seconds)}
-            if "titration_curve" in line:
-                line["titration_curve"]["reference_one_core_wall_ms"] = 1000.0 * seconds / ncurves
+        result = mc_workload(ctx, headline, args.steps, args.warmup, chains=args.chains, nprod=args.nprod, nequil=args.nequil, waves=args.waves,
+                             kernel=args.kernel, e2e=e2e, cpu=cpu, headline=True)
+    side = {}
+    if not args.workload and not args.no_side_workloads:
+        # the other BASELINE configs, short runs (W = 3 warm-up steps as the timing rules ask)
+        side["synthA"] = analytic_workload(ctx, "synthA", 10, 3, e2e=e2e, cpu=cpu)
+        side["synthM"] = mc_workload(ctx, "synthM", 2, 3, e2e=e2e, cpu=cpu)
+        side["ifp20"] = mc_workload(ctx, "ifp20", 3, 3, e2e=e2e, cpu=cpu)
+        side["defensin"] = mc_workload(ctx, "defensin", 2, 3, e2e=e2e, cpu=cpu)
+    if ctx.rank == 0:
+        line = {"metric": result["metric"], "value": result["value"], "unit": result["unit"], "n_gpus": ctx.world, "steps": result["steps"],
+                "warmup": result["warmup"], "ms_per_step": result["ms_per_step"], "higher_is_better": True, "scaling": result["scaling"],
+                "vs_baseline": None, "dtype": result["dtype"], "data": result["data"], "config": result["config"],
+                "clocks": result.get("clocks"), "gpu_launches": result["gpu_launches"] + sum(w["gpu_launches"] for w in side.values()),
+                "roofline": result.get("roofline")}
+        for key in ("e2e", "titration_curve", "cpu_baseline"):
+            if key in result:
+                line[key] = result[key]
+        if side:
+            for w in side.values():
+                w["n_gpus"] = ctx.world
+                w["higher_is_better"] = True
+            line["workloads"] = side
+        line["measured_peaks"] = dict(ctx._probes, hbm_gbs=ctx.peaks.get("hbm_gbs"), source="probes of this run; hbm_gbs from MEASURED_PEAKS.json")
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -53,6 +53,9 @@ long long pce_launch_count (int reset);
 /* measurement hook (no reference counterpart): streaming read bandwidth in GB/s of a zero-filled buffer of `bytes`
  * read `passes` times with 128-bit loads -- L2 bandwidth for buffers well below the L2 size, HBM for large ones */
 int pce_probe_read_bandwidth (int device, long long bytes, int passes, double *gb_per_s);
+/* on-chip peaks measured on this device (denominators of bench.py's rooflines): kind 0 = DFMA rate in 1e9 DFMA/s,
+ * kind 1 = conflict-free shared-memory read bandwidth in GB/s, kind 2 = issue rate in 1e9 warp-instructions/s */
+int pce_probe_on_chip (int device, int kind, double *rate);
 
 /* ---- model: allocation (EnergyModel_Allocate / _Deallocate, EnergyModel.h:64-65) ---------------- */
 int  pce_model_create (int nsites, int ninstances, double temperature, int device, pce_model **out);

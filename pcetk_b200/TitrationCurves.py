@@ -23,18 +23,15 @@ class TitrationCurves(object):
     defaultAttributes = {"curveSampling": _DefaultSampling, "curveStart": _DefaultStart, "curveStop": _DefaultStop, "unfolded": False}
 
     def __init__(self, meadModel, log=logFile, *arguments, **keywordArguments):
-        for (key, value) in self.__class__.defaultAttributes.items():
-            setattr(self, key, value)
-        for (key, value) in keywordArguments.items():
-            setattr(self, key, value)
+        settings = dict(self.defaultAttributes)
+        settings.update(keywordArguments)
+        vars(self).update(settings)
         if not meadModel.isCalculated:
             raise ContinuumElectrostaticsError("First calculate electrostatic energies.")
         self.owner = meadModel
-        self.nsteps = int((self.curveStop - self.curveStart) / self.curveSampling + 1)     # TitrationCurves.py:62
-        self.steps = None
-        self.halves = None
-        self.isHalves = False
-        self.isCalculated = False
+        self.nsteps = int((self.curveStop - self.curveStart) / self.curveSampling + 1)     # grid convention of TitrationCurves.py:62
+        self.steps = self.halves = None
+        self.isHalves = self.isCalculated = False
 
     def pHValues(self):
         return [self.curveStart + step * self.curveSampling for step in range(self.nsteps)]
@@ -84,39 +81,45 @@ class TitrationCurves(object):
             if LogFileActive(log):
                 log.Text("\nWriting curve files complete.\n")
 
+    def _CurveTable(self):
+        """The calculated curves as one array [nsteps, ninstances] (global instance order) and the pH grid."""
+        import numpy as np
+
+        table = np.array([[value for site in step for value in site] for step in self.steps], dtype=np.float64)
+        return table, self.curveStart + self.curveSampling * np.arange(self.nsteps)
+
     def CalculateHalfpKs(self):
-        """pK1/2 by linear interpolation wherever a curve crosses 0.5 (TitrationCurves.py:198-222)."""
-        if self.isCalculated:
-            halves = []
-            for site in self.owner.sites:
-                instances = []
-                for instance in site.instances:
-                    pa = self.steps[0][site.siteIndex][instance.instIndex]
-                    pKs = []
-                    for step in range(1, self.nsteps):
-                        pb = self.steps[step][site.siteIndex][instance.instIndex]
-                        if ((pa - .5) * (pb - .5)) < 0.:
-                            a = self.curveStart + (step - 1) * self.curveSampling
-                            b = self.curveStart + step * self.curveSampling
-                            pKs.append(a + (.5 - pa) * (b - a) / (pb - pa))
-                        pa = pb
-                    instances.append(pKs)
-                halves.append(instances)
-            self.halves = halves
-            self.isHalves = True
+        """pK1/2 of every instance: the pH values where its curve crosses 0.5, by linear interpolation between the two
+        grid points around the crossing (same definition as TitrationCurves.py:198-222; vectorised over the grid)."""
+        if not self.isCalculated:
+            return
+        import numpy as np
+
+        table, grid = self._CurveTable()
+        centred = table - 0.5
+        crossing = centred[:-1] * centred[1:] < 0.0                      # [nsteps - 1, ninstances]
+        self.halves, column = [], 0
+        for site in self.owner.sites:
+            perSite = []
+            for _instance in site.instances:
+                left = np.nonzero(crossing[:, column])[0]
+                pa, pb = table[left, column], table[left + 1, column]
+                perSite.append(list(grid[left] + (0.5 - pa) * (grid[left + 1] - grid[left]) / (pb - pa)))
+                column += 1
+            self.halves.append(perSite)
+        self.isHalves = True
 
     def _GetEntry(self, site, decimalPlaces=2):
-        entry = ""
-        if self.isHalves:
-            for instance in site.instances:
-                pKs = self.halves[site.siteIndex][instance.instIndex]
-                entry = "%s%7s" % (entry, instance.label)
-                if len(pKs) < 1:
-                    entry = "%s%7s" % (entry, "n/a")
-                else:
-                    for pK in pKs:
-                        entry = ("%%s%%7.%df" % decimalPlaces) % (entry, pK)
-        return entry
+        """One table cell: label and pK1/2 value(s) of every instance of the site, 7 characters per field."""
+        if not self.isHalves:
+            return ""
+        number = "%%7.%df" % decimalPlaces
+        fields = []
+        for instance in site.instances:
+            values = self.halves[site.siteIndex][instance.instIndex]
+            fields.append("%7s" % instance.label)
+            fields.extend([number % value for value in values] or ["%7s" % "n/a"])
+        return "".join(fields)
 
     def PrintHalfpKs(self, decimalPlaces=2, sortSites=False, log=logFile):
         if LogFileActive(log) and self.isCalculated:

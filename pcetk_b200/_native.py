@@ -38,6 +38,7 @@ SIGNATURES = {
     "pce_synchronize": (_int, [_void]),
     "pce_launch_count": (_ll, [_int]),
     "pce_probe_read_bandwidth": (_int, [_int, _ll, _int, C.POINTER(C.c_double)]),
+    "pce_probe_on_chip": (_int, [_int, _int, C.POINTER(C.c_double)]),
     "pce_model_create": (_int, [_int, _int, _dbl, _int, C.POINTER(_void)]),
     "pce_model_destroy": (None, [_void]),
     "pce_model_nsites": (_int, [_void]),

@@ -172,13 +172,13 @@ __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_mc_thread.  The (pH, chain) grid is linearised chain-major (g = q*nchains + chain) and cut into blocks
-// of blockDim.x threads, so the grid can be sized to whole waves whatever nchains is; every thread carries
-// its own pH.  Energies are in units of RT, the intrinsic term is fused into the cached fields and the fields
-// are relative to the first instance of each site, so a single-move proposal is at most two shared-memory
-// loads and one subtraction.  Trials are processed two per Philox block, with the next block generated ahead of
-// the dependent proposal -> accept -> update chain.  The model lives in shared memory as the difference rows E
-// (one per instance pair of a site) and the pair cross-term table: W itself is never read by the trial loop.
+// k_mc_thread.  The (pH, chain) grid is linearised pH-minor (g = chain * nph + q: consecutive threads take consecutive pH
+// values, so every warp and block carries the same mix of cheap and expensive pH values; chain-major when the per-block
+// occupancy counters of all pH values would not fit) and cut into blocks of blockDim.x threads; every thread carries its own
+// pH.  Energies are in units of RT, the intrinsic term is fused into the cached fields and the fields are relative to the
+// first instance of each site, so a single-move proposal is at most two shared-memory loads and one subtraction.  Trials are
+// processed two per Philox block (no prefetch: the registers were worth more).  The model lives in shared memory as the
+// difference rows E (one per instance pair of a site) and the pair cross-term table: W itself is never read by the trial loop.
 // ---------------------------------------------------------------------------------------------------
 // Register budgets: every SM sub-partition holds 16384 registers and a quarter of the block's warps, so a block of
 // 512 / 640 / 768 / 896 / 1024 threads may use 128 / 96 / 80 / 72 / 64 registers per thread (__launch_bounds__ would round
@@ -1390,6 +1390,9 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     pce_model *m = mc->model;
     if (nph <= 0) return PCE_OK;
     if ((long long) mc->nequil + mc->nprod > 4294967295LL) return fail (PCE_ERR_LIMIT, "too many scans");
+    // the kernels count production trials in 32 bits per chain
+    if ((double) mc->nprod * (double) (m->nsites + (int) mc->pair_a.size ()) >= 4294967295.0)
+        return fail (PCE_ERR_LIMIT, "too many production trials per chain (nprod x (nsites + npairs) must stay below 2^32)");
     int status = m->upload ();
     if (status != PCE_OK) return status;
     // the W matrix may have changed since the pairs were found (ScaleInteractions etc.): keep the reference's

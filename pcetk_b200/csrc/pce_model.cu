@@ -275,6 +275,10 @@ extern "C" int pce_model_state_from_probabilities (const pce_model *m, int32_t *
 // ---------------------------------------------------------------------------------------------------
 // upload
 // ---------------------------------------------------------------------------------------------------
+__global__ void k_scale (const double *__restrict__ in, size_t n, double factor, double *__restrict__ out) {
+    for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t) gridDim.x * blockDim.x) out[e] = __dmul_rn (factor, in[e]);
+}
+
 int pce_model::upload () {
     int status = sites_ok ();
     if (status != PCE_OK) return status;
@@ -296,19 +300,25 @@ int pce_model::upload () {
     PCE_CUDA (cudaMemcpyAsync (d_protons.ptr, protons.data (), ninst * sizeof (int32_t), cudaMemcpyHostToDevice, stream));
     PCE_CUDA (cudaMemcpyAsync (d_gintr.ptr, gintr.data (), ninst * sizeof (double), cudaMemcpyHostToDevice, stream));
     PCE_CUDA (cudaMemcpyAsync (d_gmodel.ptr, gmodel.data (), ninst * sizeof (double), cudaMemcpyHostToDevice, stream));
-    PCE_CUDA (cudaMemsetAsync (d_w.ptr, 0, (size_t) ninst * ldw * sizeof (double), stream));
-    PCE_CUDA (cudaMemcpy2DAsync (d_w.ptr, (size_t) ldw * sizeof (double), wsym.data (), (size_t) ninst * sizeof (double),
-                                 (size_t) ninst * sizeof (double), (size_t) ninst, cudaMemcpyHostToDevice, stream));
-    {   // W in units of RT for the Monte Carlo kernels: one rounding per element, identical to the chain specification
-        const double beta = 1.0 / (PCE_R * temperature);
-        std::vector<double> wb ((size_t) ninst * ldw, 0.0);
-        for (int a = 0; a < ninst; a++)
-            for (int b = 0; b < ninst; b++) wb[(size_t) a * ldw + b] = beta * wsym[(size_t) a * ninst + b];
+    {   // W on the device: row stride ldw, and the blocks between instances of ONE site zeroed.  The reference never reads those
+        // entries (energies sum over pairs of different sites, EnergyModel.c:204-224; Move / DoubleMove skip the moved sites,
+        // MCModelDefault.c:100-111, 140-160), while the cached fields of the Monte Carlo kernels sum over whole rows: zeroing
+        // them here makes an input file with non-zero same-site entries sample the reference's distribution.
+        std::vector<double> staged ((size_t) ninst * ldw, 0.0);
+        for (int a = 0; a < ninst; a++) std::memcpy (&staged[(size_t) a * ldw], &wsym[(size_t) a * ninst], (size_t) ninst * sizeof (double));
+        for (int i = 0; i < nsites; i++)
+            for (int a = first[i]; a <= last[i]; a++)
+                for (int b = first[i]; b <= last[i]; b++) staged[(size_t) a * ldw + b] = 0.0;
+        PCE_CUDA (cudaMemcpyAsync (d_w.ptr, staged.data (), staged.size () * sizeof (double), cudaMemcpyHostToDevice, stream));
+        // W in units of RT for the Monte Carlo kernels, on the device: one rounding per element (beta * w), identical to the
+        // chain specification
         PCE_CUDA (d_wb.resize ((size_t) ninst * ldw));
-        PCE_CUDA (cudaMemcpyAsync (d_wb.ptr, wb.data (), wb.size () * sizeof (double), cudaMemcpyHostToDevice, stream));
-        PCE_CUDA (cudaStreamSynchronize (stream));
+        const size_t total = (size_t) ninst * ldw;
+        k_scale<<<(unsigned) std::min<size_t> ((total + 255) / 256, 65535), 256, 0, stream>>> (d_w.ptr, total, 1.0 / (PCE_R * temperature), d_wb.ptr);
+        pce::count_launch ();
+        PCE_CUDA (cudaGetLastError ());
+        PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors die with this scope
     }
-    PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors above die with this scope
     dirty = false;
     generation++;
     return PCE_OK;
@@ -471,5 +481,95 @@ extern "C" int pce_probe_read_bandwidth (int device, long long bytes, int passes
     buffer.release (); sink.release ();
     if (err != cudaSuccess) return fail (PCE_ERR_CUDA, std::string ("bandwidth probe: ") + cudaGetErrorString (err));
     *gb_per_s = (double) n2 * sizeof (double2) * passes / (ms * 1e-3) / 1e9;
+    return PCE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// on-chip peaks (FP64, shared-memory and issue peaks are not in MEASURED_PEAKS.json and must be
+// micro-benchmarked).  kind 0: DFMA rate (8 independent chains per thread, registers only) -> 1e9 DFMA/s;
+// kind 1: shared-memory read bandwidth (conflict-free 128-bit loads, every lane its own 16 bytes) -> GB/s;
+// kind 2: issue rate (independent FP32 FMAs, 8 chains per thread: 128 lanes per SM = the issue limit) -> 1e9 warp-instructions/s.
+// bench.py uses them as measured denominators (enumeration: DFMA; chain-per-thread Monte Carlo: issue slots).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (256) k_probe_dfma (int iterations, double seed, double *sink) {
+    double a0 = seed, a1 = seed + 1.0, a2 = seed + 2.0, a3 = seed + 3.0, a4 = seed + 4.0, a5 = seed + 5.0, a6 = seed + 6.0, a7 = seed + 7.0;
+    const double m = 0.9999999 + 1e-9 * threadIdx.x, c = 1e-7;
+#pragma unroll 1
+    for (int i = 0; i < iterations; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma (a0, m, c); a1 = fma (a1, m, c); a2 = fma (a2, m, c); a3 = fma (a3, m, c);
+            a4 = fma (a4, m, c); a5 = fma (a5, m, c); a6 = fma (a6, m, c); a7 = fma (a7, m, c);
+        }
+    }
+    const double total = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (total == 123.456) *sink = total;
+}
+
+__global__ void __launch_bounds__ (256) k_probe_shared (int iterations, unsigned *sink) {
+    __shared__ uint4 buffer[2048];                           // 32 KB
+    for (int e = threadIdx.x; e < 2048; e += blockDim.x) buffer[e] = make_uint4 (e, 2u * e, 3u * e, 5u * e);
+    __syncthreads ();
+    unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int index = threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iterations; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u += 4) {                     // conflict-free 128-bit loads: consecutive lanes, consecutive 16 bytes
+            const uint4 v0 = buffer[(index + 256 * u) & 2047], v1 = buffer[(index + 256 * (u + 1)) & 2047];
+            const uint4 v2 = buffer[(index + 256 * (u + 2)) & 2047], v3 = buffer[(index + 256 * (u + 3)) & 2047];
+            a0 ^= v0.x ^ v0.y; a0 ^= v0.z ^ v0.w; a1 ^= v1.x ^ v1.y; a1 ^= v1.z ^ v1.w;
+            a2 ^= v2.x ^ v2.y; a2 ^= v2.z ^ v2.w; a3 ^= v3.x ^ v3.y; a3 ^= v3.z ^ v3.w;
+        }
+        index = (index + 32) & 2047;
+    }
+    const unsigned total = a0 ^ a1 ^ a2 ^ a3;
+    if (total == 123456789u) *sink = total;
+}
+
+// issue rate: FP32 FMAs (128 lanes per SM: one warp-instruction per scheduler and clock, the issue limit itself)
+__global__ void __launch_bounds__ (256) k_probe_issue (int iterations, float seed, float *sink) {
+    float a0 = seed, a1 = seed + 1.f, a2 = seed + 2.f, a3 = seed + 3.f, a4 = seed + 4.f, a5 = seed + 5.f, a6 = seed + 6.f, a7 = seed + 7.f;
+    const float m = 0.999999f + 1e-8f * threadIdx.x, c = 1e-6f;
+#pragma unroll 1
+    for (int i = 0; i < iterations; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fmaf (a0, m, c); a1 = fmaf (a1, m, c); a2 = fmaf (a2, m, c); a3 = fmaf (a3, m, c);
+            a4 = fmaf (a4, m, c); a5 = fmaf (a5, m, c); a6 = fmaf (a6, m, c); a7 = fmaf (a7, m, c);
+        }
+    }
+    const float total = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (total == 123.456f) *sink = total;
+}
+
+extern "C" int pce_probe_on_chip (int device, int kind, double *rate) {
+    if (rate == nullptr || kind < 0 || kind > 2) return fail (PCE_ERR_VALUE, "invalid probe");
+    PCE_CUDA (cudaSetDevice (device));
+    int sms = 0;
+    PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device));
+    pce::DeviceBuffer<double> sink;
+    PCE_CUDA (sink.resize (2));
+    cudaEvent_t start, stop;
+    PCE_CUDA (cudaEventCreate (&start)); PCE_CUDA (cudaEventCreate (&stop));
+    const int blocks = sms * 8, iterations = kind == 1 ? 4096 : 2048;
+    for (int pass = 0; pass < 2; pass++) {                   // pass 0 warms up
+        if (pass == 1) cudaEventRecord (start);
+        if (kind == 0) k_probe_dfma<<<blocks, 256>>> (iterations, 0.5, sink.ptr);
+        else if (kind == 1) k_probe_shared<<<blocks, 256>>> (iterations, (unsigned *) sink.ptr);
+        else k_probe_issue<<<blocks, 256>>> (iterations, 0.5f, (float *) sink.ptr);
+    }
+    cudaEventRecord (stop);
+    pce::count_launch (2);
+    cudaError_t err = cudaEventSynchronize (stop);
+    float ms = 0.0f;
+    if (err == cudaSuccess) err = cudaEventElapsedTime (&ms, start, stop);
+    cudaEventDestroy (start); cudaEventDestroy (stop);
+    sink.release ();
+    if (err != cudaSuccess) return fail (PCE_ERR_CUDA, std::string ("on-chip probe: ") + cudaGetErrorString (err));
+    const double threads = (double) blocks * 256.0, per_thread = (double) iterations * 64.0;
+    if (kind == 0) *rate = threads * per_thread / (ms * 1e-3) / 1e9;                 // 1e9 DFMA per second (x 2 = GFLOP/s)
+    else if (kind == 1) *rate = threads * (double) iterations * 8.0 * 16.0 / (ms * 1e-3) / 1e9;     // GB/s (8 x 128-bit loads per iteration)
+    else *rate = threads / 32.0 * per_thread / (ms * 1e-3) / 1e9;                    // 1e9 warp-instructions per second
     return PCE_OK;
 }

@@ -48,18 +48,41 @@ def test_analytic_million_states_vs_oracle_and_golden(port, name, picks):
         assert rel_err(p[k], ref) <= RTOL
 
 
-def test_wide_ph_grid_is_split_and_matches(port):
-    """pH 0..20 (BASELINE config 2 grid) needs two enumeration passes for a 21-site model; results must not depend on it."""
+def test_wide_ph_grid_in_one_pass(port):
+    """pH 0..20 (BASELINE config 2 grid): every proton-count bin carries its own scale, so ONE enumeration pass serves the
+    whole grid (round 1 needed two); results must not depend on what else is in the pH list."""
     rec, _ = load_fixture("defensin")
     model = P.MEADModel(rec, log=None)
     wsym = port.symmetrize(rec.interactions)
     grid = np.arange(0.0, 20.5, 0.5)
+    assert len(model.energyModel._phGroups(grid, 15)) == 1
     p = model.CalculateProbabilitiesBatch(grid)
     for k in (0, 13, 27, 40):
         ref, _z, _g = port.analytic(rec, wsym, float(grid[k]))
         assert rel_err(p[k], ref) <= RTOL
     single = model.CalculateProbabilitiesBatch([grid[27]])
     assert rel_err(single[0], p[27]) <= 1e-13
+    # a grid wider than one pass can serve is split by the host layer and still matches
+    wide = np.array([-30.0, 0.0, 7.0, 14.0, 45.0])
+    assert len(model.energyModel._phGroups(wide, 15)) > 1
+    pw = model.CalculateProbabilitiesBatch(wide)
+    ref, _z, _g = port.analytic(rec, wsym, 7.0)
+    assert rel_err(pw[2], ref) <= RTOL
+
+
+@pytest.mark.parametrize("name", ["defensin", "lysozyme"])
+def test_generic_accumulation_path_matches(port, name, monkeypatch):
+    """PCE_ENUM_GENERIC=1 forces the kernel variant for non-canonical sites (run-time proton groups, bins in shared memory) on
+    models that normally take the compile-time variant: same answers."""
+    rec, _ = load_fixture(name)
+    wsym = port.symmetrize(rec.interactions)
+    fast = P.MEADModel(rec, log=None).CalculateProbabilitiesBatch([2.0, 7.0, 12.0])
+    monkeypatch.setenv("PCE_ENUM_GENERIC", "1")
+    generic = P.MEADModel(rec, log=None).CalculateProbabilitiesBatch([2.0, 7.0, 12.0])
+    ref, _z, _g = port.analytic(rec, wsym, 7.0)
+    assert rel_err(generic[1], ref) <= RTOL
+    mask = fast > 1e-250
+    assert np.abs(generic[mask] / fast[mask] - 1.0).max() <= 1e-12
 
 
 def test_unfolded_and_partition_functions(port):
@@ -119,16 +142,17 @@ def test_shards_add_up():
     assert np.abs(p / q - 1.0).max() < 1e-12
 
 
-def test_synthetic_26_sites_vs_oracle_slice(port):
-    """2^26 states (the reference's own cap): GPU vs the C oracle at one pH (the oracle needs ~20 s and 512 MiB)."""
+def test_synthetic_26_sites_vs_compensated_oracle(port):
+    """2^26 states (the reference's own cap): GPU against the reference's algorithm with compensated (long double) sums,
+    held to north_star's 1e-12 -- the reference's naive serial double sum over 6.7e7 terms carries ~1e-12 of rounding itself."""
     rec = synth_a(26)
     model = P.MEADModel(rec, log=None)
     wsym = port.symmetrize(rec.interactions)
     grid = [4.0, 7.0, 10.0]
     p = model.CalculateProbabilitiesBatch(grid)
-    ref, _z, _g = port.analytic(rec, wsym, 7.0)
-    assert rel_err(p[1], ref) <= 5e-12       # the reference's naive serial sum over 6.7e7 terms carries ~1e-12 itself
-    assert np.abs(p.sum(axis=1) - 2 * 0 - rec.nsites).max() < 1e-9
+    ref, _z, _g = port.analytic_compensated(rec, wsym, 7.0)
+    assert rel_err(p[1], ref) <= RTOL
+    assert np.abs(p.sum(axis=1) - rec.nsites).max() < 1e-9
 
 
 def test_synthetic_32_sites_factorised():

@@ -269,3 +269,32 @@ def test_half_pks_of_the_reference_curves_match_its_comparison_table(name):
                 assert abs(mine[0] - expect) <= 0.1
                 exact += abs(mine[0] - expect) <= 0.051
     assert exact >= int(np.isfinite(golden).sum()) - 2
+
+
+def test_half_pks_and_table_entries_without_a_gpu():
+    """CalculateHalfpKs / _GetEntry on hand-made curves: crossings of 0.5 by linear interpolation, 'n/a' where none, two
+    values where a curve crosses twice (TitrationCurves.py:198-238 defines the numbers and the 7-character fields)."""
+    import types
+
+    import pcetk_b200 as P
+
+    inst = lambda label, index: types.SimpleNamespace(label=label, instIndex=index)
+    sites = [types.SimpleNamespace(siteIndex=0, instances=[inst("p", 0), inst("d", 1)]), types.SimpleNamespace(siteIndex=1, instances=[inst("x", 0)])]
+    owner = types.SimpleNamespace(isCalculated=True, sites=sites)
+    curves = P.TitrationCurves(owner, log=None, curveSampling=1.0, curveStart=0.0, curveStop=4.0)
+    assert curves.nsteps == 5
+    a = [0.9, 0.7, 0.4, 0.2, 0.1]            # crosses between pH 1 and 2: 1 + 0.2 / 0.3
+    x = [0.2, 0.6, 0.8, 0.3, 0.1]            # crosses twice: 0.75 and 2.6
+    curves.steps = [[[a[k], 1.0 - a[k]], [x[k]]] for k in range(5)]
+    curves.isCalculated = True
+    curves.CalculateHalfpKs()
+    assert curves.isHalves
+    assert curves.halves[0][0] == pytest.approx([1.0 + 0.2 / 0.3]) and curves.halves[0][1] == pytest.approx([1.0 + 0.2 / 0.3])
+    assert curves.halves[1][0] == pytest.approx([0.75, 2.6])
+    assert curves._GetEntry(sites[0]) == "      p   1.67      d   1.67"
+    assert curves._GetEntry(sites[1], decimalPlaces=1) == "      x    0.8    2.6"
+    flat = P.TitrationCurves(owner, log=None, curveSampling=1.0, curveStart=0.0, curveStop=4.0)
+    flat.steps = [[[0.9, 0.1], [0.9]] for _ in range(5)]
+    flat.isCalculated = True
+    flat.CalculateHalfpKs()
+    assert flat.halves == [[[], []], [[]]] and flat._GetEntry(sites[1]) == "      x    n/a"
