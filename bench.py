@@ -428,7 +428,7 @@ def mc_roofline(ctx, record, plan, name, value_per_gpu, ms_per_step, counters, c
                     peak_source="streaming 128-bit reads of an L2-resident 48 MiB buffer, measured in this run (pce_probe_read_bandwidth)",
                     note="achieved = algorithmic L2 bytes from the kernel's own move counters / launch time; the kernel's limiter next to L2 is "
                          "the L1TEX wavefront rate (profiles/README.md)")
-    digest = ctx.digests.get("k_mc_thread" if plan["kernel"] == 1 else "k_mc_warp_%s" % name, None)
+    digest = ctx.digests.get("%s_%s" % ("k_mc_thread" if plan["kernel"] == 1 else "k_mc_warp", name), None)
     if digest is None or not digest.get("warp_instructions_per_trial"):
         return dict(common, bound="issue", achieved=None, peak=ctx.probe("issue"), unit="1e9 warp-instructions/s", frac=None, traffic=None,
                     note="no ncu digest of this kernel build under profiles/ (r02_summary.json): instructions per trial unknown")

@@ -1,11 +1,17 @@
 /* pcetk_b200.h -- C ABI of the B200 microstate engine.
  *
- * Drop-in boundary for the hot path of efliks/pcetk: everything the reference's Cython layer
+ * Drop-in boundary for the hot path of efliks/pcetk: what the reference's Cython layer
  * (extensions/cython/ContinuumElectrostatics.{StateVector,EnergyModel,MCModelDefault}.pyx) binds from
  *   extensions/cinclude/StateVector.h:53-84, EnergyModel.h:64-101, MCModelDefault.h:58-71
- * has an entry point here, flattened to opaque handles, plain pointers and sizes (no torch types), so
- * that ctypes / Cython / cgo / JNI can bind it.  Each declaration names the reference interface it
- * replaces.  See INTEGRATION.md for the binding a reference maintainer would add.
+ * is reachable from here through opaque handles, plain pointers and sizes (no torch types), so that
+ * ctypes / Cython / cgo / JNI can bind it.  Data functions (setters, getters, StateVector_*) map one
+ * to one.  The compute functions map at the granularity a GPU launch has: the reference's inner-loop
+ * steps have no entry point of their own --
+ *   MCModelDefault_Metropolis / _Move / _DoubleMove / _MCScan / _UpdateProbabilities (MCModelDefault.h:63-67)
+ *     run inside pce_mc_run* (one launch = _Equilibration + _Production of every chain);
+ *   EnergyModel_CalculateZ / _CalculateProbabilitiesFromZ (EnergyModel.h:81-82) run inside pce_analytic*.
+ * Each declaration names the reference interface it replaces.  See INTEGRATION.md for the binding a
+ * reference maintainer would add (including the logging / trajectory branch of MCModelDefault.pyx:79-159).
  *
  * Conventions
  *   - every function returns a pce_status (0 = ok); pce_last_error() gives the text for the calling thread

@@ -1,0 +1,13 @@
+# ncu captures of the Monte Carlo kernels as they ship: k_mc_thread (lysozyme, one wave), k_mc_warp (synth-M; ifp20).
+# For each: the command runs once without ncu (its JSON line gives the trial count of one launch), then under ncu.
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+TAG=${1:-v1}
+run() { name=$1; kernel=$2; shift 2
+  timeout 300 python bench.py "$@" --no-cpu-baseline --no-e2e --steps 1 --warmup 1 > gpurun_out/r02_prof_${name}_${TAG}.json 2> gpurun_out/r02_prof_${name}_${TAG}.err || { echo "$name failed"; tail -3 gpurun_out/r02_prof_${name}_${TAG}.err; return; }
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^${kernel}\$" -s 1 -c 1 -o gpurun_out/r02_prof_${name}_${TAG} python bench.py "$@" --no-cpu-baseline --no-e2e --steps 1 --warmup 1 > gpurun_out/r02_ncu_${name}_${TAG}.log 2>&1
+  tail -1 gpurun_out/r02_ncu_${name}_${TAG}.log | cut -c1-120
+}
+run k_mc_thread_lysozyme k_mc_thread --workload lysozyme --nprod 200 --nequil 50 --waves 1
+run k_mc_warp_synthM k_mc_warp --workload synthM --nprod 100 --nequil 100 --waves 1
+run k_mc_warp_ifp20 k_mc_warp --workload ifp20 --nprod 400 --nequil 100 --chains 86
