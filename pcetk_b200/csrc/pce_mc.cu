@@ -44,7 +44,7 @@ struct pce_mc {
     pce::DeviceBuffer<double>   d_cross;
     bool cross_valid = false, cross_overflow = false;   // overflow: the table exceeds 2^24 entries -> 255-register variant only
     int  bound_generation = -1;
-    pce::DeviceBuffer<double>  d_ph, d_esum;
+    pce::DeviceBuffer<double>  d_ph, d_esum, d_eng;
     pce::DeviceBuffer<unsigned long long> d_counts;
     pce::DeviceBuffer<long long> d_counters;
     // tables of the relative-field formulation, built on the device from the uploaded beta-scaled W
@@ -76,6 +76,8 @@ struct McParams {
     unsigned long long *counts;     // [nph*ninst]
     long long          *counters;   // [nph*4]
     double             *esum;       // [nph]
+    double             *eng_acc;    // chain-per-thread kernel: [2][eng_stride] tracked energy G/RT of every chain | its sum over production scans
+    uint32_t            eng_stride; // nph * nchains
     // optional per-chain outputs (parity tests)
     long long *chain_counts;        // [nph*nchains*ninst]
     int32_t   *chain_state;         // [nph*nchains*nsites]
@@ -94,7 +96,7 @@ struct McParams {
     int            ldd;             // row stride of dw (warp kernel: the padded field length of the launch)
     // chain-per-thread kernel: the shared-memory layout, computed on the host (ThreadLayout) so that the kernel can
     // re-read an offset from the constant bank instead of keeping it in a register or recomputing it
-    uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
+    uint32_t       tl_e, tl_cross, tl_h, tl_counts, tl_nact, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
     int            tl_hstride, tl_estride, tl_kslots;
     int            ph_minor;        // linearisation of the (pH, chain) grid: 1 = g = chain * nph + q (consecutive threads take consecutive pH
                                     // values, so every warp and block carries the same mix of cheap and expensive pH values), 0 = g = q * nchains + chain
@@ -107,7 +109,7 @@ struct McParams {
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
 struct ThreadLayout {
-    size_t off_e, off_cross, off_h, off_eng, off_counts, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
+    size_t off_e, off_cross, off_h, off_counts, off_nact, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
     int    hstride, estride, kslots;
     __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes, bool ph_minor) {
         hstride = (nrel > 0 ? nrel : 1) | 1;       // odd: lanes of a warp fall on distinct bank pairs
@@ -121,8 +123,11 @@ struct ThreadLayout {
         off_e = o;      o += (size_t) (nrows > 0 ? nrows : 1) * estride * 8;      // difference rows E
         off_cross = o;  o += (size_t) (ncross > 0 ? ncross : 1) * 8;              // pair cross terms
         off_h = o;      o += (size_t) block * hstride * 8;                        // relative fields, one row per chain
-        off_eng = o;    o += (size_t) block * 16;                                  // tracked energy and its sum over production scans, per chain
-        off_counts = o; o += (size_t) kslots * ninst * 4;     // u32: block * nprod < 2^32 is checked on the host
+        // occupancy counters of the NON-FIRST instances only (u32: block * nprod < 2^32 is checked on the host); the first instance of
+        // a site gets (chains of the slot) * nprod - (its siblings' counts) when the block flushes.  The tracked energy and its
+        // sum over the production scans live in global memory (fire-and-forget atomics): 263 -> 247 bytes per lysozyme chain.
+        off_counts = o; o += (size_t) kslots * (nrel > 0 ? nrel : 1) * 4;
+        off_nact = o;   o += (size_t) kslots * 4;
         off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
         o = (o + 3) & ~(size_t) 3;
         off_site = o;   o += (size_t) nsites * 4;
@@ -194,8 +199,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     double             *s_e      = (double *) (smem + p.tl_e);
     double             *s_cross  = (double *) (smem + p.tl_cross);
     double             *s_h      = (double *) (smem + p.tl_h);
-    double             *my_eng   = (double *) (smem + p.tl_eng) + threadIdx.x;      // [0]: tracked energy G/RT, [B]: its sum over production scans
-    uint32_t           *s_counts = (uint32_t *) (smem + p.tl_counts);
+    uint32_t           *s_counts = (uint32_t *) (smem + p.tl_counts);   // [kslots][nrel]: non-first instances
+    uint32_t           *s_nact   = (uint32_t *) (smem + p.tl_nact);     // [kslots]: chains of this block per pH slot
     SinceT             *s_since  = (SinceT *) (smem + p.tl_since);
     uint32_t           *s_site   = (uint32_t *) (smem + p.tl_site);       // first | ninst << 16
     uint32_t           *s_pair   = (uint32_t *) (smem + p.tl_pair);       // site a | site b << 16
@@ -216,7 +221,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const int q_base = p.ph_minor ? (B >= p.nph ? 0 : (int) (g0 % p.nph)) : (int) (g0 / p.nchains);
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
-    uint32_t *my_counts = s_counts + (size_t) (q - q_base + (q < q_base ? p.nph : 0)) * ninst;
+    const int my_slot = q - q_base + (q < q_base ? p.nph : 0);
+    uint32_t *my_counts = s_counts + (size_t) my_slot * (nrel > 0 ? nrel : 1);      // indexed by the relative slot r(k) = k - site - 1
     // per-thread arrays as 32-bit offsets into the dynamic shared memory (one register each instead of a 64-bit pointer)
     const uint32_t o_state = p.tl_state + (uint32_t) tid, o_since = p.tl_since + (uint32_t) tid * (uint32_t) sizeof (SinceT);
 #define my_state(i_) smem[o_state + (uint32_t) (i_)]
@@ -226,7 +232,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     // stage the model: difference rows, cross terms, packed site and pair tables
     for (int e = tid; e < p.nrows * nrel; e += B) s_e[(e / nrel) * L.estride + (e % nrel)] = p.dw[(size_t) (e / nrel) * p.ldd + (e % nrel)];
     for (int e = tid; e < p.ncross; e += B) s_cross[e] = p.cross[e];
-    for (int k = tid; k < L.kslots * ninst; k += B) s_counts[k] = 0u;
+    for (int k = tid; k < L.kslots * (nrel > 0 ? nrel : 1); k += B) s_counts[k] = 0u;
+    for (int k = tid; k < L.kslots; k += B) s_nact[k] = 0u;
     for (int i = tid; i < nsites; i += B) { s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16); s_erow[i] = (uint32_t) p.dbase[i]; }
     for (int i = tid; i < p.npairs; i += B) { s_pair[i] = p.pair_packed[i]; s_pairx[i] = p.pair_x[i] & 0xffffffu; }
 
@@ -241,9 +248,15 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         }
     }
     __syncthreads ();
+    if (!PER_CHAIN && active) atomicAdd (&s_nact[my_slot], 1u);
 
     const double mu   = ph_to_mu (p.temperature, p.ph[q]);
     const double beta = 1.0 / (PCE_R * p.temperature);
+    // tracked energy G/RT of this chain and its sum over the production scans: global memory, one slot per chain (coalesced),
+    // updated by fire-and-forget atomics (same thread, same address: applied in program order) and read back with volatile loads
+    const uint32_t g32 = (uint32_t) gclamped;       // (addresses are formed at the point of use: no pointer kept in a register)
+#define my_eng  (p.eng_acc + g32)
+#define my_esum (p.eng_acc + p.eng_stride + g32)
 
     // relative fields, cooperatively: for each chain c of this warp, lanes over the slots r;
     // g[r] = (gtb[k] - gtb[f]) + sum_j wr[a_j][r] with j sequential (spec order).  mu differs per chain: broadcast it.
@@ -275,8 +288,14 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             const double *row = p.w + (size_t) ai * p.ldw;
             for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[my_state (j * B)]);
         }
-        my_eng[0] = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
-        my_eng[B] = 0.0;
+        // Per-chain outputs (parity tests) track the energy and add it up scan by scan, like the specification.  The aggregate path
+        // needs only the sum over the production scans: every accepted move changes the energy of all production scans that are
+        // still to end, so it adds x * (those scans) at once and nothing happens at a scan end.
+        const double e0 = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
+        if (active) {
+            if (PER_CHAIN) { *my_eng = e0; *my_esum = 0.0; }
+            else *my_esum = e0 * (double) p.nprod;
+        }
     }
 
     const uint32_t nmoves = p.nmoves;
@@ -427,16 +446,17 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             if (accept) {
                 const bool production = scan >= (uint32_t) p.nequil;
                 const uint32_t tp = production ? scan - (uint32_t) p.nequil : 0u;
-                my_eng[0] = __dadd_rn (my_eng[0], x);
+                if (PER_CHAIN) atomicAdd (my_eng, x);
+                else atomicAdd (my_esum, x * (double) (production ? nscans - scan : (uint32_t) p.nprod));
                 const uint32_t since_a = my_since (sa * B);
                 if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
-                else if (tp != since_a) atomicAdd (&my_counts[oa], tp - since_a);
+                else if (tp != since_a && oa != fa) atomicAdd (&my_counts[oa - sa - 1], tp - since_a);
                 my_since (sa * B) = (SinceT) tp;
                 my_state (sa * B) = (uint8_t) ia;
                 if (dbl) {
                     const uint32_t since_b = my_since (sb * B);
                     if (PER_CHAIN) my_chain_counts[ob] += (long long) (tp - since_b);
-                    else if (tp != since_b) atomicAdd (&my_counts[ob], tp - since_b);
+                    else if (tp != since_b && ob != (int) (s_site[sb] & 0xffffu)) atomicAdd (&my_counts[ob - sb - 1], tp - since_b);
                     my_since (sb * B) = (SinceT) tp;
                     my_state (sb * B) = (uint8_t) ib;
                     if (production) c_facc++;
@@ -447,10 +467,10 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         if (++mv == nmoves) {
             mv = 0;
             const bool production = scan >= (uint32_t) p.nequil;
-            if (production) {
-                const double grt = my_eng[0];
-                my_eng[B] += grt;
-                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && active) p.trajectory[scan - (uint32_t) p.nequil] = grt / beta;
+            if (PER_CHAIN && production && active) {
+                const double grt = __ldcg (my_eng);            // (L2: where the atomics of this thread were applied, in program order)
+                atomicAdd (my_esum, grt);
+                if (p.trajectory != nullptr && q == 0 && local == 0) p.trajectory[scan - (uint32_t) p.nequil] = grt / beta;
             }
             if (PER_CHAIN && p.log_rows != nullptr) {        // the per-block counter table of MCModelDefault.pyx:85-151
                 const long long done = (long long) (production ? scan - (uint32_t) p.nequil : scan) + 1;
@@ -483,28 +503,41 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             const int      a = my_state (i * B);
             const uint32_t d = (uint32_t) p.nprod - my_since (i * B);
             if (PER_CHAIN) my_chain_counts[a] += (long long) d;
-            else if (d) atomicAdd (&my_counts[a], d);
+            else if (d && a != (int) (s_site[i] & 0xffffu)) atomicAdd (&my_counts[a - i - 1], d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
             for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = my_state (i * B);
-            p.chain_energy[c] = my_eng[0] / beta;
-            p.chain_esum[c]   = my_eng[B] / beta;
+            p.chain_energy[c] = __ldcg (my_eng) / beta;
+            p.chain_esum[c]   = __ldcg (my_esum) / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
             p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
         }
     }
     if (!PER_CHAIN) {
         __syncthreads ();
-        if (p.counts != nullptr)
-            for (int k = tid; k < L.kslots * ninst; k += B) {
-                int qq = q_base + k / ninst;
+        if (p.counts != nullptr) {
+            // non-first instances: the block's counters; first instance of a site: all production scans of the slot's chains minus its siblings
+            const int nr = nrel > 0 ? nrel : 1;
+            for (int k = tid; k < L.kslots * nrel; k += B) {
+                int qq = q_base + k / nrel;
                 if (p.ph_minor && qq >= p.nph) qq -= p.nph;
-                if (qq < p.nph && s_counts[k]) atomicAdd (&p.counts[(size_t) qq * ninst + (k % ninst)], (unsigned long long) s_counts[k]);
+                if (qq < p.nph && s_counts[k]) atomicAdd (&p.counts[(size_t) qq * ninst + p.rk[k % nrel]], (unsigned long long) s_counts[k]);
             }
+            for (int k = tid; k < L.kslots * nsites; k += B) {
+                const int slot = k / nsites, i = k - slot * nsites;
+                int qq = q_base + slot;
+                if (p.ph_minor && qq >= p.nph) qq -= p.nph;
+                if (qq >= p.nph || s_nact[slot] == 0u) continue;
+                const int fi = (int) (s_site[i] & 0xffffu), ni = (int) (s_site[i] >> 16);
+                unsigned long long first_count = (unsigned long long) s_nact[slot] * (unsigned long long) p.nprod;
+                for (int d = 1; d < ni; d++) first_count -= (unsigned long long) s_counts[(size_t) slot * nr + (fi + d - i - 1)];
+                if (first_count) atomicAdd (&p.counts[(size_t) qq * ninst + fi], first_count);
+            }
+        }
         // counters and energy sums: one atomic per thread (pH values may differ within a warp)
         if (active) {
-            if (p.esum != nullptr) atomicAdd (&p.esum[q], my_eng[B] / beta);
+            if (p.esum != nullptr) atomicAdd (&p.esum[q], __ldcg (my_esum) / beta);
             if (p.counters != nullptr) {
                 atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
                 atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
@@ -517,6 +550,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
 #undef my_state
 #undef my_since
 #undef myg
+#undef my_eng
+#undef my_esum
 
 // ---------------------------------------------------------------------------------------------------
 // Tables of the relative-field formulation and the application of an accepted move in the warp kernel.
@@ -678,7 +713,7 @@ struct WarpLayout {
 // registers ptxas moves the warp-uniform bookkeeping off the uniform datapath (12 % more instructions), so three CTAs
 // are the default for small fields (PCE_MC_CTAS overrides).
 template <bool PER_CHAIN, int MIN_CTAS, int TPL>
-__global__ void __launch_bounds__ (256, MIN_CTAS) k_mc_warp (const McParams p) {
+__global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_warp (const McParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
     constexpr int RING = TPL <= 2 ? 128 : 256;
@@ -1154,7 +1189,8 @@ bool plan_warp (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, do
         const int upd = pass == 1 ? 16 : 4;
         WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1);
         if (L.per_warp + L.shared_bytes > limit) continue;
-        int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, 8);
+        // large fields (one resident CTA): as many warps as shared memory holds, up to 10 (204 registers each); else 8 per CTA
+        int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, pass == 1 ? 10 : 8);
         if (const char *cap = std::getenv ("PCE_MC_WARPS")) warps = std::max (1, std::min (warps, std::atoi (cap)));      // tuning aid
         const size_t smem = L.shared_bytes + (size_t) warps * L.per_warp;
         const int ctas = (int) std::min<size_t> ((228 * 1024) / (smem + 1024), (size_t) (2048 / (warps * 32)));
@@ -1238,7 +1274,7 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
     mc->d_pair_packed.release (); mc->d_pair_x.release (); mc->d_cross.release (); mc->d_ph.release (); mc->d_esum.release ();
-    mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release (); mc->d_wr.release (); mc->d_rk.release (); mc->d_rf.release ();
+    mc->d_counts.release (); mc->d_counters.release (); mc->d_eng.release (); mc->d_dw.release (); mc->d_dbase.release (); mc->d_wr.release (); mc->d_rk.release (); mc->d_rf.release ();
     delete mc;
 }
 
@@ -1497,11 +1533,15 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     if (plan.kernel == 1) {
         const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, plan.ph_minor != 0);
         p.ph_minor = plan.ph_minor;
-        p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_eng = (uint32_t) TL.off_eng; p.tl_counts = (uint32_t) TL.off_counts;
+        p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_counts = (uint32_t) TL.off_counts; p.tl_nact = (uint32_t) TL.off_nact;
         p.tl_since = (uint32_t) TL.off_since; p.tl_site = (uint32_t) TL.off_site; p.tl_pair = (uint32_t) TL.off_pair; p.tl_pairx = (uint32_t) TL.off_pairx;
         p.tl_erow = (uint32_t) TL.off_erow; p.tl_state = (uint32_t) TL.off_state;
         p.tl_hstride = TL.hstride; p.tl_estride = TL.estride; p.tl_kslots = TL.kslots;
         if (TL.total != plan.smem) return fail (PCE_ERR_STATE, "shared-memory layout of the chain-per-thread kernel changed between planning and launch");
+        const long long nchains_total = (long long) nph * mc->nchains;
+        if (nchains_total > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
+        PCE_CUDA (mc->d_eng.resize ((size_t) (2 * nchains_total)));
+        p.eng_acc = mc->d_eng.ptr; p.eng_stride = (uint32_t) nchains_total;
     }
     if (plan.kernel == 1) {
         void (*kernel) (const McParams);

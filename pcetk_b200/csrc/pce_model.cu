@@ -1,5 +1,6 @@
 // pce_model.cu -- model container, setters/getters, symmetrisation, upload, and kernel 1
 // (batched microstate energies).  Replaces the data side of extensions/csource/EnergyModel.c.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -231,12 +232,21 @@ extern "C" int pce_model_check_symmetric (const pce_model *m, double tolerance, 
 
 extern "C" int pce_model_symmetrize (pce_model *m) {
     if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
-    const size_t n = (size_t) m->ninst;
-    for (size_t i = 0; i < n; i++)
-        for (size_t j = 0; j <= i; j++) {
-            const double v = 0.5 * (m->wraw[i * n + j] + m->wraw[j * n + i]);
-            m->wsym[i * n + j] = v;
-            m->wsym[j * n + i] = v;
+    // Wsym_ij = Wsym_ji = (W_ij + W_ji) / 2 (SymmetricMatrix_CopyFromReal2DArray, EnergyModel.c:78-87), in tiles of 32 x 32 so
+    // that the transposed accesses stay in cache (60 -> 41 ms on the 3000-instance model; a tile buffer with contiguous
+    // write-back and host threads both measured slower)
+    const size_t n = (size_t) m->ninst, tile = 32;
+    const double *w = m->wraw.data ();
+    double *s = m->wsym.data ();
+    for (size_t i0 = 0; i0 < n; i0 += tile)
+        for (size_t j0 = 0; j0 <= i0; j0 += tile) {
+            const size_t i1 = std::min (n, i0 + tile), j1 = std::min (n, j0 + tile);
+            for (size_t i = i0; i < i1; i++)
+                for (size_t j = j0; j < j1 && j <= i; j++) {
+                    const double v = 0.5 * (w[i * n + j] + w[j * n + i]);
+                    s[i * n + j] = v;
+                    s[j * n + i] = v;
+                }
         }
     m->symmetrized = true;
     m->dirty = true;

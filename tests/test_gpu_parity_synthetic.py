@@ -133,53 +133,60 @@ def reference_seeds(rec, ph_values, nequil, nprod, seeds):
         return np.array(list(pool.map(one, seeds)))
 
 
-def compare_with_reference_seeds(p_gpu, p_seeds, nprod, gpu_chains, dp_max, label, tau=8.0):
+def compare_with_reference_seeds(chains, p_seeds, nprod, dp_max, label):
     """GPU ensemble against the mean over seeds of the reference sampler, both run with the SAME protocol (equilibration and
-    production scans per chain, random initial states), so that incomplete equilibration biases both alike.  Standard error of
-    the reference mean: the seed-to-seed scatter, but at least the binomial error of its scan count with an autocorrelation
-    time of `tau` scans (eight seeds that never visit an instance have zero scatter, not zero error)."""
-    nseeds = p_seeds.shape[0]
+    production scans per chain, random initial states), so that incomplete equilibration biases both alike: a two-sample test.
+    `chains` = per-chain occupancy counts of the GPU run [npH, nchains, ninst]; their chain-to-chain scatter is the measured
+    standard deviation of ONE chain's estimate (whatever the autocorrelation time is), so the reference mean over n seeds
+    carries sigma / sqrt(n) and the GPU mean sigma / sqrt(nchains)."""
+    per_chain = chains / float(nprod)
+    p_gpu = per_chain.mean(axis=1)
+    sigma = per_chain.std(axis=1, ddof=1)
+    nseeds, nchains = p_seeds.shape[0], per_chain.shape[1]
     mean = p_seeds.mean(axis=0)
-    pooled = np.clip(0.5 * (mean + p_gpu), 0.0, 1.0)
-    binomial = pooled * (1.0 - pooled) * tau / nprod
-    sem_ref = np.sqrt(np.maximum(p_seeds.var(axis=0, ddof=1) / nseeds, binomial / nseeds))
-    sem_gpu = np.sqrt(binomial / gpu_chains)
     dp = p_gpu - mean
-    z = dp / np.sqrt(sem_ref ** 2 + sem_gpu ** 2 + 1e-10)
+    sem = sigma * np.sqrt(1.0 / nseeds + 1.0 / nchains)
+    # rare visits (an instance seen in 3 of the reference's 6400 scans and hardly ever by a GPU chain) are counting noise, not
+    # Gaussian scatter: the resolution of the reference mean, a few scans out of nseeds * nprod, floors the standard error
+    z = dp / np.sqrt(sem ** 2 + (3.0 / (nseeds * nprod)) ** 2)
     assert np.abs(dp).max() <= dp_max, "%s: max |dp| %.4f" % (label, np.abs(dp).max())
-    assert np.abs(dp).max() <= 0.01 + 4.0 * sem_ref.max(), "%s: max |dp| %.4f against 0.01 + 4 sem (%.4f)" % (label, np.abs(dp).max(), sem_ref.max())
+    assert np.abs(dp).max() <= 0.01 + 4.0 * sem.max(), "%s: max |dp| %.4f against 0.01 + 4 sem (%.4f)" % (label, np.abs(dp).max(), sem.max())
     assert np.abs(z).max() <= 6.0, "%s: max |z| %.2f" % (label, np.abs(z).max())
-    assert np.sqrt(np.mean(z ** 2)) <= 1.5, "%s: rms z %.2f" % (label, np.sqrt(np.mean(z ** 2)))
-    assert np.sqrt(np.mean(dp ** 2)) <= 0.006, "%s: rms dp %.4f" % (label, np.sqrt(np.mean(dp ** 2)))
+    assert np.sqrt(np.mean(z ** 2)) <= 1.3, "%s: rms z %.2f" % (label, np.sqrt(np.mean(z ** 2)))
+    # the seed-to-seed scatter of the reference must look like the chain-to-chain scatter of the GPU sampler
+    visited = sigma > 0.02
+    ratio = p_seeds.std(axis=0, ddof=1)[visited] / sigma[visited]
+    assert 0.8 <= np.median(ratio) <= 1.25, "%s: median scatter ratio %.2f" % (label, np.median(ratio))
+    return p_gpu
 
 
 def test_synthetic_200_site_slice_vs_reference_sampler_seeds():
     """synth_m(200): 200 sites / 600 instances / 933 double-move pairs, the generator of BASELINE configs[4] at a size where
     the reference does ~900 scans per second: 16 seeds x (500 + 8000) scans at two pH values against 512 GPU chains of the
-    same protocol.  |dp| <= 0.01 (+ 4 standard errors of the reference mean), every z-score within 6."""
+    same protocol.  |dp| <= 0.01 (+ 4 standard errors of the difference), every z-score within 6, rms z ~ 1."""
     rec = synth_m(200)
     grid = [4.0, 8.0]
     seeds = reference_seeds(rec, grid, 500, 8000, [1000 + 7 * k for k in range(16)])
     model = P.MEADModel(rec, log=None)
     sampler = P.MCModelDefault(nequil=500, nprod=8000, randomSeed=424242, nchains=512)
     model.DefineMCModel(sampler, log=None)
-    p = model.CalculateProbabilitiesBatch(grid)
-    compare_with_reference_seeds(p, seeds, 8000, 512, 0.02, "synth_m(200)")
+    out = sampler.RunChains(grid)
+    compare_with_reference_seeds(out["counts"], seeds, 8000, 0.02, "synth_m(200)")
 
 
 def test_synthetic_1000_sites_vs_reference_sampler_seeds():
     """BASELINE configs[4]'s model itself (1000 sites / 3000 instances / 5526 pairs) at pH 7: the reference manages ~20 scans per
-    second and core, so it gets 8 seeds x (100 + 400) scans, whose mean carries up to ~0.05 of noise per instance -- the bound
-    that bites is the z-score (every deviation within 6 standard errors, rms z <= 1.5).  The GPU runs 1024 chains of the same
-    protocol (a chain 100 scans from a random start is not equilibrated on this model: both sides carry the same bias)."""
+    second and core, so it gets 8 seeds x (100 + 400) scans; the GPU runs 1024 chains of the same protocol (a chain 100 scans
+    from a random start is not equilibrated on this model: both sides carry the same bias).  The reference mean carries up to
+    ~0.1 of noise per instance, so the bounds that bite are the z-scores over the 3000 instances and the scatter ratio."""
     rec = synth_m(1000)
     seeds = reference_seeds(rec, [7.0], 100, 400, [31 + 5 * k for k in range(8)])
     model = P.MEADModel(rec, log=None)
     sampler = P.MCModelDefault(nequil=100, nprod=400, randomSeed=99, nchains=1024)
     model.DefineMCModel(sampler, log=None)
-    p = model.CalculateProbabilitiesBatch([7.0])
-    compare_with_reference_seeds(p, seeds, 400, 1024, 0.25, "synth_m(1000)")
-    assert np.abs(p.reshape(1, -1).sum() - rec.nsites) < 1e-6
+    out = sampler.RunChains([7.0])
+    p = compare_with_reference_seeds(out["counts"], seeds, 400, 0.3, "synth_m(1000)")
+    assert np.abs(p.sum() - rec.nsites) < 1e-6
 
 
 def test_ifp20_whole_curve_vs_reference_sampler_seeds():
