@@ -329,12 +329,12 @@ def mc_workload(ctx, name, steps, warmup, chains=0, nprod=0, nequil=-1, waves=2,
     nmoves = record.nsites + npairs
     d_counts = torch.zeros((nph, record.ninstances), dtype=torch.int64, device=ctx.device)
     d_counters = torch.zeros((nph, 4), dtype=torch.int64, device=ctx.device)
-    d_esum = torch.zeros(nph, dtype=torch.float64, device=ctx.device)
     em.Upload()
 
     def step_device():
+        # occupancy counts and move counters; no energy sums, like the reference's quiet path (MCModelDefault.pyx:60-78)
         native.check(lib.pce_mc_run_device(sampler._handle, grid, nph, 0, ctx.rank * chains, C.c_void_p(d_counts.data_ptr()),
-                                           C.c_void_p(d_counters.data_ptr()), C.c_void_p(d_esum.data_ptr())))
+                                           C.c_void_p(d_counters.data_ptr()), None))
         if ctx.world > 1:
             ctx.dist.all_reduce(d_counts)            # the path's only exchange: per-(pH, instance) occupancy counts
 
@@ -550,6 +550,8 @@ def main():
     if not args.workload and not args.no_side_workloads:
         # the other BASELINE configs, short runs (W = 3 warm-up steps as the timing rules ask)
         side["synthA"] = analytic_workload(ctx, "synthA", 10, 3, e2e=e2e, cpu=cpu)
+        # 16x the states (2^36): the strong-scaling curve whose fixed per-curve cost (reductions, the all-reduce) no longer shows
+        side["synthA36"] = analytic_workload(ctx, "synthA36", 3, 3, e2e=False, cpu=False)
         side["synthM"] = mc_workload(ctx, "synthM", 2, 3, e2e=e2e, cpu=cpu)
         side["ifp20"] = mc_workload(ctx, "ifp20", 3, 3, e2e=e2e, cpu=cpu)
         side["defensin"] = mc_workload(ctx, "defensin", 2, 3, e2e=e2e, cpu=cpu)

@@ -110,8 +110,10 @@ class MCModelDefault(object):
         _native.check(self._lib.pce_mc_set_chains(self._handle, self.nchains))
         _native.check(self._lib.pce_mc_set_kernel(self._handle, self.kernel))
 
-    def RunCounts(self, pHs, phIndexOffset=0):
-        """Raw results of one launch over a pH list: (counts[npH, ninst] int64, counters[npH, 4], esum[npH])."""
+    def RunCounts(self, pHs, phIndexOffset=0, energy=True):
+        """Raw results of one launch over a pH list: (counts[npH, ninst] int64, counters[npH, 4], esum[npH]).
+        ``energy=False`` skips the tracked chain energies (``esum`` comes back as zeros): the reference's quiet path returns
+        occupancies only, and the chain-per-thread kernel then fits more chains per SM."""
         self._requireOwner()
         self._configure()
         ph = np.ascontiguousarray(np.atleast_1d(pHs), dtype=np.float64)
@@ -120,9 +122,9 @@ class MCModelDefault(object):
         counters = np.zeros((ph.shape[0], 4), dtype=np.int64)
         esum = np.zeros(ph.shape[0], dtype=np.float64)
         _native.check(self._lib.pce_mc_run(self._handle, ph, ph.shape[0], int(phIndexOffset), int(self.chainOffset),
-                                           _native.ptr(counts), _native.ptr(counters), _native.ptr(esum)))
+                                           _native.ptr(counts), _native.ptr(counters), _native.ptr(esum) if energy else None))
         self.lastCounters = counters
-        self.lastEnergySums = esum
+        self.lastEnergySums = esum if energy else None
         return counts, counters, esum
 
     def _takeStreams(self, count, phIndexOffset=None):
@@ -137,7 +139,7 @@ class MCModelDefault(object):
         """Probabilities for a list of pH values in one launch -> p[npH, ninst]; the model keeps the last row.
         Successive calls draw fresh random streams unless ``phIndexOffset`` addresses them explicitly."""
         count = len(np.atleast_1d(pHs))
-        counts, _counters, _esum = self.RunCounts(pHs, self._takeStreams(count, phIndexOffset))
+        counts, _counters, _esum = self.RunCounts(pHs, self._takeStreams(count, phIndexOffset), energy=False)
         return counts / float(self.nchains * self.nprod)
 
     def CalculateOwnerProbabilities(self, pH=7.0, logFrequency=0, trajectoryFilename="", log=logFile):

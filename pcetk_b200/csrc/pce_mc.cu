@@ -44,7 +44,7 @@ struct pce_mc {
     pce::DeviceBuffer<double>   d_cross;
     bool cross_valid = false, cross_overflow = false;   // overflow: the table exceeds 2^24 entries -> 255-register variant only
     int  bound_generation = -1;
-    pce::DeviceBuffer<double>  d_ph, d_esum, d_eng;
+    pce::DeviceBuffer<double>  d_ph, d_esum;
     pce::DeviceBuffer<unsigned long long> d_counts;
     pce::DeviceBuffer<long long> d_counters;
     // tables of the relative-field formulation, built on the device from the uploaded beta-scaled W
@@ -76,8 +76,6 @@ struct McParams {
     unsigned long long *counts;     // [nph*ninst]
     long long          *counters;   // [nph*4]
     double             *esum;       // [nph]
-    double             *eng_acc;    // chain-per-thread kernel: [2][eng_stride] tracked energy G/RT of every chain | its sum over production scans
-    uint32_t            eng_stride; // nph * nchains
     // optional per-chain outputs (parity tests)
     long long *chain_counts;        // [nph*nchains*ninst]
     int32_t   *chain_state;         // [nph*nchains*nsites]
@@ -96,7 +94,7 @@ struct McParams {
     int            ldd;             // row stride of dw (warp kernel: the padded field length of the launch)
     // chain-per-thread kernel: the shared-memory layout, computed on the host (ThreadLayout) so that the kernel can
     // re-read an offset from the constant bank instead of keeping it in a register or recomputing it
-    uint32_t       tl_e, tl_cross, tl_h, tl_counts, tl_nact, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
+    uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_nact, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
     int            tl_hstride, tl_estride, tl_kslots;
     int            ph_minor;        // linearisation of the (pH, chain) grid: 1 = g = chain * nph + q (consecutive threads take consecutive pH
                                     // values, so every warp and block carries the same mix of cheap and expensive pH values), 0 = g = q * nchains + chain
@@ -109,9 +107,10 @@ struct McParams {
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
 struct ThreadLayout {
-    size_t off_e, off_cross, off_h, off_counts, off_nact, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
+    size_t off_e, off_cross, off_h, off_eng, off_counts, off_nact, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
     int    hstride, estride, kslots;
-    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes, bool ph_minor) {
+    __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes, bool ph_minor,
+                                      bool energy) {
         hstride = (nrel > 0 ? nrel : 1) | 1;       // odd: lanes of a warp fall on distinct bank pairs
         estride = nrel > 0 ? nrel : 1;
         // occupancy counters per pH value a block can meet: a block covers `block` consecutive (pH, chain) pairs of the
@@ -123,9 +122,12 @@ struct ThreadLayout {
         off_e = o;      o += (size_t) (nrows > 0 ? nrows : 1) * estride * 8;      // difference rows E
         off_cross = o;  o += (size_t) (ncross > 0 ? ncross : 1) * 8;              // pair cross terms
         off_h = o;      o += (size_t) block * hstride * 8;                        // relative fields, one row per chain
+        // tracked energy and its sum over production scans, per chain -- only when the caller asked for energy sums (the
+        // reference's quiet path returns occupancies only, MCModelDefault.pyx:60-78): without them a lysozyme chain takes 247
+        // instead of 263 bytes and 896 instead of 768 chains fit
+        off_eng = o;    o += energy ? (size_t) block * 16 : 0;
         // occupancy counters of the NON-FIRST instances only (u32: block * nprod < 2^32 is checked on the host); the first instance of
-        // a site gets (chains of the slot) * nprod - (its siblings' counts) when the block flushes.  The tracked energy and its
-        // sum over the production scans live in global memory (fire-and-forget atomics): 263 -> 247 bytes per lysozyme chain.
+        // a site gets (chains of the slot) * nprod - (its siblings' counts) when the block flushes
         off_counts = o; o += (size_t) kslots * (nrel > 0 ? nrel : 1) * 4;
         off_nact = o;   o += (size_t) kslots * 4;
         off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
@@ -192,13 +194,15 @@ __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
 // the planner stops at 768 threads.  To get there the loop state was put on a diet: no Philox prefetch, 32-bit scan
 // counter instead of 64-bit trial counters, tracked energy and its sum in shared memory, 32-bit shared-memory offsets
 // instead of generic pointers, the shared-memory layout passed in the kernel parameters.
-template <bool PER_CHAIN, typename SinceT, int MAX_REGS, bool SHORT_FIELDS>
+template <bool PER_CHAIN, typename SinceT, int MAX_REGS, bool SHORT_FIELDS, bool ENERGY>
 __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
+    static_assert (ENERGY || !PER_CHAIN, "per-chain outputs include the energy");
     extern __shared__ __align__ (16) unsigned char smem[];
     const int B = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp_base = tid & ~31;
     double             *s_e      = (double *) (smem + p.tl_e);
     double             *s_cross  = (double *) (smem + p.tl_cross);
     double             *s_h      = (double *) (smem + p.tl_h);
+    double             *my_eng   = (double *) (smem + p.tl_eng) + threadIdx.x;      // [0]: tracked energy G/RT, [B]: its sum over production scans (ENERGY)
     uint32_t           *s_counts = (uint32_t *) (smem + p.tl_counts);   // [kslots][nrel]: non-first instances
     uint32_t           *s_nact   = (uint32_t *) (smem + p.tl_nact);     // [kslots]: chains of this block per pH slot
     SinceT             *s_since  = (SinceT *) (smem + p.tl_since);
@@ -252,11 +256,6 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
 
     const double mu   = ph_to_mu (p.temperature, p.ph[q]);
     const double beta = 1.0 / (PCE_R * p.temperature);
-    // tracked energy G/RT of this chain and its sum over the production scans: global memory, one slot per chain (coalesced),
-    // updated by fire-and-forget atomics (same thread, same address: applied in program order) and read back with volatile loads
-    const uint32_t g32 = (uint32_t) gclamped;       // (addresses are formed at the point of use: no pointer kept in a register)
-#define my_eng  (p.eng_acc + g32)
-#define my_esum (p.eng_acc + p.eng_stride + g32)
 
     // relative fields, cooperatively: for each chain c of this warp, lanes over the slots r;
     // g[r] = (gtb[k] - gtb[f]) + sum_j wr[a_j][r] with j sequential (spec order).  mu differs per chain: broadcast it.
@@ -288,13 +287,9 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             const double *row = p.w + (size_t) ai * p.ldw;
             for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[my_state (j * B)]);
         }
-        // Per-chain outputs (parity tests) track the energy and add it up scan by scan, like the specification.  The aggregate path
-        // needs only the sum over the production scans: every accepted move changes the energy of all production scans that are
-        // still to end, so it adds x * (those scans) at once and nothing happens at a scan end.
-        const double e0 = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
-        if (active) {
-            if (PER_CHAIN) { *my_eng = e0; *my_esum = 0.0; }
-            else *my_esum = e0 * (double) p.nprod;
+        if (ENERGY) {
+            my_eng[0] = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
+            my_eng[B] = 0.0;
         }
     }
 
@@ -446,8 +441,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             if (accept) {
                 const bool production = scan >= (uint32_t) p.nequil;
                 const uint32_t tp = production ? scan - (uint32_t) p.nequil : 0u;
-                if (PER_CHAIN) atomicAdd (my_eng, x);
-                else atomicAdd (my_esum, x * (double) (production ? nscans - scan : (uint32_t) p.nprod));
+                if (ENERGY) my_eng[0] = __dadd_rn (my_eng[0], x);
                 const uint32_t since_a = my_since (sa * B);
                 if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
                 else if (tp != since_a && oa != fa) atomicAdd (&my_counts[oa - sa - 1], tp - since_a);
@@ -467,10 +461,10 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         if (++mv == nmoves) {
             mv = 0;
             const bool production = scan >= (uint32_t) p.nequil;
-            if (PER_CHAIN && production && active) {
-                const double grt = __ldcg (my_eng);            // (L2: where the atomics of this thread were applied, in program order)
-                atomicAdd (my_esum, grt);
-                if (p.trajectory != nullptr && q == 0 && local == 0) p.trajectory[scan - (uint32_t) p.nequil] = grt / beta;
+            if (ENERGY && production) {
+                const double grt = my_eng[0];
+                my_eng[B] += grt;
+                if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && active) p.trajectory[scan - (uint32_t) p.nequil] = grt / beta;
             }
             if (PER_CHAIN && p.log_rows != nullptr) {        // the per-block counter table of MCModelDefault.pyx:85-151
                 const long long done = (long long) (production ? scan - (uint32_t) p.nequil : scan) + 1;
@@ -508,8 +502,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
             for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = my_state (i * B);
-            p.chain_energy[c] = __ldcg (my_eng) / beta;
-            p.chain_esum[c]   = __ldcg (my_esum) / beta;
+            p.chain_energy[c] = my_eng[0] / beta;
+            p.chain_esum[c]   = my_eng[B] / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
             p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
         }
@@ -537,7 +531,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         }
         // counters and energy sums: one atomic per thread (pH values may differ within a warp)
         if (active) {
-            if (p.esum != nullptr) atomicAdd (&p.esum[q], __ldcg (my_esum) / beta);
+            if (ENERGY && p.esum != nullptr) atomicAdd (&p.esum[q], my_eng[B] / beta);
             if (p.counters != nullptr) {
                 atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
                 atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
@@ -550,8 +544,6 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
 #undef my_state
 #undef my_since
 #undef myg
-#undef my_eng
-#undef my_esum
 
 // ---------------------------------------------------------------------------------------------------
 // Tables of the relative-field formulation and the application of an accepted move in the warp kernel.
@@ -1119,7 +1111,7 @@ struct CostModel {
 // block size (multiple of 32, up to 768 threads -- 896 for short field vectors) that fits is priced with the cost model for
 // the `total` = nph x nchains chains of this launch: a small ensemble is spread over all SMs in small blocks (few warps per SM,
 // each running at its latency floor), a large one takes the block that puts the most warps on an SM.
-bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, double *cost_out) {
+bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, bool energy, Plan *plan, double *cost_out) {
     const pce_model *m = mc->model;
     const TableSizes t = table_sizes (mc);
     if (m->ninst > 256 || t.nrows > 16383 || t.ncross >= (1u << 24)) return false;
@@ -1137,8 +1129,10 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, 
     if (t.nrel <= 32) {
         cudaFuncAttributes attributes;
         const bool narrow = mc->nprod < 65536;
-        const cudaError_t err = narrow ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, true>)
-                                       : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, true>);
+        const cudaError_t err = narrow ? (energy ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, true, true>)
+                                                 : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, true, false>))
+                                       : (energy ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, true, true>)
+                                                 : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, true, false>));
         if (err == cudaSuccess && ((attributes.numRegs + 7) & ~7) * 32 * 7 <= 16384) most = 896;
         else if (err != cudaSuccess) (void) cudaGetLastError ();
     }
@@ -1148,7 +1142,7 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, 
     for (int block = 32; block <= (forced_block ? 1024 : most); block += 32) {
         if (forced_block && block != forced_block) continue;
         if (!forced_block && block > 768 && block % 128 != 0) continue;       // beyond 768 only whole warps per sub-partition
-        ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, ph_minor);
+        ThreadLayout L (m->nsites, m->ninst, (int) mc->pair_a.size (), t.nrel, t.nrows, (int) t.ncross, block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, ph_minor, energy);
         if (L.total > limit) continue;
         if ((double) block * (double) mc->nprod >= 4294967295.0) continue;      // per-block occupancy counters are 32-bit
         // resident CTAs: shared memory (1 KB reserved per CTA), threads, registers (88 allocated up to 640 threads, then 80 / 72)
@@ -1274,7 +1268,7 @@ extern "C" int pce_mc_create (pce_model *model, double limit, int nequil, int np
 extern "C" void pce_mc_destroy (pce_mc *mc) {
     if (mc == nullptr) return;
     mc->d_pair_packed.release (); mc->d_pair_x.release (); mc->d_cross.release (); mc->d_ph.release (); mc->d_esum.release ();
-    mc->d_counts.release (); mc->d_counters.release (); mc->d_eng.release (); mc->d_dw.release (); mc->d_dbase.release (); mc->d_wr.release (); mc->d_rk.release (); mc->d_rf.release ();
+    mc->d_counts.release (); mc->d_counters.release (); mc->d_dw.release (); mc->d_dbase.release (); mc->d_wr.release (); mc->d_rk.release (); mc->d_rf.release ();
     delete mc;
 }
 
@@ -1318,21 +1312,22 @@ extern "C" int pce_mc_get_info (const pce_mc *mc, int *kernel, int *nchains, int
     return PCE_OK;
 }
 
-static int make_mc_plan (pce_mc *mc, int nph, Plan *plan) {
+// energy: the launch tracks chain energies (per-chain outputs, or the caller asked for energy sums)
+static int make_mc_plan (pce_mc *mc, int nph, bool energy, Plan *plan) {
     size_t limit = 0;
     int status = smem_limit (mc->model->device, &limit);
     if (status != PCE_OK) return status;
     int sms = 0;
     PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, mc->model->device));
     bool ok = false;
-    if (mc->kernel == 1) ok = plan_thread (mc, limit, nph, sms, plan, nullptr);
+    if (mc->kernel == 1) ok = plan_thread (mc, limit, nph, sms, energy, plan, nullptr);
     else if (mc->kernel == 2) ok = plan_warp (mc, limit, nph, sms, plan, nullptr);
     else {
         // auto: price both kernels for this ensemble (CostModel) where both can run the model: the chain-per-thread kernel needs
         // the tables in shared memory and wins on large ensembles, the chain-per-warp kernel finishes small ones 5x sooner
         Plan thread_plan = *plan, warp_plan = *plan;
         double thread_cost = 0.0, warp_cost = 0.0;
-        const bool thread_ok = plan_thread (mc, limit, nph, sms, &thread_plan, &thread_cost);
+        const bool thread_ok = plan_thread (mc, limit, nph, sms, energy, &thread_plan, &thread_cost);
         const bool warp_ok = plan_warp (mc, limit, nph, sms, &warp_plan, &warp_cost);
         if (thread_ok && (!warp_ok || thread_cost <= warp_cost)) { *plan = thread_plan; ok = true; }
         else if (warp_ok) { *plan = warp_plan; ok = true; }
@@ -1345,7 +1340,7 @@ extern "C" int pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *c
     if (mc == nullptr) return fail (PCE_ERR_VALUE, "null sampler");
     PCE_CUDA (cudaSetDevice (mc->model->device));
     Plan plan = { 0, 0, 0, 1, 1, 4, 1, 1 };
-    int status = make_mc_plan (mc, nph, &plan);
+    int status = make_mc_plan (mc, nph, false, &plan);       // the quiet path (occupancies only)
     if (status != PCE_OK) return status;
     int sms = 0;
     PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, mc->model->device));
@@ -1490,8 +1485,9 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     PCE_CUDA (mc->d_ph.resize (nph));
     PCE_CUDA (cudaMemcpyAsync (mc->d_ph.ptr, ph, nph * sizeof (double), cudaMemcpyHostToDevice, m->stream));
 
+    const bool energy = per_chain || p.esum != nullptr;
     Plan plan = { 0, 0, 0, 1, 1, 4, 1, 1 };
-    status = make_mc_plan (mc, nph, &plan);
+    status = make_mc_plan (mc, nph, energy, &plan);
     if (status != PCE_OK) return status;
 
     p.nsites = m->nsites; p.ninst = m->ninst; p.npairs = npairs; p.ldw = m->ldw;
@@ -1531,17 +1527,14 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         p.wl_state = (uint32_t) WL.off_state; p.wl_ring = (uint32_t) WL.off_ring; p.wl_ldh = WL.ldh;
     }
     if (plan.kernel == 1) {
-        const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, plan.ph_minor != 0);
+        const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, plan.ph_minor != 0, energy);
         p.ph_minor = plan.ph_minor;
-        p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_counts = (uint32_t) TL.off_counts; p.tl_nact = (uint32_t) TL.off_nact;
+        p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_eng = (uint32_t) TL.off_eng; p.tl_counts = (uint32_t) TL.off_counts; p.tl_nact = (uint32_t) TL.off_nact;
         p.tl_since = (uint32_t) TL.off_since; p.tl_site = (uint32_t) TL.off_site; p.tl_pair = (uint32_t) TL.off_pair; p.tl_pairx = (uint32_t) TL.off_pairx;
         p.tl_erow = (uint32_t) TL.off_erow; p.tl_state = (uint32_t) TL.off_state;
         p.tl_hstride = TL.hstride; p.tl_estride = TL.estride; p.tl_kslots = TL.kslots;
         if (TL.total != plan.smem) return fail (PCE_ERR_STATE, "shared-memory layout of the chain-per-thread kernel changed between planning and launch");
-        const long long nchains_total = (long long) nph * mc->nchains;
-        if (nchains_total > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
-        PCE_CUDA (mc->d_eng.resize ((size_t) (2 * nchains_total)));
-        p.eng_acc = mc->d_eng.ptr; p.eng_stride = (uint32_t) nchains_total;
+
     }
     if (plan.kernel == 1) {
         void (*kernel) (const McParams);
@@ -1554,8 +1547,8 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
             const int allocated = (attributes.numRegs + 7) & ~7, warps_per_partition = (plan.block / 32 + 3) / 4;
             return warps_per_partition * allocated * 32 <= 16384;
         };
-#define PCE_THREAD_KERNEL(S_, R_) (short_fields ? (per_chain ? k_mc_thread<true, S_, R_, true> : k_mc_thread<false, S_, R_, true>) \
-                                                : (per_chain ? k_mc_thread<true, S_, R_, false> : k_mc_thread<false, S_, R_, false>))
+#define PCE_THREAD_KERNEL(S_, R_) (short_fields ? (per_chain ? k_mc_thread<true, S_, R_, true, true> : energy ? k_mc_thread<false, S_, R_, true, true> : k_mc_thread<false, S_, R_, true, false>) \
+                                                : (per_chain ? k_mc_thread<true, S_, R_, false, true> : energy ? k_mc_thread<false, S_, R_, false, true> : k_mc_thread<false, S_, R_, false, false>))
 #define PCE_THREAD_PICK(S_) (fits (PCE_THREAD_KERNEL (S_, 128)) ? PCE_THREAD_KERNEL (S_, 128) : fits (PCE_THREAD_KERNEL (S_, 80)) ? PCE_THREAD_KERNEL (S_, 80) \
                              : fits (PCE_THREAD_KERNEL (S_, 72)) ? PCE_THREAD_KERNEL (S_, 72) : PCE_THREAD_KERNEL (S_, 64))
         if (mc->nprod < 65536) kernel = PCE_THREAD_PICK (uint16_t);
@@ -1609,7 +1602,8 @@ extern "C" int pce_mc_run (pce_mc *mc, const double *ph, int nph, int ph_index_o
     PCE_CUDA (mc->d_counts.resize ((size_t) nph * m->ninst));
     PCE_CUDA (mc->d_counters.resize ((size_t) nph * 4));
     PCE_CUDA (mc->d_esum.resize (nph));
-    int status = pce_mc_run_device (mc, ph, nph, ph_index_offset, chain_offset, (long long *) mc->d_counts.ptr, mc->d_counters.ptr, mc->d_esum.ptr);
+    // energy sums only when the caller takes them (the quiet path of the reference returns occupancies only)
+    int status = pce_mc_run_device (mc, ph, nph, ph_index_offset, chain_offset, (long long *) mc->d_counts.ptr, mc->d_counters.ptr, esum ? mc->d_esum.ptr : nullptr);
     if (status != PCE_OK) return status;
     std::vector<long long> host_counts ((size_t) nph * m->ninst);
     PCE_CUDA (cudaMemcpyAsync (host_counts.data (), mc->d_counts.ptr, host_counts.size () * sizeof (long long), cudaMemcpyDeviceToHost, m->stream));

@@ -35,7 +35,7 @@ def _world(group=None):
     return dist.get_world_size(group)
 
 
-def mc_probabilities(sampler, pHs, total_chains, rank=0, world=1, group=None, device=None, run_counts=None, phIndexOffset=None):
+def mc_probabilities(sampler, pHs, total_chains, rank=0, world=1, group=None, device=None, run_counts=None, phIndexOffset=None, energy=False):
     """Titration-curve probabilities from ``total_chains`` chains per pH value spread over ``world`` ranks.
 
     -> (probabilities[npH, ninst], counts int64, counters int64 [npH, 4], esum[npH]), identical on every rank.
@@ -44,7 +44,8 @@ def mc_probabilities(sampler, pHs, total_chains, rank=0, world=1, group=None, de
     ``run_counts(pHs, chain_offset, nchains) -> (counts, counters, esum)`` (host arrays) replaces the launch: the CPU tests
     substitute the chain specification to exercise the sharding and the collective over gloo without a GPU.
     ``phIndexOffset``: explicit random-stream address (replayable); default: the sampler's next unused streams -- every rank
-    must have the same call history, as it has when all ranks run the same program."""
+    must have the same call history, as it has when all ranks run the same program.
+    ``energy``: also track the chain energies (``esum``; zeros otherwise, like the reference's quiet path)."""
     import torch
     import torch.distributed as dist
 
@@ -64,14 +65,14 @@ def mc_probabilities(sampler, pHs, total_chains, rank=0, world=1, group=None, de
                 sampler.nchains, sampler.chainOffset = count, offset
                 sampler._configure()
                 _native.check(sampler._lib.pce_mc_run_device(sampler._handle, ph, nph, stream_offset, int(offset), C.c_void_p(d_counts.data_ptr()),
-                                                             C.c_void_p(d_counts.data_ptr() + 8 * ncounts), C.c_void_p(d_esum.data_ptr())))
+                                                             C.c_void_p(d_counts.data_ptr() + 8 * ncounts), C.c_void_p(d_esum.data_ptr()) if energy else None))
                 sampler.owner.energyModel.Synchronize()            # the launch stream may not be torch's current stream
             packed = torch.cat([d_counts.to(torch.float64), d_esum])
         else:
             if run_counts is None:
                 def run_counts(values, chain_offset, nchains):
                     sampler.nchains, sampler.chainOffset = nchains, chain_offset
-                    return sampler.RunCounts(values, stream_offset)
+                    return sampler.RunCounts(values, stream_offset, energy=energy)
             if count > 0:
                 counts, counters, esum = run_counts(ph, offset, count)
             else:

@@ -45,7 +45,7 @@ def _worker(rank, world, port_number, path, backend):
     model = P.MEADModel(rec, log=None, device=index)
     sampler = P.MCModelDefault(nequil=50, nprod=400, randomSeed=4711, nchains=5)
     model.DefineMCModel(sampler, log=None)
-    p, counts, counters, esum = mc_probabilities(sampler, GRID, total_chains=TOTAL_CHAINS, rank=rank, world=world, device=device, phIndexOffset=0)
+    p, counts, counters, esum = mc_probabilities(sampler, GRID, total_chains=TOTAL_CHAINS, rank=rank, world=world, device=device, phIndexOffset=0, energy=True)
     assert sampler.nchains == 5 and sampler.chainOffset == 0                       # the caller's sampler is restored
     assert np.allclose(model.energyModel.GetProbabilities(), p[-1])               # every rank holds the reduced result
     model.DefineMCModel(None, log=None)

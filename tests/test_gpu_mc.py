@@ -55,6 +55,53 @@ def test_chains_equal_specification(port, name, nequil, nprod, kernel):
     assert np.array_equal(counts, out["counts"].sum(axis=1))
     assert np.array_equal(counters, out["counters"].sum(axis=1))
     assert np.abs(esum / out["esum"].sum(axis=1) - 1.0).max() < 1e-12
+    # the quiet path (no energy sums: another build of the chain-per-thread kernel, more chains per SM) walks the same chains
+    quiet_counts, quiet_counters, quiet_esum = sampler.RunCounts([2.0, 7.5], phIndexOffset=3, energy=False)
+    assert np.array_equal(quiet_counts, counts) and np.array_equal(quiet_counters, counters) and not quiet_esum.any()
+
+
+@pytest.mark.parametrize("block", [32, 96, 384, 768, 896])
+def test_chains_equal_specification_for_every_block_size(port, monkeypatch, block):
+    """The planner spreads small ensembles over the SMs in small blocks and packs large ones into blocks of up to 896 threads
+    (896 only without energy sums: a lysozyme chain then takes 247 instead of 263 bytes of shared memory): whatever the launch
+    geometry, every chain is the chain of the specification."""
+    rec, _gold, model, sampler = make("lysozyme", nequil=20, nprod=120, randomSeed=31337, nchains=70, kernel=1)
+    wsym = port.symmetrize(rec.interactions)
+    pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+    grid = [1.0, 6.5, 12.0]
+    expect = np.zeros((3, rec.ninstances), dtype=np.int64)
+    for q, ph in enumerate(grid):
+        for chain in range(70):
+            expect[q] += port.mc_philox_chain(rec, wsym, pairs, 20, 120, sampler.seed, chain, q, ph)["counts"]
+    monkeypatch.setenv("PCE_MC_BLOCK", str(block))
+    assert sampler.LaunchPlan(3)["block"] == block
+    counts, _counters, _esum = sampler.RunCounts(grid, energy=False)
+    assert np.array_equal(counts, expect)
+    if block <= 768:
+        out = sampler.RunChains(grid)
+        for q, ph in enumerate(grid):
+            for chain in (0, 33, 69):
+                spec = port.mc_philox_chain(rec, wsym, pairs, 20, 120, sampler.seed, chain, q, ph)
+                assert np.array_equal(out["counts"][q, chain], spec["counts"]) and out["esum"][q, chain] == spec["esum"]
+        counts, counters, _esum = sampler.RunCounts(grid, energy=True)
+        assert np.array_equal(counts, expect) and np.array_equal(counters, out["counters"].sum(axis=1))
+
+
+def test_planner_picks_by_ensemble_size():
+    """A default titration curve (64 chains x 41 pH) goes to the chain-per-warp kernel spread evenly over the SMs; a saturating
+    ensemble to the chain-per-thread kernel in its largest block; forced kernels are honoured."""
+    _rec, _gold, _model, sampler = make("lysozyme", nchains=64)
+    small = sampler.LaunchPlan(41)
+    assert small["kernel"] == 2 and small["block"] <= 128
+    sampler.nchains = 6000
+    large = sampler.LaunchPlan(41)
+    assert large["kernel"] == 1 and large["block"] >= 768
+    sampler.nchains, sampler.kernel = 64, 1
+    forced = sampler.LaunchPlan(41)
+    assert forced["kernel"] == 1 and forced["block"] <= 64
+    sampler.kernel = 0
+    p64 = _model.CalculateProbabilitiesBatch([7.0])[0]
+    assert abs(p64.sum() - _rec.nsites) < 1e-9
 
 
 @pytest.mark.parametrize("kernel", [1, 2])
