@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "pce_common.cuh"
@@ -45,11 +46,12 @@ __global__ void __launch_bounds__ (kBlock) k_enum_static (const EnumParams p) {
     cta.phase4 (tid);
 }
 
-// Persistent CTAs: CTA b takes chunks b, b + gridDim.x, ... of this shard's range; 128 registers (two CTAs per SM).
-template <bool CANON>
-__global__ void __launch_bounds__ (kBlock, 2) k_enum (const EnumParams p) {
+// Persistent CTAs of 128 threads: CTA b takes chunks b, b + gridDim.x, ... of this shard's range.  MODE 2 (two I x J register
+// sets per thread) runs three CTAs per SM at up to 168 registers, the others four at 128.
+template <int MODE>
+__global__ void __launch_bounds__ (kBlock, MODE == 2 ? 3 : 4) k_enum (const EnumParams p) {
     extern __shared__ __align__ (16) unsigned char smem[];
-    const pce_enum::EnumCta<CANON> cta (p, smem);
+    const pce_enum::EnumCta<MODE> cta (p, smem);
     pce_enum::EnumThread r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cta.init (tid, r);
@@ -108,20 +110,21 @@ __global__ void __launch_bounds__ (128) k_enum_reduce (const double *__restrict_
 
 // blockIdx.x: Z | (M site, digit) | (F site, digit); blockIdx.y: bin.  Elements are spread over the threads in a fixed
 // pattern and combined in a fixed order.
-__global__ void __launch_bounds__ (kBlock) k_enum_marginals (const MarginalParams p) {
-    __shared__ double s_part[kBlock / 32];
+__global__ void __launch_bounds__ (pce_enum::kMarginalBlock) k_enum_marginals (const MarginalParams p) {
+    constexpr int kThreads = pce_enum::kMarginalBlock;
+    __shared__ double s_part[kThreads / 32];
     int kind, site, digit, row;
     if (!pce_enum::marginal_target (p, (int) blockIdx.x, &kind, &site, &digit, &row)) return;
     const int tid = threadIdx.x, n_rel = (int) blockIdx.y;
     const long long count = kind == 2 ? p.nchunks_local : p.P_M;
     double acc = 0.0;
-    for (long long e = tid; e < count; e += kBlock) acc += pce_enum::marginal_term (p, kind, site, digit, n_rel, e);
+    for (long long e = tid; e < count; e += kThreads) acc += pce_enum::marginal_term (p, kind, site, digit, n_rel, e);
     acc = pce::warp_sum (acc);
     if ((tid & 31) == 0) s_part[tid >> 5] = acc;
     __syncthreads ();
     if (tid == 0) {
         double total = 0.0;
-        for (int w = 0; w < kBlock / 32; w++) total += s_part[w];
+        for (int w = 0; w < kThreads / 32; w++) total += s_part[w];
         p.bins[(size_t) row * p.Nb + p.base + n_rel] += total;
     }
 }
@@ -165,7 +168,7 @@ struct BlobLocate {
 };
 void pack_tables (const pce_enum::RunTables &T, Blob *blob) {
     blob->add (T.innerInst); blob->add (T.innerSite); blob->add (T.innerOff); blob->add (T.oInst); blob->add (T.idxM); blob->add (T.idxLo);
-    blob->add (T.idxHi); blob->add (T.idxI); blob->add (T.mlo); blob->add (T.mhi); blob->add (T.fInst); blob->add (T.nrelM); blob->add (T.nrelI);
+    blob->add (T.idxHi); blob->add (T.idxI); blob->add (T.idxJ); blob->add (T.mlo); blob->add (T.mhi); blob->add (T.fInst); blob->add (T.nrelM); blob->add (T.nrelI);
     blob->add (T.nrelO1); blob->add (T.nrelO2); blob->add (T.bO); blob->add (T.fRel); blob->add (T.fOff); blob->add (T.fRad); blob->add (T.fStride); blob->add (T.fShift);
     blob->add (T.D); blob->add (T.sigmaU); blob->add (T.digitM); blob->add (T.rowM); blob->add (T.rowMoff); blob->add (T.coverM); blob->add (T.coverF);
 }
@@ -177,7 +180,8 @@ void pack_tables (const pce_enum::RunTables &T, Blob *blob) {
 struct pce_enum_cache {
     int generation = -1, unfolded = -1;
     long long grid_slots = -1;
-    bool allow_canon = true, on_device = false, static_done = false;      // static_done: the numeric tables of every run are on the device
+    int  max_mode = 2;
+    bool on_device = false, static_done = false;      // static_done: the numeric tables of every run are on the device
     std::vector<double> ph;
     pce_enum::Plan plan;
     std::vector<pce_enum::RunTables> tables;
@@ -198,17 +202,19 @@ bool same_list (const std::vector<double> &a, const double *b, int n) {
 
 // plan (cached when the device copy of the model is current; the CPU-only finish of the tests plans afresh)
 int get_plan (pce_model *m, const double *ph, int nph, int unfolded, long long grid_slots, bool with_tables, pce_enum_cache **out) {
-    const bool allow_canon = std::getenv ("PCE_ENUM_GENERIC") == nullptr;       // test hook: force the generic accumulation path
+    // test hooks: PCE_ENUM_GENERIC=1 forces the generic accumulation path, PCE_ENUM_MODE=0|1|2 caps the kernel variant
+    int max_mode = std::getenv ("PCE_ENUM_GENERIC") != nullptr ? 0 : 2;
+    if (const char *cap = std::getenv ("PCE_ENUM_MODE")) max_mode = std::max (0, std::min (2, std::atoi (cap)));
     pce_enum_cache *cache = m->enum_cache;
     const bool current = cache != nullptr && !m->dirty && cache->generation == m->generation && cache->unfolded == unfolded && same_list (cache->ph, ph, nph) &&
-                         cache->allow_canon == allow_canon;
+                         cache->max_mode == max_mode;
     if (current && (!with_tables || (cache->grid_slots == grid_slots && !cache->tables.empty ()))) { *out = cache; return PCE_OK; }
     if (cache == nullptr) { cache = new pce_enum_cache (); m->enum_cache = cache; m->enum_cache_free = pce_enum_cache_free; }
     const pce_enum::ModelView view = view_of (m, unfolded);
     std::string message;
     cache->generation = -1;
     cache->tables.clear (); cache->blobs.clear (); cache->blob_offset.clear (); cache->on_device = false; cache->static_done = false;
-    if (pce_enum::make_plan (view, ph, nph, &cache->plan, &message, grid_slots, allow_canon)) return fail (PCE_ERR_LIMIT, message);
+    if (pce_enum::make_plan (view, ph, nph, &cache->plan, &message, grid_slots, max_mode)) return fail (PCE_ERR_LIMIT, message);
     if (with_tables) {
         cache->tables.resize (cache->plan.runs.size ());
         cache->blobs.resize (cache->plan.runs.size ());
@@ -222,7 +228,7 @@ int get_plan (pce_model *m, const double *ph, int nph, int unfolded, long long g
         cache->blob_total = total;
     }
     cache->generation = m->dirty ? -1 : m->generation;
-    cache->unfolded = unfolded; cache->grid_slots = grid_slots; cache->allow_canon = allow_canon;
+    cache->unfolded = unfolded; cache->grid_slots = grid_slots; cache->max_mode = max_mode;
     cache->ph.assign (ph, ph + nph);
     *out = cache;
     return PCE_OK;
@@ -285,7 +291,7 @@ int run_plan (pce_model *m, pce_enum_cache *cache, int unfolded, int shard, int 
         const pce_enum::EnumLayout layout (p);
         const pce_enum::StaticLayout static_layout (p);
         if (layout.total + 1024 > limit || static_layout.total + 1024 > limit) return fail (PCE_ERR_LIMIT, "too many proton-count bins for shared memory");
-        void (*kernel) (const EnumParams) = T.canon ? k_enum<true> : k_enum<false>;
+        void (*kernel) (const EnumParams) = T.mode == 2 ? k_enum<2> : T.mode == 1 ? k_enum<1> : k_enum<0>;
         int per_sm = 0;
         int status = resident_ctas (kernel, layout.total, &per_sm);
         if (status != PCE_OK) return status;
@@ -313,7 +319,7 @@ int run_plan (pce_model *m, pce_enum_cache *cache, int unfolded, int shard, int 
         mp.Nb = plan.Nb; mp.base = plan.base; mp.write_z = r == 0 ? 1 : 0; mp.grid = ctas;
         mp.chunk_begin = c0; mp.nchunks_local = p.nchunks_local; mp.ldF = p.ldF;
         mp.Mtab = d_Mtab.ptr; mp.FtabT = d_Ftab.ptr; mp.bins = d_bins;
-        k_enum_marginals<<<dim3 ((unsigned) pce_enum::marginal_rows (T), (unsigned) T.NbAll), kBlock, 0, m->stream>>> (mp);
+        k_enum_marginals<<<dim3 ((unsigned) pce_enum::marginal_rows (T), (unsigned) T.NbAll), pce_enum::kMarginalBlock, 0, m->stream>>> (mp);
         PCE_CUDA (cudaGetLastError ());
         pce::count_launch (3);
     }
@@ -362,7 +368,7 @@ extern "C" int pce_analytic_bins (pce_model *m, const double *ph, int nph, int u
     int sms = 0;
     PCE_CUDA (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, m->device));
     pce_enum_cache *cache = nullptr;
-    status = get_plan (m, ph, nph, unfolded, (long long) sms * 2 * nshards, true, &cache);      // two resident CTAs per SM on every shard
+    status = get_plan (m, ph, nph, unfolded, (long long) sms * 3 * nshards, true, &cache);      // three resident CTAs per SM on every shard
     if (status != PCE_OK) return status;
     return run_plan (m, cache, unfolded, shard, nshards, sms, d_bins);
 }

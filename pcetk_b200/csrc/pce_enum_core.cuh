@@ -50,23 +50,24 @@ struct EnumParams {
     const double *gt, *w;        // tilted intrinsic energies G[a] - protons[a] mu(pH*); W [ninst][ldw]
     double beta, gref;
     // sizes (RunTables)
-    int nM, nLo, nI, nO1, nO2, nO, nF, nS;
-    int P_lo, P_hi, P_M, P_I, P_O1, P_O2, P_O;
+    int nM, nLo, nI, nJ, nO1, nO2, nO, nF, nS;
+    int P_lo, P_hi, P_M, P_I, P_J, P_O1, P_O2, P_O;
     int nInner, nMinst, nOinst;
-    int NbC, NbCp, NbP, NbAll, nU, nV, canon, needF;
+    int NbC, NbCp, NbP, NbAll, nU, nV, mode, needF;
     unsigned flushI;
     long long chunk_begin, nchunks_local, ldF;
     // integer tables
-    const int16_t *innerInst, *innerSite, *innerOff, *oInst, *idxM, *idxLo, *idxHi, *idxI, *mlo, *mhi, *fInst;
+    const int16_t *innerInst, *innerSite, *innerOff, *oInst, *idxM, *idxLo, *idxHi, *idxI, *idxJ, *mlo, *mhi, *fInst;
     const uint8_t *nrelM, *nrelI, *nrelO1, *nrelO2, *bO, *fRel;
-    const int32_t *fOff, *fRad;
+    const int32_t *fOff, *fRad, *fShift;
     const long long *fStride;
     const double *D, *sigmaU;
     // numeric tables written by the static program
-    double *xs;                  // [kIStates][kBlock]
+    double *xs;                  // [kXStates][kBlock] static factor of (thread's M configuration, I x J configuration c = j * 16 + i)
     double *P1;                  // [kO1States][kBlock]
     double *P2lo, *P2hi;         // [P_O2][P_lo], [P_O2][P_hi]
     double *Q;                   // [P_O][kIStates]
+    double *QJ;                  // [P_O][2] the same for the two instances of the J site
     double *EO;                  // [P_O] O-O energy of the tile plus the minima taken out of the inner-O factors
     double *shiftS;              // [1] minimum taken out of xs
     // outputs of the enumeration program
@@ -87,10 +88,10 @@ struct StaticLayout {
         off_wmin = o; o += (size_t) (p.nS > 0 ? p.nS : 1) * (p.nOinst > 0 ? p.nOinst : 1) * 8;
         off_vo1 = o;  o += (size_t) (p.nInner > 0 ? p.nInner : 1) * kO1States * 8;
         off_vo2 = o;  o += (size_t) (p.nInner > 0 ? p.nInner : 1) * kO2States * 8;
-        off_vmi = o;  o += (size_t) (p.nMinst > 0 ? p.nMinst : 1) * kIStates * 8;
-        off_eii = o;  o += (size_t) kIStates * 8;
+        off_vmi = o;  o += (size_t) (p.nMinst > 0 ? p.nMinst : 1) * kXStates * 8;
+        off_eii = o;  o += (size_t) kXStates * 8;
         off_red = o;  o += (size_t) kBlock * 8;
-        off_en = o;   o += (size_t) kIStates * kBlock * 8;
+        off_en = o;   o += (size_t) kXStates * kBlock * 8;
         off_inst = o; o += align16 ((size_t) (p.nInner + p.nOinst + 2) * 4);
         off_sw = o;
         const size_t nw = (size_t) p.nInner * p.nInner + (size_t) p.nInner * p.nOinst + (size_t) p.nOinst * p.nOinst;
@@ -166,33 +167,41 @@ struct StaticCta {
                 for (int o = 0; o < p.nO2; o++) { const int b = p.bO[(size_t) t2 * p.P_O1 * kMaxO + p.nO1 + o]; v += Wio (j, b) - wmin[s * p.nOinst + b]; }
             vo2[e] = v;
         }
-        for (int e = tid; e < p.nMinst * kIStates; e += kBlock) {           // Vmi[j][i] = sum over the I sites of W[j][instance of configuration i]
-            const int j = e / kIStates, i = e - j * kIStates;
+        const int nIJ = p.nI + p.nJ;                                        // sites of an I x J configuration: idxI[c][0 .. nI) and, with a J site, idxI[c][kMaxI]
+        for (int e = tid; e < p.nMinst * kXStates; e += kBlock) {           // Vmi[j][c] = sum over the I and J sites of W[j][instance of configuration c]
+            const int j = e / kXStates, c = e - j * kXStates;
             double v = 0.0;
-            if (folded && i < p.P_I) for (int l = 0; l < p.nI; l++) v += Wii (j, p.idxI[i * kMaxI + l]);
+            if (folded && (c & (kIStates - 1)) < p.P_I && c / kIStates < p.P_J) {
+                for (int l = 0; l < p.nI; l++) v += Wii (j, p.idxI[c * (kMaxI + 1) + l]);
+                if (p.nJ) v += Wii (j, p.idxI[c * (kMaxI + 1) + kMaxI]);
+            }
             vmi[e] = v;
         }
-        for (int i = tid; i < kIStates; i += kBlock) {
+        for (int c = tid; c < kXStates; c += kBlock) {
             double v = 0.0;
-            if (folded && i < p.P_I)
-                for (int l = 0; l < p.nI; l++) for (int l2 = 0; l2 < l; l2++) v += Wii (p.idxI[i * kMaxI + l], p.idxI[i * kMaxI + l2]);
-            eii[i] = v;
+            if (folded && (c & (kIStates - 1)) < p.P_I && c / kIStates < p.P_J) {
+                int site[kMaxI + 1];
+                for (int l = 0; l < p.nI; l++) site[l] = p.idxI[c * (kMaxI + 1) + l];
+                if (p.nJ) site[p.nI] = p.idxI[c * (kMaxI + 1) + kMaxI];
+                for (int l = 0; l < nIJ; l++) for (int l2 = 0; l2 < l; l2++) v += Wii (site[l], site[l2]);
+            }
+            eii[c] = v;
         }
     }
-    // S3: static energies of thread tid, en[i][tid] = E_MM + E_MI(i) + E_II(i), and the thread's minimum
+    // S3: static energies of thread tid, en[c][tid] = E_MM + E_M(IJ)(c) + E_(IJ)(IJ)(c), and the thread's minimum
     PCE_DEV void phase3 (int tid) const {
         int idx[kMaxM];
         for (int k = 0; k < kMaxM; k++) idx[k] = p.idxM[tid * kMaxM + k];
         double emm = 0.0, vmin = DBL_MAX;
         if (!p.unfolded && tid < p.P_M)
             for (int k = 0; k < p.nM; k++) for (int k2 = 0; k2 < k; k2++) emm += Wii (idx[k], idx[k2]);
-        for (int i = 0; i < kIStates; i++) {
-            double v = emm + eii[i];
-            if (tid < p.P_M && i < p.P_I) {
-                for (int k = 0; k < p.nM; k++) v += vmi[idx[k] * kIStates + i];
+        for (int c = 0; c < kXStates; c++) {
+            double v = emm + eii[c];
+            if (tid < p.P_M && (c & (kIStates - 1)) < p.P_I && c / kIStates < p.P_J) {
+                for (int k = 0; k < p.nM; k++) v += vmi[idx[k] * kXStates + c];
                 vmin = fmin (vmin, v);
             }
-            en[i * kBlock + tid] = v;
+            en[c * kBlock + tid] = v;
         }
         red[tid] = vmin;
     }
@@ -209,7 +218,8 @@ struct StaticCta {
         const double shift = red[0];
         int idx[kMaxM];
         for (int k = 0; k < kMaxM; k++) idx[k] = p.idxM[tid * kMaxM + k];
-        for (int i = 0; i < kIStates; i++) p.xs[i * kBlock + tid] = (tid < p.P_M && i < p.P_I) ? exp (-p.beta * (en[i * kBlock + tid] - shift)) : 0.0;
+        for (int c = 0; c < kXStates; c++)
+            p.xs[c * kBlock + tid] = (tid < p.P_M && (c & (kIStates - 1)) < p.P_I && c / kIStates < p.P_J) ? exp (-p.beta * (en[c * kBlock + tid] - shift)) : 0.0;
         for (int t1 = 0; t1 < kO1States; t1++) {
             double v = 0.0;
             if (tid < p.P_M && t1 < p.P_O1) {
@@ -236,10 +246,16 @@ struct StaticCta {
             double v = 0.0;
             if (i < p.P_I) {
                 double s = 0.0;
-                for (int l = 0; l < p.nI; l++) { const int j = p.idxI[i * kMaxI + l]; s += vo1[j * kO1States + t1] + vo2[j * kO2States + t2]; }
+                for (int l = 0; l < p.nI; l++) { const int j = p.idxI[i * (kMaxI + 1) + l]; s += vo1[j * kO1States + t1] + vo2[j * kO2States + t2]; }
                 v = exp (-p.beta * s);
             }
             p.Q[e2] = v;
+        }
+        for (int e2 = tid; e2 < p.P_O * 2; e2 += kBlock) {                 // QJ[t][j]: the J instance against the tile's O configuration
+            const int t = e2 >> 1, j = e2 & 1, t2 = t / p.P_O1, t1 = t - t2 * p.P_O1;
+            double v = j == 0 ? 1.0 : 0.0;
+            if (p.nJ) { const int a = p.idxJ[j]; v = exp (-p.beta * (vo1[a * kO1States + t1] + vo2[a * kO2States + t2])); }
+            p.QJ[e2] = v;
         }
         for (int t = tid; t < p.P_O; t += kBlock) {
             const uint8_t *row = p.bO + (size_t) t * kMaxO;
@@ -259,20 +275,21 @@ struct StaticCta {
 // enumeration program: persistent CTA, chunks blockIdx.x, blockIdx.x + gridDim.x, ...
 // ---------------------------------------------------------------------------------------------------
 struct EnumLayout {
-    size_t off_pb, off_cb, off_qc, off_p2lo, off_p2hi, off_ce, off_ff, off_ef, off_minf, off_eif, off_elo, off_ehi, off_d, off_su, off_eo,
+    size_t off_pb, off_cb, off_qc, off_qj, off_p2lo, off_p2hi, off_ce, off_ff, off_ef, off_minf, off_eif, off_elo, off_ehi, off_d, off_su, off_eo,
            off_af, off_rf, off_misc, off_bo, off_nrel, off_idx, off_inner, total;
     PCE_HD EnumLayout (const EnumParams &p) {
         size_t o = 0;
         off_pb = o;   o += (size_t) p.NbP * kBlock * 8;
         off_cb = o;   o += (size_t) p.NbC * kBlock * 8;
         off_qc = o;   o += (size_t) p.P_O * kIStates * 8;
+        off_qj = o;   o += (size_t) p.P_O * 2 * 8;
         off_p2lo = o; o += (size_t) p.P_O2 * p.P_lo * 8;
         off_p2hi = o; o += (size_t) p.P_O2 * p.P_hi * 8;
         off_ce = o;   o += (size_t) p.P_O * 8;
         off_ff = o;   o += (size_t) (p.nInner + p.nOinst + p.nF + 1) * 8;
         off_ef = o;   o += (size_t) (p.nInner + 1) * 8;
         off_minf = o; o += (size_t) (p.nS + 1) * 8;
-        off_eif = o;  o += (size_t) kIStates * 8;
+        off_eif = o;  o += (size_t) (kIStates + 2) * 8;        // EIF[16] | EJF[2]
         off_elo = o;  o += (size_t) p.P_lo * 8;
         off_ehi = o;  o += (size_t) p.P_hi * 8;
         off_d = o;    o += (size_t) p.nU * p.nV * 8;
@@ -284,7 +301,7 @@ struct EnumLayout {
         off_bo = o;   o += align16 ((size_t) p.P_O * kMaxO);
         off_nrel = o; o += (size_t) (kIStates + kO1States + kO2States + kBlock);        // nrelI | nrelO1 | nrelO2 | nrelM
         o = align16 (o);
-        off_idx = o;  o += (size_t) (kIStates * kMaxI + (p.P_lo + p.P_hi) * kMaxM) * 2;      // idxI | idxLo | idxHi
+        off_idx = o;  o += (size_t) (kIStates * (kMaxI + 1) + (p.P_lo + p.P_hi) * kMaxM) * 2;      // idxI (j = 0 rows) | idxLo | idxHi
         o = align16 (o);
         off_inner = o; o += (size_t) (2 * p.nInner + p.nS + 1 + p.nOinst + 4) * 2;           // innerInst | innerSite | innerOff | oInst
         total = align16 (o);
@@ -292,30 +309,32 @@ struct EnumLayout {
 };
 
 struct EnumThread {              // per-thread registers
-    double xs[kIStates];         // static factors of the thread's M configuration (zero beyond P_I)
+    double xs[kXStates];         // static factors of the thread's M configuration, c = j * 16 + i (zero beyond P_I / P_J)
     double p1[kO1States];
     double A;                    // chunk factor of the M configuration
     int    mlo, mhi, nrelM;
 };
 
-template <bool CANON>
+// MODE 0: run-time proton groups, bins in shared memory | 1: canonical I (4 sites) and O1 (3 sites): register accumulators |
+// 2: + a canonical J site whose two instances the thread handles with two sets of register factors
+template <int MODE>
 struct EnumCta {
     const EnumParams &p;
-    double *PB, *CB, *Qc, *P2lo, *P2hi, *cE, *fF, *EF, *minF, *EIF, *ELo, *EHi, *D, *sU, *EO;
+    double *PB, *CB, *Qc, *QJc, *P2lo, *P2hi, *cE, *fF, *EF, *minF, *EIF, *EJF, *ELo, *EHi, *D, *sU, *EO;
     int32_t *aF, *rF, *misc;     // misc[0] = protons of the chunk above the F minimum
     uint8_t *bO, *nrelI, *nrelO1, *nrelO2, *nrelM;
     int16_t *idxI, *idxLo, *idxHi, *innerInst, *innerSite, *innerOff, *oInst;
 
     PCE_DEV EnumCta (const EnumParams &params, unsigned char *smem) : p (params) {
         const EnumLayout L (params);
-        PB = (double *) (smem + L.off_pb); CB = (double *) (smem + L.off_cb); Qc = (double *) (smem + L.off_qc);
+        PB = (double *) (smem + L.off_pb); CB = (double *) (smem + L.off_cb); Qc = (double *) (smem + L.off_qc); QJc = (double *) (smem + L.off_qj);
         P2lo = (double *) (smem + L.off_p2lo); P2hi = (double *) (smem + L.off_p2hi); cE = (double *) (smem + L.off_ce);
         fF = (double *) (smem + L.off_ff); EF = (double *) (smem + L.off_ef); minF = (double *) (smem + L.off_minf);
-        EIF = (double *) (smem + L.off_eif); ELo = (double *) (smem + L.off_elo); EHi = (double *) (smem + L.off_ehi);
+        EIF = (double *) (smem + L.off_eif); EJF = EIF + kIStates; ELo = (double *) (smem + L.off_elo); EHi = (double *) (smem + L.off_ehi);
         D = (double *) (smem + L.off_d); sU = (double *) (smem + L.off_su); EO = (double *) (smem + L.off_eo);
         aF = (int32_t *) (smem + L.off_af); rF = (int32_t *) (smem + L.off_rf); misc = (int32_t *) (smem + L.off_misc);
         bO = smem + L.off_bo; nrelI = smem + L.off_nrel; nrelO1 = nrelI + kIStates; nrelO2 = nrelO1 + kO1States; nrelM = nrelO2 + kO2States;
-        idxI = (int16_t *) (smem + L.off_idx); idxLo = idxI + kIStates * kMaxI; idxHi = idxLo + params.P_lo * kMaxM;
+        idxI = (int16_t *) (smem + L.off_idx); idxLo = idxI + kIStates * (kMaxI + 1); idxHi = idxLo + params.P_lo * kMaxM;
         innerInst = (int16_t *) (smem + L.off_inner); innerSite = innerInst + params.nInner; innerOff = innerSite + params.nInner;
         oInst = innerOff + params.nS + 1;
     }
@@ -332,15 +351,15 @@ struct EnumCta {
         for (int e = tid; e < kIStates; e += kBlock) nrelI[e] = p.nrelI[e];
         for (int e = tid; e < kO1States; e += kBlock) nrelO1[e] = p.nrelO1[e];
         for (int e = tid; e < kO2States; e += kBlock) nrelO2[e] = p.nrelO2[e];
-        nrelM[tid] = p.nrelM[tid];
-        for (int e = tid; e < kIStates * kMaxI; e += kBlock) idxI[e] = p.idxI[e];
+        for (int e = tid; e < kBlock; e += kBlock) nrelM[e] = p.nrelM[e];
+        for (int e = tid; e < kIStates * (kMaxI + 1); e += kBlock) idxI[e] = p.idxI[e];
         for (int e = tid; e < p.P_lo * kMaxM; e += kBlock) idxLo[e] = p.idxLo[e];
         for (int e = tid; e < p.P_hi * kMaxM; e += kBlock) idxHi[e] = p.idxHi[e];
         for (int e = tid; e < p.nInner; e += kBlock) { innerInst[e] = p.innerInst[e]; innerSite[e] = p.innerSite[e]; }
         for (int e = tid; e <= p.nS; e += kBlock) innerOff[e] = p.innerOff[e];
         for (int e = tid; e < p.nOinst; e += kBlock) oInst[e] = p.oInst[e];
         PCE_UNROLL
-        for (int i = 0; i < kIStates; i++) r.xs[i] = p.xs[i * kBlock + tid];
+        for (int c = 0; c < (MODE == 2 ? kXStates : kIStates); c++) r.xs[c] = p.xs[c * kBlock + tid];
         PCE_UNROLL
         for (int t1 = 0; t1 < kO1States; t1++) r.p1[t1] = p.P1[t1 * kBlock + tid];
         r.mlo = p.mlo[tid]; r.mhi = p.mhi[tid]; r.nrelM = p.nrelM[tid];
@@ -350,7 +369,9 @@ struct EnumCta {
     // P0: digits of the chunk
     PCE_DEV void phase0 (int tid, long long chunk) const {
         if (tid < p.nF) {
-            const int d = (int) ((unsigned long long) (chunk / p.fStride[tid]) % (unsigned long long) p.fRad[tid]);
+            const int shift = p.fShift[tid];
+            const int d = shift >= 0 ? (int) (((unsigned long long) chunk >> shift) & (unsigned long long) (p.fRad[tid] - 1))
+                                     : (int) ((unsigned long long) (chunk / p.fStride[tid]) % (unsigned long long) p.fRad[tid]);
             aF[tid] = p.fInst[p.fOff[tid] + d];
             rF[tid] = p.fRel[p.fOff[tid] + d];
         }
@@ -365,7 +386,15 @@ struct EnumCta {
             if (folded) {
                 const int nf = j < n2 ? p.nF : j - n2;          // F-F pairs once: f2 < f
                 const double *row = p.w + (size_t) a * p.ldw;
-                for (int f = 0; f < nf; f++) acc += row[aF[f]];
+                int f = 0;
+                for (; f + 4 <= nf; f += 4) {                   // four independent gathers in flight (L2 latency once per batch), added in order
+                    double v[4];
+                    PCE_UNROLL
+                    for (int u = 0; u < 4; u++) v[u] = row[aF[f + u]];
+                    PCE_UNROLL
+                    for (int u = 0; u < 4; u++) acc += v[u];
+                }
+                for (; f < nf; f++) acc += row[aF[f]];
             }
             fF[j] = acc;
         }
@@ -389,6 +418,7 @@ struct EnumCta {
     // P3: tile constants (with the bin scale of the tile's chunk + O2 protons) and the chunk factors of the I / Lo / Hi configurations
     PCE_DEV void phase3 (int tid) const {
         const int n_items = p.P_O + kIStates + p.P_lo + p.P_hi;
+        if (tid < 2) EJF[tid] = p.nJ ? EF[p.idxJ[tid]] : (tid == 0 ? 1.0 : 0.0);
         for (int e = tid; e < n_items; e += kBlock) {
             if (e < p.P_O) {
                 const int t = e;
@@ -402,7 +432,7 @@ struct EnumCta {
             } else if (e < p.P_O + kIStates) {
                 const int i = e - p.P_O;
                 double v = 0.0;
-                if (i < p.P_I) { v = 1.0; for (int l = 0; l < p.nI; l++) v *= EF[idxI[i * kMaxI + l]]; }
+                if (i < p.P_I) { v = 1.0; for (int l = 0; l < p.nI; l++) v *= EF[idxI[i * (kMaxI + 1) + l]]; }
                 EIF[i] = v;
             } else if (e < p.P_O + kIStates + p.P_lo) {
                 const int x = e - p.P_O - kIStates;
@@ -419,41 +449,58 @@ struct EnumCta {
     }
     // P4: the tile table of this chunk and the thread's chunk factor
     PCE_DEV void phase4 (int tid, EnumThread &r) const {
-        for (int e = tid; e < p.P_O * kIStates; e += kBlock) Qc[e] = p.Q[e] * (cE[e / kIStates] * EIF[e % kIStates]);
+        // (the Q entries come from L2: four loads of the thread are issued before the first store, two latencies instead of eight)
+        const int total = p.P_O * kIStates;
+        for (int e0 = tid; e0 < total; e0 += 4 * kBlock) {
+            double qv[4];
+            PCE_UNROLL
+            for (int k = 0; k < 4; k++) { const int e = e0 + k * kBlock; qv[k] = e < total ? p.Q[e] : 0.0; }
+            PCE_UNROLL
+            for (int k = 0; k < 4; k++) { const int e = e0 + k * kBlock; if (e < total) Qc[e] = qv[k] * (cE[e / kIStates] * EIF[e % kIStates]); }
+        }
+        for (int e = tid; e < p.P_O * 2; e += kBlock) QJc[e] = p.QJ[e] * EJF[e & 1];
         r.A = ELo[r.mlo] * EHi[r.mhi];
     }
 
-    // main: the thread's P_O x P_I states of this chunk
+    // main: the thread's P_O x P_I x P_J states of this chunk
     PCE_DEV void accumulate (int tid, const EnumThread &r) const {
         const int nrelF = misc[0];
         if (tid >= p.P_M) return;
-        if (CANON) {
-            // I = 4 and O1 = 3 canonical sites: protons above the minimum are popcounts, so the bins of the I x O1
-            // configurations are 8 register accumulators; flushed when the O2 proton count changes (O2 sorted by it)
-            double acc[8];
+        if constexpr (MODE > 0) {
+            // I = 4 and O1 = 3 canonical sites (and the J site): protons above the minimum are popcounts, so the bins of the
+            // I x J x O1 configurations are register accumulators indexed at compile time; flushed when the O2 proton count
+            // changes (O2 is sorted by it).  Sorted I configurations: proton groups of 1, 4, 6, 4, 1.
+            constexpr int NACC = MODE == 2 ? 9 : 8;
+            double acc[NACC];
             PCE_UNROLL
-            for (int j = 0; j < 8; j++) acc[j] = 0.0;
+            for (int j = 0; j < NACC; j++) acc[j] = 0.0;
             int g_prev = nrelO2[0];
             for (int t2 = 0; t2 < p.P_O2; t2++) {
                 const int g = nrelO2[t2];
-                if (g != g_prev) { flush_canon (tid, r, acc, nrelF, g_prev); g_prev = g; }
+                if (g != g_prev) { flush_canon<NACC> (tid, r, acc, nrelF, g_prev); g_prev = g; }
                 const double B = r.A * P2lo[t2 * p.P_lo + r.mlo] * P2hi[t2 * p.P_hi + r.mhi];
                 const double *q = Qc + (size_t) t2 * (kO1States * kIStates);
+                const double *qj = QJc + (size_t) t2 * (kO1States * 2);
                 PCE_UNROLL
                 for (int t1 = 0; t1 < kO1States; t1++) {
                     const double *qt = q + t1 * kIStates;
                     const double pb = r.p1[t1] * B;
-                    // sorted I configurations: proton groups of 1, 4, 6, 4, 1
-                    const double g0 = qt[0] * r.xs[0];
-                    const double g1 = qt[1] * r.xs[1] + qt[2] * r.xs[2] + qt[3] * r.xs[3] + qt[4] * r.xs[4];
-                    const double g2 = qt[5] * r.xs[5] + qt[6] * r.xs[6] + qt[7] * r.xs[7] + qt[8] * r.xs[8] + qt[9] * r.xs[9] + qt[10] * r.xs[10];
-                    const double g3 = qt[11] * r.xs[11] + qt[12] * r.xs[12] + qt[13] * r.xs[13] + qt[14] * r.xs[14];
-                    const double g4 = qt[15] * r.xs[15];
                     constexpr int pc[8] = { 0, 1, 1, 2, 1, 2, 2, 3 };
-                    acc[pc[t1] + 0] += pb * g0; acc[pc[t1] + 1] += pb * g1; acc[pc[t1] + 2] += pb * g2; acc[pc[t1] + 3] += pb * g3; acc[pc[t1] + 4] += pb * g4;
+                    PCE_UNROLL
+                    for (int j = 0; j < (MODE == 2 ? 2 : 1); j++) {
+                        const double *x = r.xs + j * kIStates;
+                        const double g0 = qt[0] * x[0];
+                        const double g1 = qt[1] * x[1] + qt[2] * x[2] + qt[3] * x[3] + qt[4] * x[4];
+                        const double g2 = qt[5] * x[5] + qt[6] * x[6] + qt[7] * x[7] + qt[8] * x[8] + qt[9] * x[9] + qt[10] * x[10];
+                        const double g3 = qt[11] * x[11] + qt[12] * x[12] + qt[13] * x[13] + qt[14] * x[14];
+                        const double g4 = qt[15] * x[15];
+                        const double pbj = MODE == 2 ? pb * qj[t1 * 2 + j] : pb;
+                        acc[pc[t1] + j + 0] += pbj * g0; acc[pc[t1] + j + 1] += pbj * g1; acc[pc[t1] + j + 2] += pbj * g2;
+                        acc[pc[t1] + j + 3] += pbj * g3; acc[pc[t1] + j + 4] += pbj * g4;
+                    }
                 }
             }
-            flush_canon (tid, r, acc, nrelF, g_prev);
+            flush_canon<NACC> (tid, r, acc, nrelF, g_prev);
         } else {
             for (int t2 = 0; t2 < p.P_O2; t2++) {
                 const int g = nrelO2[t2];
@@ -479,11 +526,12 @@ struct EnumCta {
             }
         }
     }
+    template <int NACC>
     PCE_DEV void flush_canon (int tid, const EnumThread &r, double *acc, int nrelF, int g) const {
         const double *drow = D + (size_t) (nrelF + g) * p.nV + r.nrelM;
         double *cb = CB + (size_t) g * kBlock + tid;
         PCE_UNROLL
-        for (int j = 0; j < 8; j++) { cb[j * kBlock] += acc[j] * drow[j]; acc[j] = 0.0; }
+        for (int j = 0; j < NACC; j++) { cb[j * kBlock] += acc[j] * drow[j]; acc[j] = 0.0; }
     }
 
     // P5a: the chunk bins go into the thread's persistent bins (own column only)
@@ -564,37 +612,38 @@ PCE_DEV double marginal_term (const MarginalParams &p, int kind, int site, int d
 // ---------------------------------------------------------------------------------------------------
 // host helpers shared by the library and the emulator: sizes and table pointers of a run into the kernel parameters
 // ---------------------------------------------------------------------------------------------------
-constexpr size_t kNumericDoubles = (size_t) kIStates * kBlock + (size_t) kO1States * kBlock + (size_t) kO2States * kBlock + (size_t) kO2States * 64 +
-                                   (size_t) kMaxTiles * kIStates + kMaxTiles + kMaxOinst + 8;
+constexpr size_t kNumericDoubles = (size_t) kXStates * kBlock + (size_t) kO1States * kBlock + (size_t) kO2States * kBlock + (size_t) kO2States * 64 +
+                                   (size_t) kMaxTiles * kIStates + (size_t) kMaxTiles * 2 + kMaxTiles + 8;
 
 // `locate (vector)` returns the address of the (host or device) copy of one of the RunTables vectors;
 // `numeric` is a buffer of kNumericDoubles doubles for the tables the static program writes
 template <typename Locate>
 inline void bind_run (const RunTables &T, EnumParams &p, MarginalParams &mp, Locate &&locate, double *numeric) {
-    p.nM = T.nM; p.nLo = T.nLo; p.nI = T.nI; p.nO1 = T.nO1; p.nO2 = T.nO2; p.nO = T.nO1 + T.nO2; p.nF = T.nF; p.nS = T.nS;
-    p.P_lo = T.P_lo; p.P_hi = T.P_hi; p.P_M = T.P_M; p.P_I = T.P_I; p.P_O1 = T.P_O1; p.P_O2 = T.P_O2; p.P_O = T.P_O;
+    p.nM = T.nM; p.nLo = T.nLo; p.nI = T.nI; p.nJ = T.nJ; p.nO1 = T.nO1; p.nO2 = T.nO2; p.nO = T.nO1 + T.nO2; p.nF = T.nF; p.nS = T.nS;
+    p.P_lo = T.P_lo; p.P_hi = T.P_hi; p.P_M = T.P_M; p.P_I = T.P_I; p.P_J = T.P_J; p.P_O1 = T.P_O1; p.P_O2 = T.P_O2; p.P_O = T.P_O;
     p.nInner = T.nInner; p.nMinst = T.nMinst; p.nOinst = T.nOinst;
-    p.NbC = T.NbC; p.NbCp = T.NbCp; p.NbP = T.NbP; p.NbAll = T.NbAll; p.nU = T.nU; p.nV = T.nV; p.canon = T.canon;
+    p.NbC = T.NbC; p.NbCp = T.NbCp; p.NbP = T.NbP; p.NbAll = T.NbAll; p.nU = T.nU; p.nV = T.nV; p.mode = T.mode;
     p.flushI = T.flushI;
     p.innerInst = locate (T.innerInst); p.innerSite = locate (T.innerSite); p.innerOff = locate (T.innerOff); p.oInst = locate (T.oInst);
-    p.idxM = locate (T.idxM); p.idxLo = locate (T.idxLo); p.idxHi = locate (T.idxHi); p.idxI = locate (T.idxI);
+    p.idxM = locate (T.idxM); p.idxLo = locate (T.idxLo); p.idxHi = locate (T.idxHi); p.idxI = locate (T.idxI); p.idxJ = locate (T.idxJ);
     p.mlo = locate (T.mlo); p.mhi = locate (T.mhi); p.fInst = locate (T.fInst);
     p.nrelM = locate (T.nrelM); p.nrelI = locate (T.nrelI); p.nrelO1 = locate (T.nrelO1); p.nrelO2 = locate (T.nrelO2);
-    p.bO = locate (T.bO); p.fRel = locate (T.fRel); p.fOff = locate (T.fOff); p.fRad = locate (T.fRad); p.fStride = locate (T.fStride);
+    p.bO = locate (T.bO); p.fRel = locate (T.fRel); p.fOff = locate (T.fOff); p.fRad = locate (T.fRad); p.fStride = locate (T.fStride); p.fShift = locate (T.fShift);
     p.D = locate (T.D); p.sigmaU = locate (T.sigmaU);
     double *o = numeric;
-    p.xs = o; o += (size_t) kIStates * kBlock;
+    p.xs = o; o += (size_t) kXStates * kBlock;
     p.P1 = o; o += (size_t) kO1States * kBlock;
     p.P2lo = o; o += (size_t) kO2States * kBlock;
     p.P2hi = o; o += (size_t) kO2States * 64;
     p.Q = o; o += (size_t) kMaxTiles * kIStates;
+    p.QJ = o; o += (size_t) kMaxTiles * 2;
     p.EO = o; o += kMaxTiles;
     p.shiftS = o;
     p.needF = 0;
     for (int f = 0; f < T.nF; f++) if (T.coverF[(size_t) f]) p.needF = 1;
     mp.NbP = T.NbP; mp.NbAll = T.NbAll; mp.P_M = T.P_M; mp.nM = T.nM; mp.nF = T.nF;
     mp.nrelM = p.nrelM; mp.digitM = locate (T.digitM); mp.rowM = locate (T.rowM); mp.rowMoff = locate (T.rowMoff);
-    mp.fInst = p.fInst; mp.fOff = p.fOff; mp.fRad = p.fRad; mp.fStride = p.fStride; mp.fShift = locate (T.fShift);
+    mp.fInst = p.fInst; mp.fOff = p.fOff; mp.fRad = p.fRad; mp.fStride = p.fStride; mp.fShift = p.fShift;
     mp.coverM = locate (T.coverM); mp.coverF = locate (T.coverF);
 }
 

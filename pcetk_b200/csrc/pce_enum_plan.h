@@ -8,8 +8,10 @@
 // :252-281, :318-337): instead of one energy evaluation per microstate and pH value, sites take ROLES and the Boltzmann
 // factor of a state is a product of table entries (see pce_enum_core.cuh):
 //
-//   M   <= 8 sites, <= 256 configurations: one configuration per thread, fixed for the whole kernel (split Lo x Hi)
+//   M   <= 8 sites, <= 128 configurations: one configuration per thread, fixed for the whole kernel (split Lo x Hi)
 //   I   <= 4 sites, <= 16 configurations: the innermost loop, one DFMA per state, proton-count groups known in advance
+//   J   one binary site (fastest kernel variant only): both of its instances are handled by the same thread with two sets
+//       of register factors, so every tile-table entry fetched from shared memory feeds two DFMAs
 //   O1  <= 3 sites, <= 8 configurations: unrolled loop around it ("tile" = one configuration of O1 x O2)
 //   O2  <= 16 configurations, sorted by proton count: rolled loop
 //   F   all remaining sites: a configuration of them is a "chunk"; chunks are dealt out to persistent CTAs
@@ -31,10 +33,12 @@
 
 namespace pce_enum {
 
-constexpr int kBlock    = 256;   // threads per CTA = max configurations of the M group
+constexpr int kBlock    = 128;   // threads per CTA = max configurations of the M group
+constexpr int kMarginalBlock = 256;   // threads per block of the marginal program
 constexpr int kMaxM     = 8;
 constexpr int kMaxI     = 4;
-constexpr int kIStates  = 16;    // max configurations of the I group (per-thread register table)
+constexpr int kIStates  = 16;    // max configurations of the I group (tile table columns)
+constexpr int kXStates  = 32;    // I x J configurations (per-thread register factors)
 constexpr int kMaxO1    = 3;
 constexpr int kO1States = 8;
 constexpr int kMaxO2    = 7;
@@ -43,7 +47,7 @@ constexpr int kMaxTiles = kO1States * kO2States;
 constexpr int kMaxO     = kMaxO1 + kMaxO2;
 constexpr int kMaxF     = 96;
 constexpr int kMaxRadix = 8;     // instances per site in the M / I / O roles
-constexpr int kMaxInner = (kMaxM + kMaxI) * kMaxRadix;   // instances of the M and I sites
+constexpr int kMaxInner = (kMaxM + kMaxI + 1) * kMaxRadix;   // instances of the M, I and J sites
 constexpr int kMaxOinst = kMaxO * kMaxRadix;
 constexpr double kR = 0.001987165392, kLn10 = 2.302585092994;      // EnergyModel.h:31-32
 
@@ -62,10 +66,10 @@ inline double mu_of (double temperature, double ph) { return -kR * temperature *
 // roles of one enumeration
 // ---------------------------------------------------------------------------------------------------
 struct RunPlan {
-    std::vector<int> M, I, O1, O2, F;      // site ids per role
+    std::vector<int> M, I, J, O1, O2, F;   // site ids per role (J: none or one)
     int nLo = 0;
     std::vector<uint8_t> coverM, coverF;   // this run provides the bins of the site's instances
-    bool canon = false;                    // I = 4 and O1 = 3 sites, all binary with instances one proton apart
+    int  mode = 0;                         // 0 generic | 1: I = 4 and O1 = 3 canonical sites (binary, one proton apart) | 2: + a canonical J site
 };
 
 struct Plan {
@@ -153,9 +157,9 @@ inline int protons_of (const ModelView &m, const std::vector<int> &a) {
 // ---------------------------------------------------------------------------------------------------
 // make_plan: reference pH and energy, bin scales, and the role assignment of every run
 // ---------------------------------------------------------------------------------------------------
-// grid_slots: CTAs the enumeration kernel keeps resident over all shards (sizes the O2 role); allow_canon = false forces the
-// generic accumulation path (test hook)
-inline int make_plan (const ModelView &m, const double *ph, int nph, Plan *plan, std::string *error, long long grid_slots = 0, bool allow_canon = true) {
+// grid_slots: CTAs the enumeration kernel keeps resident over all shards (sizes the O2 role); max_mode caps the kernel variant
+// (test hook: 0 forces the generic accumulation path, 1 the variant without the J site)
+inline int make_plan (const ModelView &m, const double *ph, int nph, Plan *plan, std::string *error, long long grid_slots = 0, int max_mode = 2) {
     auto bad = [&] (const char *text) { if (error) *error = text; return 1; };
     if (nph < 1) return bad ("empty pH list");
     for (int k = 0; k < m.ninst; k++) if (m.protons[k] < 0) return bad ("negative proton count");
@@ -201,7 +205,7 @@ inline int make_plan (const ModelView &m, const double *ph, int nph, Plan *plan,
         }
     }
 
-    if (m.nsites > kMaxF + kMaxM + kMaxI + kMaxO) return bad ("too many sites for analytic enumeration");
+    if (m.nsites > kMaxF + kMaxM + kMaxI + 1 + kMaxO) return bad ("too many sites for analytic enumeration");
     std::vector<uint8_t> covered (m.nsites, 0);
     int ncovered = 0;
     plan->runs.clear ();
@@ -239,10 +243,12 @@ inline int make_plan (const ModelView &m, const double *ph, int nph, Plan *plan,
         };
         int ncanon = 0;
         for (int s = 0; s < m.nsites; s++) if (!used[s] && canonical (m, s)) ncanon++;
-        run.canon = allow_canon && ncanon >= kMaxI + kMaxO1;
-        pick (run.I, kMaxI, kIStates, run.canon);
-        pick (run.O1, kMaxO1, kO1States, run.canon);
-        if (!run.canon) { pick (run.I, kMaxI, kIStates, false); pick (run.O1, kMaxO1, kO1States, false); }
+        run.mode = ncanon >= kMaxI + 1 + kMaxO1 ? 2 : ncanon >= kMaxI + kMaxO1 ? 1 : 0;
+        run.mode = std::min (run.mode, max_mode);
+        pick (run.I, kMaxI, kIStates, run.mode > 0);
+        if (run.mode == 2) pick (run.J, 1, 2, true);
+        pick (run.O1, kMaxO1, kO1States, run.mode > 0);
+        if (run.mode == 0) { pick (run.I, kMaxI, kIStates, false); pick (run.O1, kMaxO1, kO1States, false); }
         // O2: further sites looped inside a chunk.  A chunk costs a fixed overhead (~ one O2 configuration's worth of work) and the
         // chunks are dealt out to grid_slots CTAs, so the prefix of candidate sites with the least
         // ceil (chunks / slots) * (1 + P_O2) is taken; without a grid size, as many sites as fit.
@@ -293,22 +299,24 @@ inline int make_plan (const ModelView &m, const double *ph, int nph, Plan *plan,
 // ---------------------------------------------------------------------------------------------------
 struct RunTables {
     // sizes
-    int nM = 0, nLo = 0, nI = 0, nO1 = 0, nO2 = 0, nF = 0, nS = 0;      // nS = nM + nI inner sites
-    int P_lo = 1, P_hi = 1, P_M = 1, P_I = 1, P_O1 = 1, P_O2 = 1, P_O = 1;
-    int nInner = 0, nMinst = 0, nOinst = 0;       // instances in M + I sites (M first), in M sites, in O1 + O2 sites (O1 first)
+    int nM = 0, nLo = 0, nI = 0, nJ = 0, nO1 = 0, nO2 = 0, nF = 0, nS = 0;      // nS = nM + nI + nJ inner sites
+    int P_lo = 1, P_hi = 1, P_M = 1, P_I = 1, P_J = 1, P_O1 = 1, P_O2 = 1, P_O = 1;
+    int nInner = 0, nMinst = 0, nOinst = 0;       // instances in M + I + J sites (in this order), in M sites, in O1 + O2 sites (O1 first)
     int maxrelM = 0, maxrelI = 0, maxrelO1 = 0, maxrelO2 = 0, maxrelF = 0;
     int NbC = 1, NbCp = 1, NbP = 1, NbAll = 1;    // rows of: chunk bins relative to thread protons | absolute in thread protons | persistent | all relative
     int nU = 1, nV = 1, cbar = 0;
-    int canon = 0;
+    int mode = 0;
     long long nchunks = 1;
     unsigned flushI = 1;                          // bit i: sorted I configuration i is the last of its proton count
     // integer tables (device copies are made of exactly these arrays, in this order: see upload in pce_analytic.cu)
     std::vector<int16_t> innerInst, innerSite, innerOff;        // [nInner] global instance, inner site index; [nS + 1] start of each inner site
     std::vector<int16_t> oInst, oOff;                           // [nOinst] global instance of every O instance; [nO + 1]
     std::vector<int16_t> idxM;        // [kBlock][kMaxM] compact inner index of every M site's instance in thread tid's configuration
-    std::vector<int16_t> idxLo, idxHi, idxI;      // [P_lo][kMaxM], [P_hi][kMaxM], [kIStates][kMaxI] compact inner indices (I: sorted order)
+    std::vector<int16_t> idxLo, idxHi, idxI;      // [P_lo][kMaxM], [P_hi][kMaxM], [kXStates][kMaxI + 1] compact inner indices of configuration c = j * 16 + i
+                                                  // (i: I configurations sorted by proton count; last entry: the J instance)
+    std::vector<int16_t> idxJ;                    // [2] compact inner index of the J instances
     std::vector<int16_t> mlo, mhi;                // [kBlock] Lo / Hi configuration of thread tid
-    std::vector<uint8_t> nrelM, nrelI, nrelO1, nrelO2;          // protons above the role's minimum: [kBlock], [kIStates], [kO1States], [kO2States]
+    std::vector<uint8_t> nrelM, nrelI, nrelO1, nrelO2;          // protons above the role's minimum: [kBlock], [kXStates] (I + J), [kO1States], [kO2States]
     std::vector<uint8_t> bO;                      // [P_O][kMaxO] compact O-instance index of every O site in tile t = t2 * P_O1 + t1
     std::vector<int16_t> fInst;                   // [nF][kMaxF-digit <= 255]: flattened with fOff: instance (global) of digit d of F site f
     std::vector<int32_t> fOff, fRad;              // [nF + 1], [nF]
@@ -326,9 +334,13 @@ inline int build_tables (const ModelView &m, const Plan &plan, const RunPlan &ru
     auto bad = [&] (const char *text) { if (error) *error = text; return 1; };
     RunTables &T = *t;
     T = RunTables ();
-    T.nM = (int) run.M.size (); T.nLo = run.nLo; T.nI = (int) run.I.size (); T.nO1 = (int) run.O1.size (); T.nO2 = (int) run.O2.size ();
-    T.nF = (int) run.F.size (); T.nS = T.nM + T.nI;
-    T.canon = run.canon && T.nI == kMaxI && T.nO1 == kMaxO1 ? 1 : 0;
+    T.nM = (int) run.M.size (); T.nLo = run.nLo; T.nI = (int) run.I.size (); T.nJ = (int) run.J.size ();
+    T.nO1 = (int) run.O1.size (); T.nO2 = (int) run.O2.size ();
+    T.nF = (int) run.F.size (); T.nS = T.nM + T.nI + T.nJ;
+    T.mode = run.mode;
+    if (T.mode > 0 && (T.nI != kMaxI || T.nO1 != kMaxO1)) T.mode = 0;
+    if (T.mode == 2 && T.nJ != 1) T.mode = 1;
+    if (T.mode < 2 && T.nJ != 0) return bad ("internal: J site without its kernel variant");
     T.coverM = run.coverM; T.coverF = run.coverF;
     if (T.coverM.empty ()) T.coverM.push_back (0);
     if (T.coverF.empty ()) T.coverF.push_back (0);
@@ -345,6 +357,8 @@ inline int build_tables (const ModelView &m, const Plan &plan, const RunPlan &ru
     for (int s : run.M) add_inner (s, radM);
     T.nMinst = (int) T.innerInst.size ();
     for (int s : run.I) add_inner (s, radI);
+    std::vector<int> radJ;
+    for (int s : run.J) add_inner (s, radJ);
     T.innerOff.push_back ((int16_t) T.innerInst.size ());
     T.nInner = (int) T.innerInst.size ();
     if (T.nInner > kMaxInner) return bad ("too many instances in the thread-level sites");
@@ -364,10 +378,11 @@ inline int build_tables (const ModelView &m, const Plan &plan, const RunPlan &ru
     for (int i = 0; i < T.nM; i++) { if (i < T.nLo) T.P_lo *= radM[i]; else T.P_hi *= radM[i]; }
     T.P_M = T.P_lo * T.P_hi;
     for (int r : radI) T.P_I *= r;
+    for (int r : radJ) T.P_J *= r;
     for (int r : radO1) T.P_O1 *= r;
     for (int r : radO2) T.P_O2 *= r;
     T.P_O = T.P_O1 * T.P_O2;
-    if (T.P_M > kBlock || T.P_hi > 64 || T.P_I > kIStates || T.P_O1 > kO1States || T.P_O2 > kO2States) return bad ("internal: role sizes out of range");
+    if (T.P_M > kBlock || T.P_hi > 64 || T.P_I > kIStates || T.P_J > 2 || T.P_O1 > kO1States || T.P_O2 > kO2States) return bad ("internal: role sizes out of range");
 
     // M configurations: thread tid = m_lo + P_lo * m_hi, site 0 the fastest digit
     T.idxM.assign ((size_t) kBlock * kMaxM, 0); T.digitM.assign ((size_t) kBlock * kMaxM, 0);
@@ -396,15 +411,24 @@ inline int build_tables (const ModelView &m, const Plan &plan, const RunPlan &ru
             cfg.push_back (std::make_pair (np, c));
         }
         std::stable_sort (cfg.begin (), cfg.end ());
-        T.idxI.assign ((size_t) kIStates * kMaxI, 0); T.nrelI.assign (kIStates, 0);
+        T.idxI.assign ((size_t) kXStates * (kMaxI + 1), 0); T.nrelI.assign (kXStates, 0);
+        T.idxJ.assign (2, 0);
         T.flushI = 0;
-        for (int i = 0; i < T.P_I; i++) {
-            int x = cfg[i].second;
-            for (int k = 0; k < T.nI; k++) { T.idxI[(size_t) i * kMaxI + k] = (int16_t) (T.innerOff[T.nM + k] + x % radI[k]); x /= radI[k]; }
-            T.nrelI[i] = (uint8_t) cfg[i].first;
-            T.maxrelI = std::max (T.maxrelI, cfg[i].first);
-            if (i + 1 == T.P_I || cfg[i + 1].first != cfg[i].first) T.flushI |= 1u << i;
+        for (int j = 0; j < T.P_J; j++) {
+            const int jinst = T.nJ ? T.innerOff[T.nM + T.nI] + j : 0;
+            const int jrel = T.nJ ? rel (T.innerInst[jinst], run.J[0]) : 0;
+            if (T.nJ) T.idxJ[j] = (int16_t) jinst;
+            for (int i = 0; i < T.P_I; i++) {
+                int x = cfg[i].second;
+                int16_t *row = &T.idxI[(size_t) (j * kIStates + i) * (kMaxI + 1)];
+                for (int k = 0; k < T.nI; k++) { row[k] = (int16_t) (T.innerOff[T.nM + k] + x % radI[k]); x /= radI[k]; }
+                row[kMaxI] = (int16_t) jinst;
+                T.nrelI[j * kIStates + i] = (uint8_t) (cfg[i].first + jrel);
+                T.maxrelI = std::max (T.maxrelI, cfg[i].first + jrel);
+                if (j == 0 && (i + 1 == T.P_I || cfg[i + 1].first != cfg[i].first)) T.flushI |= 1u << i;
+            }
         }
+        if (T.mode == 2 && (T.nrelI[kIStates] != 1 || T.nrelI[0] != 0)) return bad ("internal: canonical J site out of order");
     }
     // O1 configurations in natural order (canonical: protons above the minimum = popcount of t1); O2 sorted by proton count
     T.nrelO1.assign (kO1States, 0); T.nrelO2.assign (kO2States, 0);
@@ -430,7 +454,7 @@ inline int build_tables (const ModelView &m, const Plan &plan, const RunPlan &ru
             x = o2cfg[t2];
             for (int i = 0; i < T.nO2; i++) { row[T.nO1 + i] = (uint8_t) (T.oOff[T.nO1 + i] + x % radO2[i]); x /= radO2[i]; }
         }
-    if (T.canon) for (int t1 = 0; t1 < T.P_O1; t1++) if (T.nrelO1[t1] != __builtin_popcount ((unsigned) t1)) return bad ("internal: canonical O1 sites out of order");
+    if (T.mode > 0) for (int t1 = 0; t1 < T.P_O1; t1++) if (T.nrelO1[t1] != __builtin_popcount ((unsigned) t1)) return bad ("internal: canonical O1 sites out of order");
     // F sites: digit tables, strides (site 0 of the role is the fastest digit of the chunk index)
     {
         long long stride = 1;

@@ -582,6 +582,21 @@ __global__ void k_build_dw (const double *__restrict__ wr, int nrel, int ldr, in
 // unpredicated 128-bit loads per lane and row, all issued before the first use
 template <int U>
 __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, const double2 *r1, uint32_t f1, const double2 *r2, uint32_t f2, bool two) {
+    if (n2 <= 32) {      // field vectors of up to 64 slots (lysozyme, defensin): one 128-bit load per lane, no batches
+        if (lane < n2) {
+            const double2 a = __ldg (r1 + lane);
+            double2 v = h2[lane];
+            v.x = __dadd_rn (v.x, flip_sign (a.x, f1));
+            v.y = __dadd_rn (v.y, flip_sign (a.y, f1));
+            if (two) {
+                const double2 b = __ldg (r2 + lane);
+                v.x = __dadd_rn (v.x, flip_sign (b.x, f2));
+                v.y = __dadd_rn (v.y, flip_sign (b.y, f2));
+            }
+            h2[lane] = v;
+        }
+        return;
+    }
     if (!two) {
         for (int k0 = lane; k0 < n2; k0 += 32 * U) {
             double2 a[U];
@@ -1180,7 +1195,9 @@ bool plan_warp (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, do
     // small fields: 4-deep update batches and two or three resident CTAs of 8 warps (128 / 80 registers); large fields
     // (one CTA fits): 255 registers and 16-deep batches
     for (int pass = 0; pass < 3; pass++) {
-        const int upd = pass == 1 ? 16 : 4;
+        // 128-bit loads per lane and batch of the field update: 16 for large fields, 4 for small ones, 1 when the whole vector
+        // (instance-indexed: ninst slots) fits one load per lane
+        const int upd = pass == 1 ? 16 : m->ninst <= 64 ? 1 : 4;
         WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1);
         if (L.per_warp + L.shared_bytes > limit) continue;
         // large fields (one resident CTA): as many warps as shared memory holds, up to 10 (204 registers each); else 8 per CTA
@@ -1560,7 +1577,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     } else {
         // one resident CTA (large fields): up to 255 registers; two: 128
         void (*kernel) (const McParams);
-#define PCE_WARP_KERNEL(TPL_) (plan.upd != 4 ? (per_chain ? k_mc_warp<true, 1, TPL_> : k_mc_warp<false, 1, TPL_>) \
+#define PCE_WARP_KERNEL(TPL_) (plan.upd == 16 ? (per_chain ? k_mc_warp<true, 1, TPL_> : k_mc_warp<false, 1, TPL_>) \
                               : plan.ctas_per_sm >= 4 ? (per_chain ? k_mc_warp<true, 4, TPL_> : k_mc_warp<false, 4, TPL_>) \
                               : plan.ctas_per_sm == 3 ? (per_chain ? k_mc_warp<true, 3, TPL_> : k_mc_warp<false, 3, TPL_>) \
                                                       : (per_chain ? k_mc_warp<true, 2, TPL_> : k_mc_warp<false, 2, TPL_>))

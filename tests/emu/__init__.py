@@ -33,8 +33,9 @@ def library():
     return _lib
 
 
-def analytic_bins(rec, wsym, ph, unfolded=False, shard=0, nshards=1, grid=3, grid_slots=0, allow_canon=True):
-    """-> (bins[(1 + ninst), Nb] scaled by exp(sigma[n]), sigma[Nb], info dict)"""
+def analytic_bins(rec, wsym, ph, unfolded=False, shard=0, nshards=1, grid=3, grid_slots=0, max_mode=2):
+    """-> (bins[(1 + ninst), Nb] scaled by exp(sigma[n]), sigma[Nb], info dict); info['modes'] = kernel variant of every run
+    (0 generic, 1 canonical I and O1 sites, 2 with a J site)"""
     lib = library()
     ph = np.ascontiguousarray(np.atleast_1d(ph), dtype=np.float64)
     nb_max = int(np.sum([rec.protons[f:l + 1].max() for f, l in zip(rec.site_first, rec.site_last)])) + 1
@@ -46,11 +47,11 @@ def analytic_bins(rec, wsym, ph, unfolded=False, shard=0, nshards=1, grid=3, gri
     status = lib.emu_analytic_bins(rec.nsites, rec.ninstances, np.ascontiguousarray(rec.site_first, dtype=np.int32),
                                    np.ascontiguousarray(rec.site_last, dtype=np.int32), np.ascontiguousarray(rec.protons, dtype=np.int32),
                                    np.ascontiguousarray(g, dtype=np.float64), np.ascontiguousarray(wsym, dtype=np.float64), float(rec.temperature),
-                                   int(bool(unfolded)), ph, len(ph), shard, nshards, grid, grid_slots, int(bool(allow_canon)), bins, sigma, info, error, 256)
+                                   int(bool(unfolded)), ph, len(ph), shard, nshards, grid, grid_slots, int(max_mode), bins, sigma, info, error, 256)
     if status != 0:
         raise RuntimeError("emulator: " + error.value.decode())
     assert info[1] == nb_max
-    return bins, sigma, dict(runs=int(info[0]), canon_mask=int(info[2]), P_O2=int(info[3]))
+    return bins, sigma, dict(runs=int(info[0]), modes=[(int(info[2]) >> (2 * r)) & 3 for r in range(int(info[0]))], P_O2=int(info[3]))
 
 
 def finish(rec, bins, sigma, ph):

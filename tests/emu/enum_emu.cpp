@@ -23,13 +23,13 @@ double butterfly_sum (double *v) {         // the order of warp_sum (__shfl_xor 
     return v[0];
 }
 
-template <bool CANON>
+template <int MODE>
 void run_enum (const EnumParams &p, int grid) {
     const EnumLayout L (p);
     std::vector<unsigned char> smem (L.total + 64);
     std::vector<EnumThread> regs (kBlock);
     for (int cta = 0; cta < grid; cta++) {
-        EnumCta<CANON> c (p, smem.data ());
+        EnumCta<MODE> c (p, smem.data ());
         for (int tid = 0; tid < kBlock; tid++) c.init (tid, regs[tid]);
         for (long long chunk = cta; chunk < p.nchunks_local; chunk += grid) {
             for (int tid = 0; tid < kBlock; tid++) c.phase0 (tid, p.chunk_begin + chunk);
@@ -55,12 +55,12 @@ void run_enum (const EnumParams &p, int grid) {
 // bins: [(1 + ninst)][Nb] (scaled by exp (sigma[n])), sigma: [Nb].  grid = emulated CTAs of the enumeration program.
 extern "C" int emu_analytic_bins (int nsites, int ninst, const int32_t *first, const int32_t *last, const int32_t *protons, const double *g,
                                   const double *w, double temperature, int unfolded, const double *ph, int nph, int shard, int nshards,
-                                  int grid, int grid_slots, int allow_canon, double *bins, double *sigma, int *info, char *error, int error_length) {
+                                  int grid, int grid_slots, int max_mode, double *bins, double *sigma, int *info, char *error, int error_length) {
     ModelView m = { nsites, ninst, first, last, protons, g, w, temperature, unfolded };
     Plan plan;
     std::string message;
     auto fail = [&] (int code) { snprintf (error, (size_t) error_length, "%s", message.c_str ()); return code; };
-    if (make_plan (m, ph, nph, &plan, &message, grid_slots, allow_canon != 0)) return fail (1);
+    if (make_plan (m, ph, nph, &plan, &message, grid_slots, max_mode)) return fail (1);
     const int Nb = plan.Nb;
     for (int n = 0; n < Nb; n++) sigma[n] = plan.sigma[(size_t) n];
     for (size_t e = 0; e < (size_t) (1 + ninst) * Nb; e++) bins[e] = 0.0;
@@ -80,7 +80,7 @@ extern "C" int emu_analytic_bins (int nsites, int ninst, const int32_t *first, c
         p.beta = 1.0 / (kR * temperature); p.gref = plan.gref;
         const long long c0 = T.nchunks * shard / nshards, c1 = T.nchunks * (shard + 1) / nshards;
         p.chunk_begin = c0; p.nchunks_local = c1 - c0; p.ldF = p.nchunks_local;
-        info[2] |= T.canon << r; info[3] = (int) T.P_O2;
+        info[2] |= T.mode << (2 * r); info[3] = (int) T.P_O2;
         if (p.nchunks_local <= 0) continue;
         const int g_ctas = (int) std::min<long long> (grid, p.nchunks_local);
         std::vector<double> Tbuf ((size_t) g_ctas * T.NbP * kBlock, 0.0), Ftab ((size_t) T.NbAll * p.ldF, 0.0), Mtab ((size_t) T.NbP * kBlock, 0.0);
@@ -97,7 +97,7 @@ extern "C" int emu_analytic_bins (int nsites, int ninst, const int32_t *first, c
             for (int tid = 0; tid < kBlock; tid++) s.phase3b (tid);
             for (int tid = 0; tid < kBlock; tid++) s.phase4 (tid);
         }
-        if (T.canon) run_enum<true> (p, g_ctas); else run_enum<false> (p, g_ctas);
+        if (T.mode == 2) run_enum<2> (p, g_ctas); else if (T.mode == 1) run_enum<1> (p, g_ctas); else run_enum<0> (p, g_ctas);
         for (size_t e = 0; e < Mtab.size (); e++) { double v = 0.0; for (int c = 0; c < g_ctas; c++) v += Tbuf[(size_t) c * Mtab.size () + e]; Mtab[e] = v; }
         mp.Nb = Nb; mp.base = plan.base; mp.write_z = r == 0 ? 1 : 0; mp.grid = g_ctas;
         mp.chunk_begin = c0; mp.nchunks_local = p.nchunks_local; mp.ldF = p.ldF; mp.Mtab = Mtab.data (); mp.FtabT = Ftab.data (); mp.bins = bins;
@@ -107,18 +107,18 @@ extern "C" int emu_analytic_bins (int nsites, int ninst, const int32_t *first, c
             if (!marginal_target (mp, b, &kind, &site, &digit, &row)) continue;
             const long long count = kind == 2 ? mp.nchunks_local : mp.P_M;
             for (int n_rel = 0; n_rel < T.NbAll; n_rel++) {
-                double part[kBlock / 32];
-                for (int warp = 0; warp < kBlock / 32; warp++) {
+                double part[kMarginalBlock / 32];
+                for (int warp = 0; warp < kMarginalBlock / 32; warp++) {
                     double v[32];
                     for (int lane = 0; lane < 32; lane++) {
                         double acc = 0.0;
-                        for (long long e = warp * 32 + lane; e < count; e += kBlock) acc += marginal_term (mp, kind, site, digit, n_rel, e);
+                        for (long long e = warp * 32 + lane; e < count; e += kMarginalBlock) acc += marginal_term (mp, kind, site, digit, n_rel, e);
                         v[lane] = acc;
                     }
                     part[warp] = butterfly_sum (v);
                 }
                 double total = 0.0;
-                for (int warp = 0; warp < kBlock / 32; warp++) total += part[warp];
+                for (int warp = 0; warp < kMarginalBlock / 32; warp++) total += part[warp];
                 bins[(size_t) row * Nb + plan.base + n_rel] += total;
             }
         }
