@@ -387,29 +387,42 @@ extern "C" int pce_analytic_finish (pce_model *m, const double *bins, const doub
     const int Nb = plan.Nb;
     const long double beta = 1.0L / ((long double) PCE_R * m->temperature);
     const long double mu_star = pce::mu_of (m->temperature, plan.ph_star);
-    std::vector<long double> weight (Nb), logw (Nb);
+    std::vector<long double> logw (Nb), logb (Nb, 0.0L);
+    std::vector<double> weight (Nb);
+    for (int n = 0; n < Nb; n++) if (bins[n] > 0.0) logb[n] = logl ((long double) bins[n]);
+    // e^x for an extended-precision x: the double-precision exponential of its leading part, corrected by the remainder
+    // (x87 expl costs ~100 ns; nph * nbins of them dominated this function)
+    auto exp_split = [] (long double x) -> double {
+        if (x < -700.0L) return x < -745.0L ? 0.0 : (double) expl (x);
+        if (x > 690.0L) return (double) std::min (expl (x), 1.0e300L);
+        const double hi = (double) x, lo = (double) (x - (long double) hi);
+        return std::exp (hi) * (1.0 + lo);
+    };
     for (int q = 0; q < nph; q++) {
+        // logarithmic weights in extended precision (their range is that of the bin scales, e^(+-700) and beyond); the weighted sums
+        // themselves are sums of at most ~100 positive doubles <= 1 and stay in double precision
         const long double mu = pce::mu_of (m->temperature, ph[q]);
         long double shift = -1.0e300L;
         for (int n = 0; n < Nb; n++) {
             logw[n] = -(long double) plan.sigma[(size_t) n] - beta * n * (mu_star - mu);
-            if (bins[n] > 0.0) shift = std::max (shift, logl ((long double) bins[n]) + logw[n]);
+            if (bins[n] > 0.0) shift = std::max (shift, logb[n] + logw[n]);
         }
-        long double z = 0.0L;
+        double z = 0.0;
         for (int n = 0; n < Nb; n++) {
-            weight[n] = expl (logw[n] - shift);
-            z += (long double) bins[n] * weight[n];
+            weight[n] = bins[n] > 0.0 ? exp_split (logw[n] - shift) : 0.0;      // bins[n] * weight[n] <= 1
+            z += bins[n] * weight[n];
         }
-        if (!(z > 0.0L)) return fail (PCE_ERR_STATE, "partition function underflowed; split the pH grid");
+        if (!(z > 0.0)) return fail (PCE_ERR_STATE, "partition function underflowed; split the pH grid");
+        const double inv = 1.0 / z;
         for (int a = 0; a < m->ninst; a++) {
             const double *row = bins + (size_t) (1 + a) * Nb;
-            long double s = 0.0L;
-            for (int n = 0; n < Nb; n++) s += (long double) row[n] * weight[n];
-            const double value = (double) (s / z);
+            double s = 0.0;
+            for (int n = 0; n < Nb; n++) s += row[n] * weight[n];
+            const double value = s * inv;
             if (out_p) out_p[(size_t) q * m->ninst + a] = value;
             if (q == nph - 1) m->prob[a] = value;
         }
-        if (out_lnz) out_lnz[q] = (double) (logl (z) + shift - beta * ((long double) plan.gref - gzero));
+        if (out_lnz) out_lnz[q] = (double) (logl ((long double) z) + shift - beta * ((long double) plan.gref - gzero));
     }
     return PCE_OK;
 }

@@ -111,10 +111,16 @@ inline void sorted_instances (const ModelView &m, int s, int *out) {
 
 // A low-energy state at the given pH by coordinate descent (started from `a`, or from the per-site minima of the
 // tilted intrinsic energies when a is empty).  Returns its energy at that pH; only rough optimality matters.
-inline double descend (const ModelView &m, double ph, std::vector<int> &a) {
+// `field` caches sum_j W[k][a_j] for every instance k (the site's own instances contribute nothing: same-site entries are
+// ignored throughout); it is built on the first call and updated per changed site, so a warm-started descent for the next
+// pH value of a grid costs O(ninst) per sweep instead of O(ninst * nsites).
+inline double descend (const ModelView &m, double ph, std::vector<int> &a, std::vector<double> *field_cache = nullptr) {
     const double mu = mu_of (m.temperature, ph);
     const size_t n = (size_t) m.ninst;
     auto tilted = [&] (int k) { return m.g[k] - m.protons[k] * mu; };
+    std::vector<double> local;
+    std::vector<double> &field = field_cache ? *field_cache : local;
+    bool fresh = false;
     if ((int) a.size () != m.nsites) {
         a.assign (m.nsites, 0);
         for (int i = 0; i < m.nsites; i++) {
@@ -122,30 +128,44 @@ inline double descend (const ModelView &m, double ph, std::vector<int> &a) {
             for (int k = m.first[i]; k <= m.last[i]; k++) if (tilted (k) < tilted (best)) best = k;
             a[i] = best;
         }
+        fresh = true;
     }
+    std::vector<int> site_of;
     if (!m.unfolded) {
+        site_of.resize (n);
+        for (int i = 0; i < m.nsites; i++) for (int k = m.first[i]; k <= m.last[i]; k++) site_of[(size_t) k] = i;
+        if (fresh || field.size () != n) {
+            field.assign (n, 0.0);
+            for (size_t k = 0; k < n; k++) {
+                double f = 0.0;
+                for (int j = 0; j < m.nsites; j++) if (j != site_of[k]) f += m.w[k * n + a[j]];
+                field[k] = f;
+            }
+        }
         for (int sweep = 0; sweep < 20; sweep++) {
             bool changed = false;
             for (int i = 0; i < m.nsites; i++) {
                 int    best = a[i];
-                double ebest = 0.0;
-                bool   have = false;
+                double ebest = tilted (a[i]) + field[(size_t) a[i]];
                 for (int k = m.first[i]; k <= m.last[i]; k++) {
-                    double e = tilted (k);
-                    for (int j = 0; j < m.nsites; j++) if (j != i) e += m.w[(size_t) k * n + a[j]];
-                    if (!have || e < ebest) { have = true; ebest = e; best = k; }
+                    const double e = tilted (k) + field[(size_t) k];
+                    if (e < ebest) { ebest = e; best = k; }
                 }
-                if (best != a[i]) { a[i] = best; changed = true; }
+                if (best != a[i]) {
+                    const double *w_new = m.w + (size_t) best * n, *w_old = m.w + (size_t) a[i] * n;       // W is symmetric: rows serve as columns
+                    for (size_t k = 0; k < n; k++) if (site_of[k] != i) field[k] += w_new[k] - w_old[k];
+                    a[i] = best; changed = true;
+                }
             }
             if (!changed) break;
         }
     }
-    double e = 0.0;
+    double e = 0.0, pairs = 0.0;
     for (int i = 0; i < m.nsites; i++) {
         e += tilted (a[i]);
-        if (!m.unfolded) for (int j = 0; j < i; j++) e += m.w[(size_t) a[i] * n + a[j]];
+        if (!m.unfolded) pairs += field[(size_t) a[i]];
     }
-    return e;
+    return e + 0.5 * pairs;
 }
 
 inline int protons_of (const ModelView &m, const std::vector<int> &a) {
@@ -190,9 +210,10 @@ inline int make_plan (const ModelView &m, const double *ph, int nph, Plan *plan,
         const double beta = 1.0 / (kR * m.temperature);
         std::vector<double> tn, te, ts;
         std::vector<int> state;
+        std::vector<double> field;
         for (int q = 0; q < nph; q++) {
             if (q > 0 && sorted[q] == sorted[q - 1]) continue;
-            const double eq = descend (m, sorted[q], state);                 // energy at pH q, warm-started from the previous pH
+            const double eq = descend (m, sorted[q], state, &field);                 // energy at pH q, warm-started from the previous pH
             const int    nq = protons_of (m, state);
             const double delta = mu_of (m.temperature, sorted[q]) - mu_star;
             tn.push_back ((double) nq); te.push_back (eq + nq * delta - plan->gref); ts.push_back (delta);     // E(pH*) = E(q) + n (mu_q - mu*)

@@ -185,3 +185,37 @@ def test_warp_kernel_on_the_1000_site_model_matches_specification(port, monkeypa
         spec = port.mc_philox_chain(rec, wsym, pairs, 1, 3, sampler.seed, chain, 0, 7.0)
         assert np.array_equal(out["counts"][0, chain], spec["counts"])
         assert np.array_equal(out["state"][0, chain], spec["state"])
+
+
+def test_same_site_interactions_are_ignored(port):
+    """W entries between instances of ONE site: the reference's energy function never reads them (EnergyModel.c:204-224), its
+    Move does, its DoubleMove does not.  Here they are ignored throughout: a model with junk in those blocks walks exactly the
+    chains of the clean model and enumerates to the same probabilities."""
+    rec, _gold = load_fixture("defensin")
+    junk = rec.interactions.copy()
+    rng = np.random.default_rng(8)
+    for f, l in zip(rec.site_first, rec.site_last):
+        junk[f:l + 1, f:l + 1] = rng.normal(0.0, 3.0, (l - f + 1, l - f + 1))
+    dirty = P.ModelRecord(name="defensin_junk", site_first=rec.site_first, site_last=rec.site_last, protons=rec.protons, gmodel=rec.gmodel,
+                          gintr=rec.gintr, interactions=junk, temperature=rec.temperature, site_labels=rec.site_labels, inst_labels=rec.inst_labels)
+    results = []
+    for record in (rec, dirty):
+        model = P.MEADModel(record, log=None)
+        exact = model.CalculateProbabilitiesBatch([3.0, 7.0])
+        for kernel in (1, 2):
+            sampler = P.MCModelDefault(nequil=10, nprod=150, randomSeed=77, nchains=40, kernel=kernel)
+            model.DefineMCModel(sampler, log=None)
+            results.append((exact, sampler.RunChains([3.0, 7.0])["counts"]))
+    for (exact_a, counts_a), (exact_b, counts_b) in zip(results[:2], results[2:]):
+        assert np.array_equal(counts_a, counts_b)
+        assert np.abs(exact_a / exact_b - 1.0).max() < 1e-13
+
+
+def test_too_many_production_trials_are_refused():
+    """A chain counts its production trials in 32 bits: nprod x (nsites + npairs) >= 2^32 is refused, not wrapped."""
+    rec, _gold = load_fixture("lysozyme")
+    model = P.MEADModel(rec, log=None)
+    sampler = P.MCModelDefault(nequil=0, nprod=2 ** 31 - 1, randomSeed=1, nchains=1)
+    model.DefineMCModel(sampler, log=None)
+    with pytest.raises(P.CLibraryError, match="too many production trials"):
+        sampler.RunCounts([7.0])
