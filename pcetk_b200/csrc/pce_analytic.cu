@@ -142,7 +142,7 @@ pce_enum::ModelView view_of (const pce_model *m, int unfolded) {
     v.nsites = m->nsites; v.ninst = m->ninst;
     v.first = m->first.data (); v.last = m->last.data (); v.protons = m->protons.data ();
     v.g = unfolded ? m->gmodel.data () : m->gintr.data ();
-    v.w = m->wsym.data ();
+    v.w = const_cast<pce_model *> (m)->host_wsym ();
     v.temperature = m->temperature; v.unfolded = unfolded;
     return v;
 }

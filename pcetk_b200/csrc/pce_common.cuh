@@ -65,7 +65,13 @@ struct pce_model {
     std::vector<int32_t> protons;              // [ninst]
     std::vector<double>  gmodel, gintr, prob;  // [ninst]
     std::vector<double>  wraw;                 // [ninst*ninst] EnergyModel.h:46 "interactions"
-    std::vector<double>  wsym;                 // [ninst*ninst] full square of EnergyModel.h:48 "symmetricmatrix"
+    std::vector<double>  wraw_alt;             // second raw buffer: a bulk load while `sym_src` views wraw lands here and the two swap
+    std::vector<double>  wsym;                 // [ninst*ninst] full square of EnergyModel.h:48 "symmetricmatrix"; allocated when first materialised
+    // SymmetrizeInteractions does not touch 2 x ninst^2 doubles on the host: it records which raw buffer the symmetric matrix
+    // is the average of (`sym_src`), the device forms it during the upload, and the host copy is made when a host reader
+    // asks for the whole matrix (materialize_wsym).  Single elements are averaged on the fly (wsym_at).
+    const double *sym_src = nullptr;
+    const void   *pinned[2] = { nullptr, nullptr };     // raw buffers registered with the driver for the upload
     bool   symmetrized = false;
     bool   dirty       = true;                 // host copy newer than device copy
     int    generation  = 0;                    // bumped by every real upload (derived device tables key on it)
@@ -75,6 +81,7 @@ struct pce_model {
     int ldw = 0;                               // row stride of d_w in doubles (multiple of 4)
     pce::DeviceBuffer<int32_t> d_first, d_nsite_inst, d_site_of_inst, d_protons;
     pce::DeviceBuffer<double>  d_gintr, d_gmodel, d_w, d_wb;   // d_wb = W / (R T), for the Monte Carlo kernels
+    pce::DeviceBuffer<double>  d_raw;                          // raw interactions as uploaded (input of the device-side symmetrisation)
 
     // scratch of the enumeration kernel (grow-only)
     pce::DeviceBuffer<double>  s_gt, s_T, s_Mtab, s_Ftab, s_seg, s_xs;
@@ -86,6 +93,13 @@ struct pce_model {
 
     int  sites_ok () const;                    // PCE_OK when every site is set, contiguous and ascending
     int  upload ();
+    void materialize_wsym ();                  // host copy of the symmetric matrix, if it is still a view of a raw buffer
+    const double *host_wsym () { materialize_wsym (); return wsym.data (); }
+    double wsym_at (size_t a, size_t b) const {
+        const size_t n = (size_t) ninst;
+        if (sym_src != nullptr) return 0.5 * (sym_src[a * n + b] + sym_src[b * n + a]);      // the same rounding as the full pass
+        return wsym.empty () ? 0.0 : wsym[a * n + b];
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -1245,15 +1245,16 @@ bool plan_warp (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, do
 static int find_pairs (pce_mc *mc) {
     // MCModelDefault_FindPairs + _FindMaxInteraction, MCModelDefault.c:231-288: sites i > j are a pair
     // when max |W| over their instances reaches the limit; order (i ascending, j < i ascending).
-    const pce_model *m = mc->model;
+    pce_model *m = mc->model;
     const size_t n = (size_t) m->ninst;
+    const double *ws = m->host_wsym ();
     mc->pair_a.clear (); mc->pair_b.clear (); mc->pair_wmax.clear ();
     for (int i = 0; i < m->nsites; i++)
         for (int j = 0; j < i; j++) {
             double wmax = 0.0;
             for (int a = m->first[i]; a <= m->last[i]; a++)
                 for (int b = m->first[j]; b <= m->last[j]; b++) {
-                    const double v = std::fabs (m->wsym[(size_t) a * n + b]);
+                    const double v = std::fabs (ws[(size_t) a * n + b]);
                     if (v > wmax) wmax = v;
                 }
             if (wmax >= mc->limit) { mc->pair_a.push_back (i); mc->pair_b.push_back (j); mc->pair_wmax.push_back (wmax); }
@@ -1475,8 +1476,8 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
                         for (int kb = 0; kb < nb - 1; kb++) {
                             const int oa = fa + la, ob = fb + lb, ia = fa + ka + (fa + ka >= oa ? 1 : 0), ib = fb + kb + (fb + kb >= ob ? 1 : 0);
                             // volatile: every product and difference is rounded on its own (no host-side contraction)
-                            volatile double c0 = beta * m->wsym[ia * n + ib], c1 = beta * m->wsym[ia * n + ob];
-                            volatile double c2 = beta * m->wsym[oa * n + ib], c3 = beta * m->wsym[oa * n + ob];
+                            volatile double c0 = beta * m->wsym_at (ia, ib), c1 = beta * m->wsym_at (ia, ob);
+                            volatile double c2 = beta * m->wsym_at (oa, ib), c3 = beta * m->wsym_at (oa, ob);
                             volatile double t1 = c0 - c1, t2 = t1 - c2;
                             const double cross = t2 + c3;
                             table.push_back (cross);

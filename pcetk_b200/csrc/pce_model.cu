@@ -59,8 +59,7 @@ extern "C" int pce_model_create (int nsites, int ninstances, double temperature,
         m->first.assign (nsites, 0); m->last.assign (nsites, -1); m->site_set.assign (nsites, 0);
         m->protons.assign (ninstances, 0);
         m->gmodel.assign (ninstances, 0.0); m->gintr.assign (ninstances, 0.0); m->prob.assign (ninstances, 0.0);
-        m->wraw.assign ((size_t) ninstances * ninstances, 0.0);
-        m->wsym.assign ((size_t) ninstances * ninstances, 0.0);
+        m->wraw.assign ((size_t) ninstances * ninstances, 0.0);      // (the symmetric matrix is allocated when first materialised)
     } catch (const std::bad_alloc &) {
         delete m;
         return fail (PCE_ERR_ALLOC, "Cannot allocate energy model.");
@@ -75,7 +74,8 @@ extern "C" void pce_model_destroy (pce_model *m) {
     if (cudaGetDevice (&current) == cudaSuccess) {
         cudaSetDevice (m->device);
         m->d_first.release (); m->d_nsite_inst.release (); m->d_site_of_inst.release (); m->d_protons.release ();
-        m->d_gintr.release (); m->d_gmodel.release (); m->d_w.release (); m->d_wb.release ();
+        m->d_gintr.release (); m->d_gmodel.release (); m->d_w.release (); m->d_wb.release (); m->d_raw.release ();
+        for (const void *&buffer : m->pinned) if (buffer != nullptr) { cudaHostUnregister (const_cast<void *> (buffer)); buffer = nullptr; }
         m->s_gt.release (); m->s_T.release (); m->s_Mtab.release (); m->s_Ftab.release (); m->s_seg.release (); m->s_xs.release (); m->s_ms.release ();
         cudaSetDevice (current);
     }
@@ -162,6 +162,7 @@ extern "C" int pce_model_set_protons (pce_model *m, int k, int v) { CHECK_INSTAN
 extern "C" int pce_model_set_probability (pce_model *m, int k, double v) { CHECK_INSTANCE (m, k); m->prob[k] = v; return PCE_OK; }
 extern "C" int pce_model_set_interaction (pce_model *m, int a, int b, double v) {
     CHECK_INSTANCE (m, a); CHECK_INSTANCE (m, b);
+    if (m->sym_src == m->wraw.data ()) m->materialize_wsym ();      // the symmetric matrix must not follow this write
     m->wraw[(size_t) a * m->ninst + b] = v;    // raw matrix only; the symmetric copy changes on Symmetrize (EnergyModel.c:197-199)
     return PCE_OK;
 }
@@ -176,7 +177,7 @@ extern "C" int pce_model_get_interaction (const pce_model *m, int a, int b, doub
 }
 extern "C" int pce_model_get_interaction_symmetric (const pce_model *m, int a, int b, double *v) {
     CHECK_INSTANCE (m, a); CHECK_INSTANCE (m, b);
-    *v = m->wsym[(size_t) a * m->ninst + b];
+    *v = m->wsym_at ((size_t) a, (size_t) b);
     return PCE_OK;
 }
 extern "C" int pce_model_get_deviation (const pce_model *m, int a, int b, double *v) {
@@ -192,7 +193,16 @@ extern "C" int pce_model_load (pce_model *m, const double *gintr, const double *
     if (gintr) std::memcpy (m->gintr.data (), gintr, n * sizeof (double));
     if (gmodel) std::memcpy (m->gmodel.data (), gmodel, n * sizeof (double));
     if (protons) std::memcpy (m->protons.data (), protons, n * sizeof (int32_t));
-    if (interactions) std::memcpy (m->wraw.data (), interactions, n * n * sizeof (double));
+    if (interactions) {
+        if (m->sym_src == m->wraw.data ()) {
+            // the symmetric matrix is still a view of the buffer about to be overwritten: the new raw matrix goes into the
+            // other buffer (the symmetric matrix changes on Symmetrize only, EnergyModel.c:197-199)
+            try { if (m->wraw_alt.size () != n * n) m->wraw_alt.resize (n * n); }
+            catch (const std::bad_alloc &) { return fail (PCE_ERR_ALLOC, "Cannot allocate energy model."); }
+            std::swap (m->wraw, m->wraw_alt);
+        }
+        std::memcpy (m->wraw.data (), interactions, n * n * sizeof (double));
+    }
     m->dirty = true;
     return PCE_OK;
 }
@@ -209,7 +219,9 @@ extern "C" int pce_model_set_probabilities (pce_model *m, const double *p) {
 }
 extern "C" int pce_model_get_symmetric_matrix (const pce_model *m, double *w) {
     if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
-    std::memcpy (w, m->wsym.data (), (size_t) m->ninst * m->ninst * sizeof (double));
+    const size_t n = (size_t) m->ninst;
+    if (m->sym_src == nullptr && m->wsym.empty ()) { std::fill (w, w + n * n, 0.0); return PCE_OK; }
+    std::memcpy (w, const_cast<pce_model *> (m)->host_wsym (), n * n * sizeof (double));
     return PCE_OK;
 }
 
@@ -230,14 +242,18 @@ extern "C" int pce_model_check_symmetric (const pce_model *m, double tolerance, 
     return PCE_OK;
 }
 
-extern "C" int pce_model_symmetrize (pce_model *m) {
-    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+void pce_model::materialize_wsym () {
+    const size_t n = (size_t) ninst, tile = 32;
+    if (sym_src == nullptr) {
+        if (wsym.size () != n * n) wsym.assign (n * n, 0.0);
+        return;
+    }
     // Wsym_ij = Wsym_ji = (W_ij + W_ji) / 2 (SymmetricMatrix_CopyFromReal2DArray, EnergyModel.c:78-87), in tiles of 32 x 32 so
     // that the transposed accesses stay in cache (60 -> 41 ms on the 3000-instance model; a tile buffer with contiguous
     // write-back and host threads both measured slower)
-    const size_t n = (size_t) m->ninst, tile = 32;
-    const double *w = m->wraw.data ();
-    double *s = m->wsym.data ();
+    if (wsym.size () != n * n) wsym.resize (n * n);
+    const double *w = sym_src;
+    double *s = wsym.data ();
     for (size_t i0 = 0; i0 < n; i0 += tile)
         for (size_t j0 = 0; j0 <= i0; j0 += tile) {
             const size_t i1 = std::min (n, i0 + tile), j1 = std::min (n, j0 + tile);
@@ -248,6 +264,13 @@ extern "C" int pce_model_symmetrize (pce_model *m) {
                     s[j * n + i] = v;
                 }
         }
+    sym_src = nullptr;
+}
+
+extern "C" int pce_model_symmetrize (pce_model *m) {
+    if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    // the averaging itself runs on the device during the upload (k_symmetrize_stage); the host copy is made on demand
+    m->sym_src = m->wraw.data ();
     m->symmetrized = true;
     m->dirty = true;
     return PCE_OK;
@@ -255,7 +278,8 @@ extern "C" int pce_model_symmetrize (pce_model *m) {
 
 extern "C" int pce_model_reset_interactions (pce_model *m) {
     if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
-    std::fill (m->wsym.begin (), m->wsym.end (), 0.0);
+    m->sym_src = nullptr;
+    m->wsym.assign ((size_t) m->ninst * m->ninst, 0.0);
     m->symmetrized = true;
     m->dirty = true;
     return PCE_OK;
@@ -263,6 +287,7 @@ extern "C" int pce_model_reset_interactions (pce_model *m) {
 
 extern "C" int pce_model_scale_interactions (pce_model *m, double scale) {
     if (m == nullptr) return fail (PCE_ERR_VALUE, "null model");
+    m->materialize_wsym ();
     for (double &v : m->wsym) v *= scale;
     m->dirty = true;
     return PCE_OK;
@@ -287,6 +312,29 @@ extern "C" int pce_model_state_from_probabilities (const pce_model *m, int32_t *
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_scale (const double *__restrict__ in, size_t n, double factor, double *__restrict__ out) {
     for (size_t e = (size_t) blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t) gridDim.x * blockDim.x) out[e] = __dmul_rn (factor, in[e]);
+}
+
+// Symmetric, staged and scaled interactions from the raw matrix: w[i][j] = (raw[i][j] + raw[j][i]) / 2 for instances of
+// different sites, 0 inside a site and in the padding columns; wb = beta * w.  One 32 x 32 tile per block, the transposed
+// operand through shared memory so that both reads are coalesced.
+__global__ void __launch_bounds__ (256) k_symmetrize_stage (const double *__restrict__ raw, int n, int ldw, const int32_t *__restrict__ site_of,
+                                                            double beta, double *__restrict__ w, double *__restrict__ wb) {
+    __shared__ double t[32][33];
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int row = j0 + r, col = i0 + threadIdx.x;
+        t[r][threadIdx.x] = (row < n && col < n) ? raw[(size_t) row * n + col] : 0.0;
+    }
+    __syncthreads ();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = i0 + r, j = j0 + threadIdx.x;
+        if (i < n && j < ldw) {
+            double v = 0.0;
+            if (j < n && site_of[i] != site_of[j]) v = __dmul_rn (0.5, __dadd_rn (raw[(size_t) i * n + j], t[threadIdx.x][r]));
+            w[(size_t) i * ldw + j]  = v;
+            wb[(size_t) i * ldw + j] = __dmul_rn (beta, v);
+        }
+    }
 }
 
 int pce_model::upload () {
@@ -314,20 +362,41 @@ int pce_model::upload () {
         // entries (energies sum over pairs of different sites, EnergyModel.c:204-224; Move / DoubleMove skip the moved sites,
         // MCModelDefault.c:100-111, 140-160), while the cached fields of the Monte Carlo kernels sum over whole rows: zeroing
         // them here makes an input file with non-zero same-site entries sample the reference's distribution.
-        std::vector<double> staged ((size_t) ninst * ldw, 0.0);
-        for (int a = 0; a < ninst; a++) std::memcpy (&staged[(size_t) a * ldw], &wsym[(size_t) a * ninst], (size_t) ninst * sizeof (double));
-        for (int i = 0; i < nsites; i++)
-            for (int a = first[i]; a <= last[i]; a++)
-                for (int b = first[i]; b <= last[i]; b++) staged[(size_t) a * ldw + b] = 0.0;
-        PCE_CUDA (cudaMemcpyAsync (d_w.ptr, staged.data (), staged.size () * sizeof (double), cudaMemcpyHostToDevice, stream));
-        // W in units of RT for the Monte Carlo kernels, on the device: one rounding per element (beta * w), identical to the
-        // chain specification
-        PCE_CUDA (d_wb.resize ((size_t) ninst * ldw));
+        // d_wb = W in units of RT for the Monte Carlo kernels: one rounding per element (beta * w), identical to the chain
+        // specification.
         const size_t total = (size_t) ninst * ldw;
-        k_scale<<<(unsigned) std::min<size_t> ((total + 255) / 256, 65535), 256, 0, stream>>> (d_w.ptr, total, 1.0 / (PCE_R * temperature), d_wb.ptr);
-        pce::count_launch ();
-        PCE_CUDA (cudaGetLastError ());
-        PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors die with this scope
+        const double beta = 1.0 / (PCE_R * temperature);
+        PCE_CUDA (d_wb.resize (total));
+        if (sym_src != nullptr) {
+            // symmetric matrix still a view of a raw buffer: upload the raw matrix (page-locked in place, once per buffer) and
+            // average, zero and scale on the device
+            const size_t bytes = (size_t) ninst * ninst * sizeof (double);
+            if (bytes >= ((size_t) 1 << 20) && pinned[0] != sym_src && pinned[1] != sym_src) {
+                const int slot = pinned[0] == nullptr ? 0 : 1;
+                if (pinned[slot] != nullptr) { cudaHostUnregister (const_cast<void *> (pinned[slot])); pinned[slot] = nullptr; }
+                if (cudaHostRegister (const_cast<double *> (sym_src), bytes, cudaHostRegisterDefault) == cudaSuccess) pinned[slot] = sym_src;
+                else cudaGetLastError ();        // pageable copy instead
+            }
+            PCE_CUDA (d_raw.resize ((size_t) ninst * ninst));
+            PCE_CUDA (cudaMemcpyAsync (d_raw.ptr, sym_src, bytes, cudaMemcpyHostToDevice, stream));
+            const dim3 grid ((unsigned) ((ldw + 31) / 32), (unsigned) ((ninst + 31) / 32)), block (32, 8);
+            k_symmetrize_stage<<<grid, block, 0, stream>>> (d_raw.ptr, ninst, ldw, d_site_of_inst.ptr, beta, d_w.ptr, d_wb.ptr);
+            pce::count_launch ();
+            PCE_CUDA (cudaGetLastError ());
+            PCE_CUDA (cudaStreamSynchronize (stream));   // the small staging vectors above die with this scope
+        } else {
+            const double *ws = host_wsym ();
+            std::vector<double> staged (total, 0.0);
+            for (int a = 0; a < ninst; a++) std::memcpy (&staged[(size_t) a * ldw], &ws[(size_t) a * ninst], (size_t) ninst * sizeof (double));
+            for (int i = 0; i < nsites; i++)
+                for (int a = first[i]; a <= last[i]; a++)
+                    for (int b = first[i]; b <= last[i]; b++) staged[(size_t) a * ldw + b] = 0.0;
+            PCE_CUDA (cudaMemcpyAsync (d_w.ptr, staged.data (), staged.size () * sizeof (double), cudaMemcpyHostToDevice, stream));
+            k_scale<<<(unsigned) std::min<size_t> ((total + 255) / 256, 65535), 256, 0, stream>>> (d_w.ptr, total, beta, d_wb.ptr);
+            pce::count_launch ();
+            PCE_CUDA (cudaGetLastError ());
+            PCE_CUDA (cudaStreamSynchronize (stream));   // the staging vectors die with this scope
+        }
     }
     dirty = false;
     generation++;

@@ -298,3 +298,40 @@ def test_half_pks_and_table_entries_without_a_gpu():
     flat.isCalculated = True
     flat.CalculateHalfpKs()
     assert flat.halves == [[[], []], [[]]] and flat._GetEntry(sites[1]) == "      x    n/a"
+
+
+def test_symmetric_matrix_changes_on_symmetrize_only():
+    """The host copy of the symmetric matrix is made on demand (the device averages the raw matrix during the upload); whatever
+    the order of loads, single-element writes and reads, it must behave like the reference's eager copy
+    (EnergyModel.c:78-87: SymmetrizeInteractions; :197-199: SetInteraction writes the raw matrix only)."""
+    rng = np.random.default_rng(11)
+    rec = synth_a(6)
+    n = rec.ninstances
+    model = P.MEADModel(rec, log=None)
+    em = model.energyModel
+    first = rng.normal(size=(n, n))
+    second = rng.normal(size=(n, n))
+    em.Load(interactions=first)
+    em.SymmetrizeInteractions(log=None)
+    expect = 0.5 * (first + first.T)
+    assert em.GetInteractionSymmetric(2, 5) == expect[2, 5] == em.GetInteractionSymmetric(5, 2)       # read through the view
+    em.Load(interactions=second)                                     # raw matrix replaced, symmetric matrix untouched
+    assert em.GetInteraction(2, 5) == second[2, 5]
+    assert em.GetInteractionSymmetric(2, 5) == expect[2, 5]
+    np.testing.assert_array_equal(em.GetSymmetricMatrix(), expect)
+    em.SymmetrizeInteractions(log=None)
+    expect2 = 0.5 * (second + second.T)
+    em.SetInteraction(2, 5, 123.0)                                   # a single write after Symmetrize: raw only
+    assert em.GetInteraction(2, 5) == 123.0
+    assert em.GetInteractionSymmetric(2, 5) == expect2[2, 5]
+    np.testing.assert_array_equal(em.GetSymmetricMatrix(), expect2)
+    em.Load(interactions=first)
+    em.SymmetrizeInteractions(log=None)
+    em.Load(interactions=second)
+    em.Load(interactions=first * 2.0)                                # two loads in a row while the view is pending
+    np.testing.assert_array_equal(em.GetSymmetricMatrix(), expect)
+    em.SymmetrizeInteractions(log=None)
+    em.ScaleInteractions(0.5)
+    np.testing.assert_array_equal(em.GetSymmetricMatrix(), 0.5 * (2.0 * expect))
+    em.ResetInteractions()
+    assert not em.GetSymmetricMatrix().any()
