@@ -94,7 +94,7 @@ struct McParams {
     int            ldd;             // row stride of dw (warp kernel: the padded field length of the launch)
     // chain-per-thread kernel: the shared-memory layout, computed on the host (ThreadLayout) so that the kernel can
     // re-read an offset from the constant bank instead of keeping it in a register or recomputing it
-    uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_nact, tl_since, tl_site, tl_pair, tl_pairx, tl_erow, tl_state;
+    uint32_t       tl_e, tl_cross, tl_h, tl_eng, tl_counts, tl_nact, tl_since, tl_move, tl_erow, tl_state;
     int            tl_hstride, tl_estride, tl_kslots;
     int            ph_minor;        // linearisation of the (pH, chain) grid: 1 = g = chain * nph + q (consecutive threads take consecutive pH
                                     // values, so every warp and block carries the same mix of cheap and expensive pH values), 0 = g = q * nchains + chain
@@ -107,7 +107,7 @@ struct McParams {
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
 struct ThreadLayout {
-    size_t off_e, off_cross, off_h, off_eng, off_counts, off_nact, off_since, off_site, off_pair, off_pairx, off_erow, off_state, total;
+    size_t off_e, off_cross, off_h, off_eng, off_counts, off_nact, off_since, off_move, off_erow, off_state, total;
     int    hstride, estride, kslots;
     __host__ __device__ ThreadLayout (int nsites, int ninst, int npairs, int nrel, int nrows, int ncross, int block, int nchains, int nph, int since_bytes, bool ph_minor,
                                       bool energy) {
@@ -128,14 +128,14 @@ struct ThreadLayout {
         off_eng = o;    o += energy ? (size_t) block * 16 : 0;
         // occupancy counters of the NON-FIRST instances only (u32: block * nprod < 2^32 is checked on the host); the first instance of
         // a site gets (chains of the slot) * nprod - (its siblings' counts) when the block flushes
-        off_counts = o; o += (size_t) kslots * (nrel > 0 ? nrel : 1) * 4;
+        // (+ one slot that the idle threads of the last block count into: they run a chain like everybody else, so the trial loop
+        // carries no "active" flag)
+        off_counts = o; o += (size_t) (kslots + 1) * (nrel > 0 ? nrel : 1) * 4;
         off_nact = o;   o += (size_t) kslots * 4;
         off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
-        o = (o + 3) & ~(size_t) 3;
-        off_site = o;   o += (size_t) nsites * 4;
-        off_pair = o;   o += (size_t) (npairs > 0 ? npairs : 1) * 4;
-        off_pairx = o;  o += (size_t) (npairs > 0 ? npairs : 1) * 4;
-        off_erow = o;   o += (size_t) nsites * 4;
+        o = (o + 15) & ~(size_t) 15;
+        off_move = o;   o += (size_t) (nsites + npairs) * 16;      // one 16-byte entry per move (sites, then pairs)
+        off_erow = o;   o += (size_t) (nrows > 0 ? nrows : 1) * 8;      // per (current, drawn) instance of a site: its difference row and direction
         off_state = o;  o += (size_t) nsites * block;
         total = (o + 15) & ~(size_t) 15;
     }
@@ -155,12 +155,15 @@ __device__ __noinline__ bool metropolis_exact (double x, uint32_t w1) {
     return ((double) w1 * (1.0 / 4294967296.0)) < exp (-x);
 }
 
+// (called by whole warps.  ex2.approx.ftz flushes results below 2^-126 to zero: there u < exp(-x) can only hold for u = 0, which
+// lands in the exact path through `uf <= 0`, and so does x > 500, where the exact rule rejects.)
 __device__ __forceinline__ bool metropolis (double x, uint32_t w1) {
     const float uf = __uint2float_rn (w1) * 2.3283064365386963e-10f;
-    const float ef = __expf (-(float) x);
+    float ef;
+    asm ("ex2.approx.ftz.f32 %0, %1;" : "=f"(ef) : "f"((float) x * -1.4426950408889634f));
     bool accept = (x < 0.0) || (uf < ef * 0.999f);
-    const bool unsure = !accept && (uf <= ef * 1.001f) && (x <= 500.0);
-    if (__any_sync (__activemask (), unsure)) {
+    const bool unsure = !accept && (uf <= ef * 1.001f);
+    if (__any_sync (0xffffffffu, unsure)) {
         if (unsure) accept = metropolis_exact (x, w1);
     }
     return accept;
@@ -173,6 +176,24 @@ __device__ __forceinline__ double lds_f64 (uint32_t address) {
 }
 __device__ __forceinline__ void sts_f64 (uint32_t address, double v) {
     asm volatile ("st.shared.f64 [%0], %1;" : : "r"(address), "d"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8 (uint32_t address) {
+    uint32_t v;
+    asm volatile ("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(address) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8 (uint32_t address, uint32_t v) {
+    asm volatile ("st.shared.u8 [%0], %1;" : : "r"(address), "r"(v) : "memory");
+}
+template <typename T> __device__ __forceinline__ uint32_t lds_stamp (uint32_t address) {
+    uint32_t v;
+    if (sizeof (T) == 2) asm volatile ("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(address) : "memory");
+    else asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(address) : "memory");
+    return v;
+}
+template <typename T> __device__ __forceinline__ void sts_stamp (uint32_t address, uint32_t v) {
+    if (sizeof (T) == 2) asm volatile ("st.shared.u16 [%0], %1;" : : "r"(address), "r"(v) : "memory");
+    else asm volatile ("st.shared.u32 [%0], %1;" : : "r"(address), "r"(v) : "memory");
 }
 __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
     return __hiloint2double (__double2hiint (v) ^ (int) mask, __double2loint (v));
@@ -194,7 +215,7 @@ __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
 // the planner stops at 768 threads.  To get there the loop state was put on a diet: no Philox prefetch, 32-bit scan
 // counter instead of 64-bit trial counters, tracked energy and its sum in shared memory, 32-bit shared-memory offsets
 // instead of generic pointers, the shared-memory layout passed in the kernel parameters.
-template <bool PER_CHAIN, typename SinceT, int MAX_REGS, bool SHORT_FIELDS, bool ENERGY>
+template <bool PER_CHAIN, typename SinceT, int MAX_REGS, int SHORT_FIELDS, bool ENERGY>      // SHORT_FIELDS: 0 nrel > 32, 1 nrel <= 32, 2 nrel <= 16
 __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     static_assert (ENERGY || !PER_CHAIN, "per-chain outputs include the energy");
     extern __shared__ __align__ (16) unsigned char smem[];
@@ -206,10 +227,13 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     uint32_t           *s_counts = (uint32_t *) (smem + p.tl_counts);   // [kslots][nrel]: non-first instances
     uint32_t           *s_nact   = (uint32_t *) (smem + p.tl_nact);     // [kslots]: chains of this block per pH slot
     SinceT             *s_since  = (SinceT *) (smem + p.tl_since);
-    uint32_t           *s_site   = (uint32_t *) (smem + p.tl_site);       // first | ninst << 16
-    uint32_t           *s_pair   = (uint32_t *) (smem + p.tl_pair);       // site a | site b << 16
-    uint32_t           *s_pairx  = (uint32_t *) (smem + p.tl_pairx);      // base of the pair in the cross-term table
-    uint32_t           *s_erow   = (uint32_t *) (smem + p.tl_erow);       // first difference row of the site
+    // one entry per move, fetched with ONE 128-bit load per trial: x = site a | site b << 16 (single move: b = a),
+    // y = (n_a - 1) | g_a << 16, z = (n_b - 1) | g_b << 16, w = base of the pair in the cross-term table (15 bits) | base of
+    // site a in the row table << 15 (16 bits) | invalid << 31 (a site with one instance).  g = 8 * (first - site): local index l >= 1 of the site owns the field slot at byte g + 8 l - 8.
+    uint4              *s_move   = (uint4 *) (smem + p.tl_move);
+    // difference row of every single-site move: entry 2 * (first row of the site) + current * (n - 1) + draw -> the row (its shared-memory
+    // address in the short-field build) | 1 << 31 when the move runs against the row's direction (new < old)
+    uint32_t           *s_rowtab = (uint32_t *) (smem + p.tl_erow);
     uint8_t            *s_state  = smem + p.tl_state;
     struct { int hstride, estride, kslots; } L = { p.tl_hstride, p.tl_estride, p.tl_kslots };
 
@@ -226,29 +250,51 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const uint32_t chain = (uint32_t) (p.chain_offset + local);
     const uint32_t phidx = (uint32_t) (p.ph_index_offset + q);
     const int my_slot = q - q_base + (q < q_base ? p.nph : 0);
-    uint32_t *my_counts = s_counts + (size_t) my_slot * (nrel > 0 ? nrel : 1);      // indexed by the relative slot r(k) = k - site - 1
-    // per-thread arrays as 32-bit offsets into the dynamic shared memory (one register each instead of a 64-bit pointer)
-    const uint32_t o_state = p.tl_state + (uint32_t) tid, o_since = p.tl_since + (uint32_t) tid * (uint32_t) sizeof (SinceT);
-#define my_state(i_) smem[o_state + (uint32_t) (i_)]
-#define my_since(i_) (*(SinceT *) (smem + o_since + (uint32_t) (i_) * (uint32_t) sizeof (SinceT)))
+    uint32_t *my_counts = s_counts + (size_t) (active ? my_slot : L.kslots) * (nrel > 0 ? nrel : 1);      // indexed by the relative slot r(k) = k - site - 1
+    // per-thread arrays as 32-bit shared-memory addresses (one register each instead of a 64-bit pointer; explicit ld/st.shared, so
+    // that no generic-to-shared window arithmetic is left in the trial loop)
+    const uint32_t s_base = (uint32_t) __cvta_generic_to_shared (smem);
+    const uint32_t o_state = s_base + p.tl_state + (uint32_t) tid, o_since = s_base + p.tl_since + (uint32_t) tid * (uint32_t) sizeof (SinceT);
+#define my_state(i_) ((int) lds_u8 (o_state + (uint32_t) (i_)))
+#define set_state(i_, v_) sts_u8 (o_state + (uint32_t) (i_), (uint32_t) (v_))
+#define my_since(i_) lds_stamp<SinceT> (o_since + (uint32_t) (i_) * (uint32_t) sizeof (SinceT))
+#define set_since(i_, v_) sts_stamp<SinceT> (o_since + (uint32_t) (i_) * (uint32_t) sizeof (SinceT), (uint32_t) (v_))
     long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
 
     // stage the model: difference rows, cross terms, packed site and pair tables
     for (int e = tid; e < p.nrows * nrel; e += B) s_e[(e / nrel) * L.estride + (e % nrel)] = p.dw[(size_t) (e / nrel) * p.ldd + (e % nrel)];
     for (int e = tid; e < p.ncross; e += B) s_cross[e] = p.cross[e];
-    for (int k = tid; k < L.kslots * (nrel > 0 ? nrel : 1); k += B) s_counts[k] = 0u;
+    for (int k = tid; k < (L.kslots + 1) * (nrel > 0 ? nrel : 1); k += B) s_counts[k] = 0u;
     for (int k = tid; k < L.kslots; k += B) s_nact[k] = 0u;
-    for (int i = tid; i < nsites; i += B) { s_site[i] = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16); s_erow[i] = (uint32_t) p.dbase[i]; }
-    for (int i = tid; i < p.npairs; i += B) { s_pair[i] = p.pair_packed[i]; s_pairx[i] = p.pair_x[i] & 0xffffffu; }
+    for (int i = tid; i < nsites; i += B) {
+        const int n = p.nsi[i], base = p.dbase[i];
+        for (int o = 0; o < n; o++)
+            for (int k = 0; k < n - 1; k++) {
+                const int l = k + (k >= o ? 1 : 0), mx = l > o ? l : o, mn = l > o ? o : l;
+                const uint32_t row = (uint32_t) (base + ((mx * (mx - 1)) >> 1) + mn);
+                s_rowtab[2 * base + o * (n - 1) + k] = (SHORT_FIELDS ? (uint32_t) __cvta_generic_to_shared (s_e) + row * (uint32_t) (L.estride * 8) : row) | (l < o ? 0x80000000u : 0u);
+            }
+    }
+    for (int i = tid; i < nsites + p.npairs; i += B) {
+        const uint32_t pr = i < nsites ? (uint32_t) i | ((uint32_t) i << 16) : p.pair_packed[i - nsites];
+        const int a = (int) (pr & 0xffffu), b = (int) (pr >> 16), na = p.nsi[a], nb = p.nsi[b];
+        uint4 entry;
+        entry.x = pr;
+        entry.y = (uint32_t) (na - 1) | ((uint32_t) (p.first[a] - a) << 19);
+        entry.z = (uint32_t) (nb - 1) | ((uint32_t) (p.first[b] - b) << 19);
+        entry.w = (i < nsites ? 0u : p.pair_x[i - nsites] & 0x7fffu) | ((uint32_t) (2 * p.dbase[a]) << 15) | ((na < 2 || nb < 2) ? 0x80000000u : 0u);
+        s_move[i] = entry;
+    }
 
-    // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i)
+    // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i); the state array holds
+    // LOCAL instance indices (0 .. n_i - 1), so that the trial loop never subtracts the site's first instance
     {
         pce::Philox4 r = { 0, 0, 0, 0 };
         for (int i = 0; i < nsites; i++) {
             if ((i & 3) == 0) r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
             const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-            my_state (i * B) = (uint8_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
-            my_since (i * B) = (SinceT) 0;
+            set_state (i * B, __umulhi (word, (uint32_t) p.nsi[i]));
+            set_since (i * B, 0u);
         }
     }
     __syncthreads ();
@@ -268,24 +314,25 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             const double gk = __dmul_rn (beta, __dsub_rn (p.gintr[k], __dmul_rn ((double) p.protons[k], mu_c)));
             const double gf = __dmul_rn (beta, __dsub_rn (p.gintr[f], __dmul_rn ((double) p.protons[f], mu_c)));
             double acc = __dsub_rn (gk, gf);
-            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, p.wr[(size_t) sc[j * B] * p.ldr + r]);
+            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, p.wr[(size_t) (p.first[j] + sc[j * B]) * p.ldr + r]);
             hc[r] = acc;
         }
     }
     __syncwarp ();
-    const uint32_t o_g = p.tl_h + (uint32_t) (tid * L.hstride) * 8u;
-#define myg(i_) (*(const double *) (smem + o_g + (uint32_t) (i_) * 8u))
+    uint32_t o_g = s_base + p.tl_h + (uint32_t) (tid * L.hstride) * 8u - 8u;      // slot -1: local index 1 of a site with (first - site) = 0 reads slot 0
+    asm volatile ("" : "+r"(o_g));            // opaque: kept in a register instead of being rebuilt from the parameters at every use
+#define fld(base_, l_) lds_f64 ((base_) + (uint32_t) (l_) * 8u)      // field of local index l >= 1; base = o_g + g of the site
 
     // initial energy in the reference's order (EnergyModel.c:204-224), then to units of RT
     {
         double gi = 0.0, ws = 0.0;
         int    np = 0;
         for (int i = 0; i < nsites; i++) {
-            const int ai = my_state (i * B);
+            const int ai = p.first[i] + my_state (i * B);
             gi = __dadd_rn (gi, p.gintr[ai]);
             np += p.protons[ai];
             const double *row = p.w + (size_t) ai * p.ldw;
-            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[my_state (j * B)]);
+            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[p.first[j] + my_state (j * B)]);
         }
         if (ENERGY) {
             my_eng[0] = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
@@ -306,42 +353,45 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         const unsigned long long prod = (unsigned long long) w0 * nmoves;
         const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
         const bool     dbl = idx >= (uint32_t) nsites;
-        const uint32_t pr  = dbl ? s_pair[idx - nsites] : (idx | (idx << 16));     // single move: site b = site a
-        const int sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
-        const uint32_t ia_info = s_site[sa];
-        const int fa = (int) (ia_info & 0xffffu), na = (int) (ia_info >> 16), oa = my_state (sa * B);
-        bool valid = active && na >= 2;
-        const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
+        const uint4    move = s_move[idx];
+        const int sa = (int) (move.x & 0xffffu), sb = (int) (move.x >> 16);
+        // local indices throughout: l* = proposed, o* = current instance of the site; the first instance of a site is the zero
+        // of its relative fields
+        const uint32_t nam1 = move.y & 0xffffu;
+        uint32_t a_fld = o_g + (move.y >> 16);
+        const int oa = my_state (sa * B);
+        const bool valid = (int) move.w >= 0;
+        const unsigned long long proda = (unsigned long long) lo * nam1;
         const int ka = (int) (proda >> 32);
-        int ia = fa + ka;
-        if (ia >= oa) ia++;
-        int ib = 0, ob = 0;
+        int la = ka + (ka >= oa ? 1 : 0);
+        int lb = 0, ob = 0;
+        uint32_t b_fld = 0u;
         double x;
-        // G(k) = relative field of instance k: 0 for the first instance of its site, else g[k - site - 1]
+#define PCE_PIN(v_) asm volatile ("" : "+r"(v_))       /* evaluated once, here: ptxas otherwise re-derives it under every predicate that uses it */
         if (has_pairs) {
             // evaluated for every lane (a warp almost always holds a double move; no divergent branch); for single
-            // moves ib == ob and the cross term is zero, so the value equals the single-move formula bit for bit
-            const uint32_t ib_info = s_site[sb];
-            const int fb = (int) (ib_info & 0xffffu), nb = (int) (ib_info >> 16);
+            // moves lb == ob and the cross term is zero, so the value equals the single-move formula bit for bit
+            const uint32_t nbm1 = move.z & 0xffffu;
+            b_fld = o_g + (move.z >> 16);
             ob = my_state (sb * B);
-            const int kb = (int) __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
-            ib = fb + kb;
-            if (ib >= ob) ib++;
-            if (dbl && nb < 2) valid = false;
-            if (!dbl) ib = ob;
-            if (!valid) { ia = oa; ib = ob; }
+            const int kb = (int) __umulhi ((uint32_t) proda, nbm1);
+            lb = kb + (kb >= ob ? 1 : 0);
+            if (!dbl || !valid) lb = ob;
+            if (!valid) la = oa;
+            PCE_PIN (la); PCE_PIN (lb); PCE_PIN (a_fld); PCE_PIN (b_fld);
             double cross = 0.0;
-            if (dbl && valid) cross = s_cross[s_pairx[idx - nsites] + (uint32_t) (((oa - fa) * (na - 1) + ka) * (nb * (nb - 1)) + (ob - fb) * (nb - 1) + kb)];
-            const double gan = ia != fa ? myg (ia - sa - 1) : 0.0, gao = oa != fa ? myg (oa - sa - 1) : 0.0;
-            const double gbn = ib != fb ? myg (ib - sb - 1) : 0.0, gbo = ob != fb ? myg (ob - sb - 1) : 0.0;
+            if (dbl && valid) cross = s_cross[(move.w & 0x7fffu) + ((uint32_t) oa * nam1 + (uint32_t) ka) * (nbm1 * (nbm1 + 1u)) + (uint32_t) ob * nbm1 + (uint32_t) kb];
+            const double gan = la ? fld (a_fld, la) : 0.0, gao = oa ? fld (a_fld, oa) : 0.0;
+            const double gbn = lb ? fld (b_fld, lb) : 0.0, gbo = ob ? fld (b_fld, ob) : 0.0;
             x = __dadd_rn (__dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo)), cross);
-            if (scan >= (uint32_t) p.nequil && dbl) c_flips++;
+            c_flips += dbl ? 1u : 0u;                    // (the counters restart when the production scans begin)
         } else {
-            if (!valid) ia = oa;
-            const double gan = ia != fa ? myg (ia - sa - 1) : 0.0, gao = oa != fa ? myg (oa - sa - 1) : 0.0;
+            if (!valid) la = oa;
+            PCE_PIN (la); PCE_PIN (a_fld);
+            const double gan = la ? fld (a_fld, la) : 0.0, gao = oa ? fld (a_fld, oa) : 0.0;
             x = __dsub_rn (gan, gao);
         }
-        const bool accept = valid && metropolis (x, w1);
+        const bool accept = metropolis (x, w1) && valid;       // (every lane takes part in the vote inside)
         if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) { lg_f++; lg_fa += accept; } else { lg_m++; lg_ma += accept; } }
 
         // apply accepted moves: two accepting chains per round, one per half-warp; each lane updates slots
@@ -358,18 +408,14 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 // the time, so their second row takes a separate, warp-uniform pass).
                 uint32_t pa = 0u, pb = 0u;
                 if (accept) {
-                    const int la = ia - fa, lo_a = oa - fa;
-                    const int mxa = la > lo_a ? la : lo_a, mna = la > lo_a ? lo_a : la;
-                    pa = (e_addr + (s_erow[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) * (uint32_t) (L.estride * 8)) | (la < lo_a ? 0x80000000u : 0u);
+                    pa = s_rowtab[((move.w >> 15) & 0xffffu) + (uint32_t) oa * nam1 + (uint32_t) ka];
                     if (dbl) {
-                        const int fb = (int) (s_site[sb] & 0xffffu), lb = ib - fb, lo_b = ob - fb;
-                        const int mxb = lb > lo_b ? lb : lo_b, mnb = lb > lo_b ? lo_b : lb;
-                        pb = (e_addr + (s_erow[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) * (uint32_t) (L.estride * 8)) | (lb < lo_b ? 0x80000000u : 0u);
+                        pb = s_rowtab[((s_move[sb].w >> 15) & 0xffffu) + (uint32_t) ob * (move.z & 0xffffu) + (uint32_t) (lb - (lb > ob ? 1 : 0))];
                         pa |= 0x40000000u;
                     }
                 }
                 const bool     second   = __any_sync (0xffffffffu, accept && dbl);
-                const bool     pairwise = nrel <= 16;
+                constexpr bool pairwise = SHORT_FIELDS == 2;
                 const int      sub   = pairwise ? (lane & 15) : lane;
                 const bool     mine  = sub < nrel;
                 const uint32_t o     = (uint32_t) sub * 8u;
@@ -383,7 +429,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                         if (lane >> 4) src = s1;
                     }
                     const uint32_t y = __shfl_sync (0xffffffffu, pa, src);       // (the source lane is taken modulo 32: -1 reads lane 31, unused)
-                    const bool     work = mine && src >= 0;
+                    const bool     work = pairwise ? (mine && src >= 0) : mine;
                     const uint32_t hslot = hbase + (uint32_t) src * hs8;
                     if (work) sts_f64 (hslot, __dadd_rn (lds_f64 (hslot), flip_sign (lds_f64 ((y & 0x3fffffffu) + o), y & 0x80000000u)));
                     if (second) {        // warp-uniform and rare
@@ -395,13 +441,11 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             // difference row and direction of each changed site: row | reverse << 14, site b in the upper half, double << 30
             uint32_t packed = 0u;
             if (accept) {
-                const int la = ia - fa, lo_a = oa - fa;
-                const int mxa = la > lo_a ? la : lo_a, mna = la > lo_a ? lo_a : la;
-                packed = (s_erow[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) | (la < lo_a ? 1u << 14 : 0u);
+                const uint32_t ta = s_rowtab[((move.w >> 15) & 0xffffu) + (uint32_t) oa * nam1 + (uint32_t) ka];
+                packed = (ta & 0x3fffu) | (ta >> 31 << 14);
                 if (dbl) {
-                    const int fb = (int) (s_site[sb] & 0xffffu), lb = ib - fb, lo_b = ob - fb;
-                    const int mxb = lb > lo_b ? lb : lo_b, mnb = lb > lo_b ? lo_b : lb;
-                    packed |= ((s_erow[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) << 15) | (lb < lo_b ? 1u << 29 : 0u) | (1u << 30);
+                    const uint32_t tb = s_rowtab[((s_move[sb].w >> 15) & 0xffffu) + (uint32_t) ob * (move.z & 0xffffu) + (uint32_t) (lb - (lb > ob ? 1 : 0))];
+                    packed |= ((tb & 0x3fffu) << 15) | (tb >> 31 << 29) | (1u << 30);
                 }
             }
             // longer field vectors: two chains per round (16 lanes each) up to 48 slots, else one chain per round (32 lanes)
@@ -443,18 +487,18 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 const uint32_t tp = production ? scan - (uint32_t) p.nequil : 0u;
                 if (ENERGY) my_eng[0] = __dadd_rn (my_eng[0], x);
                 const uint32_t since_a = my_since (sa * B);
-                if (PER_CHAIN) my_chain_counts[oa] += (long long) (tp - since_a);
-                else if (tp != since_a && oa != fa) atomicAdd (&my_counts[oa - sa - 1], tp - since_a);
-                my_since (sa * B) = (SinceT) tp;
-                my_state (sa * B) = (uint8_t) ia;
+                if (PER_CHAIN) { if (active) my_chain_counts[(int) (move.y >> 19) + sa + oa] += (long long) (tp - since_a); }       // (idle threads run the last chain again)
+                else if (tp != since_a && oa) atomicAdd (&my_counts[(int) (move.y >> 19) + oa - 1], tp - since_a);
+                set_since (sa * B, tp);
+                set_state (sa * B, la);
                 if (dbl) {
                     const uint32_t since_b = my_since (sb * B);
-                    if (PER_CHAIN) my_chain_counts[ob] += (long long) (tp - since_b);
-                    else if (tp != since_b && ob != (int) (s_site[sb] & 0xffffu)) atomicAdd (&my_counts[ob - sb - 1], tp - since_b);
-                    my_since (sb * B) = (SinceT) tp;
-                    my_state (sb * B) = (uint8_t) ib;
-                    if (production) c_facc++;
-                } else if (production) c_macc++;
+                    if (PER_CHAIN) { if (active) my_chain_counts[(int) (move.z >> 19) + sb + ob] += (long long) (tp - since_b); }
+                    else if (tp != since_b && ob) atomicAdd (&my_counts[(int) (move.z >> 19) + ob - 1], tp - since_b);
+                    set_since (sb * B, tp);
+                    set_state (sb * B, lb);
+                    c_facc++;
+                } else c_macc++;
             }
         }
         // scan bookkeeping (MCModelDefault.c:298-312): after the last trial of a production scan the energy is recorded
@@ -478,6 +522,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 if (!production && scan + 1 == (uint32_t) p.nequil) lg_m = lg_ma = lg_f = lg_fa = 0;
             }
             scan++;
+            if (scan == (uint32_t) p.nequil) c_macc = c_flips = c_facc = 0u;      // the move counters cover the production scans
         }
     };
 
@@ -494,14 +539,14 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (active) {
         for (int i = 0; i < nsites; i++) {
-            const int      a = my_state (i * B);
+            const int      a = my_state (i * B), gi = (int) (s_move[i].y >> 19);       // local index, first - site
             const uint32_t d = (uint32_t) p.nprod - my_since (i * B);
-            if (PER_CHAIN) my_chain_counts[a] += (long long) d;
-            else if (d && a != (int) (s_site[i] & 0xffffu)) atomicAdd (&my_counts[a - i - 1], d);
+            if (PER_CHAIN) my_chain_counts[gi + i + a] += (long long) d;
+            else if (d && a) atomicAdd (&my_counts[gi + a - 1], d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
-            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = my_state (i * B);
+            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = (int) (s_move[i].y >> 19) + i + my_state (i * B);
             p.chain_energy[c] = my_eng[0] / beta;
             p.chain_esum[c]   = my_eng[B] / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
@@ -523,10 +568,10 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 int qq = q_base + slot;
                 if (p.ph_minor && qq >= p.nph) qq -= p.nph;
                 if (qq >= p.nph || s_nact[slot] == 0u) continue;
-                const int fi = (int) (s_site[i] & 0xffffu), ni = (int) (s_site[i] >> 16);
+                const int gi = (int) (s_move[i].y >> 19), ni = (int) (s_move[i].y & 0xffffu) + 1;
                 unsigned long long first_count = (unsigned long long) s_nact[slot] * (unsigned long long) p.nprod;
-                for (int d = 1; d < ni; d++) first_count -= (unsigned long long) s_counts[(size_t) slot * nr + (fi + d - i - 1)];
-                if (first_count) atomicAdd (&p.counts[(size_t) qq * ninst + fi], first_count);
+                for (int d = 1; d < ni; d++) first_count -= (unsigned long long) s_counts[(size_t) slot * nr + (gi + d - 1)];
+                if (first_count) atomicAdd (&p.counts[(size_t) qq * ninst + gi + i], first_count);
             }
         }
         // counters and energy sums: one atomic per thread (pH values may differ within a warp)
@@ -542,8 +587,11 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     }
 }
 #undef my_state
+#undef set_state
 #undef my_since
-#undef myg
+#undef set_since
+#undef fld
+#undef PCE_PIN
 
 // ---------------------------------------------------------------------------------------------------
 // Tables of the relative-field formulation and the application of an accepted move in the warp kernel.
@@ -1129,7 +1177,7 @@ struct CostModel {
 bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, bool energy, Plan *plan, double *cost_out) {
     const pce_model *m = mc->model;
     const TableSizes t = table_sizes (mc);
-    if (m->ninst > 256 || t.nrows > 16383 || t.ncross >= (1u << 24)) return false;
+    if (m->ninst > 256 || t.nrows > 16383 || t.ncross >= (1u << 15)) return false;       // field widths of the packed move table (the tables must fit in shared memory anyway)
     const char *forced = std::getenv ("PCE_MC_BLOCK");      // tuning aid: force the block size
     const int forced_block = forced ? std::atoi (forced) : 0;
     // measured on lysozyme (moves/s): 640 threads 7.6e10, 768 (the largest block the uncapped 79-register build fits) 8.5e10,
@@ -1144,10 +1192,10 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, bool energy,
     if (t.nrel <= 32) {
         cudaFuncAttributes attributes;
         const bool narrow = mc->nprod < 65536;
-        const cudaError_t err = narrow ? (energy ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, true, true>)
-                                                 : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, true, false>))
-                                       : (energy ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, true, true>)
-                                                 : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, true, false>));
+        const cudaError_t err = narrow ? (energy ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, 1, true>)
+                                                 : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint16_t, 128, 1, false>))
+                                       : (energy ? cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, 1, true>)
+                                                 : cudaFuncGetAttributes (&attributes, k_mc_thread<false, uint32_t, 128, 1, false>));
         if (err == cudaSuccess && ((attributes.numRegs + 7) & ~7) * 32 * 7 <= 16384) most = 896;
         else if (err != cudaSuccess) (void) cudaGetLastError ();
     }
@@ -1548,7 +1596,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         const ThreadLayout TL (m->nsites, m->ninst, npairs, p.nrel, p.nrows, p.ncross, plan.block, mc->nchains, nph, mc->nprod < 65536 ? 2 : 4, plan.ph_minor != 0, energy);
         p.ph_minor = plan.ph_minor;
         p.tl_e = (uint32_t) TL.off_e; p.tl_cross = (uint32_t) TL.off_cross; p.tl_h = (uint32_t) TL.off_h; p.tl_eng = (uint32_t) TL.off_eng; p.tl_counts = (uint32_t) TL.off_counts; p.tl_nact = (uint32_t) TL.off_nact;
-        p.tl_since = (uint32_t) TL.off_since; p.tl_site = (uint32_t) TL.off_site; p.tl_pair = (uint32_t) TL.off_pair; p.tl_pairx = (uint32_t) TL.off_pairx;
+        p.tl_since = (uint32_t) TL.off_since; p.tl_move = (uint32_t) TL.off_move;
         p.tl_erow = (uint32_t) TL.off_erow; p.tl_state = (uint32_t) TL.off_state;
         p.tl_hstride = TL.hstride; p.tl_estride = TL.estride; p.tl_kslots = TL.kslots;
         if (TL.total != plan.smem) return fail (PCE_ERR_STATE, "shared-memory layout of the chain-per-thread kernel changed between planning and launch");
@@ -1556,7 +1604,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     }
     if (plan.kernel == 1) {
         void (*kernel) (const McParams);
-        const bool short_fields = p.nrel <= 32;      // one field slot per lane when an accepted move is applied
+        const int short_fields = p.nrel <= 16 ? 2 : p.nrel <= 32 ? 1 : 0;      // one field slot per lane (half-warp) when an accepted move is applied
         // the first build (fewest instructions first) whose registers fit: a quarter of the block's warps share the 16384
         // registers of an SM sub-partition, allocated in units of 8 per thread
         auto fits = [&] (void (*candidate) (const McParams)) -> bool {
@@ -1565,14 +1613,15 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
             const int allocated = (attributes.numRegs + 7) & ~7, warps_per_partition = (plan.block / 32 + 3) / 4;
             return warps_per_partition * allocated * 32 <= 16384;
         };
-#define PCE_THREAD_KERNEL(S_, R_) (short_fields ? (per_chain ? k_mc_thread<true, S_, R_, true, true> : energy ? k_mc_thread<false, S_, R_, true, true> : k_mc_thread<false, S_, R_, true, false>) \
-                                                : (per_chain ? k_mc_thread<true, S_, R_, false, true> : energy ? k_mc_thread<false, S_, R_, false, true> : k_mc_thread<false, S_, R_, false, false>))
+#define PCE_THREAD_VARIANT(S_, R_, F_) (per_chain ? k_mc_thread<true, S_, R_, F_, true> : energy ? k_mc_thread<false, S_, R_, F_, true> : k_mc_thread<false, S_, R_, F_, false>)
+#define PCE_THREAD_KERNEL(S_, R_) (short_fields == 2 ? PCE_THREAD_VARIANT (S_, R_, 2) : short_fields == 1 ? PCE_THREAD_VARIANT (S_, R_, 1) : PCE_THREAD_VARIANT (S_, R_, 0))
 #define PCE_THREAD_PICK(S_) (fits (PCE_THREAD_KERNEL (S_, 128)) ? PCE_THREAD_KERNEL (S_, 128) : fits (PCE_THREAD_KERNEL (S_, 80)) ? PCE_THREAD_KERNEL (S_, 80) \
                              : fits (PCE_THREAD_KERNEL (S_, 72)) ? PCE_THREAD_KERNEL (S_, 72) : PCE_THREAD_KERNEL (S_, 64))
         if (mc->nprod < 65536) kernel = PCE_THREAD_PICK (uint16_t);
         else kernel = PCE_THREAD_PICK (uint32_t);
 #undef PCE_THREAD_PICK
 #undef PCE_THREAD_KERNEL
+#undef PCE_THREAD_VARIANT
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         kernel<<<(unsigned) blocks, plan.block, plan.smem, m->stream>>> (p);
     } else {
