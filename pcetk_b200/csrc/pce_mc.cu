@@ -132,11 +132,13 @@ struct ThreadLayout {
         // carries no "active" flag)
         off_counts = o; o += (size_t) (kslots + 1) * (nrel > 0 ? nrel : 1) * 4;
         off_nact = o;   o += (size_t) kslots * 4;
-        off_since = o;  o += (size_t) nsites * block * since_bytes;      // residence stamps: u16 when nprod < 65536
+        // residence stamps (u16 when nprod < 65536) and states are site-major; rows of block + 4 bytes (stamps: words) so that lanes
+        // working on different sites fall into different banks (a row of `block` bytes is a multiple of 128: 4-way conflicts)
+        off_since = o;  o += (size_t) nsites * (block * since_bytes + 4);
         o = (o + 15) & ~(size_t) 15;
         off_move = o;   o += (size_t) (nsites + npairs) * 16;      // one 16-byte entry per move (sites, then pairs)
         off_erow = o;   o += (size_t) (nrows > 0 ? nrows : 1) * 8;      // per (current, drawn) instance of a site: its difference row and direction
-        off_state = o;  o += (size_t) nsites * block;
+        off_state = o;  o += (size_t) nsites * (block + 4);
         total = (o + 15) & ~(size_t) 15;
     }
 };
@@ -255,10 +257,11 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     // that no generic-to-shared window arithmetic is left in the trial loop)
     const uint32_t s_base = (uint32_t) __cvta_generic_to_shared (smem);
     const uint32_t o_state = s_base + p.tl_state + (uint32_t) tid, o_since = s_base + p.tl_since + (uint32_t) tid * (uint32_t) sizeof (SinceT);
-#define my_state(i_) ((int) lds_u8 (o_state + (uint32_t) (i_)))
-#define set_state(i_, v_) sts_u8 (o_state + (uint32_t) (i_), (uint32_t) (v_))
-#define my_since(i_) lds_stamp<SinceT> (o_since + (uint32_t) (i_) * (uint32_t) sizeof (SinceT))
-#define set_since(i_, v_) sts_stamp<SinceT> (o_since + (uint32_t) (i_) * (uint32_t) sizeof (SinceT), (uint32_t) (v_))
+    const uint32_t Bs = (uint32_t) B + 4u, Bt = (uint32_t) B * (uint32_t) sizeof (SinceT) + 4u;       // padded row lengths in bytes (ThreadLayout)
+#define my_state(site_) ((int) lds_u8 (o_state + (uint32_t) (site_) * Bs))
+#define set_state(site_, v_) sts_u8 (o_state + (uint32_t) (site_) * Bs, (uint32_t) (v_))
+#define my_since(site_) lds_stamp<SinceT> (o_since + (uint32_t) (site_) * Bt)
+#define set_since(site_, v_) sts_stamp<SinceT> (o_since + (uint32_t) (site_) * Bt, (uint32_t) (v_))
     long long *my_chain_counts = PER_CHAIN ? p.chain_counts + ((size_t) q * p.nchains + local) * ninst : nullptr;
 
     // stage the model: difference rows, cross terms, packed site and pair tables
@@ -293,8 +296,8 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         for (int i = 0; i < nsites; i++) {
             if ((i & 3) == 0) r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
             const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
-            set_state (i * B, __umulhi (word, (uint32_t) p.nsi[i]));
-            set_since (i * B, 0u);
+            set_state (i, __umulhi (word, (uint32_t) p.nsi[i]));
+            set_since (i, 0u);
         }
     }
     __syncthreads ();
@@ -314,7 +317,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             const double gk = __dmul_rn (beta, __dsub_rn (p.gintr[k], __dmul_rn ((double) p.protons[k], mu_c)));
             const double gf = __dmul_rn (beta, __dsub_rn (p.gintr[f], __dmul_rn ((double) p.protons[f], mu_c)));
             double acc = __dsub_rn (gk, gf);
-            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, p.wr[(size_t) (p.first[j] + sc[j * B]) * p.ldr + r]);
+            for (int j = 0; j < nsites; j++) acc = __dadd_rn (acc, p.wr[(size_t) (p.first[j] + sc[(size_t) j * Bs]) * p.ldr + r]);
             hc[r] = acc;
         }
     }
@@ -328,11 +331,11 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         double gi = 0.0, ws = 0.0;
         int    np = 0;
         for (int i = 0; i < nsites; i++) {
-            const int ai = p.first[i] + my_state (i * B);
+            const int ai = p.first[i] + my_state (i);
             gi = __dadd_rn (gi, p.gintr[ai]);
             np += p.protons[ai];
             const double *row = p.w + (size_t) ai * p.ldw;
-            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[p.first[j] + my_state (j * B)]);
+            for (int j = 0; j < i; j++) ws = __dadd_rn (ws, row[p.first[j] + my_state (j)]);
         }
         if (ENERGY) {
             my_eng[0] = __dmul_rn (beta, __dadd_rn (__dsub_rn (gi, __dmul_rn ((double) np, mu)), ws));
@@ -359,7 +362,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         // of its relative fields
         const uint32_t nam1 = move.y & 0xffffu;
         uint32_t a_fld = o_g + (move.y >> 16);
-        const int oa = my_state (sa * B);
+        const int oa = my_state (sa);
         const bool valid = (int) move.w >= 0;
         const unsigned long long proda = (unsigned long long) lo * nam1;
         const int ka = (int) (proda >> 32);
@@ -373,7 +376,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
             // moves lb == ob and the cross term is zero, so the value equals the single-move formula bit for bit
             const uint32_t nbm1 = move.z & 0xffffu;
             b_fld = o_g + (move.z >> 16);
-            ob = my_state (sb * B);
+            ob = my_state (sb);
             const int kb = (int) __umulhi ((uint32_t) proda, nbm1);
             lb = kb + (kb >= ob ? 1 : 0);
             if (!dbl || !valid) lb = ob;
@@ -419,13 +422,16 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 const int      sub   = pairwise ? (lane & 15) : lane;
                 const bool     mine  = sub < nrel;
                 const uint32_t o     = (uint32_t) sub * 8u;
-                const uint32_t hs8   = (uint32_t) L.hstride * 8u, hbase = h_addr + (uint32_t) warp_base * hs8 + o;
+                const uint32_t hs8   = (uint32_t) L.hstride * 8u;
+                uint32_t hbase = h_addr + (uint32_t) warp_base * hs8 + o;
+                asm volatile ("" : "+r"(hbase));
                 do {
-                    int src = __ffs (pending) - 1;
-                    pending &= pending - 1;
+                    // highest accepting lane first (one FLO instead of BREV + FLO; the chains are independent, any order does)
+                    int src = 31 - __clz ((int) pending);
+                    pending ^= 1u << src;
                     if (pairwise) {
-                        const int s1 = __ffs (pending) - 1;      // -1 when no second chain is waiting
-                        pending &= pending - 1;                  // (0 stays 0)
+                        const int s1 = 31 - __clz ((int) pending);      // -1 when no second chain is waiting
+                        if (pending) pending ^= 1u << s1;
                         if (lane >> 4) src = s1;
                     }
                     const uint32_t y = __shfl_sync (0xffffffffu, pa, src);       // (the source lane is taken modulo 32: -1 reads lane 31, unused)
@@ -486,23 +492,24 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 const bool production = scan >= (uint32_t) p.nequil;
                 const uint32_t tp = production ? scan - (uint32_t) p.nequil : 0u;
                 if (ENERGY) my_eng[0] = __dadd_rn (my_eng[0], x);
-                const uint32_t since_a = my_since (sa * B);
+                const uint32_t since_a = my_since (sa);
                 if (PER_CHAIN) { if (active) my_chain_counts[(int) (move.y >> 19) + sa + oa] += (long long) (tp - since_a); }       // (idle threads run the last chain again)
                 else if (tp != since_a && oa) atomicAdd (&my_counts[(int) (move.y >> 19) + oa - 1], tp - since_a);
-                set_since (sa * B, tp);
-                set_state (sa * B, la);
+                set_since (sa, tp);
+                set_state (sa, la);
                 if (dbl) {
-                    const uint32_t since_b = my_since (sb * B);
+                    const uint32_t since_b = my_since (sb);
                     if (PER_CHAIN) { if (active) my_chain_counts[(int) (move.z >> 19) + sb + ob] += (long long) (tp - since_b); }
                     else if (tp != since_b && ob) atomicAdd (&my_counts[(int) (move.z >> 19) + ob - 1], tp - since_b);
-                    set_since (sb * B, tp);
-                    set_state (sb * B, lb);
+                    set_since (sb, tp);
+                    set_state (sb, lb);
                     c_facc++;
                 } else c_macc++;
             }
         }
         // scan bookkeeping (MCModelDefault.c:298-312): after the last trial of a production scan the energy is recorded
-        if (++mv == nmoves) {
+        if (__builtin_expect (++mv == nmoves, 0)) {       // (warp-uniform)
+            __syncwarp ();        // keeps this block a branch target: predicated, its dozen instructions would issue after every trial
             mv = 0;
             const bool production = scan >= (uint32_t) p.nequil;
             if (ENERGY && production) {
@@ -539,14 +546,14 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (active) {
         for (int i = 0; i < nsites; i++) {
-            const int      a = my_state (i * B), gi = (int) (s_move[i].y >> 19);       // local index, first - site
-            const uint32_t d = (uint32_t) p.nprod - my_since (i * B);
+            const int      a = my_state (i), gi = (int) (s_move[i].y >> 19);       // local index, first - site
+            const uint32_t d = (uint32_t) p.nprod - my_since (i);
             if (PER_CHAIN) my_chain_counts[gi + i + a] += (long long) d;
             else if (d && a) atomicAdd (&my_counts[gi + a - 1], d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
-            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = (int) (s_move[i].y >> 19) + i + my_state (i * B);
+            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = (int) (s_move[i].y >> 19) + i + my_state (i);
             p.chain_energy[c] = my_eng[0] / beta;
             p.chain_esum[c]   = my_eng[B] / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
