@@ -102,7 +102,8 @@ struct McParams {
     uint32_t       wl_shared, wl_per_warp, wl_since, wl_state, wl_ring;
     int            wl_ldh;
     uint32_t       nmoves;          // nsites + npairs
-    unsigned long long ntrials;     // (nequil + nprod) * nmoves
+    unsigned long long ntrials;     // (nequil + nprod) * nmoves (< 2^32, checked at launch)
+    uint32_t       nmoves_magic;    // floor (2^32 / nmoves) + 1 when a round can cross several scan ends (2 <= nmoves <= 64), else 0
 };
 
 // shared-memory carve-up of k_mc_thread; identical on host (sizing) and device (pointers)
@@ -888,7 +889,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     }
 
     const uint32_t nmoves = p.nmoves;
-    const unsigned long long ntrials = p.ntrials;
+    const uint32_t ntrials = (uint32_t) p.ntrials;       // 32-bit trial counters: the launch refuses longer chains
     uint32_t c_macc = 0, c_flips = 0, c_facc = 0;
     double   esum = 0.0;
     long long scan = 0;
@@ -911,25 +912,25 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     };
 
     const bool use_cross = p.cross != nullptr;
-    unsigned long long tcur = 0, tfill = 0;        // next trial to decide; trials [tcur, tfill) are in the ring
+    uint32_t tcur = 0, tfill = 0;        // next trial to decide; trials [tcur, tfill) are in the ring
     while (tcur < ntrials) {
-        while (tfill - tcur < (unsigned long long) (32 * TPL)) {
-            const unsigned long long bl = (tfill >> 1) + (unsigned long long) lane;
-            const pce::Philox4 r = pce::philox4x32_10 ((uint32_t) bl, (uint32_t) (bl >> 32), chain, phidx, p.k0, p.k1);
+        while (tfill - tcur < (uint32_t) (32 * TPL)) {
+            const uint32_t bl = (tfill >> 1) + (uint32_t) lane;
+            const pce::Philox4 r = pce::philox4x32_10 (bl, 0u, chain, phidx, p.k0, p.k1);
             const uint32_t slot = ((uint32_t) tfill & (uint32_t) (RING - 1)) + 2u * (uint32_t) lane;
             *(uint2 *) &ring (slot)            = make_uint2 (r.x, r.z);
             *(uint2 *) &ring (RING + slot)     = make_uint2 (r.y, r.w);
             *(uint2 *) &ring (2 * RING + slot) = make_uint2 (target (r.x), target (r.z));
             *(uint2 *) &ring (3 * RING + slot) = make_uint2 (pair_extra (r.x), pair_extra (r.z));
-            tfill += 64ull;
+            tfill += 64u;
         }
         __syncwarp ();
 
         // ---- evaluate 32*TPL trials against the current state ----
         // A round may run across scan ends (a scan of a small model is shorter than a round: lysozyme 24 trials); only the
         // logging / trajectory mode, which reports per scan, keeps its rounds within one scan.
-        const unsigned long long left_total = ntrials - tcur;
-        uint32_t n_act = left_total < (unsigned long long) (32 * TPL) ? (uint32_t) left_total : (uint32_t) (32 * TPL);
+        const uint32_t left_total = ntrials - tcur;
+        uint32_t n_act = left_total < (uint32_t) (32 * TPL) ? left_total : (uint32_t) (32 * TPL);
         if (per_scan && nmoves - mv < n_act) n_act = nmoves - mv;
         uint32_t e_pr[TPL], e_a[TPL], e_b[TPL], e_w1[TPL];     // sa | sb << 16,  ia | oa << 16,  ib | ob << 16
         double   e_x[TPL], e_c[TPL][4];
@@ -1022,21 +1023,35 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         // scan ends inside the consumed trials: k_before of them lie before the last consumed trial (they see the energy as
         // it was), k_total counts the one right after it as well (it sees the energy after an accepted move)
         uint32_t k_before = 0, k_total = 0;
-        if (mv + consumed >= nmoves) { k_before = (mv + consumed - 1) / nmoves; k_total = (mv + consumed) / nmoves; }
-        // first consumed trial that belongs to the production phase
-        uint32_t j_prod = 0;
-        if (!production) {
-            const long long wait = (long long) (p.nequil - scan) * (long long) nmoves - (long long) mv;
-            j_prod = wait > (long long) (32 * TPL) ? (uint32_t) (32 * TPL) : (uint32_t) wait;
+        if (mv + consumed >= nmoves) {
+            const uint32_t past = mv + consumed;
+            // small models: multiply-high by the reciprocal, exact as long as past * nmoves < 2^32 (not in the large-field build, whose
+            // warp-uniform bookkeeping stays on the uniform datapath)
+            if (ABS && p.nmoves_magic) { k_before = __umulhi (past - 1u, p.nmoves_magic); k_total = __umulhi (past, p.nmoves_magic); }
+            else if (nmoves > (uint32_t) (32 * TPL)) { k_before = past - 1u >= nmoves ? 1u : 0u; k_total = 1u; }      // at most one scan end
+            else { k_before = (past - 1u) / nmoves; k_total = past / nmoves; }
         }
         uint32_t ndbl = 0, ndbl_prod = 0;
+        if (production) {
 #pragma unroll
-        for (int u = 0; u < TPL; u++) {
-            const int c = (int) consumed - u * 32, c0 = (int) j_prod - u * 32;
-            const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
-            const unsigned m0 = c0 >= 32 ? 0xffffffffu : c0 <= 0 ? 0u : ((1u << c0) - 1u);
-            ndbl += (uint32_t) __popc (dblm[u] & m);
-            ndbl_prod += (uint32_t) __popc (dblm[u] & m & ~m0);
+            for (int u = 0; u < TPL; u++) {
+                const int c = (int) consumed - u * 32;
+                const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
+                ndbl += (uint32_t) __popc (dblm[u] & m);
+            }
+            ndbl_prod = ndbl;
+        } else {
+            // the round may run into the production phase: j_prod = first consumed trial that belongs to it
+            const long long wait = (long long) (p.nequil - scan) * (long long) nmoves - (long long) mv;
+            const uint32_t j_prod = wait > (long long) (32 * TPL) ? (uint32_t) (32 * TPL) : (uint32_t) wait;
+#pragma unroll
+            for (int u = 0; u < TPL; u++) {
+                const int c = (int) consumed - u * 32, c0 = (int) j_prod - u * 32;
+                const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
+                const unsigned m0 = c0 >= 32 ? 0xffffffffu : c0 <= 0 ? 0u : ((1u << c0) - 1u);
+                ndbl += (uint32_t) __popc (dblm[u] & m);
+                ndbl_prod += (uint32_t) __popc (dblm[u] & m & ~m0);
+            }
         }
         c_flips += ndbl_prod;
         if (PER_CHAIN && p.log_rows != nullptr) { lg_f += ndbl; lg_m += consumed - ndbl; }
@@ -1091,7 +1106,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan + k_before - p.nequil] = grt / beta;
         }
         mv = mv + consumed - k_total * nmoves;
-        tcur += (unsigned long long) consumed;
+        tcur += consumed;
         if (k_total) {     // scan bookkeeping (MCModelDefault.c:298-312)
             if (PER_CHAIN && p.log_rows != nullptr) {       // per_scan mode: k_total == 1
                 const long long done = (production ? scan - p.nequil : scan) + 1;
@@ -1494,9 +1509,9 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     pce_model *m = mc->model;
     if (nph <= 0) return PCE_OK;
     if ((long long) mc->nequil + mc->nprod > 4294967295LL) return fail (PCE_ERR_LIMIT, "too many scans");
-    // the kernels count production trials in 32 bits per chain
-    if ((double) mc->nprod * (double) (m->nsites + (int) mc->pair_a.size ()) >= 4294967295.0)
-        return fail (PCE_ERR_LIMIT, "too many production trials per chain (nprod x (nsites + npairs) must stay below 2^32)");
+    // the kernels count the trials of a chain in 32 bits
+    if (((double) mc->nequil + (double) mc->nprod) * (double) (m->nsites + (int) mc->pair_a.size ()) >= 4294967295.0 - 256.0)
+        return fail (PCE_ERR_LIMIT, "too many trials per chain ((nequil + nprod) x (nsites + npairs) must stay below 2^32)");
     int status = m->upload ();
     if (status != PCE_OK) return status;
     // the W matrix may have changed since the pairs were found (ScaleInteractions etc.): keep the reference's
@@ -1594,6 +1609,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     if (blocks > 2147483647LL) return fail (PCE_ERR_LIMIT, "too many chains in one launch");
     p.nmoves = (uint32_t) (m->nsites + npairs);
     p.ntrials = (unsigned long long) ((long long) mc->nequil + mc->nprod) * p.nmoves;
+    p.nmoves_magic = (p.nmoves >= 2u && p.nmoves <= 64u) ? (uint32_t) (4294967296ull / p.nmoves) + 1u : 0u;
     if (plan.kernel == 2) {
         const WarpLayout WL (m->nsites, m->ninst, plan.tpl, plan.upd, plan.upd != 16);
         p.wl_shared = (uint32_t) WL.shared_bytes; p.wl_per_warp = (uint32_t) WL.per_warp; p.wl_since = (uint32_t) WL.off_since;

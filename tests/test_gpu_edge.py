@@ -211,11 +211,11 @@ def test_same_site_interactions_are_ignored(port):
         assert np.abs(exact_a / exact_b - 1.0).max() < 1e-13
 
 
-def test_too_many_production_trials_are_refused():
-    """A chain counts its production trials in 32 bits: nprod x (nsites + npairs) >= 2^32 is refused, not wrapped."""
+def test_too_many_trials_per_chain_are_refused():
+    """A chain counts its trials in 32 bits: (nequil + nprod) x (nsites + npairs) >= 2^32 is refused, not wrapped."""
     rec, _gold = load_fixture("lysozyme")
     model = P.MEADModel(rec, log=None)
     sampler = P.MCModelDefault(nequil=0, nprod=2 ** 31 - 1, randomSeed=1, nchains=1)
     model.DefineMCModel(sampler, log=None)
-    with pytest.raises(P.CLibraryError, match="too many production trials"):
+    with pytest.raises(P.CLibraryError, match="too many trials per chain"):
         sampler.RunCounts([7.0])
