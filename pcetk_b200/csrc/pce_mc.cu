@@ -724,8 +724,10 @@ __device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s
         f2 = lb < pb ? 0x80000000u : 0u;
     }
     if (ROWS_ONLY || p.dw != nullptr) {
-        const double2 *r1 = (const double2 *) (p.dw + (size_t) (__ldg (p.dbase + sa) + ((mxa * (mxa - 1)) >> 1) + mna) * p.ldd), *r2 = r1;
-        if (dbl) r2 = (const double2 *) (p.dw + (size_t) (__ldg (p.dbase + sb) + ((mxb * (mxb - 1)) >> 1) + mnb) * p.ldd);
+        // (first difference row of a site: second half of the CTA's site table; the table of rows holds < 2^32 doubles)
+        const uint32_t *s_dbase = s_site + p.nsites;
+        const double2 *r1 = (const double2 *) (p.dw + (s_dbase[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) * (uint32_t) p.ldd), *r2 = r1;
+        if (dbl) r2 = (const double2 *) (p.dw + (s_dbase[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) * (uint32_t) p.ldd);
         apply_diff_rows<U> (h2, ldh >> 1, lane, r1, f1, r2, f2, dbl);
     } else {
         apply_wr_rows<(U < 8 ? U : 8)> (h2, p.ldr >> 1, lane, (const double2 *) (p.wr + (size_t) (fa + mxa) * p.ldr), (const double2 *) (p.wr + (size_t) (fa + mna) * p.ldr), f1,
@@ -759,7 +761,7 @@ struct WarpLayout {
         const int nfield = abs ? ninst : (ninst > nsites ? ninst - nsites : 1);
         ldh  = (nfield + 64 * upd - 1) / (64 * upd) * (64 * upd);       // whole batches of the field update (apply_diff_rows)
         ring = tpl <= 2 ? 128 : 256;
-        shared_bytes = ((size_t) nsites * 4 + 15) & ~(size_t) 15;     // packed site table, one copy per CTA
+        shared_bytes = ((size_t) nsites * 8 + 15) & ~(size_t) 15;     // packed site table and first difference row per site, one copy per CTA
         off_site = 0;
         size_t o = 0;
         off_h = o;     o += (size_t) ldh * 8;
@@ -793,7 +795,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
 #define ring(i_)   (*(uint32_t *) (smem + o_warp + p.wl_ring + 4u * (uint32_t) (i_)))   /* [0,RING) w0 | w1 | target | cross-table base and bound */
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
-    for (int i = threadIdx.x; i < nsites; i += blockDim.x) s_site (i) = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16);
+    for (int i = threadIdx.x; i < nsites; i += blockDim.x) { s_site (i) = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16); s_site (nsites + i) = (uint32_t) p.dbase[i]; }
     __syncthreads ();
     const long long gidx = (long long) blockIdx.x * warps + wib;       // chain-major linear (pH, chain) index
     if (gidx >= (long long) p.nph * p.nchains) return;              // whole warp leaves together (no later block barrier)
@@ -900,15 +902,21 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
                                            : p.counts + (size_t) q * ninst;
     uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
 
-    // proposal target of a random word: site (single move, b = a) or packed pair
-    auto target = [&] (const uint32_t w0) -> uint32_t {
-        const uint32_t idx = __umulhi (w0, nmoves);
-        return idx >= (uint32_t) nsites ? __ldg (p.pair_packed + (idx - nsites)) : (idx | (idx << 16));
-    };
-
-    auto pair_extra = [&] (const uint32_t w0) -> uint32_t {       // cross-table base | quantised bound of the pair
-        const uint32_t idx = __umulhi (w0, nmoves);
-        return idx >= (uint32_t) nsites ? __ldg (p.pair_x + (idx - nsites)) : 0u;
+    // The state-independent part of a trial is decoded ONCE, when its random words are generated (a trial is evaluated in every
+    // round until it is consumed, 2-3 times on average): the proposal target (site | site << 16 for a single move, b = a, or the
+    // packed pair), the drawn instances before they skip the current one (first + draw, 16 bits per site; 0xffffffff: a site with a
+    // single instance, nothing to propose) and the pair's entry (cross-table base | quantised bound).
+    auto decode = [&] (const uint32_t w0, uint32_t &pr, uint32_t &draws, uint32_t &px) {
+        const unsigned long long prod = (unsigned long long) w0 * nmoves;
+        const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
+        const bool dbl = idx >= (uint32_t) nsites;
+        pr = dbl ? __ldg (p.pair_packed + (idx - nsites)) : (idx | (idx << 16));
+        px = dbl ? __ldg (p.pair_x + (idx - nsites)) : 0u;
+        const uint32_t a_info = s_site (pr & 0xffffu), b_info = s_site (pr >> 16);
+        const uint32_t na = a_info >> 16, nb = b_info >> 16;
+        const unsigned long long proda = (unsigned long long) lo * (na - 1u);
+        const uint32_t ka = (uint32_t) (proda >> 32), kb = __umulhi ((uint32_t) proda, nb - 1u);
+        draws = (na >= 2u && nb >= 2u) ? (((a_info & 0xffffu) + ka) | (((b_info & 0xffffu) + kb) << 16)) : 0xffffffffu;
     };
 
     const bool use_cross = p.cross != nullptr;
@@ -918,10 +926,13 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             const uint32_t bl = (tfill >> 1) + (uint32_t) lane;
             const pce::Philox4 r = pce::philox4x32_10 (bl, 0u, chain, phidx, p.k0, p.k1);
             const uint32_t slot = ((uint32_t) tfill & (uint32_t) (RING - 1)) + 2u * (uint32_t) lane;
-            *(uint2 *) &ring (slot)            = make_uint2 (r.x, r.z);
+            uint32_t pr0, pr1, dr0, dr1, px0, px1;
+            decode (r.x, pr0, dr0, px0);
+            decode (r.z, pr1, dr1, px1);
+            *(uint2 *) &ring (slot)            = make_uint2 (dr0, dr1);
             *(uint2 *) &ring (RING + slot)     = make_uint2 (r.y, r.w);
-            *(uint2 *) &ring (2 * RING + slot) = make_uint2 (target (r.x), target (r.z));
-            *(uint2 *) &ring (3 * RING + slot) = make_uint2 (pair_extra (r.x), pair_extra (r.z));
+            *(uint2 *) &ring (2 * RING + slot) = make_uint2 (pr0, pr1);
+            *(uint2 *) &ring (3 * RING + slot) = make_uint2 (px0, px1);
             tfill += 64u;
         }
         __syncwarp ();
@@ -944,21 +955,16 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         for (int u = 0; u < TPL; u++) {
             const uint32_t off  = (uint32_t) (u * 32 + lane);
             const uint32_t slot = ((uint32_t) tcur + off) & (uint32_t) (RING - 1);
-            const uint32_t w0 = ring (slot), pr = ring (2 * RING + slot);
+            const uint32_t draws = ring (slot), pr = ring (2 * RING + slot);
             e_w1[u] = ring (RING + slot);
             const uint32_t px = ring (3 * RING + slot);
             const float pbound = 0.25f * (float) (px >> 24);                     // the pair's bound, quantised upwards (0: none)
             const bool act = off < n_act;
-            const unsigned long long prod = (unsigned long long) w0 * nmoves;
-            const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
-            const bool dbl = idx >= (uint32_t) nsites;
             const int  sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
-            const uint32_t ia_info = s_site (sa);
-            const int na = (int) (ia_info >> 16), oa = state (sa);
-            bool valid = na >= 2;
-            const unsigned long long proda = (unsigned long long) lo * (uint32_t) (na - 1);
-            const int ka = (int) (proda >> 32);
-            int ia = (int) (ia_info & 0xffffu) + ka;
+            const bool dbl = sa != sb;                                           // (a pair joins two different sites)
+            const bool valid = draws != 0xffffffffu;
+            const int  oa = state (sa);
+            int ia = (int) (draws & 0xffffu);
             if (ia >= oa) ia++;
             if (!valid) ia = oa;
             int ib = 0, ob = 0;
@@ -966,16 +972,14 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             e_need[u] = false;
             double x = 0.0;
             if (dbl) {
-                const uint32_t ib_info = s_site (sb);
-                const int nb = (int) (ib_info >> 16);
                 ob = state (sb);
-                if (nb < 2) valid = false;
-                const int kb = (int) __umulhi ((uint32_t) proda, (uint32_t) (nb - 1));
-                ib = (int) (ib_info & 0xffffu) + kb;
+                ib = (int) (draws >> 16);
                 if (ib >= ob) ib++;
-                if (!valid) { ib = ob; ia = oa; }
-                const int fa = (int) (ia_info & 0xffffu), fb = (int) (ib_info & 0xffffu);
+                if (!valid) ib = ob;
                 // relative fields: 0 for a first instance (stored as such in the instance-indexed layout)
+                uint32_t ia_info = 0u, ib_info = 0u;
+                if (!ABS) { ia_info = s_site (sa); ib_info = s_site (sb); }
+                const int fa = (int) (ia_info & 0xffffu), fb = (int) (ib_info & 0xffffu);
                 const double gan = ABS ? h (ia) : ia != fa ? h (ia - sa - 1) : 0.0, gao = ABS ? h (oa) : oa != fa ? h (oa - sa - 1) : 0.0;
                 const double gbn = ABS ? h (ib) : ib != fb ? h (ib - sb - 1) : 0.0, gbo = ABS ? h (ob) : ob != fb ? h (ob - sb - 1) : 0.0;
                 x = __dadd_rn (__dsub_rn (gan, gao), __dsub_rn (gbn, gbo));
@@ -986,7 +990,9 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
                 if (act && valid && !certain) {
                     if (!FALLBACK || use_cross) {
                         // one gather: the cross term of (old a, draw a, old b, draw b), precomputed with the same operations
-                        const int la = oa - (int) (ia_info & 0xffffu), lb = ob - (int) (ib_info & 0xffffu);
+                        if (ABS) { ia_info = s_site (sa); ib_info = s_site (sb); }
+                        const int f_a = (int) (ia_info & 0xffffu), f_b = (int) (ib_info & 0xffffu), na = (int) (ia_info >> 16), nb = (int) (ib_info >> 16);
+                        const int la = oa - f_a, lb = ob - f_b, ka = (int) (draws & 0xffffu) - f_a, kb = (int) (draws >> 16) - f_b;
                         const uint32_t e = (px & 0xffffffu) + (uint32_t) ((la * (na - 1) + ka) * (nb * (nb - 1)) + lb * (nb - 1) + kb);
                         e_c[u][0] = __ldg (p.cross + e);
                     } else {
@@ -996,7 +1002,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
                     e_need[u] = true;
                 }
             } else {
-                const int fa = (int) (ia_info & 0xffffu);
+                const int fa = ABS ? 0 : (int) (s_site (sa) & 0xffffu);
                 const double gan = ABS ? h (ia) : ia != fa ? h (ia - sa - 1) : 0.0, gao = ABS ? h (oa) : oa != fa ? h (oa - sa - 1) : 0.0;
                 x = __dsub_rn (gan, gao);
                 e_need[u] = act && valid;
