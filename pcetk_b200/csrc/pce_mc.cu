@@ -745,12 +745,12 @@ __device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s
 // evaluation (the chain specification), at 1/32 .. 1/64 of the instructions when acceptance is low, and the four
 // pair cross-term gathers of up to 64 trials are in flight together instead of one trial's.
 //
-// Random words live in a per-warp shared-memory ring (w0 | w1 | proposal target per trial), refilled 64 trials at a
-// time: lane l generates Philox block b + l (two trials) and fetches the two proposal targets (site, or packed pair
-// from the pair table -- state independent, so its L2 latency is paid long before the trial is evaluated).
+// The trials wait in a per-warp shared-memory ring (16 bytes each: drawn instances | w1 | proposal target | pair entry), refilled
+// 64 trials at a time: lane l generates Philox block b + l (two trials) and decodes everything that does not depend on the
+// chain's state -- target site or pair (its L2 latency is paid long before the trial is evaluated) and the drawn instances.
 // A round never crosses the end of a scan, so the per-scan bookkeeping stays once per scan.
 // Accepted moves are applied by all lanes with 128-bit loads of the beta-scaled W rows from L2.
-// Shared memory per warp: g[ldh] doubles (relative fields) | since[nsites] u32 | state[nsites] u16 | ring[4][RING] u32
+// Shared memory per warp: g[ldh] doubles (relative fields) | since[nsites] u32 | state[nsites] u16 | ring[RING] uint4
 // ---------------------------------------------------------------------------------------------------
 struct WarpLayout {
     size_t off_site, off_h, off_since, off_state, off_ring, per_warp, shared_bytes;
@@ -767,8 +767,8 @@ struct WarpLayout {
         off_h = o;     o += (size_t) ldh * 8;
         off_since = o; o += (size_t) nsites * 4;
         off_state = o; o += (size_t) nsites * 2;
-        o = (o + 7) & ~(size_t) 7;
-        off_ring = o;  o += (size_t) ring * 16;
+        o = (o + 15) & ~(size_t) 15;
+        off_ring = o;  o += (size_t) ring * 16;      // one 16-byte entry per trial
         per_warp = (o + 15) & ~(size_t) 15;
     }
 };
@@ -777,8 +777,9 @@ struct WarpLayout {
 // 2 CTAs 128, 3 CTAs 80, 4 CTAs 64.  Measured on ifp20: 3.4e10 / 3.8e10 / 3.7e10 moves/s for 2 / 3 / 4 CTAs -- at 64
 // registers ptxas moves the warp-uniform bookkeeping off the uniform datapath (12 % more instructions), so three CTAs
 // are the default for small fields (PCE_MC_CTAS overrides).
-template <bool PER_CHAIN, int MIN_CTAS, int TPL>
+template <bool PER_CHAIN, int MIN_CTAS, int TPL, bool ENERGY>
 __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_warp (const McParams p) {
+    static_assert (ENERGY || !PER_CHAIN, "per-chain outputs include the energy");
     extern __shared__ __align__ (16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
     constexpr int RING = TPL <= 2 ? 128 : 256;
@@ -792,7 +793,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
 #define h(i_)      (*(double *)   (smem + o_warp + 8u * (uint32_t) (i_)))
 #define since(i_)  (*(uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) (i_)))
 #define state(i_)  (*(uint16_t *) (smem + o_warp + p.wl_state + 2u * (uint32_t) (i_)))
-#define ring(i_)   (*(uint32_t *) (smem + o_warp + p.wl_ring + 4u * (uint32_t) (i_)))   /* [0,RING) w0 | w1 | target | cross-table base and bound */
+#define ring(i_)   (*(uint4 *)    (smem + o_warp + p.wl_ring + 16u * (uint32_t) (i_)))  /* per trial: drawn instances | w1 | target | cross-table base and bound */
 
     const int nsites = p.nsites, ninst = p.ninst, ldw = p.ldw;
     for (int i = threadIdx.x; i < nsites; i += blockDim.x) { s_site (i) = (uint32_t) p.first[i] | ((uint32_t) p.nsi[i] << 16); s_site (nsites + i) = (uint32_t) p.dbase[i]; }
@@ -872,8 +873,8 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     // initial energy in units of RT: sum_i gtb[a_i] + sum_{i > j} wb[a_i][a_j], lanes over i and the partial sums combined, so
     // the value may differ from the serial reference-order sum (EnergyModel.c:204-224) in the last bits.  It only seeds
     // the tracked energy (informational output).
-    double grt;
-    {
+    double grt = 0.0;
+    if (ENERGY) {
         double gi = 0.0, ws = 0.0;
         for (int i0 = 0; i0 < nsites; i0 += 32) {          // trip counts are warp-uniform (keeps the whole kernel on the uniform datapath)
             const int  i  = i0 + lane;
@@ -898,6 +899,9 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     uint32_t  mv = 0;
     bool      production = p.nequil == 0;
     const bool per_scan = PER_CHAIN && (p.log_rows != nullptr || p.trajectory != nullptr);
+    // the chain's energy is followed only in the ENERGY build (energy sums, per-chain outputs): the reference's quiet path returns
+    // occupancies only (MCModelDefault.pyx:60-78)
+    constexpr bool track = ENERGY;
     unsigned long long *counts = PER_CHAIN ? (unsigned long long *) (p.chain_counts + ((size_t) q * p.nchains + local) * ninst)
                                            : p.counts + (size_t) q * ninst;
     uint32_t lg_m = 0, lg_ma = 0, lg_f = 0, lg_fa = 0;
@@ -929,10 +933,8 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             uint32_t pr0, pr1, dr0, dr1, px0, px1;
             decode (r.x, pr0, dr0, px0);
             decode (r.z, pr1, dr1, px1);
-            *(uint2 *) &ring (slot)            = make_uint2 (dr0, dr1);
-            *(uint2 *) &ring (RING + slot)     = make_uint2 (r.y, r.w);
-            *(uint2 *) &ring (2 * RING + slot) = make_uint2 (pr0, pr1);
-            *(uint2 *) &ring (3 * RING + slot) = make_uint2 (px0, px1);
+            ring (slot)      = make_uint4 (dr0, r.y, pr0, px0);
+            ring (slot + 1u) = make_uint4 (dr1, r.w, pr1, px1);
             tfill += 64u;
         }
         __syncwarp ();
@@ -955,9 +957,9 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         for (int u = 0; u < TPL; u++) {
             const uint32_t off  = (uint32_t) (u * 32 + lane);
             const uint32_t slot = ((uint32_t) tcur + off) & (uint32_t) (RING - 1);
-            const uint32_t draws = ring (slot), pr = ring (2 * RING + slot);
-            e_w1[u] = ring (RING + slot);
-            const uint32_t px = ring (3 * RING + slot);
+            const uint4 entry = ring (slot);
+            const uint32_t draws = entry.x, pr = entry.z, px = entry.w;
+            e_w1[u] = entry.y;
             const float pbound = 0.25f * (float) (px >> 24);                     // the pair's bound, quantised upwards (0: none)
             const bool act = off < n_act;
             const int  sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
@@ -1062,7 +1064,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         c_flips += ndbl_prod;
         if (PER_CHAIN && p.log_rows != nullptr) { lg_f += ndbl; lg_m += consumed - ndbl; }
         // energy of the production scans that ended before the last consumed trial
-        for (uint32_t k = 0; k < k_before; k++) {
+        for (uint32_t k = 0; track && k < k_before; k++) {
             if (scan + (long long) k >= (long long) p.nequil) {
                 esum += grt;
                 if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan + k - p.nequil] = grt / beta;
@@ -1077,7 +1079,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             s_pr = __shfl_sync (0xffffffffu, s_pr, lstar);
             s_a  = __shfl_sync (0xffffffffu, s_a, lstar);
             s_b  = __shfl_sync (0xffffffffu, s_b, lstar);
-            const double x = __shfl_sync (0xffffffffu, s_x, lstar);
+            if (track) grt = __dadd_rn (grt, __shfl_sync (0xffffffffu, s_x, lstar));
             bool dbl = false;
 #pragma unroll
             for (int u = 0; u < TPL; u++) if (u == ustar) dbl = (dblm[u] >> lstar) & 1u;
@@ -1085,7 +1087,6 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             const int ia = (int) (s_a & 0xffffu), oa = (int) (s_a >> 16), ib = (int) (s_b & 0xffffu), ob = (int) (s_b >> 16);
             if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) lg_fa++; else lg_ma++; }
             apply_move<UPD, ABS> (p, (const uint32_t *) smem, &h (0), p.wl_ldh, lane, sa, sb, ia, oa, ib, ob, dbl);
-            grt = __dadd_rn (grt, x);
             // the accepted trial lies in scan `scan + k_before`: production there decides the stamp and the counters
             const long long scan_acc = scan + (long long) k_before;
             const bool      prod_acc = scan_acc >= (long long) p.nequil;
@@ -1107,7 +1108,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         __syncwarp ();       // state, stamps and fields of this round are visible to every lane before the next one
 
         // the scan (if any) that ends right after the last consumed trial
-        if (k_total > k_before && scan + (long long) k_before >= (long long) p.nequil) {
+        if (track && k_total > k_before && scan + (long long) k_before >= (long long) p.nequil) {
             esum += grt;
             if (PER_CHAIN && p.trajectory != nullptr && q == 0 && local == 0 && lane == 0) p.trajectory[scan + k_before - p.nequil] = grt / beta;
         }
@@ -1146,7 +1147,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             p.chain_counters[c * 4 + 2] = c_flips; p.chain_counters[c * 4 + 3] = c_facc;
         }
     } else if (lane == 0) {
-        if (p.esum != nullptr) atomicAdd (&p.esum[q], esum / beta);
+        if (ENERGY && p.esum != nullptr) atomicAdd (&p.esum[q], esum / beta);
         if (p.counters != nullptr) {
             atomicAdd ((unsigned long long *) &p.counters[q * 4 + 0], (unsigned long long) c_moves);
             atomicAdd ((unsigned long long *) &p.counters[q * 4 + 1], (unsigned long long) c_macc);
@@ -1656,13 +1657,13 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     } else {
         // one resident CTA (large fields): up to 255 registers; two: 128
         void (*kernel) (const McParams);
-#define PCE_WARP_KERNEL(TPL_) (plan.upd == 16 ? (per_chain ? k_mc_warp<true, 1, TPL_> : k_mc_warp<false, 1, TPL_>) \
-                              : plan.ctas_per_sm >= 4 ? (per_chain ? k_mc_warp<true, 4, TPL_> : k_mc_warp<false, 4, TPL_>) \
-                              : plan.ctas_per_sm == 3 ? (per_chain ? k_mc_warp<true, 3, TPL_> : k_mc_warp<false, 3, TPL_>) \
-                                                      : (per_chain ? k_mc_warp<true, 2, TPL_> : k_mc_warp<false, 2, TPL_>))
+#define PCE_WARP_VARIANT(C_, TPL_) (per_chain ? k_mc_warp<true, C_, TPL_, true> : energy ? k_mc_warp<false, C_, TPL_, true> : k_mc_warp<false, C_, TPL_, false>)
+#define PCE_WARP_KERNEL(TPL_) (plan.upd == 16 ? PCE_WARP_VARIANT (1, TPL_) : plan.ctas_per_sm >= 4 ? PCE_WARP_VARIANT (4, TPL_) \
+                              : plan.ctas_per_sm == 3 ? PCE_WARP_VARIANT (3, TPL_) : PCE_WARP_VARIANT (2, TPL_))
         if (plan.tpl == 2) kernel = PCE_WARP_KERNEL (2);
         else kernel = PCE_WARP_KERNEL (1);
 #undef PCE_WARP_KERNEL
+#undef PCE_WARP_VARIANT
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         // shared-memory carveout for exactly the planned number of resident CTAs (the rest of the 228 KB stays L1 for the
         // difference rows and the cross-term table); without __launch_bounds__ the driver has no occupancy hint of its own
