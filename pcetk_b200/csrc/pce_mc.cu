@@ -788,7 +788,8 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     constexpr bool ABS = MIN_CTAS != 1;               // small fields: instance-indexed slots (see WarpLayout)
     // The shared-memory layout (WarpLayout) comes from the host in the kernel parameters and every array is addressed by a
     // 32-bit offset: nothing of it has to stay live across the round loop or be recomputed inside it.
-    const uint32_t o_warp = p.wl_shared + (uint32_t) wib * p.wl_per_warp;          // this warp's slice; fields first
+    uint32_t o_warp = p.wl_shared + (uint32_t) wib * p.wl_per_warp;          // this warp's slice; fields first
+    asm volatile ("" : "+r"(o_warp));       // kept in a register (ptxas otherwise rebuilds it from the thread index inside the round loop)
 #define s_site(i_) (*(uint32_t *) (smem + 4u * (uint32_t) (i_)))                     /* first | ninst << 16 per site (CTA-wide) */
 #define h(i_)      (*(double *)   (smem + o_warp + 8u * (uint32_t) (i_)))
 #define since(i_)  (*(uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) (i_)))
@@ -1076,13 +1077,13 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             double   s_x = 0.0;
 #pragma unroll
             for (int u = 0; u < TPL; u++) if (u == ustar) { s_pr = e_pr[u]; s_a = e_a[u]; s_b = e_b[u]; s_x = e_x[u]; }
-            s_pr = __shfl_sync (0xffffffffu, s_pr, lstar);
-            s_a  = __shfl_sync (0xffffffffu, s_a, lstar);
-            s_b  = __shfl_sync (0xffffffffu, s_b, lstar);
-            if (track) grt = __dadd_rn (grt, __shfl_sync (0xffffffffu, s_x, lstar));
             bool dbl = false;
 #pragma unroll
             for (int u = 0; u < TPL; u++) if (u == ustar) dbl = (dblm[u] >> lstar) & 1u;
+            s_pr = __shfl_sync (0xffffffffu, s_pr, lstar);
+            s_a  = __shfl_sync (0xffffffffu, s_a, lstar);
+            if (dbl) s_b = __shfl_sync (0xffffffffu, s_b, lstar);       // (warp-uniform: the winner's flag comes from a ballot)
+            if (track) grt = __dadd_rn (grt, __shfl_sync (0xffffffffu, s_x, lstar));
             const int sa = (int) (s_pr & 0xffffu), sb = (int) (s_pr >> 16);
             const int ia = (int) (s_a & 0xffffu), oa = (int) (s_a >> 16), ib = (int) (s_b & 0xffffu), ob = (int) (s_b >> 16);
             if (PER_CHAIN && p.log_rows != nullptr) { if (dbl) lg_fa++; else lg_ma++; }
