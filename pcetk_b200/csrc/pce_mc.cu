@@ -1042,11 +1042,14 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         }
         uint32_t ndbl = 0, ndbl_prod = 0;
         if (production) {
+            if (TPL == 1) ndbl = (uint32_t) __popc (dblm[0] & (0xffffffffu >> (32u - consumed)));        // 1 <= consumed <= 32
+            else {
 #pragma unroll
-            for (int u = 0; u < TPL; u++) {
-                const int c = (int) consumed - u * 32;
-                const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
-                ndbl += (uint32_t) __popc (dblm[u] & m);
+                for (int u = 0; u < TPL; u++) {
+                    const int c = (int) consumed - u * 32;
+                    const unsigned m = c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
+                    ndbl += (uint32_t) __popc (dblm[u] & m);
+                }
             }
             ndbl_prod = ndbl;
         } else {
