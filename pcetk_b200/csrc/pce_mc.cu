@@ -99,7 +99,7 @@ struct McParams {
     int            ph_minor;        // linearisation of the (pH, chain) grid: 1 = g = chain * nph + q (consecutive threads take consecutive pH
                                     // values, so every warp and block carries the same mix of cheap and expensive pH values), 0 = g = q * nchains + chain
     // chain-per-warp kernel: the shared-memory layout (WarpLayout), likewise
-    uint32_t       wl_shared, wl_per_warp, wl_since, wl_state, wl_ring;
+    uint32_t       wl_shared, wl_per_warp, wl_since, wl_state, wl_ring, wl_since16;
     int            wl_ldh;
     uint32_t       nmoves;          // nsites + npairs
     unsigned long long ntrials;     // (nequil + nprod) * nmoves (< 2^32, checked at launch)
@@ -757,7 +757,9 @@ struct WarpLayout {
     int    ldh, ring;
     // abs: the relative fields are stored at the instance's own index with a zero at every first instance (small models:
     // no index arithmetic in the proposal); else compactly, without the first instances (large models: ninst - nsites slots)
-    __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd, bool abs) {
+    // since_bytes: width of the residence stamps (2 when nprod < 65536: a 1000-site chain then takes 21.9 instead of 23.9 KB and ten
+    // instead of nine fit an SM)
+    __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd, bool abs, int since_bytes) {
         const int nfield = abs ? ninst : (ninst > nsites ? ninst - nsites : 1);
         ldh  = (nfield + 64 * upd - 1) / (64 * upd) * (64 * upd);       // whole batches of the field update (apply_diff_rows)
         ring = tpl <= 2 ? 128 : 256;
@@ -765,7 +767,7 @@ struct WarpLayout {
         off_site = 0;
         size_t o = 0;
         off_h = o;     o += (size_t) ldh * 8;
-        off_since = o; o += (size_t) nsites * 4;
+        off_since = o; o += ((size_t) nsites * since_bytes + 3) & ~(size_t) 3;
         off_state = o; o += (size_t) nsites * 2;
         o = (o + 15) & ~(size_t) 15;
         off_ring = o;  o += (size_t) ring * 16;      // one 16-byte entry per trial
@@ -792,7 +794,14 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     asm volatile ("" : "+r"(o_warp));       // kept in a register (ptxas otherwise rebuilds it from the thread index inside the round loop)
 #define s_site(i_) (*(uint32_t *) (smem + 4u * (uint32_t) (i_)))                     /* first | ninst << 16 per site (CTA-wide) */
 #define h(i_)      (*(double *)   (smem + o_warp + 8u * (uint32_t) (i_)))
-#define since(i_)  (*(uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) (i_)))
+    // residence stamps: 16-bit when nprod < 65536 (warp-uniform choice; they are touched by one lane per accepted move)
+    auto since = [&] (int i) -> uint32_t {
+        return p.wl_since16 ? (uint32_t) *(const uint16_t *) (smem + o_warp + p.wl_since + 2u * (uint32_t) i) : *(const uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) i);
+    };
+    auto set_since = [&] (int i, uint32_t v) {
+        if (p.wl_since16) *(uint16_t *) (smem + o_warp + p.wl_since + 2u * (uint32_t) i) = (uint16_t) v;
+        else *(uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) i) = v;
+    };
 #define state(i_)  (*(uint16_t *) (smem + o_warp + p.wl_state + 2u * (uint32_t) (i_)))
 #define ring(i_)   (*(uint4 *)    (smem + o_warp + p.wl_ring + 16u * (uint32_t) (i_)))  /* per trial: drawn instances | w1 | target | cross-table base and bound */
 
@@ -813,7 +822,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
         pce::Philox4 r = pce::philox4x32_10 ((uint32_t) (i >> 2), 0xFFFFFFFFu, chain, phidx, p.k0, p.k1);
         const uint32_t word = (i & 3) == 0 ? r.x : (i & 3) == 1 ? r.y : (i & 3) == 2 ? r.z : r.w;
         state (i) = (uint16_t) (p.first[i] + (int) __umulhi (word, (uint32_t) p.nsi[i]));
-        since (i) = 0u;
+        set_since (i, 0u);
     }
     __syncwarp ();
     const double mu   = ph_to_mu (p.temperature, p.ph[q]);
@@ -1098,12 +1107,12 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             if (lane == 0) {
                 const uint32_t since_a = since (sa);
                 if (tp_acc != since_a) atomicAdd (&counts[oa], (unsigned long long) (tp_acc - since_a));
-                since (sa) = tp_acc;
+                set_since (sa, tp_acc);
                 state (sa) = (uint16_t) ia;
                 if (dbl) {
                     const uint32_t since_b = since (sb);
                     if (tp_acc != since_b) atomicAdd (&counts[ob], (unsigned long long) (tp_acc - since_b));
-                    since (sb) = tp_acc;
+                    set_since (sb, tp_acc);
                     state (sb) = (uint16_t) ib;
                 }
             }
@@ -1162,7 +1171,6 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
 }
 #undef s_site
 #undef h
-#undef since
 #undef state
 #undef ring
 
@@ -1279,7 +1287,7 @@ bool plan_warp (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, do
         // 128-bit loads per lane and batch of the field update: 16 for large fields, 4 for small ones, 1 when the whole vector
         // (instance-indexed: ninst slots) fits one load per lane
         const int upd = pass == 1 ? 16 : m->ninst <= 64 ? 1 : 4;
-        WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1);
+        WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1, mc->nprod < 65536 ? 2 : 4);
         if (L.per_warp + L.shared_bytes > limit) continue;
         // large fields (one resident CTA): as many warps as shared memory holds, up to 10 (204 registers each); else 8 per CTA
         int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, pass == 1 ? 10 : 8);
@@ -1602,7 +1610,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         // row stride of the difference rows: the padded field length of a chain-per-warp launch, else the slot count
         const int nrel = std::max (m->ninst - m->nsites, 1);
         const bool abs = plan.kernel == 2 && plan.upd != 16;         // small-field variants of the warp kernel: instance-indexed slots
-        const int ldd = plan.kernel == 2 ? WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd, abs).ldh : ((nrel + 3) & ~3);
+        const int ldd = plan.kernel == 2 ? WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd, abs, mc->nprod < 65536 ? 2 : 4).ldh : ((nrel + 3) & ~3);
         status = build_relative_tables (mc, ldd, abs);
         if (status != PCE_OK) return status;
         if (plan.kernel == 1 && (!mc->dw_valid || (npairs > 0 && !mc->cross_valid)))
@@ -1622,7 +1630,8 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     p.ntrials = (unsigned long long) ((long long) mc->nequil + mc->nprod) * p.nmoves;
     p.nmoves_magic = (p.nmoves >= 2u && p.nmoves <= 64u) ? (uint32_t) (4294967296ull / p.nmoves) + 1u : 0u;
     if (plan.kernel == 2) {
-        const WarpLayout WL (m->nsites, m->ninst, plan.tpl, plan.upd, plan.upd != 16);
+        const WarpLayout WL (m->nsites, m->ninst, plan.tpl, plan.upd, plan.upd != 16, mc->nprod < 65536 ? 2 : 4);
+        p.wl_since16 = mc->nprod < 65536 ? 1u : 0u;
         p.wl_shared = (uint32_t) WL.shared_bytes; p.wl_per_warp = (uint32_t) WL.per_warp; p.wl_since = (uint32_t) WL.off_since;
         p.wl_state = (uint32_t) WL.off_state; p.wl_ring = (uint32_t) WL.off_ring; p.wl_ldh = WL.ldh;
     }

@@ -185,6 +185,29 @@ def test_warp_kernel_on_the_1000_site_model_matches_specification(port, monkeypa
         spec = port.mc_philox_chain(rec, wsym, pairs, 1, 3, sampler.seed, chain, 0, 7.0)
         assert np.array_equal(out["counts"][0, chain], spec["counts"])
         assert np.array_equal(out["state"][0, chain], spec["state"])
+    # the quiet build of the large-field kernel (no energy tracking) walks the same chains
+    quiet, counters, esum = sampler.RunCounts([7.0], energy=False)
+    assert np.array_equal(quiet[0], out["counts"][0].sum(axis=0)) and np.array_equal(counters[0], out["counters"][0].sum(axis=0)) and not esum.any()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_mc_one_site_model(port, kernel):
+    """A model of ONE site: a scan is a single trial, so a round of the chain-per-warp kernel crosses up to 32 scan ends (and the
+    production boundary somewhere inside a round)."""
+    rec = ragged_model(1, tautomers=False)
+    model = P.MEADModel(rec, log=None)
+    wsym = port.symmetrize(rec.interactions)
+    sampler = P.MCModelDefault(nequil=45, nprod=700, randomSeed=77, nchains=35, kernel=kernel)
+    model.DefineMCModel(sampler, log=None)
+    assert sampler.npairs == 0
+    out = sampler.RunChains([4.0, 9.0])
+    for q, ph in enumerate([4.0, 9.0]):
+        for chain in (0, 34):
+            spec = port.mc_philox_chain(rec, wsym, ([], []), 45, 700, sampler.seed, chain, q, ph)
+            assert np.array_equal(out["counts"][q, chain], spec["counts"]) and out["counters"][q, chain].tolist() == spec["counters"].tolist()
+            assert abs(out["esum"][q, chain] - spec["esum"]) <= 1e-9 * max(1.0, abs(spec["esum"]))
+    counts, counters, _e = sampler.RunCounts([4.0, 9.0], energy=False)
+    assert np.array_equal(counts, out["counts"].sum(axis=1)) and np.array_equal(counters, out["counters"].sum(axis=1))
 
 
 def test_same_site_interactions_are_ignored(port):
