@@ -23,6 +23,7 @@
 //                streamed from L1/L2 with 128-bit loads.  For everything else (ifp20; the 1000-site
 //                synthetic, whose 60 MB of difference rows are L2-resident).
 #include <algorithm>
+#include <type_traits>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -137,7 +138,9 @@ struct ThreadLayout {
         // working on different sites fall into different banks (a row of `block` bytes is a multiple of 128: 4-way conflicts)
         off_since = o;  o += (size_t) nsites * (block * since_bytes + 4);
         o = (o + 15) & ~(size_t) 15;
-        off_move = o;   o += (size_t) (nsites + npairs) * 16;      // one 16-byte entry per move (sites, then pairs)
+        // one 16-byte entry per move (sites, then pairs), FOUR interleaved copies: lane l reads copy l & 3, so the random entries of a
+        // quarter-warp's 128-bit loads fall into at most two instead of up to eight entries per bank group
+        off_move = o;   o += (size_t) (nsites + npairs) * 64;
         off_erow = o;   o += (size_t) (nrows > 0 ? nrows : 1) * 8;      // per (current, drawn) instance of a site: its difference row and direction
         off_state = o;  o += (size_t) nsites * (block + 4);
         total = (o + 15) & ~(size_t) 15;
@@ -233,7 +236,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     // one entry per move, fetched with ONE 128-bit load per trial: x = site a | site b << 16 (single move: b = a),
     // y = (n_a - 1) | g_a << 16, z = (n_b - 1) | g_b << 16, w = base of the pair in the cross-term table (15 bits) | base of
     // site a in the row table << 15 (16 bits) | invalid << 31 (a site with one instance).  g = 8 * (first - site): local index l >= 1 of the site owns the field slot at byte g + 8 l - 8.
-    uint4              *s_move   = (uint4 *) (smem + p.tl_move);
+    uint4              *s_move   = (uint4 *) (smem + p.tl_move);             // entry i of copy c: s_move[4 * i + c]
     // difference row of every single-site move: entry 2 * (first row of the site) + current * (n - 1) + draw -> the row (its shared-memory
     // address in the short-field build) | 1 << 31 when the move runs against the row's direction (new < old)
     uint32_t           *s_rowtab = (uint32_t *) (smem + p.tl_erow);
@@ -287,7 +290,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
         entry.y = (uint32_t) (na - 1) | ((uint32_t) (p.first[a] - a) << 19);
         entry.z = (uint32_t) (nb - 1) | ((uint32_t) (p.first[b] - b) << 19);
         entry.w = (i < nsites ? 0u : p.pair_x[i - nsites] & 0x7fffu) | ((uint32_t) (2 * p.dbase[a]) << 15) | ((na < 2 || nb < 2) ? 0x80000000u : 0u);
-        s_move[i] = entry;
+        s_move[4 * i] = entry; s_move[4 * i + 1] = entry; s_move[4 * i + 2] = entry; s_move[4 * i + 3] = entry;
     }
 
     // initial state: Philox block (i>>2, 0xFFFFFFFF, chain, pH index), word i&3 -> first_i + mulhi(word, n_i); the state array holds
@@ -352,12 +355,13 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
 
     // one trial: proposal from (w0), Metropolis with (w1), cooperative application of accepted moves
     const bool has_pairs = p.npairs > 0;
+    const uint4 *my_move = s_move + (lane & 3);
     const uint32_t h_addr = (uint32_t) __cvta_generic_to_shared (s_h), e_addr = (uint32_t) __cvta_generic_to_shared (s_e);
     auto trial = [&] (const uint32_t w0, const uint32_t w1) {
         const unsigned long long prod = (unsigned long long) w0 * nmoves;
         const uint32_t idx = (uint32_t) (prod >> 32), lo = (uint32_t) prod;
         const bool     dbl = idx >= (uint32_t) nsites;
-        const uint4    move = s_move[idx];
+        const uint4    move = my_move[4u * idx];
         const int sa = (int) (move.x & 0xffffu), sb = (int) (move.x >> 16);
         // local indices throughout: l* = proposed, o* = current instance of the site; the first instance of a site is the zero
         // of its relative fields
@@ -414,7 +418,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 if (accept) {
                     pa = s_rowtab[((move.w >> 15) & 0xffffu) + (uint32_t) oa * nam1 + (uint32_t) ka];
                     if (dbl) {
-                        pb = s_rowtab[((s_move[sb].w >> 15) & 0xffffu) + (uint32_t) ob * (move.z & 0xffffu) + (uint32_t) (lb - (lb > ob ? 1 : 0))];
+                        pb = s_rowtab[((s_move[4 * sb].w >> 15) & 0xffffu) + (uint32_t) ob * (move.z & 0xffffu) + (uint32_t) (lb - (lb > ob ? 1 : 0))];
                         pa |= 0x40000000u;
                     }
                 }
@@ -451,7 +455,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 const uint32_t ta = s_rowtab[((move.w >> 15) & 0xffffu) + (uint32_t) oa * nam1 + (uint32_t) ka];
                 packed = (ta & 0x3fffu) | (ta >> 31 << 14);
                 if (dbl) {
-                    const uint32_t tb = s_rowtab[((s_move[sb].w >> 15) & 0xffffu) + (uint32_t) ob * (move.z & 0xffffu) + (uint32_t) (lb - (lb > ob ? 1 : 0))];
+                    const uint32_t tb = s_rowtab[((s_move[4 * sb].w >> 15) & 0xffffu) + (uint32_t) ob * (move.z & 0xffffu) + (uint32_t) (lb - (lb > ob ? 1 : 0))];
                     packed |= ((tb & 0x3fffu) << 15) | (tb >> 31 << 29) | (1u << 30);
                 }
             }
@@ -547,14 +551,14 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     const uint32_t c_moves = (uint32_t) ((unsigned long long) p.nprod * nmoves - c_flips);
     if (active) {
         for (int i = 0; i < nsites; i++) {
-            const int      a = my_state (i), gi = (int) (s_move[i].y >> 19);       // local index, first - site
+            const int      a = my_state (i), gi = (int) (s_move[4 * i].y >> 19);       // local index, first - site
             const uint32_t d = (uint32_t) p.nprod - my_since (i);
             if (PER_CHAIN) my_chain_counts[gi + i + a] += (long long) d;
             else if (d && a) atomicAdd (&my_counts[gi + a - 1], d);
         }
         if (PER_CHAIN) {
             const size_t c = (size_t) q * p.nchains + local;
-            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = (int) (s_move[i].y >> 19) + i + my_state (i);
+            for (int i = 0; i < nsites; i++) p.chain_state[c * nsites + i] = (int) (s_move[4 * i].y >> 19) + i + my_state (i);
             p.chain_energy[c] = my_eng[0] / beta;
             p.chain_esum[c]   = my_eng[B] / beta;
             p.chain_counters[c * 4 + 0] = c_moves; p.chain_counters[c * 4 + 1] = c_macc;
@@ -576,7 +580,7 @@ __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
                 int qq = q_base + slot;
                 if (p.ph_minor && qq >= p.nph) qq -= p.nph;
                 if (qq >= p.nph || s_nact[slot] == 0u) continue;
-                const int gi = (int) (s_move[i].y >> 19), ni = (int) (s_move[i].y & 0xffffu) + 1;
+                const int gi = (int) (s_move[4 * i].y >> 19), ni = (int) (s_move[4 * i].y & 0xffffu) + 1;
                 unsigned long long first_count = (unsigned long long) s_nact[slot] * (unsigned long long) p.nprod;
                 for (int d = 1; d < ni; d++) first_count -= (unsigned long long) s_counts[(size_t) slot * nr + (gi + d - 1)];
                 if (first_count) atomicAdd (&p.counts[(size_t) qq * ninst + gi + i], first_count);
@@ -653,7 +657,39 @@ __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, 
         }
         return;
     }
-    if (!two) {
+    if (U < 16) {       // small fields: one copy of each loop, the direction as a sign flip per element
+        if (!two) {
+            for (int k0 = lane; k0 < n2; k0 += 32 * U) {
+                double2 a[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) a[u] = __ldg (r1 + k0 + 32 * u);
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    double2 v = h2[k0 + 32 * u];
+                    v.x = __dadd_rn (v.x, flip_sign (a[u].x, f1));
+                    v.y = __dadd_rn (v.y, flip_sign (a[u].y, f1));
+                    h2[k0 + 32 * u] = v;
+                }
+            }
+        } else {
+            for (int k0 = lane; k0 < n2; k0 += 32 * U) {
+                double2 a[U], b[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) { a[u] = __ldg (r1 + k0 + 32 * u); b[u] = __ldg (r2 + k0 + 32 * u); }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    double2 v = h2[k0 + 32 * u];
+                    v.x = __dadd_rn (__dadd_rn (v.x, flip_sign (a[u].x, f1)), flip_sign (b[u].x, f2));
+                    v.y = __dadd_rn (__dadd_rn (v.y, flip_sign (a[u].y, f1)), flip_sign (b[u].y, f2));
+                    h2[k0 + 32 * u] = v;
+                }
+            }
+        }
+        return;
+    }
+    // large fields (64 elements per lane and row): the directions are warp-uniform, so there is one loop per sign pattern with the
+    // negation folded into the add (v - a == v + (-a) bit for bit) instead of a sign flip per element
+    auto one = [&] (auto neg1) {
         for (int k0 = lane; k0 < n2; k0 += 32 * U) {
             double2 a[U];
 #pragma unroll
@@ -661,12 +697,13 @@ __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, 
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 double2 v = h2[k0 + 32 * u];
-                v.x = __dadd_rn (v.x, flip_sign (a[u].x, f1));
-                v.y = __dadd_rn (v.y, flip_sign (a[u].y, f1));
+                v.x = decltype (neg1)::value ? __dsub_rn (v.x, a[u].x) : __dadd_rn (v.x, a[u].x);
+                v.y = decltype (neg1)::value ? __dsub_rn (v.y, a[u].y) : __dadd_rn (v.y, a[u].y);
                 h2[k0 + 32 * u] = v;
             }
         }
-    } else {
+    };
+    auto both = [&] (auto neg1, auto neg2) {
         for (int k0 = lane; k0 < n2; k0 += 32 * U) {
             double2 a[U], b[U];
 #pragma unroll
@@ -674,12 +711,19 @@ __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, 
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 double2 v = h2[k0 + 32 * u];
-                v.x = __dadd_rn (__dadd_rn (v.x, flip_sign (a[u].x, f1)), flip_sign (b[u].x, f2));
-                v.y = __dadd_rn (__dadd_rn (v.y, flip_sign (a[u].y, f1)), flip_sign (b[u].y, f2));
+                v.x = decltype (neg1)::value ? __dsub_rn (v.x, a[u].x) : __dadd_rn (v.x, a[u].x);
+                v.y = decltype (neg1)::value ? __dsub_rn (v.y, a[u].y) : __dadd_rn (v.y, a[u].y);
+                v.x = decltype (neg2)::value ? __dsub_rn (v.x, b[u].x) : __dadd_rn (v.x, b[u].x);
+                v.y = decltype (neg2)::value ? __dsub_rn (v.y, b[u].y) : __dadd_rn (v.y, b[u].y);
                 h2[k0 + 32 * u] = v;
             }
         }
-    }
+    };
+    using T = std::true_type;
+    using F = std::false_type;
+    if (!two) { if (f1) one (T ()); else one (F ()); }
+    else if (f1) { if (f2) both (T (), T ()); else both (T (), F ()); }
+    else { if (f2) both (F (), T ()); else both (F (), F ()); }
 }
 
 // the same from the two wr rows of each instance pair (models whose difference rows exceed the memory budget); nr2 = ldr / 2
@@ -794,12 +838,12 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     asm volatile ("" : "+r"(o_warp));       // kept in a register (ptxas otherwise rebuilds it from the thread index inside the round loop)
 #define s_site(i_) (*(uint32_t *) (smem + 4u * (uint32_t) (i_)))                     /* first | ninst << 16 per site (CTA-wide) */
 #define h(i_)      (*(double *)   (smem + o_warp + 8u * (uint32_t) (i_)))
-    // residence stamps: 16-bit when nprod < 65536 (warp-uniform choice; they are touched by one lane per accepted move)
+    // residence stamps: 16-bit in the large-field build when nprod < 65536 (warp-uniform choice; one lane touches them per accepted move)
     auto since = [&] (int i) -> uint32_t {
-        return p.wl_since16 ? (uint32_t) *(const uint16_t *) (smem + o_warp + p.wl_since + 2u * (uint32_t) i) : *(const uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) i);
+        return (!ABS && p.wl_since16) ? (uint32_t) *(const uint16_t *) (smem + o_warp + p.wl_since + 2u * (uint32_t) i) : *(const uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) i);
     };
     auto set_since = [&] (int i, uint32_t v) {
-        if (p.wl_since16) *(uint16_t *) (smem + o_warp + p.wl_since + 2u * (uint32_t) i) = (uint16_t) v;
+        if (!ABS && p.wl_since16) *(uint16_t *) (smem + o_warp + p.wl_since + 2u * (uint32_t) i) = (uint16_t) v;
         else *(uint32_t *) (smem + o_warp + p.wl_since + 4u * (uint32_t) i) = v;
     };
 #define state(i_)  (*(uint16_t *) (smem + o_warp + p.wl_state + 2u * (uint32_t) (i_)))
@@ -935,18 +979,24 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
 
     const bool use_cross = p.cross != nullptr;
     uint32_t tcur = 0, tfill = 0;        // next trial to decide; trials [tcur, tfill) are in the ring
+    auto refill = [&] () {               // 64 more trials: lane l generates Philox block tfill / 2 + l and decodes its two trials
+        const uint32_t bl = (tfill >> 1) + (uint32_t) lane;
+        const pce::Philox4 r = pce::philox4x32_10 (bl, 0u, chain, phidx, p.k0, p.k1);
+        const uint32_t slot = ((uint32_t) tfill & (uint32_t) (RING - 1)) + 2u * (uint32_t) lane;
+        uint32_t pr0, pr1, dr0, dr1, px0, px1;
+        decode (r.x, pr0, dr0, px0);
+        decode (r.z, pr1, dr1, px1);
+        ring (slot)      = make_uint4 (dr0, r.y, pr0, px0);
+        ring (slot + 1u) = make_uint4 (dr1, r.w, pr1, px1);
+        tfill += 64u;
+    };
+    // Large fields, one trial per lane: the ring is topped up in the shadow of the round's cross-term gathers (below) instead of
+    // at the start of a round, where the L2 round trip of the pair table would be exposed; the ring then holds the current
+    // round, the next one and the 64 new trials (32 + 32 + 64 = RING).
+    constexpr bool EARLY_REFILL = !ABS && TPL == 1;
+    if (EARLY_REFILL) refill ();
     while (tcur < ntrials) {
-        while (tfill - tcur < (uint32_t) (32 * TPL)) {
-            const uint32_t bl = (tfill >> 1) + (uint32_t) lane;
-            const pce::Philox4 r = pce::philox4x32_10 (bl, 0u, chain, phidx, p.k0, p.k1);
-            const uint32_t slot = ((uint32_t) tfill & (uint32_t) (RING - 1)) + 2u * (uint32_t) lane;
-            uint32_t pr0, pr1, dr0, dr1, px0, px1;
-            decode (r.x, pr0, dr0, px0);
-            decode (r.z, pr1, dr1, px1);
-            ring (slot)      = make_uint4 (dr0, r.y, pr0, px0);
-            ring (slot + 1u) = make_uint4 (dr1, r.w, pr1, px1);
-            tfill += 64u;
-        }
+        if (!EARLY_REFILL) while (tfill - tcur < (uint32_t) (32 * TPL)) refill ();
         __syncwarp ();
 
         // ---- evaluate 32*TPL trials against the current state ----
@@ -1023,6 +1073,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             dblm[u] = __ballot_sync (0xffffffffu, act && dbl);
             e_pr[u] = pr; e_a[u] = (uint32_t) ia | ((uint32_t) oa << 16); e_b[u] = (uint32_t) ib | ((uint32_t) ob << 16);
         }
+        if (EARLY_REFILL && tfill - tcur < 64u) refill ();       // (writes slots [tfill, tfill + 64): none of this round's)
         // phase 2: cross terms and Metropolis tests
 #pragma unroll
         for (int u = 0; u < TPL; u++) {
@@ -1287,7 +1338,7 @@ bool plan_warp (const pce_mc *mc, size_t limit, int nph, int sms, Plan *plan, do
         // 128-bit loads per lane and batch of the field update: 16 for large fields, 4 for small ones, 1 when the whole vector
         // (instance-indexed: ninst slots) fits one load per lane
         const int upd = pass == 1 ? 16 : m->ninst <= 64 ? 1 : 4;
-        WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1, mc->nprod < 65536 ? 2 : 4);
+        WarpLayout L (m->nsites, m->ninst, tpl, upd, pass != 1, (pass == 1 && mc->nprod < 65536) ? 2 : 4);
         if (L.per_warp + L.shared_bytes > limit) continue;
         // large fields (one resident CTA): as many warps as shared memory holds, up to 10 (204 registers each); else 8 per CTA
         int warps = (int) std::min<size_t> ((limit - L.shared_bytes) / L.per_warp, pass == 1 ? 10 : 8);
@@ -1610,7 +1661,7 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
         // row stride of the difference rows: the padded field length of a chain-per-warp launch, else the slot count
         const int nrel = std::max (m->ninst - m->nsites, 1);
         const bool abs = plan.kernel == 2 && plan.upd != 16;         // small-field variants of the warp kernel: instance-indexed slots
-        const int ldd = plan.kernel == 2 ? WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd, abs, mc->nprod < 65536 ? 2 : 4).ldh : ((nrel + 3) & ~3);
+        const int ldd = plan.kernel == 2 ? WarpLayout (m->nsites, m->ninst, plan.tpl, plan.upd, abs, (!abs && mc->nprod < 65536) ? 2 : 4).ldh : ((nrel + 3) & ~3);
         status = build_relative_tables (mc, ldd, abs);
         if (status != PCE_OK) return status;
         if (plan.kernel == 1 && (!mc->dw_valid || (npairs > 0 && !mc->cross_valid)))
@@ -1630,8 +1681,9 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     p.ntrials = (unsigned long long) ((long long) mc->nequil + mc->nprod) * p.nmoves;
     p.nmoves_magic = (p.nmoves >= 2u && p.nmoves <= 64u) ? (uint32_t) (4294967296ull / p.nmoves) + 1u : 0u;
     if (plan.kernel == 2) {
-        const WarpLayout WL (m->nsites, m->ninst, plan.tpl, plan.upd, plan.upd != 16, mc->nprod < 65536 ? 2 : 4);
-        p.wl_since16 = mc->nprod < 65536 ? 1u : 0u;
+        const bool since16 = plan.upd == 16 && mc->nprod < 65536;        // (large-field build only)
+        const WarpLayout WL (m->nsites, m->ninst, plan.tpl, plan.upd, plan.upd != 16, since16 ? 2 : 4);
+        p.wl_since16 = since16 ? 1u : 0u;
         p.wl_shared = (uint32_t) WL.shared_bytes; p.wl_per_warp = (uint32_t) WL.per_warp; p.wl_since = (uint32_t) WL.off_since;
         p.wl_state = (uint32_t) WL.off_state; p.wl_ring = (uint32_t) WL.off_ring; p.wl_ldh = WL.ldh;
     }
