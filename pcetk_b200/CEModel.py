@@ -186,9 +186,25 @@ class CEModel(object):
         return self.energyModel.CalculateMicrostateEnergy(stateVector, pH=pH)
 
     def _Gather(self, row=None):
+        """Probabilities of one pH value as the reference's nested lists [site][instance] (CEModel.py:491-497)."""
         if row is None:
             row = self.energyModel.GetProbabilities()
-        return [[float(row[instance._instIndexGlobal]) for instance in site.instances] for site in self.sites]
+        return self._GatherRows([row])[0]
+
+    def _GatherRows(self, table):
+        """The same for many pH values at once: rows of p[npH, ninst] -> [step][site][instance] (one bulk conversion, then slices)."""
+        spans = getattr(self, "_siteSpans", None)
+        if spans is None or len(spans) != len(self.sites):
+            spans = []
+            for site in self.sites:
+                indices = [instance._instIndexGlobal for instance in site.instances]
+                contiguous = indices == list(range(indices[0], indices[0] + len(indices)))
+                spans.append((indices[0], indices[0] + len(indices)) if contiguous else indices)
+            self._siteSpans = spans
+        rows = [list(map(float, row)) for row in table] if not hasattr(table, "tolist") else table.tolist()
+        if all(isinstance(span, tuple) for span in spans):
+            return [[row[first:last] for first, last in spans] for row in rows]
+        return [[row[span[0]:span[1]] if isinstance(span, tuple) else [row[k] for k in span] for span in spans] for row in rows]
 
     def CalculateProbabilities(self, pH=7.0, unfolded=False, isCalculateCurves=False, logFrequency=-1, trajectoryFilename="", log=logFile):
         """Calculate probabilities (CEModel.py:466-499): the sampler if one is attached, else exhaustive enumeration."""

@@ -52,7 +52,8 @@ class TitrationCurves(object):
                 steps = [owner.CalculateProbabilities(pH=pH, log=None, isCalculateCurves=True, unfolded=self.unfolded) for pH in values]
             else:
                 table = owner.CalculateProbabilitiesBatch(values, unfolded=self.unfolded)
-                steps = [owner._Gather(row) for row in table]
+                steps = owner._GatherRows(table)
+                self._table = table
             if LogFileActive(log):
                 if printTable:
                     log.Table([("%10d" % step, "%10.2f" % pH) for step, pH in enumerate(values)], title="Step / pH")
@@ -85,7 +86,9 @@ class TitrationCurves(object):
         """The calculated curves as one array [nsteps, ninstances] (global instance order) and the pH grid."""
         import numpy as np
 
-        table = np.array([[value for site in step for value in site] for step in self.steps], dtype=np.float64)
+        table = getattr(self, "_table", None)          # kept by the batched path; rebuilt from the nested lists otherwise
+        if table is None or len(table) != len(self.steps):
+            table = np.array([[value for site in step for value in site] for step in self.steps], dtype=np.float64)
         return table, self.curveStart + self.curveSampling * np.arange(self.nsteps)
 
     def CalculateHalfpKs(self):
@@ -98,15 +101,15 @@ class TitrationCurves(object):
         table, grid = self._CurveTable()
         centred = table - 0.5
         crossing = centred[:-1] * centred[1:] < 0.0                      # [nsteps - 1, ninstances]
+        columns, left = np.nonzero(crossing.T)                           # every crossing, ordered by instance, then by pH
+        pa, pb = table[left, columns], table[left + 1, columns]
+        values = (grid[left] + (0.5 - pa) * (grid[left + 1] - grid[left]) / (pb - pa)).tolist()
+        bounds = np.searchsorted(columns, np.arange(table.shape[1] + 1)).tolist()
         self.halves, column = [], 0
         for site in self.owner.sites:
-            perSite = []
-            for _instance in site.instances:
-                left = np.nonzero(crossing[:, column])[0]
-                pa, pb = table[left, column], table[left + 1, column]
-                perSite.append(list(grid[left] + (0.5 - pa) * (grid[left + 1] - grid[left]) / (pb - pa)))
-                column += 1
-            self.halves.append(perSite)
+            count = len(site.instances)
+            self.halves.append([values[bounds[k]:bounds[k + 1]] for k in range(column, column + count)])
+            column += count
         self.isHalves = True
 
     def _GetEntry(self, site, decimalPlaces=2):

@@ -994,10 +994,12 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
     // at the start of a round, where the L2 round trip of the pair table would be exposed; the ring then holds the current
     // round, the next one and the 64 new trials (32 + 32 + 64 = RING).
     constexpr bool EARLY_REFILL = !ABS && TPL == 1;
-    if (EARLY_REFILL) refill ();
+    if (EARLY_REFILL) { refill (); __syncwarp (); }
     while (tcur < ntrials) {
-        if (!EARLY_REFILL) while (tfill - tcur < (uint32_t) (32 * TPL)) refill ();
-        __syncwarp ();
+        if (!EARLY_REFILL && tfill - tcur < (uint32_t) (32 * TPL)) {
+            do refill (); while (tfill - tcur < (uint32_t) (32 * TPL));
+            __syncwarp ();       // (otherwise the barrier that ends a round has already ordered the ring)
+        }
 
         // ---- evaluate 32*TPL trials against the current state ----
         // A round may run across scan ends (a scan of a small model is shorter than a round: lysozyme 24 trials); only the

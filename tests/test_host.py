@@ -105,6 +105,9 @@ class _FakeModel(object):
     def _Gather(self, row):
         return self.inner._Gather(row)
 
+    def _GatherRows(self, table):
+        return self.inner._GatherRows(table)
+
     def CalculateProbabilitiesBatch(self, phs, unfolded=False):
         return np.stack([self._row(ph) for ph in phs])
 
