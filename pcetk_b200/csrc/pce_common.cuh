@@ -74,7 +74,8 @@ struct pce_model {
     const void   *pinned[2] = { nullptr, nullptr };     // raw buffers registered with the driver for the upload
     bool   symmetrized = false;
     bool   dirty       = true;                 // host copy newer than device copy
-    int    generation  = 0;                    // bumped by every real upload (derived device tables key on it)
+    int    generation  = 0;                    // bumped by every upload of NEW content (derived device tables key on it)
+    std::vector<unsigned char> uploaded;       // snapshot of the last uploaded content (small models), see upload ()
     cudaStream_t stream = nullptr;
 
     // device mirror

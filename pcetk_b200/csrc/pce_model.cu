@@ -399,7 +399,25 @@ int pce_model::upload () {
         }
     }
     dirty = false;
-    generation++;
+    // The generation (which the derived device tables and the enumeration plan key on) moves only when the uploaded CONTENT
+    // changed: a caller that re-loads the very same arrays before every call -- the reference's scripts do -- pays the copies
+    // above but keeps its tables.  Exact comparison against a snapshot of the last upload, for models of up to 4 MB.
+    {
+        const double *wsrc = sym_src != nullptr ? sym_src : wsym.data ();
+        const size_t nw = (sym_src != nullptr || !wsym.empty ()) ? (size_t) ninst * ninst : 0;
+        const size_t bytes = (size_t) nsites * 8 + (size_t) ninst * 20 + nw * 8 + 16;
+        std::vector<unsigned char> snap;
+        if (bytes <= ((size_t) 4 << 20)) {
+            snap.reserve (bytes);
+            auto put = [&] (const void *data, size_t n) { const unsigned char *c = (const unsigned char *) data; snap.insert (snap.end (), c, c + n); };
+            const unsigned char pending = sym_src != nullptr ? 1 : 0;
+            put (&pending, 1); put (&temperature, sizeof (double));
+            put (first.data (), (size_t) nsites * 4); put (last.data (), (size_t) nsites * 4);
+            put (protons.data (), (size_t) ninst * 4); put (gintr.data (), (size_t) ninst * 8); put (gmodel.data (), (size_t) ninst * 8);
+            if (nw) put (wsrc, nw * 8);
+        }
+        if (snap.empty () || snap != uploaded) { generation++; uploaded.swap (snap); }
+    }
     return PCE_OK;
 }
 

@@ -242,3 +242,41 @@ def test_too_many_trials_per_chain_are_refused():
     model.DefineMCModel(sampler, log=None)
     with pytest.raises(P.CLibraryError, match="too many trials per chain"):
         sampler.RunCounts([7.0])
+
+
+def test_reloading_the_same_model_keeps_its_tables_and_a_changed_model_does_not(port):
+    """The tables derived from a model (enumeration plan, difference rows, cross terms) are keyed on the uploaded CONTENT:
+    re-loading identical arrays reuses them, changing one energy rebuilds them -- the results must follow the model either way."""
+    rec, _gold = load_fixture("defensin")
+    model = P.MEADModel(rec, log=None)
+    em = model.energyModel
+    wsym = port.symmetrize(rec.interactions)
+    grid = [3.0, 7.0, 11.0]
+    first = model.CalculateProbabilitiesBatch(grid)
+    em.Load(gintr=rec.gintr, gmodel=rec.gmodel, protons=rec.protons, interactions=rec.interactions)
+    em.SymmetrizeInteractions(log=None)
+    assert np.array_equal(model.CalculateProbabilitiesBatch(grid), first)
+    changed = ModelRecord(rec.name + "c", rec.site_first, rec.site_last, rec.protons, rec.gmodel, rec.gintr.copy(), rec.interactions.copy(),
+                          rec.temperature, rec.site_labels, rec.inst_labels)
+    changed.gintr[3] += 1.5
+    changed.interactions[2, 9] += 0.75
+    changed.interactions[9, 2] += 0.75
+    em.Load(gintr=changed.gintr, interactions=changed.interactions)
+    em.SymmetrizeInteractions(log=None)
+    wchanged = port.symmetrize(changed.interactions)
+    p = model.CalculateProbabilitiesBatch(grid)
+    assert not np.array_equal(p, first)
+    for row, ph in zip(p, grid):
+        ref, _z, _g = port.analytic(changed, wchanged, ph)
+        assert rel_err(row, ref) <= 1e-12
+    # the same for the sampler's tables (both kernels): chains of the changed model, then of the original one again
+    for kernel in (1, 2):
+        sampler = P.MCModelDefault(nequil=10, nprod=150, randomSeed=4242, nchains=33, kernel=kernel)
+        model.DefineMCModel(sampler, log=None)
+        pairs = ([a for a, _b, _w in sampler.GetPairs()], [b for _a, b, _w in sampler.GetPairs()])
+        for current, w in ((changed, wchanged), (rec, wsym), (rec, wsym)):
+            em.Load(gintr=current.gintr, gmodel=current.gmodel, protons=current.protons, interactions=current.interactions)
+            em.SymmetrizeInteractions(log=None)
+            out = sampler.RunChains([6.0], phIndexOffset=0)
+            spec = port.mc_philox_chain(current, w, pairs, 10, 150, sampler.seed, 32, 0, 6.0)
+            assert np.array_equal(out["counts"][0, 32], spec["counts"])
