@@ -398,6 +398,7 @@ extern "C" int pce_analytic_finish (pce_model *m, const double *bins, const doub
         const double hi = (double) x, lo = (double) (x - (long double) hi);
         return std::exp (hi) * (1.0 + lo);
     };
+    std::vector<double> wn ((size_t) Nb * nph);          // normalised weights [bin][pH]: pH innermost, so the sums below vectorise
     for (int q = 0; q < nph; q++) {
         // logarithmic weights in extended precision (their range is that of the bin scales, e^(+-700) and beyond); the weighted sums
         // themselves are sums of at most ~100 positive doubles <= 1 and stay in double precision
@@ -414,15 +415,21 @@ extern "C" int pce_analytic_finish (pce_model *m, const double *bins, const doub
         }
         if (!(z > 0.0)) return fail (PCE_ERR_STATE, "partition function underflowed; split the pH grid");
         const double inv = 1.0 / z;
-        for (int a = 0; a < m->ninst; a++) {
-            const double *row = bins + (size_t) (1 + a) * Nb;
-            double s = 0.0;
-            for (int n = 0; n < Nb; n++) s += row[n] * weight[n];
-            const double value = s * inv;
-            if (out_p) out_p[(size_t) q * m->ninst + a] = value;
-            if (q == nph - 1) m->prob[a] = value;
-        }
+        for (int n = 0; n < Nb; n++) wn[(size_t) n * nph + q] = weight[n] * inv;
         if (out_lnz) out_lnz[q] = (double) (logl ((long double) z) + shift - beta * ((long double) plan.gref - gzero));
+    }
+    std::vector<double> acc (nph);
+    for (int a = 0; a < m->ninst; a++) {
+        const double *row = bins + (size_t) (1 + a) * Nb;
+        std::fill (acc.begin (), acc.end (), 0.0);
+        double *__restrict__ sum = acc.data ();
+        for (int n = 0; n < Nb; n++) {
+            const double r = row[n];
+            const double *__restrict__ w = &wn[(size_t) n * nph];
+            for (int q = 0; q < nph; q++) sum[q] += r * w[q];
+        }
+        if (out_p) for (int q = 0; q < nph; q++) out_p[(size_t) q * m->ninst + a] = acc[q];
+        m->prob[a] = acc[nph - 1];
     }
     return PCE_OK;
 }
