@@ -214,13 +214,16 @@ __device__ __forceinline__ double flip_sign (double v, uint32_t mask) {
 // processed two per Philox block (no prefetch: the registers were worth more).  The model lives in shared memory as the
 // difference rows E (one per instance pair of a site) and the pair cross-term table: W itself is never read by the trial loop.
 // ---------------------------------------------------------------------------------------------------
+// A trial starts with ONE 128-bit load of its move-table entry (both sites, their instance counts and field bases, the pair's
+// cross-term base, the row-table base); states are LOCAL instance indices; the difference row of an accepted move comes from a
+// row table indexed by (current, draw); every per-thread array is addressed with explicit 32-bit ld / st.shared.
 // Register budgets: every SM sub-partition holds 16384 registers and a quarter of the block's warps, so a block of
 // 512 / 640 / 768 / 896 / 1024 threads may use 128 / 96 / 80 / 72 / 64 registers per thread (__launch_bounds__ would round
-// the block up to the next multiple of 256 threads and allow fewer).  Uncapped, the kernel takes 79 (8.9 warp-instructions
-// per trial); capped below that ptxas rematerialises loop invariants inside the trial loop (10.6 at 72, 13 at 64), so
-// the planner stops at 768 threads.  To get there the loop state was put on a diet: no Philox prefetch, 32-bit scan
-// counter instead of 64-bit trial counters, tracked energy and its sum in shared memory, 32-bit shared-memory offsets
-// instead of generic pointers, the shared-memory layout passed in the kernel parameters.
+// the block up to the next multiple of 256 threads and allow fewer).  Uncapped, the short-field build takes 72 registers and
+// 272 instructions in the trial loop (6.0 warp-instructions per trial); under a smaller cap ptxas rematerialises loop invariants
+// inside the loop (310 at 64), so the launch code picks the uncapped build whenever its registers fit the block (896 threads for
+// the fixtures) and the capped ones otherwise.  The loop state is on a diet: no Philox prefetch, a 32-bit scan counter, the
+// tracked energy (ENERGY builds) in shared memory, the layout passed in the kernel parameters.
 template <bool PER_CHAIN, typename SinceT, int MAX_REGS, int SHORT_FIELDS, bool ENERGY>      // SHORT_FIELDS: 0 nrel > 32, 1 nrel <= 32, 2 nrel <= 16
 __global__ void __maxnreg__ (MAX_REGS) k_mc_thread (const McParams p) {
     static_assert (ENERGY || !PER_CHAIN, "per-chain outputs include the energy");
