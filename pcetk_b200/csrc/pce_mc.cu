@@ -1277,14 +1277,14 @@ bool plan_thread (const pce_mc *mc, size_t limit, int nph, int sms, bool energy,
     if (m->ninst > 256 || t.nrows > 16383 || t.ncross >= (1u << 15)) return false;       // field widths of the packed move table (the tables must fit in shared memory anyway)
     const char *forced = std::getenv ("PCE_MC_BLOCK");      // tuning aid: force the block size
     const int forced_block = forced ? std::atoi (forced) : 0;
-    // measured on lysozyme (moves/s): 640 threads 7.6e10, 768 (the largest block the uncapped 79-register build fits) 8.5e10,
-    // 832 / 896 with the 72-register build 7.1e10 / 7.3e10 -- so blocks beyond 768 are only taken when forced
+    // (round 1, lysozyme, moves/s: 640 threads 7.6e10, 768 threads 8.5e10; round 2: 768 threads 1.06e11, 896 threads -- the quiet build
+    // of the short-field kernel, see below -- 1.12e11, and 1.45e11 after the trial front end was rewritten)
     // pH-minor linearisation (load balance: acceptance, hence cost, varies 10x over a titration curve) unless the per-block
     // occupancy counters of all pH values would take more than 48 KB of shared memory
     const bool ph_minor = (size_t) std::min (nph, 768) * m->ninst * 4 <= 48 * 1024 && std::getenv ("PCE_MC_CHAIN_MAJOR") == nullptr;
     // Short field vectors (nrel <= 32, SHORT_FIELDS build): the uncapped build takes 72 registers, which fits 896 threads
-    // (7 warps per sub-partition x 72 x 32 = 16128 registers) -- taken when the chains also fit in shared memory
-    // (defensin: 1.10e11 -> 1.17e11 moves/s; lysozyme's 263 B per chain stop at 832, whose uneven 7/7/6/6 warps do not pay).
+    // (7 warps per sub-partition x 72 x 32 = 16128 registers) -- taken when the chains also fit in shared memory (lysozyme:
+    // 247 B per chain without energy tracking; with it, 263 B stop at 832 threads, whose uneven 7/7/6/6 warps do not pay).
     int most = 768;
     if (t.nrel <= 32) {
         cudaFuncAttributes attributes;
