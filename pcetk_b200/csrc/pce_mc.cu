@@ -1026,7 +1026,6 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             const uint32_t draws = entry.x, pr = entry.z, px = entry.w;
             e_w1[u] = entry.y;
             const float pbound = 0.25f * (float) (px >> 24);                     // the pair's bound, quantised upwards (0: none)
-            const bool act = off < n_act;
             const int  sa = (int) (pr & 0xffffu), sb = (int) (pr >> 16);
             const bool dbl = sa != sb;                                           // (a pair joins two different sites)
             const bool valid = draws != 0xffffffffu;
@@ -1054,7 +1053,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
                 const float ulow = __uint2float_rd (e_w1[u]) * 2.3283064365386963e-10f;  // <= u
                 // (small fields: the cross-term table is cache-resident, the gather is cheaper than the test)
                 const bool certain = !ABS && (px >> 24) != 0u && xlow > 0.0f && ulow > __expf (-xlow) * 1.001f;
-                if (act && valid && !certain) {
+                if (valid && !certain) {
                     if (!FALLBACK || use_cross) {
                         // one gather: the cross term of (old a, draw a, old b, draw b), precomputed with the same operations
                         if (ABS) { ia_info = s_site (sa); ib_info = s_site (sb); }
@@ -1072,10 +1071,10 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
                 const int fa = ABS ? 0 : (int) (s_site (sa) & 0xffffu);
                 const double gan = ABS ? h (ia) : ia != fa ? h (ia - sa - 1) : 0.0, gao = ABS ? h (oa) : oa != fa ? h (oa - sa - 1) : 0.0;
                 x = __dsub_rn (gan, gao);
-                e_need[u] = act && valid;
+                e_need[u] = valid;
             }
             e_dbl[u] = dbl; e_x[u] = x;
-            dblm[u] = __ballot_sync (0xffffffffu, act && dbl);
+            dblm[u] = __ballot_sync (0xffffffffu, dbl);
             e_pr[u] = pr; e_a[u] = (uint32_t) ia | ((uint32_t) oa << 16); e_b[u] = (uint32_t) ib | ((uint32_t) ob << 16);
         }
         if (EARLY_REFILL && tfill - tcur < 64u) refill ();       // (writes slots [tfill, tfill + 64): none of this round's)
@@ -1087,6 +1086,15 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             const bool accept = metropolis (x, e_w1[u]) && e_need[u];
             accm[u] = __ballot_sync (0xffffffffu, accept);
             e_x[u] = x;
+        }
+        // every lane has evaluated a trial; in the last round of a chain (and in the per-scan mode, whose rounds stop at scan ends)
+        // only the first n_act of them exist -- warp-uniform and rare, so the lanes carry no "active" flag through the phases above
+        if (n_act < (uint32_t) (32 * TPL)) {
+#pragma unroll
+            for (int u = 0; u < TPL; u++) {
+                const int c = (int) n_act - u * 32;
+                accm[u] &= c >= 32 ? 0xffffffffu : c <= 0 ? 0u : ((1u << c) - 1u);
+            }
         }
 
         // ---- the first accepted trial ends the round ----
