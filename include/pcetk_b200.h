@@ -101,13 +101,15 @@ int pce_model_get_symmetric_matrix (const pce_model *model, double *w /* ninstan
 /* EnergyModel_CheckInteractionsSymmetric / _SymmetrizeInteractions / _ResetInteractions /
  * _ScaleInteractions (EnergyModel.h:68-71) */
 int pce_model_check_symmetric (const pce_model *model, double tolerance, double *max_deviation, int *is_symmetric);
-int pce_model_symmetrize (pce_model *model);
+int pce_model_symmetrize (pce_model *model);      /* the averaging runs on the device at the next upload; host readers of the symmetric
+                                                    * matrix see the same values (formed on demand); it changes on this call only */
 int pce_model_reset_interactions (pce_model *model);
 int pce_model_scale_interactions (pce_model *model, double scale);
 /* EnergyModel_StateVectorFromProbabilities (EnergyModel.h:72), without the reference's off-by-one */
 int pce_model_state_from_probabilities (const pce_model *model, int32_t *state_global);
 
-/* copy the model to its device (done implicitly by compute calls when the host copy changed) */
+/* copy the model to its device (done implicitly by compute calls when the host copy changed).  Device tables derived from the
+ * model (sampler tables, enumeration plan) are rebuilt only when the uploaded content differs from the previous upload. */
 int pce_model_upload (pce_model *model);
 
 /* ---- state vector (StateVector.h:53-84; host object, bound by ContinuumElectrostatics.StateVector.pyx) ----------------
@@ -205,7 +207,8 @@ int  pce_mc_plan (pce_mc *mc, int nph, int *kernel, int *block, int *ctas_per_sm
  *   counts  [nph * ninst]  production scans during which each instance was active, summed over chains
  *   counters[nph * 4]      moves, moves accepted, double moves, double moves accepted (production)
  *   esum    [nph]          sum over chains and production scans of the microstate energy
- * pce_mc_run also stores counts/(nchains*nprod) of the LAST pH value in the model's probabilities. */
+ * pce_mc_run also stores counts/(nchains*nprod) of the LAST pH value in the model's probabilities.
+ * A chain counts its trials in 32 bits: (nequil + nprod) * (nsites + npairs) >= 2^32 returns PCE_ERR_LIMIT. */
 int pce_mc_run (pce_mc *mc, const double *ph, int nph, int ph_index_offset, long long chain_offset,
                 long long *counts, long long *counters, double *esum);
 int pce_mc_run_device (pce_mc *mc, const double *ph /* host */, int nph, int ph_index_offset, long long chain_offset,
