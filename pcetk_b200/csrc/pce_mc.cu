@@ -775,7 +775,10 @@ __device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s
         const uint32_t *s_dbase = s_site + p.nsites;
         const double2 *r1 = (const double2 *) (p.dw + (s_dbase[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) * (uint32_t) p.ldd), *r2 = r1;
         if (dbl) r2 = (const double2 *) (p.dw + (s_dbase[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) * (uint32_t) p.ldd);
-        apply_diff_rows<U> (h2, ldh >> 1, lane, r1, f1, r2, f2, dbl);
+        const int n2 = ldh >> 1;
+        if (U == 4 && n2 == 64) apply_diff_rows<2> (h2, n2, lane, r1, f1, r2, f2, dbl);             // (warp-uniform choice of the batch depth)
+        else if (U == 4 && n2 == 96) apply_diff_rows<3> (h2, n2, lane, r1, f1, r2, f2, dbl);
+        else apply_diff_rows<U> (h2, n2, lane, r1, f1, r2, f2, dbl);
     } else {
         apply_wr_rows<(U < 8 ? U : 8)> (h2, p.ldr >> 1, lane, (const double2 *) (p.wr + (size_t) (fa + mxa) * p.ldr), (const double2 *) (p.wr + (size_t) (fa + mna) * p.ldr), f1,
                                        (const double2 *) (p.wr + (size_t) (fb + mxb) * p.ldr), (const double2 *) (p.wr + (size_t) (fb + mnb) * p.ldr), f2, dbl);
@@ -808,7 +811,10 @@ struct WarpLayout {
     // instead of nine fit an SM)
     __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd, bool abs, int since_bytes) {
         const int nfield = abs ? ninst : (ninst > nsites ? ninst - nsites : 1);
-        ldh  = (nfield + 64 * upd - 1) / (64 * upd) * (64 * upd);       // whole batches of the field update (apply_diff_rows)
+        // whole batches of the field update (apply_diff_rows: unpredicated loads).  Small fields of up to 256 slots are updated in ONE
+        // batch of 1 .. 4 loads per lane, so they are padded to whole warps of double2 only (ifp20: 192 instead of 256 slots per move)
+        const int gran = (abs && nfield <= 256) ? 64 : 64 * upd;
+        ldh  = (nfield + gran - 1) / gran * gran;
         ring = tpl <= 2 ? 128 : 256;
         shared_bytes = ((size_t) nsites * 8 + 15) & ~(size_t) 15;     // packed site table and first difference row per site, one copy per CTA
         off_site = 0;
