@@ -645,7 +645,7 @@ __global__ void k_build_dw (const double *__restrict__ wr, int nrel, int ldr, in
 // unpredicated 128-bit loads per lane and row, all issued before the first use
 template <int U>
 __device__ __forceinline__ void apply_diff_rows (double2 *h2, int n2, int lane, const double2 *r1, uint32_t f1, const double2 *r2, uint32_t f2, bool two) {
-    if (n2 <= 32) {      // field vectors of up to 64 slots (lysozyme, defensin): one 128-bit load per lane, no batches
+    if (U == 1) {        // field vectors of up to 64 slots (lysozyme, defensin; their own build): one 128-bit load per lane, no batches
         if (lane < n2) {
             const double2 a = __ldg (r1 + lane);
             double2 v = h2[lane];
@@ -775,10 +775,8 @@ __device__ __forceinline__ void apply_move (const McParams &p, const uint32_t *s
         const uint32_t *s_dbase = s_site + p.nsites;
         const double2 *r1 = (const double2 *) (p.dw + (s_dbase[sa] + (uint32_t) (((mxa * (mxa - 1)) >> 1) + mna)) * (uint32_t) p.ldd), *r2 = r1;
         if (dbl) r2 = (const double2 *) (p.dw + (s_dbase[sb] + (uint32_t) (((mxb * (mxb - 1)) >> 1) + mnb)) * (uint32_t) p.ldd);
-        const int n2 = ldh >> 1;
-        if (U == 4 && n2 == 64) apply_diff_rows<2> (h2, n2, lane, r1, f1, r2, f2, dbl);             // (warp-uniform choice of the batch depth)
-        else if (U == 4 && n2 == 96) apply_diff_rows<3> (h2, n2, lane, r1, f1, r2, f2, dbl);
-        else apply_diff_rows<U> (h2, n2, lane, r1, f1, r2, f2, dbl);
+        if (U == 4 && ldh == 192) apply_diff_rows<3> (h2, 96, lane, r1, f1, r2, f2, dbl);       // (warp-uniform)
+        else apply_diff_rows<U> (h2, ldh >> 1, lane, r1, f1, r2, f2, dbl);
     } else {
         apply_wr_rows<(U < 8 ? U : 8)> (h2, p.ldr >> 1, lane, (const double2 *) (p.wr + (size_t) (fa + mxa) * p.ldr), (const double2 *) (p.wr + (size_t) (fa + mna) * p.ldr), f1,
                                        (const double2 *) (p.wr + (size_t) (fb + mxb) * p.ldr), (const double2 *) (p.wr + (size_t) (fb + mnb) * p.ldr), f2, dbl);
@@ -811,9 +809,9 @@ struct WarpLayout {
     // instead of nine fit an SM)
     __host__ __device__ WarpLayout (int nsites, int ninst, int tpl, int upd, bool abs, int since_bytes) {
         const int nfield = abs ? ninst : (ninst > nsites ? ninst - nsites : 1);
-        // whole batches of the field update (apply_diff_rows: unpredicated loads).  Small fields of up to 256 slots are updated in ONE
-        // batch of 1 .. 4 loads per lane, so they are padded to whole warps of double2 only (ifp20: 192 instead of 256 slots per move)
-        const int gran = (abs && nfield <= 256) ? 64 : 64 * upd;
+        // whole batches of the field update (apply_diff_rows: unpredicated loads); small fields of 129 .. 192 slots (ifp20: 171) are
+        // updated in one batch of THREE loads per lane instead of four
+        const int gran = (abs && upd == 4 && nfield > 128 && nfield <= 192) ? 192 : 64 * upd;
         ldh  = (nfield + gran - 1) / gran * gran;
         ring = tpl <= 2 ? 128 : 256;
         shared_bytes = ((size_t) nsites * 8 + 15) & ~(size_t) 15;     // packed site table and first difference row per site, one copy per CTA
@@ -832,13 +830,16 @@ struct WarpLayout {
 // 2 CTAs 128, 3 CTAs 80, 4 CTAs 64.  Measured on ifp20: 3.4e10 / 3.8e10 / 3.7e10 moves/s for 2 / 3 / 4 CTAs -- at 64
 // registers ptxas moves the warp-uniform bookkeeping off the uniform datapath (12 % more instructions), so three CTAs
 // are the default for small fields (PCE_MC_CTAS overrides).
-template <bool PER_CHAIN, int MIN_CTAS, int TPL, bool ENERGY>
+// TINY: field vectors of up to 64 slots get a build of their own without the batched row loops -- the round loop of the default
+// titration curve is latency-bound down to its instruction-cache footprint (59.4 ms against 61.8 with one more loop compiled in)
+template <bool PER_CHAIN, int MIN_CTAS, int TPL, bool ENERGY, bool TINY>
 __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_warp (const McParams p) {
     static_assert (ENERGY || !PER_CHAIN, "per-chain outputs include the energy");
+    static_assert (!TINY || MIN_CTAS != 1, "the large-field build has no tiny variant");
     extern __shared__ __align__ (16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
     constexpr int RING = TPL <= 2 ? 128 : 256;
-    constexpr int UPD  = MIN_CTAS == 1 ? 16 : 4;      // 128-bit loads per lane, row and batch when a move is applied
+    constexpr int UPD  = MIN_CTAS == 1 ? 16 : TINY ? 1 : 4;      // 128-bit loads per lane, row and batch when a move is applied
     constexpr bool FALLBACK = MIN_CTAS == 1;          // only the 255-register variant carries the four-gather cross-term path
     constexpr bool ABS = MIN_CTAS != 1;               // small fields: instance-indexed slots (see WarpLayout)
     // The shared-memory layout (WarpLayout) comes from the host in the kernel parameters and every array is addressed by a
@@ -1741,12 +1742,14 @@ static int launch_mc (pce_mc *mc, const double *ph, int nph, int ph_index_offset
     } else {
         // one resident CTA (large fields): up to 255 registers; two: 128
         void (*kernel) (const McParams);
-#define PCE_WARP_VARIANT(C_, TPL_) (per_chain ? k_mc_warp<true, C_, TPL_, true> : energy ? k_mc_warp<false, C_, TPL_, true> : k_mc_warp<false, C_, TPL_, false>)
-#define PCE_WARP_KERNEL(TPL_) (plan.upd == 16 ? PCE_WARP_VARIANT (1, TPL_) : plan.ctas_per_sm >= 4 ? PCE_WARP_VARIANT (4, TPL_) \
-                              : plan.ctas_per_sm == 3 ? PCE_WARP_VARIANT (3, TPL_) : PCE_WARP_VARIANT (2, TPL_))
+#define PCE_WARP_VARIANT(C_, TPL_, T_) (per_chain ? k_mc_warp<true, C_, TPL_, true, T_> : energy ? k_mc_warp<false, C_, TPL_, true, T_> : k_mc_warp<false, C_, TPL_, false, T_>)
+#define PCE_WARP_SMALL(C_, TPL_) (plan.upd == 1 ? PCE_WARP_VARIANT (C_, TPL_, true) : PCE_WARP_VARIANT (C_, TPL_, false))
+#define PCE_WARP_KERNEL(TPL_) (plan.upd == 16 ? PCE_WARP_VARIANT (1, TPL_, false) : plan.ctas_per_sm >= 4 ? PCE_WARP_SMALL (4, TPL_) \
+                              : plan.ctas_per_sm == 3 ? PCE_WARP_SMALL (3, TPL_) : PCE_WARP_SMALL (2, TPL_))
         if (plan.tpl == 2) kernel = PCE_WARP_KERNEL (2);
         else kernel = PCE_WARP_KERNEL (1);
 #undef PCE_WARP_KERNEL
+#undef PCE_WARP_SMALL
 #undef PCE_WARP_VARIANT
         PCE_CUDA (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) plan.smem));
         // shared-memory carveout for exactly the planned number of resident CTAs (the rest of the 228 KB stays L1 for the

@@ -10,3 +10,9 @@ import json
 d = json.load(open("gpurun_out/c39_ifp20.json"))
 print("ifp20", d.get("value"), (d.get("e2e") or {}).get("value"), d.get("ms_per_step"), d["config"].get("launch"))
 PY
+timeout 600 python bench.py --workload lysozyme --no-cpu-baseline --no-side-workloads > gpurun_out/c39_lysozyme.json 2> gpurun_out/c39_lysozyme.err
+python - <<PY
+import json
+d = json.load(open("gpurun_out/c39_lysozyme.json"))
+print("lysozyme", d.get("value"), d["titration_curve"]["defaults"]["wall_ms_runs"], d["titration_curve"]["reference_effort"]["wall_ms"])
+PY
