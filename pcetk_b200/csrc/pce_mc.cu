@@ -1118,6 +1118,7 @@ __global__ void __launch_bounds__ (MIN_CTAS == 1 ? 320 : 256, MIN_CTAS) k_mc_war
             // warp-uniform bookkeeping stays on the uniform datapath)
             if (ABS && p.nmoves_magic) { k_before = __umulhi (past - 1u, p.nmoves_magic); k_total = __umulhi (past, p.nmoves_magic); }
             else if (nmoves > (uint32_t) (32 * TPL)) { k_before = past - 1u >= nmoves ? 1u : 0u; k_total = 1u; }      // at most one scan end
+            else if (ABS) { k_before = past - 1u; k_total = past; }        // the reciprocal covers 2 <= nmoves <= 64: this is a model of one site
             else { k_before = (past - 1u) / nmoves; k_total = past / nmoves; }
         }
         uint32_t ndbl = 0, ndbl_prod = 0;
