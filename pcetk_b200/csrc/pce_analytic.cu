@@ -387,36 +387,42 @@ extern "C" int pce_analytic_finish (pce_model *m, const double *bins, const doub
     const int Nb = plan.Nb;
     const long double beta = 1.0L / ((long double) PCE_R * m->temperature);
     const long double mu_star = pce::mu_of (m->temperature, plan.ph_star);
-    std::vector<long double> logw (Nb), logb (Nb, 0.0L);
-    std::vector<double> weight (Nb);
-    for (int n = 0; n < Nb; n++) if (bins[n] > 0.0) logb[n] = logl ((long double) bins[n]);
-    // e^x for an extended-precision x: the double-precision exponential of its leading part, corrected by the remainder
-    // (x87 expl costs ~100 ns; nph * nbins of them dominated this function)
-    auto exp_split = [] (long double x) -> double {
-        if (x < -700.0L) return x < -745.0L ? 0.0 : (double) expl (x);
-        if (x > 690.0L) return (double) std::min (expl (x), 1.0e300L);
-        const double hi = (double) x, lo = (double) (x - (long double) hi);
-        return std::exp (hi) * (1.0 + lo);
-    };
+    // Logarithmic weights with ~32 digits (pairs of doubles: the range is that of the bin scales, e^(+-700) and beyond, and the weights
+    // must come out to 1e-16 relative); the weighted sums themselves are sums of at most ~100 positive doubles <= 1 and stay in double
+    // precision.  (x87 long double arithmetic and expl took 75 us per 41-point curve here; this takes 10.)
+    struct Pair { double hi, lo; };
+    auto two_sum = [] (double a, double b) -> Pair { const double s = a + b, bb = s - a; return { s, (a - (s - bb)) + (b - bb) }; };
+    std::vector<double> logb (Nb, 0.0), weight (Nb), whi (Nb), wlo (Nb);
+    for (int n = 0; n < Nb; n++) if (bins[n] > 0.0) logb[n] = std::log (bins[n]);          // (only picks the shift: any value near the maximum does)
     std::vector<double> wn ((size_t) Nb * nph);          // normalised weights [bin][pH]: pH innermost, so the sums below vectorise
     for (int q = 0; q < nph; q++) {
-        // logarithmic weights in extended precision (their range is that of the bin scales, e^(+-700) and beyond); the weighted sums
-        // themselves are sums of at most ~100 positive doubles <= 1 and stay in double precision
-        const long double mu = pce::mu_of (m->temperature, ph[q]);
-        long double shift = -1.0e300L;
+        const long double c = beta * (mu_star - (long double) pce::mu_of (m->temperature, ph[q]));      // log-weight of one more proton
+        const double c_hi = (double) c, c_lo = (double) (c - (long double) c_hi);
+        double shift = -1.0e300;
         for (int n = 0; n < Nb; n++) {
-            logw[n] = -(long double) plan.sigma[(size_t) n] - beta * n * (mu_star - mu);
-            if (bins[n] > 0.0) shift = std::max (shift, logb[n] + logw[n]);
+            // logw = -sigma[n] - n c
+            const double p_hi = (double) n * c_hi, p_lo = std::fma ((double) n, c_hi, -p_hi) + (double) n * c_lo;
+            Pair w = two_sum (-plan.sigma[(size_t) n], -p_hi);
+            w.lo -= p_lo;
+            whi[n] = w.hi; wlo[n] = w.lo;
+            if (bins[n] > 0.0) shift = std::max (shift, logb[n] + w.hi);
         }
         double z = 0.0;
         for (int n = 0; n < Nb; n++) {
-            weight[n] = bins[n] > 0.0 ? exp_split (logw[n] - shift) : 0.0;      // bins[n] * weight[n] <= 1
-            z += bins[n] * weight[n];
+            double value = 0.0;
+            if (bins[n] > 0.0) {
+                Pair a = two_sum (whi[n], -shift);
+                a.lo += wlo[n];
+                const double hi = a.hi + a.lo, lo = a.lo - (hi - a.hi);
+                value = hi < -745.0 ? 0.0 : hi > 690.0 ? 1.0e300 : std::exp (hi) * (1.0 + lo);       // bins[n] * weight[n] <= ~1
+            }
+            weight[n] = value;
+            z += bins[n] * value;
         }
         if (!(z > 0.0)) return fail (PCE_ERR_STATE, "partition function underflowed; split the pH grid");
         const double inv = 1.0 / z;
         for (int n = 0; n < Nb; n++) wn[(size_t) n * nph + q] = weight[n] * inv;
-        if (out_lnz) out_lnz[q] = (double) (logl ((long double) z) + shift - beta * ((long double) plan.gref - gzero));
+        if (out_lnz) out_lnz[q] = (double) (logl ((long double) z) + (long double) shift - beta * ((long double) plan.gref - gzero));
     }
     std::vector<double> acc (nph);
     for (int a = 0; a < m->ninst; a++) {
