@@ -2,17 +2,20 @@
 """Static size of the trial loop of one k_mc_* variant: builds nothing, reads an object file.
 
 usage: sass_loop.py OBJECT SUBSTRING [--dump]
-Finds the function whose mangled name contains SUBSTRING, the innermost-largest backward branch region that contains MUFU.EX2
-(the Metropolis screen), and prints instruction counts by opcode class for that region."""
+Finds the function whose mangled name contains SUBSTRING, the largest backward-branch region that contains MUFU.EX2 (the
+Metropolis screen), and prints instruction counts by opcode class for that region."""
 import collections
 import re
 import subprocess
 import sys
 
 
-def main():
-    obj, key = sys.argv[1], sys.argv[2]
-    text = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+def disassemble(obj):
+    return subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
+
+
+def loop_region(text, key):
+    """[(address, instruction text)] of the trial / round loop of the function whose name contains `key`."""
     functions = re.split(r"\n\s*Function : ", text)
     body = next(f for f in functions if key in f.split("\n", 1)[0])
     instr = []
@@ -29,7 +32,12 @@ def main():
             if any("MUFU.EX2" in t for _, t in instr[j:i + 1]) and (best is None or i - j > best[1] - best[0]):
                 best = (j, i)
     j, i = best
-    region = instr[j:i + 1]
+    return instr[j:i + 1]
+
+
+def main():
+    obj, key = sys.argv[1], sys.argv[2]
+    region = loop_region(disassemble(obj), key)
     classes = collections.Counter()
     for _, s in region:
         op = s.split()[1] if s.startswith("@") else s.split()[0]
@@ -41,4 +49,5 @@ def main():
             print("%05x  %s" % (a, s))
 
 
-main()
+if __name__ == "__main__":
+    main()
